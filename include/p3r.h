@@ -1,0 +1,270 @@
+/*
+ * p3r.h — C ABI of the B200-native batch-STARK prover behind Plonky3-recursion's
+ *         `BatchStarkProver::prove_all_tables` / `ProverData::from_airs_and_degrees`.
+ *
+ * This is the drop-in boundary. A Rust `GpuBatchStarkProver<SC>` keeps the
+ * reference signatures
+ *     prove_all_tables(&self, &Traces<EF>, &CircuitProverData<SC>)      circuit-prover/src/batch_stark_prover.rs:1203-1222
+ *     ProverData::from_airs_and_degrees(..)                              recursion/src/recursion.rs:376,487,737
+ * and calls the functions below through a `-sys` crate (see INTEGRATION.md for the binding stub).
+ * Fiat–Shamir stays on the host (`SC::Challenger`); every function that needs a challenge takes it
+ * as an argument and every function that produces transcript material returns it in caller memory.
+ *
+ * Conventions
+ *  - return value 0 = OK, non-zero = p3r_status (mapped to BatchStarkProverError on the Rust side,
+ *    circuit-prover/src/batch_stark_prover.rs:786-808); p3r_last_error() gives a message.
+ *  - every field element is a u32 in Montgomery form (R = 2^32), little-endian, the in-memory form of
+ *    p3's MontyField31; an extension element is 4 consecutive coefficients (BinomialExtensionField<F,4>).
+ *  - host matrices are row-major (p3 RowMajorMatrix); the library transposes to its column-major
+ *    device layout on upload. Caller owns all host buffers; handles own device memory.
+ *  - one session = one CUDA stream; a ctx is bound to one device; sessions of one ctx are not
+ *    concurrently callable.
+ *  - there is NO CPU fallback: every entry point fails with P3R_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef P3R_H
+#define P3R_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct p3r_ctx p3r_ctx;
+typedef struct p3r_prep p3r_prep;
+typedef struct p3r_session p3r_session;
+
+typedef enum {
+    P3R_OK = 0,
+    P3R_ERR_INVALID_ARG = 1,   /* shape / parameter error            -> BatchStarkProverError::InvalidTableShape-like */
+    P3R_ERR_CUDA = 2,          /* CUDA runtime error / no device     -> BatchStarkProverError::Backend               */
+    P3R_ERR_OOM = 3,           /* device or host allocation failed                                                    */
+    P3R_ERR_STATE = 4,         /* phase called out of order                                                           */
+    P3R_ERR_UNSUPPORTED = 5,   /* field / width / option not built                                                    */
+    P3R_ERR_BUFFER = 6,        /* caller buffer too small (needed size is written to the size out-param)              */
+    P3R_ERR_POW = 7            /* no proof-of-work witness found                                                      */
+} p3r_status;
+
+enum { P3R_FIELD_KOALABEAR = 0, P3R_FIELD_BABYBEAR = 1 };
+
+/* Field description. `w` is the binomial constant x^4 = w that the reference obtains from
+ * ExtractBinomialW::extract_w (circuit-prover/src/field_params.rs:34-41) and records in the proof
+ * (batch_stark_prover.rs:627). Values are CANONICAL (not Montgomery) integers. */
+typedef struct {
+    uint32_t field_id;      /* P3R_FIELD_*                                    */
+    uint32_t p;             /* modulus, must match field_id                   */
+    uint32_t w;             /* binomial non-residue (3 KoalaBear, 11 BabyBear) */
+    uint32_t generator;     /* F::GENERATOR = coset shift of every LDE        */
+} p3r_field_desc;
+
+/* Poseidon2 width-16 parameters (round constants are injected, Montgomery form).
+ * Reference: poseidon2-circuit-air/src/public_types.rs:48-53,99-104,220-226,272-278. */
+typedef struct {
+    uint32_t width;                 /* 16                                           */
+    uint32_t sbox_degree;           /* 3 (KoalaBear) or 7 (BabyBear)                */
+    uint32_t rounds_f;              /* 8 (4 initial + 4 terminal)                   */
+    uint32_t rounds_p;              /* 20 (KoalaBear) or 13 (BabyBear)              */
+    const uint32_t* external_rc;    /* rounds_f * 16 words: initial rounds then terminal rounds */
+    const uint32_t* internal_rc;    /* rounds_p words                                */
+    const uint32_t* internal_diag;  /* 16 words V: s_i <- V_i * s_i + sum(s)         */
+} p3r_poseidon2_consts;
+
+/* FRI / MMCS parameters (recursion/examples/common/mod.rs:464-486, circuit-prover/src/config.rs:129-136). */
+typedef struct {
+    uint32_t log_blowup;
+    uint32_t log_final_poly_len;
+    uint32_t max_log_arity;
+    uint32_t num_queries;
+    uint32_t commit_pow_bits;
+    uint32_t query_pow_bits;
+    uint32_t cap_height;            /* Merkle cap has 2^cap_height digests */
+} p3r_fri_params;
+
+/* Row-major host matrix of Montgomery words (p3 RowMajorMatrix<Val>). */
+typedef struct {
+    const uint32_t* data;
+    uint32_t height;
+    uint32_t width;
+} p3r_matrix_u32;
+
+/* ------------------------------------------------------------------------------------------------
+ * Constraint bytecode. The Rust side compiles the (base, ext) SymbolicExpression DAGs returned by
+ * p3_batch_stark::symbolic::get_symbolic_constraints (the call the recursive verifier makes,
+ * recursion/src/traits/air.rs:160) into this SSA form once per circuit shape; node kinds follow
+ * circuit/src/symbolic/compiler.rs:86-118,183-189. Two register files: base slots (1 word) and
+ * extension slots (4 words). `a`/`b` name slots unless stated otherwise.
+ * Folding follows recursion/src/traits/air.rs:170-181: acc = acc*alpha + c over all base constraints
+ * in order, then all extension constraints; ASSERT_*'s `dst` is the position in that combined order.
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum {
+    P3R_OP_B_MAIN = 0,    /* B[dst] = main[col=a][row + b]          b in {0,1}                  */
+    P3R_OP_B_PREP = 1,    /* B[dst] = preprocessed[col=a][row + b]                               */
+    P3R_OP_B_PUB = 2,     /* B[dst] = public_values[a]                                           */
+    P3R_OP_B_SEL = 3,     /* B[dst] = selector a: 0 is_first_row, 1 is_last_row, 2 is_transition */
+    P3R_OP_B_CONST = 4,   /* B[dst] = a (Montgomery immediate)                                   */
+    P3R_OP_B_ADD = 5,
+    P3R_OP_B_SUB = 6,
+    P3R_OP_B_MUL = 7,
+    P3R_OP_B_NEG = 8,
+    P3R_OP_E_PERM = 16,   /* E[dst] = permutation EF column a at row + b                         */
+    P3R_OP_E_CHAL = 17,   /* E[dst] = challenge a: 2c = bus prefix of lookup c, 2c+1 = beta      */
+    P3R_OP_E_PVAL = 18,   /* E[dst] = permutation value a (the AIR's LogUp terminal)             */
+    P3R_OP_E_CONST = 19,  /* E[dst] = ext_consts[a]                                              */
+    P3R_OP_E_FROMB = 20,  /* E[dst] = lift(B[a])                                                 */
+    P3R_OP_E_ADD = 21,
+    P3R_OP_E_SUB = 22,
+    P3R_OP_E_MUL = 23,
+    P3R_OP_E_NEG = 24,
+    P3R_OP_E_MULB = 25,   /* E[dst] = E[a] * B[b]                                                */
+    P3R_OP_E_ADDB = 26,   /* E[dst] = E[a] + B[b]                                                */
+    P3R_OP_E_SUBB = 27,   /* E[dst] = E[a] - B[b]                                                */
+    P3R_OP_ASSERT_B = 32, /* constraint #dst (fold order) = B[a]                                 */
+    P3R_OP_ASSERT_E = 33, /* constraint #dst (fold order) = E[a]                                 */
+    P3R_OP_OUT_B = 34     /* lookup-input programs: out[dst] = B[a]                              */
+} p3r_opcode;
+
+typedef struct {
+    uint32_t op, dst, a, b;
+} p3r_insn;
+
+typedef struct {
+    const p3r_insn* insns;
+    uint32_t n_insns;
+    uint32_t n_base_slots;
+    uint32_t n_ext_slots;
+    const uint32_t* ext_consts;     /* 4 Montgomery words each */
+    uint32_t n_ext_consts;
+    uint32_t n_constraints;         /* base + ext, constraint programs */
+    uint32_t n_outputs;             /* lookup-input programs           */
+} p3r_program;
+
+/* LogUp (`WitnessChecks` bus) description of one AIR after pack_same_bus
+ * (circuit-prover/src/batch_stark_prover.rs:925-941). One p3r_lookup = one fraction column
+ * (permutation column c+1, recursion/src/verifier/batch_stark.rs:902-912); its interactions are
+ * (multiplicity, tuple) pairs whose values the `lookup_inputs` program writes with OUT_B. */
+typedef struct {
+    uint32_t mult_out;          /* OUT_B index of the multiplicity             */
+    uint32_t elem_out_first;    /* OUT_B index of tuple element 0               */
+    uint32_t n_elems;           /* tuple length; elements are consecutive OUT_B */
+} p3r_interaction;
+
+typedef struct {
+    uint32_t bus;               /* global bus id (recursion/src/verifier/batch_stark.rs:1055-1083) */
+    uint32_t first_interaction;
+    uint32_t n_interactions;
+} p3r_lookup;
+
+/* One table (AIR instance). Order of instances is the reference's
+ * [Const, Public, ALU, NPOs...] (circuit-prover/src/batch_stark_prover.rs:1493-1519). */
+typedef struct {
+    uint32_t log_height;            /* log2 of the padded trace height                                  */
+    uint32_t main_width;
+    uint32_t prep_width;            /* 0 = no preprocessed columns                                      */
+    uint32_t n_public;
+    uint32_t log_quotient_chunks;
+    uint32_t uses_next_row;         /* main trace is opened at zeta*g (recursion/src/traits/air.rs:103-109) */
+    p3r_program constraints;        /* AIR + LogUp constraints                                          */
+    p3r_program lookup_inputs;      /* n_outputs = values consumed by `interactions`                    */
+    const p3r_lookup* lookups;
+    uint32_t n_lookups;
+    const p3r_interaction* interactions;
+    uint32_t n_interactions;
+} p3r_instance_desc;
+
+/* ---------------------------------------------------------------------------------------------- */
+
+/* Library/ABI version and a description of the build (arch, fields). */
+uint32_t p3r_abi_version(void);
+const char* p3r_build_info(void);
+
+/* Create a prover context on CUDA device `device`. Replaces building `StarkConfig`/`MyPcs`
+ * (recursion/examples/common/mod.rs:464-486; circuit-prover/src/config.rs:92-137). */
+int p3r_ctx_create(int device, const p3r_field_desc* field, const p3r_poseidon2_consts* poseidon2,
+                   const p3r_fri_params* fri, p3r_ctx** out);
+void p3r_ctx_destroy(p3r_ctx* ctx);
+const char* p3r_last_error(const p3r_ctx* ctx);
+
+/* Replaces ProverData::from_airs_and_degrees (recursion/src/recursion.rs:376): uploads the
+ * instance descriptions (bytecode, lookups), LDEs + commits all preprocessed matrices into one
+ * global MMCS tree that stays device-resident, and writes its cap (8 << cap_height words).
+ * `prep[i].data` may be NULL when descs[i].prep_width == 0. `cap_out` is untouched when no
+ * instance has preprocessed columns (then *has_prep_out = 0). */
+int p3r_prep_commit(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_desc* descs,
+                    const p3r_matrix_u32* prep, p3r_prep** out, uint32_t* cap_out, uint32_t* has_prep_out);
+void p3r_prep_free(p3r_prep* prep);
+
+/* Phase-stepped proving session; replaces p3_batch_stark::prove_batch
+ * (call site circuit-prover/src/batch_stark_prover.rs:1595). Phases must be called in the order
+ * they are declared. `public_values[i]` has descs[i].n_public words (may be NULL when 0). */
+int p3r_prove_begin(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces,
+                    const uint32_t* const* public_values, p3r_session** out);
+/* LDE + MMCS commit of all main traces. cap_out: 8 << cap_height words. */
+int p3r_commit_main(p3r_session* s, uint32_t* cap_out);
+/* LogUp permutation traces for (alpha, beta), LDE + commit. terminals_out: 4 words per instance
+ * that has lookups, in instance order. No-op returning P3R_OK when no instance has lookups. */
+int p3r_commit_perm(p3r_session* s, const uint32_t alpha[4], const uint32_t beta[4], uint32_t* cap_out,
+                    uint32_t* terminals_out);
+/* Quotient evaluation with folding challenge alpha, chunk split, LDE + commit. */
+int p3r_commit_quotient(p3r_session* s, const uint32_t alpha[4], uint32_t* cap_out);
+/* Out-of-domain openings at zeta (and zeta*g_i). Layout of opened_out, per instance i in order:
+ *   main_local[main_width*4], main_next[main_width*4] (iff uses_next_row),
+ *   prep_local[prep_width*4], prep_next[prep_width*4] (iff prep_width>0),
+ *   perm_local[aux*4*4], perm_next[aux*4*4] (iff n_lookups>0; aux = n_lookups+1; one EF per flattened base column),
+ *   quotient_chunks[2^log_qc][4*4]
+ * (every opened value is an EF element = 4 words). *n_words receives the size. */
+int p3r_open(p3r_session* s, const uint32_t zeta[4], uint32_t* opened_out, size_t cap_words, size_t* n_words);
+/* Reduced openings per height with alpha_fri; fixes the arity schedule. log_arities_out: up to 32 entries. */
+int p3r_fri_begin(p3r_session* s, const uint32_t alpha_fri[4], uint32_t* n_rounds_out, uint32_t* log_arities_out);
+/* Commit FRI round `round` (matrix of folded-height rows x arity EF), write its cap. */
+int p3r_fri_commit(p3r_session* s, uint32_t round, uint32_t* cap_out);
+/* Fold round `round` with beta and roll in the reduced opening of the folded height. */
+int p3r_fri_fold(p3r_session* s, uint32_t round, const uint32_t beta[4]);
+/* Final polynomial coefficients: 4 << log_final_poly_len words. */
+int p3r_fri_final_poly(p3r_session* s, uint32_t* coeffs_out);
+/* Query openings for `n` indices (each < 2^log_global_max_height). Blob layout, per query:
+ *   for each input round in [main, quotient, preprocessed?, permutation?]:
+ *       for each matrix of the round in commit order: the opened row (width words)
+ *       Merkle path: (log_max_height_of_round - cap_height) digests of 8 words, leaf to cap
+ *   for each FRI round r: (2^log_arity_r - 1) sibling EF values (4 words each, group order with own slot removed),
+ *       Merkle path of (log_folded_height_r - cap_height) digests */
+int p3r_fri_query(p3r_session* s, const uint32_t* indices, uint32_t n, uint32_t* out, size_t cap_words,
+                  size_t* n_words);
+void p3r_session_free(p3r_session* s);
+
+/* DuplexChallenger::grind on the device (p3-challenger GrindingChallenger::grind; check restated at
+ * recursion/src/challenger/circuit.rs:409-430). `state` = 16 sponge words, `pending` = the n_pending (<8)
+ * words in the challenger's input buffer. Returns the SMALLEST canonical witness w such that after
+ * observe(w) the next sample has `bits` low zero bits (deterministic, unlike a parallel find_any). */
+int p3r_grind(p3r_ctx* ctx, const uint32_t state[16], const uint32_t* pending, uint32_t n_pending, uint32_t bits,
+              uint32_t* witness_out);
+
+/* One-shot prove: runs the host DuplexChallenger transcript (host C++ mirror of BatchStarkProver::prove,
+ * circuit-prover/src/batch_stark_prover.rs:1275-1642) over the phases above and writes the flat proof
+ * blob described in DESIGN.md §"Proof blob". */
+int p3r_prove(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces,
+              const uint32_t* const* public_values, uint32_t* proof_out, size_t cap_words, size_t* n_words);
+
+/* ---- isolated kernels (LDE + Merkle + FRI-fold sweep). Host pointers. ---- */
+/* Coset LDE of a row-major height x width matrix -> row-major (height<<log_blowup) x width, rows bit-reversed
+ * (TwoAdicFriPcs::commit -> Radix2DitParallel::coset_lde_batch, circuit-prover/src/config.rs:17,131). */
+int p3r_coset_lde(p3r_ctx* ctx, const p3r_matrix_u32* in, uint32_t log_blowup, uint32_t* out);
+/* MerkleTreeMmcs::commit over mixed-height row-major matrices; cap_out 8<<cap_height words. */
+int p3r_mmcs_commit(p3r_ctx* ctx, uint32_t n_mats, const p3r_matrix_u32* mats, uint32_t* cap_out);
+/* Poseidon2 permutation of n states of 16 words (in place). */
+int p3r_poseidon2_permute(p3r_ctx* ctx, uint32_t* states, uint32_t n);
+/* Device-resident benchmark of the commit path (LDE + Merkle) on a synthetic matrix:
+ * returns CUDA-event milliseconds per phase, averaged over `iters`. times_ms_out: [lde, leaves, tree]. */
+int p3r_bench_commit(p3r_ctx* ctx, uint32_t log_height, uint32_t width, uint32_t iters, uint64_t seed,
+                     float* times_ms_out);
+
+/* Per-session device timings (CUDA events on the session stream) of the last one-shot p3r_prove:
+ * names_out receives a pointer to a static NUL-separated list; ms_out up to cap entries. */
+int p3r_last_phase_times(p3r_ctx* ctx, const char** names_out, float* ms_out, uint32_t cap, uint32_t* n_out);
+/* Number of kernel launches issued by this ctx since creation (for bench.py's gpu_launches). */
+uint64_t p3r_launch_count(const p3r_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P3R_H */

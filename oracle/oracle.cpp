@@ -1,0 +1,1711 @@
+// oracle.cpp — CPU restatement of the batch-STARK prover AND verifier that sit behind
+// Plonky3-recursion's `prove_next_layer` (recursion/src/recursion.rs:401-502 ->
+// circuit-prover/src/batch_stark_prover.rs:1595 `p3_batch_stark::prove_batch`).
+//
+// *** TEST INFRASTRUCTURE ONLY. *** Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// `--impl reference` legs may load this library. The product (libp3r_b200.so) never links or calls it.
+//
+// PARITY STATUS: "parity unpinned" at the proof-byte level. The arithmetic of this path lives in the
+// crates.io `p3-*` 0.6 crates (Cargo.toml:45-73, no Cargo.lock) which are absent from /root/reference and
+// cannot be fetched or built here (no cargo, no network). The reference tree holds no golden proof bytes
+// (SURVEY.md §8c). What IS pinned: (a) Poseidon2 round constants — regenerated with the Poseidon2 paper's
+// Grain LFSR and cross-checked against the p3 `BABYBEAR_RC16_*` / `KOALABEAR_RC16_*` tables as recalled
+// (tests/test_oracle_kat.py); (b) the transcript order, domains, LogUp layout, FRI fold, MMCS and challenger
+// semantics, each restated from the in-tree recursive verifier cited at every function below; (c) the AIR
+// column-count goldens of circuit-prover/src/air/shape_golden.rs:33-68 (tests/test_airs.py).
+//
+// Arithmetic here is deliberately naive: canonical residues, `%` reduction, textbook NTT, Horner evaluation,
+// so that it shares no code or algorithmic shortcut with the Montgomery/CUDA implementation it checks.
+// At the C boundary every field word is Montgomery (R = 2^32) exactly as in include/p3r.h.
+
+#include <algorithm>
+#include <cassert>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <type_traits>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../include/p3r.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Field: canonical residues mod P (KoalaBear 0x7f000001 / BabyBear 0x78000001;
+// circuit-prover/src/batch_stark_prover/tests.rs:704-705,731-732).
+// ------------------------------------------------------------------------------------------------
+uint32_t P = 0;       // modulus
+uint32_t Wnr = 0;     // binomial constant: x^4 = Wnr  (circuit-prover/src/field_params.rs:34-41)
+uint32_t GEN = 0;     // multiplicative generator = LDE coset shift (recursion/src/pcs/fri/verifier.rs:960)
+uint32_t TWO_ADICITY = 0;
+
+struct Fp {
+    uint32_t v;
+};
+inline Fp mk(uint64_t x) { return Fp{(uint32_t)(x % P)}; }
+inline Fp operator+(Fp a, Fp b) { return mk((uint64_t)a.v + b.v); }
+inline Fp operator-(Fp a, Fp b) { return mk((uint64_t)a.v + P - b.v); }
+inline Fp operator*(Fp a, Fp b) { return mk((uint64_t)a.v * b.v); }
+inline Fp operator-(Fp a) { return mk((uint64_t)P - a.v); }
+inline bool operator==(Fp a, Fp b) { return a.v == b.v; }
+inline bool operator!=(Fp a, Fp b) { return a.v != b.v; }
+Fp fpow(Fp a, uint64_t e) {
+    Fp r{1};
+    while (e) {
+        if (e & 1) r = r * a;
+        a = a * a;
+        e >>= 1;
+    }
+    return r;
+}
+Fp finv(Fp a) {
+    if (a.v == 0) throw std::runtime_error("oracle: inverse of zero");
+    return fpow(a, (uint64_t)P - 2);
+}
+// Montgomery <-> canonical at the C boundary: monty(x) = x * 2^32 mod P.
+inline uint32_t to_monty(Fp a) { return (uint32_t)((((uint64_t)a.v) << 32) % P); }
+Fp R_INV{0};
+inline Fp from_monty(uint32_t m) { return mk((uint64_t)(m % P)) * R_INV; }
+
+// two_adic_generator(k) = GENERATOR^((p-1)/2^k)  (SURVEY.md §7 H2 derivation).
+Fp two_adic_gen(uint32_t bits) {
+    if (bits > TWO_ADICITY) throw std::runtime_error("oracle: two-adicity exceeded");
+    return fpow(Fp{GEN}, ((uint64_t)P - 1) >> bits);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Degree-4 binomial extension F[x]/(x^4 - W); multiplication as restated at
+// circuit-prover/src/air/alu_air.rs:715-733.
+// ------------------------------------------------------------------------------------------------
+struct Ext {
+    Fp c[4];
+};
+inline Ext ext_zero() { return Ext{{Fp{0}, Fp{0}, Fp{0}, Fp{0}}}; }
+inline Ext ext_one() { return Ext{{Fp{1}, Fp{0}, Fp{0}, Fp{0}}}; }
+inline Ext lift(Fp a) { return Ext{{a, Fp{0}, Fp{0}, Fp{0}}}; }
+inline Ext operator+(const Ext& a, const Ext& b) {
+    Ext r;
+    for (int i = 0; i < 4; i++) r.c[i] = a.c[i] + b.c[i];
+    return r;
+}
+inline Ext operator-(const Ext& a, const Ext& b) {
+    Ext r;
+    for (int i = 0; i < 4; i++) r.c[i] = a.c[i] - b.c[i];
+    return r;
+}
+inline Ext operator-(const Ext& a) {
+    Ext r;
+    for (int i = 0; i < 4; i++) r.c[i] = -a.c[i];
+    return r;
+}
+inline Ext operator*(const Ext& a, const Ext& b) {
+    Fp t[7];
+    for (auto& x : t) x = Fp{0};
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) t[i + j] = t[i + j] + a.c[i] * b.c[j];
+    Ext r;
+    Fp w{Wnr};
+    for (int i = 0; i < 4; i++) r.c[i] = t[i];
+    for (int i = 4; i < 7; i++) r.c[i - 4] = r.c[i - 4] + w * t[i];
+    return r;
+}
+inline Ext operator*(const Ext& a, Fp b) {
+    Ext r;
+    for (int i = 0; i < 4; i++) r.c[i] = a.c[i] * b;
+    return r;
+}
+inline Ext operator+(const Ext& a, Fp b) {
+    Ext r = a;
+    r.c[0] = r.c[0] + b;
+    return r;
+}
+inline Ext operator-(const Ext& a, Fp b) {
+    Ext r = a;
+    r.c[0] = r.c[0] - b;
+    return r;
+}
+inline bool operator==(const Ext& a, const Ext& b) {
+    for (int i = 0; i < 4; i++)
+        if (a.c[i] != b.c[i]) return false;
+    return true;
+}
+inline bool is_zero(const Ext& a) { return a == ext_zero(); }
+Ext epow(Ext a, uint64_t e) {
+    Ext r = ext_one();
+    while (e) {
+        if (e & 1) r = r * a;
+        a = a * a;
+        e >>= 1;
+    }
+    return r;
+}
+// Inverse through the tower F -> F(y=x^2) -> F(x): a = A + B x with A = a0 + a2 y, B = a1 + a3 y;
+// a * (A - B x) = A^2 - y B^2 =: N in F(y); 1/N = conj(N) / (n0^2 - W n1^2).
+Ext einv(const Ext& a) {
+    Fp w{Wnr};
+    // A^2 = (a0^2 + w a2^2) + (2 a0 a2) y ;  B^2 = (a1^2 + w a3^2) + (2 a1 a3) y ; y*B^2 = w*(2 a1 a3) + (a1^2 + w a3^2) y
+    Fp a0 = a.c[0], a1 = a.c[1], a2 = a.c[2], a3 = a.c[3];
+    Fp n0 = a0 * a0 + w * a2 * a2 - w * (a1 * a3 + a1 * a3);
+    Fp n1 = (a0 * a2 + a0 * a2) - (a1 * a1 + w * a3 * a3);
+    Fp d = n0 * n0 - w * n1 * n1;
+    if (d.v == 0) throw std::runtime_error("oracle: ext inverse of zero");
+    Fp di = finv(d);
+    Fp m0 = n0 * di, m1 = -(n1 * di);  // 1/N = m0 + m1 y
+    // result = (A - B x) * (m0 + m1 y), with (A - Bx) = a0 - a1 x + a2 x^2 - a3 x^3 and y = x^2
+    Ext conj{{a0, -a1, a2, -a3}};
+    Ext m{{m0, Fp{0}, m1, Fp{0}}};
+    return conj * m;
+}
+
+// Generic helpers so the constraint interpreter can run over Fp (prover rows) or Ext (verifier at zeta).
+inline Ext to_ext(Fp a) { return lift(a); }
+inline Ext to_ext(const Ext& a) { return a; }
+inline Ext mulmix(const Ext& a, Fp b) { return a * b; }
+inline Ext mulmix(const Ext& a, const Ext& b) { return a * b; }
+
+// ------------------------------------------------------------------------------------------------
+// Bit tricks
+// ------------------------------------------------------------------------------------------------
+inline uint32_t bitrev(uint32_t x, uint32_t bits) {
+    uint32_t r = 0;
+    for (uint32_t i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
+    return r;
+}
+inline uint32_t log2_strict(size_t n) {
+    uint32_t l = 0;
+    while (((size_t)1 << l) < n) l++;
+    if (((size_t)1 << l) != n) throw std::runtime_error("oracle: not a power of two");
+    return l;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Textbook radix-2 NTT (natural in, natural out). Reference routine replaced on the GPU:
+// Radix2DitParallel (circuit-prover/src/config.rs:17,131).
+// ------------------------------------------------------------------------------------------------
+template <class T>
+void ntt_inplace(std::vector<T>& a, bool inverse) {
+    size_t n = a.size();
+    uint32_t lg = log2_strict(n);
+    for (size_t i = 0; i < n; i++) {
+        size_t j = bitrev((uint32_t)i, lg);
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    for (uint32_t s = 1; s <= lg; s++) {
+        size_t m = (size_t)1 << s;
+        Fp wm = two_adic_gen(s);
+        if (inverse) wm = finv(wm);
+        for (size_t k = 0; k < n; k += m) {
+            Fp w{1};
+            for (size_t j = 0; j < m / 2; j++) {
+                T t = a[k + j + m / 2] * w;
+                T u = a[k + j];
+                a[k + j] = u + t;
+                a[k + j + m / 2] = u - t;
+                w = w * wm;
+            }
+        }
+    }
+    if (inverse) {
+        Fp ninv = finv(mk(n));
+        for (auto& x : a) x = x * ninv;
+    }
+}
+
+struct Mat {  // row-major, canonical
+    size_t h = 0, w = 0;
+    std::vector<Fp> d;
+    Fp& at(size_t r, size_t c) { return d[r * w + c]; }
+    const Fp& at(size_t r, size_t c) const { return d[r * w + c]; }
+};
+
+// Coefficients of the polynomial whose evaluations over in_shift*H_n are `evals` (natural order).
+std::vector<Fp> interpolate(const std::vector<Fp>& evals, Fp in_shift) {
+    std::vector<Fp> c = evals;
+    ntt_inplace(c, true);
+    Fp si = finv(in_shift), s{1};
+    for (auto& x : c) {
+        x = x * s;
+        s = s * si;
+    }
+    return c;
+}
+// Evaluations of coefficient vector `c` over shift*H_N in natural order.
+std::vector<Fp> evaluate_on_coset(const std::vector<Fp>& c, size_t N, Fp shift) {
+    std::vector<Fp> v(N, Fp{0});
+    Fp s{1};
+    for (size_t k = 0; k < c.size(); k++) {
+        if (k >= N) {
+            if (c[k].v != 0) throw std::runtime_error("oracle: degree too high for domain");
+            continue;
+        }
+        v[k] = c[k] * s;
+        s = s * shift;
+    }
+    ntt_inplace(v, false);
+    return v;
+}
+template <class T>
+Ext horner(const std::vector<T>& c, const Ext& z) {
+    Ext acc = ext_zero();
+    for (size_t k = c.size(); k-- > 0;) acc = acc * z + to_ext(c[k]);
+    return acc;
+}
+
+// TwoAdicFriPcs::commit's LDE: evaluations of the column polynomials over
+// GENERATOR * H_{n*2^log_blowup}, rows stored bit-reversed. `in_shift` is the shift of the input domain.
+Mat coset_lde(const Mat& m, uint32_t log_blowup, Fp in_shift) {
+    size_t N = m.h << log_blowup;
+    uint32_t lgN = log2_strict(N);
+    Mat out;
+    out.h = N;
+    out.w = m.w;
+    out.d.resize(N * m.w);
+#pragma omp parallel for schedule(dynamic)
+    for (size_t c = 0; c < m.w; c++) {
+        std::vector<Fp> col(m.h);
+        for (size_t r = 0; r < m.h; r++) col[r] = m.at(r, c);
+        std::vector<Fp> coef = interpolate(col, in_shift);
+        std::vector<Fp> ev = evaluate_on_coset(coef, N, Fp{GEN});
+        for (size_t r = 0; r < N; r++) out.at(bitrev((uint32_t)r, lgN), c) = ev[r];
+    }
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Poseidon2 width 16 (p3-poseidon2 [P3-EXT]; structure recalled in SURVEY.md §8c; constants injected).
+// ------------------------------------------------------------------------------------------------
+struct Poseidon2 {
+    uint32_t sbox = 0, rf = 0, rp = 0;
+    std::vector<Fp> ext_rc, int_rc, diag;
+} P2;
+
+inline Fp sbox_pow(Fp x) {
+    if (P2.sbox == 3) return x * x * x;
+    if (P2.sbox == 7) {
+        Fp x2 = x * x, x3 = x2 * x, x4 = x2 * x2;
+        return x3 * x4;
+    }
+    return fpow(x, P2.sbox);
+}
+void external_linear(Fp* s) {
+    // circ(2*M4, M4, M4, M4) with M4 = [[2,3,1,1],[1,2,3,1],[1,1,2,3],[3,1,1,2]]
+    for (int k = 0; k < 4; k++) {
+        Fp a = s[4 * k], b = s[4 * k + 1], c = s[4 * k + 2], d = s[4 * k + 3];
+        Fp two{2}, three{3};
+        s[4 * k] = two * a + three * b + c + d;
+        s[4 * k + 1] = a + two * b + three * c + d;
+        s[4 * k + 2] = a + b + two * c + three * d;
+        s[4 * k + 3] = three * a + b + c + two * d;
+    }
+    Fp sums[4];
+    for (int j = 0; j < 4; j++) sums[j] = s[j] + s[4 + j] + s[8 + j] + s[12 + j];
+    for (int i = 0; i < 16; i++) s[i] = s[i] + sums[i % 4];
+}
+void poseidon2_permute(Fp* s) {
+    external_linear(s);
+    uint32_t half = P2.rf / 2;
+    for (uint32_t r = 0; r < half; r++) {
+        for (int i = 0; i < 16; i++) s[i] = sbox_pow(s[i] + P2.ext_rc[16 * r + i]);
+        external_linear(s);
+    }
+    for (uint32_t r = 0; r < P2.rp; r++) {
+        s[0] = sbox_pow(s[0] + P2.int_rc[r]);
+        Fp sum{0};
+        for (int i = 0; i < 16; i++) sum = sum + s[i];
+        for (int i = 0; i < 16; i++) s[i] = sum + P2.diag[i] * s[i];
+    }
+    for (uint32_t r = half; r < P2.rf; r++) {
+        for (int i = 0; i < 16; i++) s[i] = sbox_pow(s[i] + P2.ext_rc[16 * r + i]);
+        external_linear(s);
+    }
+}
+
+struct Digest {
+    Fp d[8];
+};
+// PaddingFreeSponge<Perm,16,8,8> in overwrite mode (recursion/src/pcs/mmcs.rs:16-24).
+Digest sponge_hash(const std::vector<Fp>& in) {
+    Fp st[16];
+    for (auto& x : st) x = Fp{0};
+    for (size_t off = 0; off < in.size(); off += 8) {
+        size_t n = std::min<size_t>(8, in.size() - off);
+        for (size_t i = 0; i < n; i++) st[i] = in[off + i];
+        poseidon2_permute(st);
+    }
+    Digest dg;
+    for (int i = 0; i < 8; i++) dg.d[i] = st[i];
+    return dg;
+}
+// TruncatedPermutation<Perm,2,8,16> (poseidon2-circuit-air/src/air.rs:808-817).
+Digest compress2(const Digest& l, const Digest& r) {
+    Fp st[16];
+    for (int i = 0; i < 8; i++) {
+        st[i] = l.d[i];
+        st[8 + i] = r.d[i];
+    }
+    poseidon2_permute(st);
+    Digest dg;
+    for (int i = 0; i < 8; i++) dg.d[i] = st[i];
+    return dg;
+}
+
+// ------------------------------------------------------------------------------------------------
+// MerkleTreeMmcs over mixed-height matrices (recursion/src/pcs/mmcs.rs:319-432,
+// circuit/src/ops/mmcs.rs:122-185).
+// ------------------------------------------------------------------------------------------------
+uint32_t CAP_HEIGHT = 0;
+struct MerkleTree {
+    std::vector<const Mat*> mats;            // commit order
+    std::vector<std::vector<Digest>> layers;  // layers[0] = leaf level (max height) ... last = cap
+    uint32_t log_max_h = 0;
+    std::vector<Digest> cap() const { return layers.back(); }
+};
+std::vector<Fp> concat_rows(const std::vector<const Mat*>& ms, size_t row) {
+    std::vector<Fp> v;
+    for (auto* m : ms)
+        for (size_t c = 0; c < m->w; c++) v.push_back(m->at(row, c));
+    return v;
+}
+MerkleTree mmcs_commit(const std::vector<const Mat*>& mats) {
+    MerkleTree t;
+    t.mats = mats;
+    size_t max_h = 0;
+    for (auto* m : mats) max_h = std::max(max_h, m->h);
+    t.log_max_h = log2_strict(max_h);
+    if (t.log_max_h < CAP_HEIGHT) throw std::runtime_error("oracle: tree shorter than cap");
+    auto at_height = [&](size_t h) {
+        std::vector<const Mat*> v;  // stable: commit order within a height
+        for (auto* m : mats)
+            if (m->h == h) v.push_back(m);
+        return v;
+    };
+    auto tallest = at_height(max_h);
+    std::vector<Digest> layer(max_h);
+#pragma omp parallel for
+    for (size_t r = 0; r < max_h; r++) layer[r] = sponge_hash(concat_rows(tallest, r));
+    t.layers.push_back(layer);
+    while (t.layers.back().size() > ((size_t)1 << CAP_HEIGHT)) {
+        const auto& prev = t.layers.back();
+        size_t n = prev.size() / 2;
+        auto inject = at_height(n);
+        std::vector<Digest> next(n);
+#pragma omp parallel for
+        for (size_t i = 0; i < n; i++) {
+            Digest d = compress2(prev[2 * i], prev[2 * i + 1]);
+            if (!inject.empty()) d = compress2(d, sponge_hash(concat_rows(inject, i)));
+            next[i] = d;
+        }
+        t.layers.push_back(next);
+    }
+    return t;
+}
+struct BatchOpening {
+    std::vector<std::vector<Fp>> rows;  // per matrix in commit order
+    std::vector<Digest> path;
+};
+BatchOpening mmcs_open(const MerkleTree& t, size_t index) {
+    BatchOpening o;
+    for (auto* m : t.mats) {
+        uint32_t lh = log2_strict(m->h);
+        size_t r = index >> (t.log_max_h - lh);
+        std::vector<Fp> row(m->w);
+        for (size_t c = 0; c < m->w; c++) row[c] = m->at(r, c);
+        o.rows.push_back(row);
+    }
+    for (uint32_t i = 0; i + 1 < t.layers.size(); i++) o.path.push_back(t.layers[i][(index >> i) ^ 1]);
+    return o;
+}
+// dims: heights per matrix (commit order). Returns true iff the path leads to cap[index >> depth].
+bool mmcs_verify(const std::vector<Digest>& cap, const std::vector<size_t>& heights, size_t index,
+                 const std::vector<std::vector<Fp>>& rows, const std::vector<Digest>& path) {
+    size_t max_h = 0;
+    for (auto h : heights) max_h = std::max(max_h, h);
+    uint32_t log_max_h = log2_strict(max_h);
+    if (path.size() != log_max_h - CAP_HEIGHT) return false;
+    auto rows_at = [&](size_t h) {
+        std::vector<Fp> v;
+        for (size_t i = 0; i < heights.size(); i++)
+            if (heights[i] == h) v.insert(v.end(), rows[i].begin(), rows[i].end());
+        return v;
+    };
+    Digest node = sponge_hash(rows_at(max_h));
+    size_t cur = max_h;
+    for (size_t i = 0; i < path.size(); i++) {
+        node = (index & 1) ? compress2(path[i], node) : compress2(node, path[i]);
+        index >>= 1;
+        cur >>= 1;
+        auto v = rows_at(cur);
+        if (!v.empty()) node = compress2(node, sponge_hash(v));
+    }
+    if (index >= cap.size()) return false;
+    for (int i = 0; i < 8; i++)
+        if (cap[index].d[i] != node.d[i]) return false;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// DuplexChallenger<F,Perm,16,8> (recursion/src/challenger/circuit.rs:97-156,337-430).
+// ------------------------------------------------------------------------------------------------
+struct Challenger {
+    Fp st[16];
+    std::vector<Fp> in, out;
+    Challenger() {
+        for (auto& x : st) x = Fp{0};
+    }
+    void duplex() {
+        size_t n = in.size();
+        for (size_t i = 0; i < n; i++) st[i] = in[i];
+        if (n > 0) {
+            for (size_t i = n; i < 8; i++) st[i] = Fp{0};
+            st[8] = st[8] + mk(n);
+        }
+        in.clear();
+        poseidon2_permute(st);
+        out.assign(st, st + 8);
+    }
+    void observe(Fp v) {
+        out.clear();
+        in.push_back(v);
+        if (in.size() == 8) duplex();
+    }
+    void observe_ext(const Ext& e) {
+        for (int i = 0; i < 4; i++) observe(e.c[i]);
+    }
+    void observe_lifted(uint64_t v) { observe_ext(lift(mk(v))); }  // observe_base_as_algebra_element
+    void observe_digest(const Digest& d) {
+        for (int i = 0; i < 8; i++) observe(d.d[i]);
+    }
+    void observe_cap(const std::vector<Digest>& cap) {
+        for (auto& d : cap) observe_digest(d);
+    }
+    Fp sample() {
+        if (!in.empty() || out.empty()) duplex();
+        Fp v = out.back();
+        out.pop_back();
+        return v;
+    }
+    Ext sample_ext() {
+        Ext e;
+        for (int i = 0; i < 4; i++) e.c[i] = sample();
+        return e;
+    }
+    uint32_t sample_bits(uint32_t bits) { return sample().v & (((uint32_t)1 << bits) - 1); }
+    bool check_witness(uint32_t bits, Fp w) {
+        if (bits == 0) return true;
+        observe(w);
+        return sample_bits(bits) == 0;
+    }
+    // GrindingChallenger::grind, made deterministic: smallest witness.
+    Fp grind(uint32_t bits) {
+        if (bits == 0) return Fp{0};
+        for (uint32_t w = 0; w < P; w++) {
+            Challenger c = *this;
+            if (c.check_witness(bits, Fp{w})) {
+                check_witness(bits, Fp{w});
+                return Fp{w};
+            }
+        }
+        throw std::runtime_error("oracle: no PoW witness");
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Instances + constraint bytecode interpreter (format: include/p3r.h).
+// ------------------------------------------------------------------------------------------------
+struct Program {
+    std::vector<p3r_insn> insns;
+    uint32_t nb = 0, ne = 0, n_constraints = 0, n_outputs = 0;
+    std::vector<Ext> ext_consts;
+};
+struct Inst {
+    uint32_t log_h, main_w, prep_w, n_pub, log_qc, uses_next;
+    Program cons, lk;
+    std::vector<p3r_lookup> lookups;
+    std::vector<p3r_interaction> inter;
+    uint32_t aux_w() const { return lookups.empty() ? 0 : (uint32_t)lookups.size() + 1; }
+};
+Program load_program(const p3r_program& p) {
+    Program q;
+    q.insns.assign(p.insns, p.insns + p.n_insns);
+    for (auto& in : q.insns)
+        if (in.op == P3R_OP_B_CONST) in.a = from_monty(in.a).v;  // keep canonical immediates
+    q.nb = p.n_base_slots;
+    q.ne = p.n_ext_slots;
+    q.n_constraints = p.n_constraints;
+    q.n_outputs = p.n_outputs;
+    for (uint32_t i = 0; i < p.n_ext_consts; i++) {
+        Ext e;
+        for (int k = 0; k < 4; k++) e.c[k] = from_monty(p.ext_consts[4 * i + k]);
+        q.ext_consts.push_back(e);
+    }
+    return q;
+}
+Inst load_inst(const p3r_instance_desc& d) {
+    Inst s;
+    s.log_h = d.log_height;
+    s.main_w = d.main_width;
+    s.prep_w = d.prep_width;
+    s.n_pub = d.n_public;
+    s.log_qc = d.log_quotient_chunks;
+    s.uses_next = d.uses_next_row;
+    s.cons = load_program(d.constraints);
+    s.lk = load_program(d.lookup_inputs);
+    s.lookups.assign(d.lookups, d.lookups + d.n_lookups);
+    s.inter.assign(d.interactions, d.interactions + d.n_interactions);
+    return s;
+}
+
+// Row view handed to the interpreter. BT = Fp on domain rows, Ext at the out-of-domain point.
+template <class BT>
+struct RowCtx {
+    const BT* main[2] = {nullptr, nullptr};
+    const BT* prep[2] = {nullptr, nullptr};
+    const Ext* perm[2] = {nullptr, nullptr};  // recomposed EF columns
+    const Fp* pub = nullptr;
+    BT sel[3];                                // is_first_row, is_last_row, is_transition
+    const Ext* chal = nullptr;
+    const Ext* pval = nullptr;
+};
+// Runs `p`; constraints land in cons_b/cons_e style single vector `cons` (as Ext) at their fold position;
+// OUT_B values land in `outs`.
+template <class BT>
+void run_program(const Program& p, const RowCtx<BT>& rc, std::vector<Ext>* cons, std::vector<BT>* outs) {
+    std::vector<BT> B(p.nb);
+    std::vector<Ext> E(p.ne, ext_zero());
+    for (const auto& in : p.insns) {
+        switch (in.op) {
+            case P3R_OP_B_MAIN: B[in.dst] = rc.main[in.b][in.a]; break;
+            case P3R_OP_B_PREP: B[in.dst] = rc.prep[in.b][in.a]; break;
+            case P3R_OP_B_PUB:
+                if constexpr (std::is_same<BT, Fp>::value) B[in.dst] = rc.pub[in.a];
+                else B[in.dst] = lift(rc.pub[in.a]);
+                break;
+            case P3R_OP_B_SEL: B[in.dst] = rc.sel[in.a]; break;
+            case P3R_OP_B_CONST:
+                if constexpr (std::is_same<BT, Fp>::value) B[in.dst] = Fp{in.a};
+                else B[in.dst] = lift(Fp{in.a});
+                break;
+            case P3R_OP_B_ADD: B[in.dst] = B[in.a] + B[in.b]; break;
+            case P3R_OP_B_SUB: B[in.dst] = B[in.a] - B[in.b]; break;
+            case P3R_OP_B_MUL: B[in.dst] = B[in.a] * B[in.b]; break;
+            case P3R_OP_B_NEG: B[in.dst] = -B[in.a]; break;
+            case P3R_OP_E_PERM: E[in.dst] = rc.perm[in.b][in.a]; break;
+            case P3R_OP_E_CHAL: E[in.dst] = rc.chal[in.a]; break;
+            case P3R_OP_E_PVAL: E[in.dst] = rc.pval[in.a]; break;
+            case P3R_OP_E_CONST: E[in.dst] = p.ext_consts[in.a]; break;
+            case P3R_OP_E_FROMB: E[in.dst] = to_ext(B[in.a]); break;
+            case P3R_OP_E_ADD: E[in.dst] = E[in.a] + E[in.b]; break;
+            case P3R_OP_E_SUB: E[in.dst] = E[in.a] - E[in.b]; break;
+            case P3R_OP_E_MUL: E[in.dst] = E[in.a] * E[in.b]; break;
+            case P3R_OP_E_NEG: E[in.dst] = -E[in.a]; break;
+            case P3R_OP_E_MULB: E[in.dst] = mulmix(E[in.a], B[in.b]); break;
+            case P3R_OP_E_ADDB: E[in.dst] = E[in.a] + to_ext(B[in.b]); break;
+            case P3R_OP_E_SUBB: E[in.dst] = E[in.a] - to_ext(B[in.b]); break;
+            case P3R_OP_ASSERT_B: (*cons)[in.dst] = to_ext(B[in.a]); break;
+            case P3R_OP_ASSERT_E: (*cons)[in.dst] = E[in.a]; break;
+            case P3R_OP_OUT_B: (*outs)[in.dst] = B[in.a]; break;
+            default: throw std::runtime_error("oracle: bad opcode");
+        }
+    }
+}
+// recursion/src/traits/air.rs:170-181: acc = acc*alpha + c, base constraints first then extension ones
+// (the compiler already numbered them in that order).
+Ext fold_constraints(const std::vector<Ext>& cons, const Ext& alpha) {
+    Ext acc = ext_zero();
+    for (const auto& c : cons) acc = acc * alpha + c;
+    return acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LogUp challenges layout (recursion/src/verifier/batch_stark.rs:1031-1110): gamma = beta^W with W the
+// widest message over all lookups of all instances; bus_prefix[b] = alpha + (b+1)*gamma; per lookup the
+// challenge pair is [bus_prefix[bus], beta].
+// ------------------------------------------------------------------------------------------------
+std::vector<std::vector<Ext>> perm_challenges(const std::vector<Inst>& insts, const Ext& alpha, const Ext& beta) {
+    uint32_t maxw = 1, nbus = 0;
+    for (auto& s : insts) {
+        for (auto& it : s.inter) maxw = std::max(maxw, it.n_elems);
+        for (auto& l : s.lookups) nbus = std::max(nbus, l.bus + 1);
+    }
+    Ext gamma = beta;
+    for (uint32_t i = 1; i < maxw; i++) gamma = gamma * beta;
+    std::vector<Ext> prefix(nbus);
+    Ext pr = alpha;
+    for (uint32_t b = 0; b < nbus; b++) {
+        pr = pr + gamma;
+        prefix[b] = pr;
+    }
+    std::vector<std::vector<Ext>> out;
+    for (auto& s : insts) {
+        std::vector<Ext> v;
+        for (auto& l : s.lookups) {
+            v.push_back(prefix[l.bus]);
+            v.push_back(beta);
+        }
+        out.push_back(v);
+    }
+    return out;
+}
+
+// LogUp permutation trace of one AIR (recursion/src/verifier/batch_stark.rs:902-912):
+// EF column 0 = running accumulator (acc[0]=0, acc[r+1]=acc[r]+sum_c frac_c[r]); column c+1 = fraction column
+// of lookup c, frac_c[r] = sum_j mult_j / (bus_prefix + sum_k beta^k elem_{j,k}). Flattened to 4*aux base cols.
+// The denominator's sign/power convention is [P3-EXT] (p3-lookup 0.6 not in tree) — fixed here and in DESIGN.md.
+Mat logup_trace(const Inst& s, const Mat& main, const Mat* prep, const Fp* pub, const std::vector<Ext>& chal,
+                Ext* terminal) {
+    size_t n = main.h;
+    uint32_t aux = s.aux_w();
+    Mat out;
+    out.h = n;
+    out.w = aux * 4;
+    out.d.assign(n * out.w, Fp{0});
+    std::vector<Ext> rowsum(n, ext_zero());
+#pragma omp parallel for
+    for (size_t r = 0; r < n; r++) {
+        RowCtx<Fp> rc;
+        rc.main[0] = &main.d[r * main.w];
+        rc.main[1] = &main.d[((r + 1) % n) * main.w];
+        if (prep) {
+            rc.prep[0] = &prep->d[r * prep->w];
+            rc.prep[1] = &prep->d[((r + 1) % n) * prep->w];
+        }
+        rc.pub = pub;
+        rc.sel[0] = Fp{r == 0};
+        rc.sel[1] = Fp{r == n - 1};
+        rc.sel[2] = Fp{r != n - 1};
+        std::vector<Fp> outs(s.lk.n_outputs, Fp{0});
+        run_program<Fp>(s.lk, rc, nullptr, &outs);
+        Ext total = ext_zero();
+        for (size_t c = 0; c < s.lookups.size(); c++) {
+            const auto& l = s.lookups[c];
+            Ext prefix = chal[2 * c], beta = chal[2 * c + 1];
+            Ext frac = ext_zero();
+            for (uint32_t j = 0; j < l.n_interactions; j++) {
+                const auto& it = s.inter[l.first_interaction + j];
+                Ext den = prefix, bp = ext_one();
+                for (uint32_t k = 0; k < it.n_elems; k++) {
+                    den = den + bp * outs[it.elem_out_first + k];
+                    bp = bp * beta;
+                }
+                Fp m = outs[it.mult_out];
+                if (m.v != 0) frac = frac + einv(den) * m;
+            }
+            for (int k = 0; k < 4; k++) out.at(r, 4 * (c + 1) + k) = frac.c[k];
+            total = total + frac;
+        }
+        rowsum[r] = total;
+    }
+    Ext acc = ext_zero();
+    for (size_t r = 0; r < n; r++) {
+        for (int k = 0; k < 4; k++) out.at(r, k) = acc.c[k];
+        acc = acc + rowsum[r];
+    }
+    *terminal = acc;
+    return out;
+}
+
+// Selectors of the trace domain H_n (shift 1) at point x (p3 TwoAdicMultiplicativeCoset::selectors_*;
+// in-circuit: recursion/src/verifier/batch_stark.rs:979 `selectors_at_point_circuit`).
+template <class T>
+struct Selectors {
+    T is_first, is_last, is_transition, inv_vanishing;
+};
+Selectors<Fp> selectors_at(Fp x, uint32_t log_n) {
+    Fp ginv = finv(two_adic_gen(log_n));
+    Fp z = fpow(x, (uint64_t)1 << log_n) - Fp{1};
+    return {z * finv(x - Fp{1}), z * finv(x - ginv), x - ginv, finv(z)};
+}
+Selectors<Ext> selectors_at(const Ext& x, uint32_t log_n) {
+    Fp ginv = finv(two_adic_gen(log_n));
+    Ext z = epow(x, (uint64_t)1 << log_n) - Fp{1};
+    return {z * einv(x - Fp{1}), z * einv(x - ginv), x - ginv, einv(z)};
+}
+
+// ------------------------------------------------------------------------------------------------
+// Arity schedule of the FRI commit phase ([P3-EXT] rule): fold by as much as max_log_arity
+// allows without skipping the next input height or the final height.
+// ------------------------------------------------------------------------------------------------
+p3r_fri_params FRI;
+std::vector<uint32_t> arity_schedule(const std::vector<uint32_t>& input_log_heights_desc) {
+    std::vector<uint32_t> sched;
+    uint32_t log_final = FRI.log_blowup + FRI.log_final_poly_len;
+    uint32_t h = input_log_heights_desc[0];
+    size_t next = 1;
+    while (h > log_final) {
+        uint32_t k = std::min(FRI.max_log_arity, h - log_final);
+        if (next < input_log_heights_desc.size()) k = std::min(k, h - input_log_heights_desc[next]);
+        if (k == 0) throw std::runtime_error("oracle: bad arity schedule");
+        h -= k;
+        if (next < input_log_heights_desc.size() && input_log_heights_desc[next] == h) next++;
+        sched.push_back(k);
+    }
+    if (next != input_log_heights_desc.size()) throw std::runtime_error("oracle: FRI input below final height");
+    return sched;
+}
+// One arity-2 fold of a bit-reversed vector (recursion/src/pcs/fri/verifier.rs:564-585):
+// out[i] = e0 + (beta - x0)(e1 - e0)/(x1 - x0), x0 = w_L^{bitrev(i)}, x1 = -x0.
+std::vector<Ext> fold_once(const std::vector<Ext>& v, const Ext& beta) {
+    size_t L = v.size();
+    uint32_t lg = log2_strict(L);
+    Fp g = two_adic_gen(lg);
+    std::vector<Ext> out(L / 2);
+    for (size_t i = 0; i < L / 2; i++) {
+        Fp x0 = fpow(g, bitrev((uint32_t)i, lg - 1));
+        Ext e0 = v[2 * i], e1 = v[2 * i + 1];
+        Fp inv = finv(-(x0 + x0));  // 1/(x1-x0)
+        out[i] = e0 + (beta - x0) * ((e1 - e0) * inv);
+    }
+    return out;
+}
+Ext fold_row(std::vector<Ext> evals, size_t row_index, uint32_t log_folded_height, Ext beta) {
+    // Fold the 2^k evaluations of commit-phase row `row_index` down to one value.
+    uint32_t k = log2_strict(evals.size());
+    for (uint32_t step = 0; step < k; step++) {
+        uint32_t lg_cur = log_folded_height + k - step;  // log height of the vector being folded
+        Fp g = two_adic_gen(lg_cur);
+        size_t half = evals.size() / 2;
+        std::vector<Ext> nx(half);
+        for (size_t j = 0; j < half; j++) {
+            size_t gi = row_index * half + j;  // index in the half-length folded vector
+            Fp x0 = fpow(g, bitrev((uint32_t)gi, lg_cur - 1));
+            Fp inv = finv(-(x0 + x0));
+            nx[j] = evals[2 * j] + (beta - x0) * ((evals[2 * j + 1] - evals[2 * j]) * inv);
+        }
+        evals = nx;
+        beta = beta * beta;
+    }
+    return evals[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Proof blob writer/reader (layout: DESIGN.md "Proof blob"; all field words Montgomery).
+// ------------------------------------------------------------------------------------------------
+struct Writer {
+    std::vector<uint32_t> w;
+    void u(uint32_t x) { w.push_back(x); }
+    void f(Fp x) { w.push_back(to_monty(x)); }
+    void e(const Ext& x) {
+        for (int i = 0; i < 4; i++) f(x.c[i]);
+    }
+    void dg(const Digest& d) {
+        for (int i = 0; i < 8; i++) f(d.d[i]);
+    }
+    void cap(const std::vector<Digest>& c) {
+        for (auto& d : c) dg(d);
+    }
+};
+struct Reader {
+    const uint32_t* p;
+    size_t n, i = 0;
+    uint32_t u() {
+        if (i >= n) throw std::runtime_error("oracle: proof truncated");
+        return p[i++];
+    }
+    Fp f() {
+        uint32_t m = u();
+        if (m >= P) throw std::runtime_error("oracle: non-canonical word");
+        return from_monty(m);
+    }
+    Ext e() {
+        Ext x;
+        for (int k = 0; k < 4; k++) x.c[k] = f();
+        return x;
+    }
+    Digest dg() {
+        Digest d;
+        for (int k = 0; k < 8; k++) d.d[k] = f();
+        return d;
+    }
+    std::vector<Digest> cap(size_t n_) {
+        std::vector<Digest> c(n_);
+        for (auto& d : c) d = dg();
+        return c;
+    }
+};
+const uint32_t MAGIC = 0x50335250u;
+
+struct OpenedInst {
+    std::vector<Ext> main_local, main_next, prep_local, prep_next, perm_local, perm_next;
+    std::vector<std::vector<Ext>> qchunks;  // [chunk][4]
+};
+
+Mat mat_from_abi(const p3r_matrix_u32& m) {
+    Mat r;
+    r.h = m.height;
+    r.w = m.width;
+    r.d.resize(r.h * r.w);
+    for (size_t i = 0; i < r.d.size(); i++) r.d[i] = from_monty(m.data[i]);
+    return r;
+}
+
+struct Common {
+    std::vector<Inst> insts;
+    bool has_perm = false, has_prep = false;
+    uint32_t n_perm_inst = 0;
+};
+Common load_common(uint32_t n, const p3r_instance_desc* descs) {
+    Common c;
+    for (uint32_t i = 0; i < n; i++) {
+        c.insts.push_back(load_inst(descs[i]));
+        if (!c.insts.back().lookups.empty()) {
+            c.has_perm = true;
+            c.n_perm_inst++;
+        }
+        if (c.insts.back().prep_w) c.has_prep = true;
+    }
+    return c;
+}
+
+// Transcript head (recursion/src/verifier/batch_stark.rs:521-578).
+void transcript_head(Challenger& ch, const Common& cm, const std::vector<Digest>& main_cap,
+                     const std::vector<std::vector<Fp>>& pubs, const std::vector<Digest>* prep_cap) {
+    ch.observe_lifted(cm.insts.size());
+    for (auto& s : cm.insts) {
+        ch.observe_lifted(s.log_h);                      // ext_degree_bits (non-ZK: equal)
+        ch.observe_lifted(s.log_h);                      // base_degree_bits
+        ch.observe_lifted(s.main_w);                     // air.width()
+        ch.observe_lifted((uint64_t)1 << s.log_qc);      // quotient_degree
+    }
+    ch.observe_cap(main_cap);
+    for (auto& pv : pubs)
+        for (auto v : pv) ch.observe(v);
+    for (auto& s : cm.insts) ch.observe_lifted(s.prep_w);
+    if (prep_cap) ch.observe_cap(*prep_cap);
+}
+
+// Per-round opening structure shared by prover and verifier: for each input round (commit order
+// [main, quotient, preprocessed, permutation]; recursion/src/generation.rs:253-424) the matrices with their
+// LDE log-height and, per matrix, the opening points with the opened values.
+struct MatOpen {
+    uint32_t log_h;                               // LDE log height
+    std::vector<Ext> points;
+    std::vector<std::vector<Ext>> values;         // [point][col]
+};
+typedef std::vector<MatOpen> RoundOpen;
+
+std::vector<RoundOpen> build_rounds(const Common& cm, const std::vector<OpenedInst>& ov, const Ext& zeta) {
+    std::vector<RoundOpen> rounds;
+    auto znext = [&](const Inst& s) { return zeta * two_adic_gen(s.log_h); };
+    RoundOpen mainr, quotr, prepr, permr;
+    for (size_t i = 0; i < cm.insts.size(); i++) {
+        const Inst& s = cm.insts[i];
+        uint32_t lh = s.log_h + FRI.log_blowup;
+        MatOpen m{lh, {zeta}, {ov[i].main_local}};
+        if (s.uses_next) {
+            m.points.push_back(znext(s));
+            m.values.push_back(ov[i].main_next);
+        }
+        mainr.push_back(m);
+        for (auto& qc : ov[i].qchunks) quotr.push_back(MatOpen{lh, {zeta}, {qc}});
+        if (s.prep_w) prepr.push_back(MatOpen{lh, {zeta, znext(s)}, {ov[i].prep_local, ov[i].prep_next}});
+        if (!s.lookups.empty())
+            permr.push_back(MatOpen{lh, {zeta, znext(s)}, {ov[i].perm_local, ov[i].perm_next}});
+    }
+    rounds.push_back(mainr);
+    rounds.push_back(quotr);
+    if (cm.has_prep) rounds.push_back(prepr);
+    if (cm.has_perm) rounds.push_back(permr);
+    return rounds;
+}
+void observe_openings(Challenger& ch, const std::vector<RoundOpen>& rounds) {
+    for (auto& r : rounds)
+        for (auto& m : r)
+            for (auto& pt : m.values)
+                for (auto& v : pt) ch.observe_ext(v);
+}
+
+void write_opened(Writer& w, const Common& cm, const std::vector<OpenedInst>& ov) {
+    for (size_t i = 0; i < cm.insts.size(); i++) {
+        for (auto& v : ov[i].main_local) w.e(v);
+        for (auto& v : ov[i].main_next) w.e(v);
+        for (auto& v : ov[i].prep_local) w.e(v);
+        for (auto& v : ov[i].prep_next) w.e(v);
+        for (auto& v : ov[i].perm_local) w.e(v);
+        for (auto& v : ov[i].perm_next) w.e(v);
+        for (auto& c : ov[i].qchunks)
+            for (auto& v : c) w.e(v);
+    }
+}
+std::vector<OpenedInst> read_opened(Reader& r, const Common& cm) {
+    std::vector<OpenedInst> ov(cm.insts.size());
+    for (size_t i = 0; i < cm.insts.size(); i++) {
+        const Inst& s = cm.insts[i];
+        auto rd = [&](std::vector<Ext>& v, size_t n) {
+            v.resize(n);
+            for (auto& x : v) x = r.e();
+        };
+        rd(ov[i].main_local, s.main_w);
+        if (s.uses_next) rd(ov[i].main_next, s.main_w);
+        if (s.prep_w) {
+            rd(ov[i].prep_local, s.prep_w);
+            rd(ov[i].prep_next, s.prep_w);
+        }
+        if (!s.lookups.empty()) {
+            rd(ov[i].perm_local, s.aux_w() * 4);
+            rd(ov[i].perm_next, s.aux_w() * 4);
+        }
+        ov[i].qchunks.resize((size_t)1 << s.log_qc);
+        for (auto& c : ov[i].qchunks) rd(c, 4);
+    }
+    return ov;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PROVER  (p3_batch_stark::prove_batch restated from the verifier side: transcript
+// recursion/src/generation.rs:138-232 + 459-545; domains recursion/src/verifier/batch_stark.rs:701-717;
+// FRI recursion/src/pcs/fri/verifier.rs:564-1355).
+// ------------------------------------------------------------------------------------------------
+struct ProveOut {
+    std::vector<uint32_t> blob;
+    std::vector<Digest> prep_cap;
+};
+
+ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector<Mat>& traces,
+               const std::vector<std::vector<Fp>>& pubs) {
+    const size_t n_inst = cm.insts.size();
+    const uint32_t lb = FRI.log_blowup;
+    for (size_t i = 0; i < n_inst; i++) {
+        const Inst& s = cm.insts[i];
+        if (traces[i].h != ((size_t)1 << s.log_h) || traces[i].w != s.main_w)
+            throw std::runtime_error("oracle: trace shape mismatch");
+        if (s.log_qc > lb) throw std::runtime_error("oracle: quotient degree exceeds blowup");
+    }
+    Challenger ch;
+
+    // -- preprocessed (ProverData::from_airs_and_degrees) --
+    std::vector<Mat> prep_lde(n_inst);
+    std::vector<const Mat*> prep_ptrs;
+    for (size_t i = 0; i < n_inst; i++)
+        if (cm.insts[i].prep_w) {
+            prep_lde[i] = coset_lde(prep[i], lb, Fp{1});
+            prep_ptrs.push_back(&prep_lde[i]);
+        }
+    MerkleTree prep_tree;
+    if (cm.has_prep) prep_tree = mmcs_commit(prep_ptrs);
+
+    // -- main commit --
+    std::vector<Mat> main_lde(n_inst);
+    std::vector<const Mat*> main_ptrs;
+    for (size_t i = 0; i < n_inst; i++) {
+        main_lde[i] = coset_lde(traces[i], lb, Fp{1});
+        main_ptrs.push_back(&main_lde[i]);
+    }
+    MerkleTree main_tree = mmcs_commit(main_ptrs);
+    std::vector<Digest> prep_cap;
+    if (cm.has_prep) prep_cap = prep_tree.cap();
+    transcript_head(ch, cm, main_tree.cap(), pubs, cm.has_prep ? &prep_cap : nullptr);
+
+    // -- permutation --
+    std::vector<std::vector<Ext>> chal(n_inst);
+    std::vector<Mat> perm(n_inst), perm_lde(n_inst);
+    std::vector<Ext> terminals(n_inst, ext_zero());
+    MerkleTree perm_tree;
+    if (cm.has_perm) {
+        Ext pa = ch.sample_ext();
+        Ext pb = ch.sample_ext();
+        chal = perm_challenges(cm.insts, pa, pb);
+        std::vector<const Mat*> ptrs;
+        for (size_t i = 0; i < n_inst; i++)
+            if (!cm.insts[i].lookups.empty()) {
+                perm[i] = logup_trace(cm.insts[i], traces[i], cm.insts[i].prep_w ? &prep[i] : nullptr,
+                                      pubs[i].data(), chal[i], &terminals[i]);
+                perm_lde[i] = coset_lde(perm[i], lb, Fp{1});
+                ptrs.push_back(&perm_lde[i]);
+            }
+        perm_tree = mmcs_commit(ptrs);
+        ch.observe_cap(perm_tree.cap());
+        for (size_t i = 0; i < n_inst; i++)
+            if (!cm.insts[i].lookups.empty()) ch.observe_ext(terminals[i]);
+    }
+    Ext alpha = ch.sample_ext();
+
+    // -- quotient --
+    std::vector<std::vector<Mat>> qchunk_lde(n_inst);
+    std::vector<std::vector<Mat>> qchunk(n_inst);
+    for (size_t i = 0; i < n_inst; i++) {
+        const Inst& s = cm.insts[i];
+        size_t n = (size_t)1 << s.log_h;
+        uint32_t lq = s.log_h + s.log_qc;
+        size_t NQ = (size_t)1 << lq, qc = (size_t)1 << s.log_qc;
+        // evaluations of every column on GENERATOR*H_NQ in natural order, from coefficients
+        auto on_qdomain = [&](const Mat& m) {
+            Mat o;
+            o.h = NQ;
+            o.w = m.w;
+            o.d.resize(NQ * m.w);
+            for (size_t c = 0; c < m.w; c++) {
+                std::vector<Fp> col(m.h);
+                for (size_t r = 0; r < m.h; r++) col[r] = m.at(r, c);
+                auto ev = evaluate_on_coset(interpolate(col, Fp{1}), NQ, Fp{GEN});
+                for (size_t r = 0; r < NQ; r++) o.at(r, c) = ev[r];
+            }
+            return o;
+        };
+        Mat mq = on_qdomain(traces[i]);
+        Mat pq, rq;
+        if (s.prep_w) pq = on_qdomain(prep[i]);
+        if (!s.lookups.empty()) rq = on_qdomain(perm[i]);
+        std::vector<Ext> Q(NQ);
+        Fp wq = two_adic_gen(lq);
+        uint32_t aux = s.aux_w();
+#pragma omp parallel for
+        for (size_t r = 0; r < NQ; r++) {
+            size_t rn = (r + qc) % NQ;
+            Fp x = Fp{GEN} * fpow(wq, r);
+            auto sel = selectors_at(x, s.log_h);
+            RowCtx<Fp> rc;
+            rc.main[0] = &mq.d[r * mq.w];
+            rc.main[1] = &mq.d[rn * mq.w];
+            if (s.prep_w) {
+                rc.prep[0] = &pq.d[r * pq.w];
+                rc.prep[1] = &pq.d[rn * pq.w];
+            }
+            std::vector<Ext> pl(aux), pn(aux);
+            for (uint32_t c = 0; c < aux; c++)
+                for (int k = 0; k < 4; k++) {
+                    pl[c].c[k] = rq.at(r, 4 * c + k);
+                    pn[c].c[k] = rq.at(rn, 4 * c + k);
+                }
+            rc.perm[0] = pl.data();
+            rc.perm[1] = pn.data();
+            rc.pub = pubs[i].data();
+            rc.sel[0] = sel.is_first;
+            rc.sel[1] = sel.is_last;
+            rc.sel[2] = sel.is_transition;
+            rc.chal = chal[i].data();
+            rc.pval = &terminals[i];
+            std::vector<Ext> cons(s.cons.n_constraints, ext_zero());
+            run_program<Fp>(s.cons, rc, &cons, nullptr);
+            Q[r] = fold_constraints(cons, alpha) * sel.inv_vanishing;
+        }
+        // split_evals: chunk c row r = Q[r*qc + c]; chunk domain shift = GEN * wq^c
+        for (size_t c = 0; c < qc; c++) {
+            Mat m;
+            m.h = n;
+            m.w = 4;
+            m.d.resize(n * 4);
+            for (size_t r = 0; r < n; r++)
+                for (int k = 0; k < 4; k++) m.at(r, k) = Q[r * qc + c].c[k];
+            qchunk_lde[i].push_back(coset_lde(m, lb, Fp{GEN} * fpow(wq, c)));
+            qchunk[i].push_back(m);
+        }
+    }
+    std::vector<const Mat*> qptrs;
+    for (size_t i = 0; i < n_inst; i++)
+        for (auto& m : qchunk_lde[i]) qptrs.push_back(&m);
+    MerkleTree quot_tree = mmcs_commit(qptrs);
+    ch.observe_cap(quot_tree.cap());
+    Ext zeta = ch.sample_ext();
+
+    // -- openings: evaluate the committed polynomials at zeta / zeta*g by Horner on their coefficients --
+    auto eval_cols = [&](const Mat& m, Fp in_shift, const Ext& z) {
+        std::vector<Ext> out(m.w);
+        for (size_t c = 0; c < m.w; c++) {
+            std::vector<Fp> col(m.h);
+            for (size_t r = 0; r < m.h; r++) col[r] = m.at(r, c);
+            out[c] = horner(interpolate(col, in_shift), z);
+        }
+        return out;
+    };
+    std::vector<OpenedInst> ov(n_inst);
+    for (size_t i = 0; i < n_inst; i++) {
+        const Inst& s = cm.insts[i];
+        Ext zn = zeta * two_adic_gen(s.log_h);
+        ov[i].main_local = eval_cols(traces[i], Fp{1}, zeta);
+        if (s.uses_next) ov[i].main_next = eval_cols(traces[i], Fp{1}, zn);
+        if (s.prep_w) {
+            ov[i].prep_local = eval_cols(prep[i], Fp{1}, zeta);
+            ov[i].prep_next = eval_cols(prep[i], Fp{1}, zn);
+        }
+        if (!s.lookups.empty()) {
+            ov[i].perm_local = eval_cols(perm[i], Fp{1}, zeta);
+            ov[i].perm_next = eval_cols(perm[i], Fp{1}, zn);
+        }
+        Fp wq = two_adic_gen(s.log_h + s.log_qc);
+        for (size_t c = 0; c < qchunk[i].size(); c++)
+            ov[i].qchunks.push_back(eval_cols(qchunk[i][c], Fp{GEN} * fpow(wq, c), zeta));
+    }
+    std::vector<RoundOpen> rounds = build_rounds(cm, ov, zeta);
+    observe_openings(ch, rounds);
+    Ext alpha_fri = ch.sample_ext();
+
+    // -- reduced openings per height --
+    std::vector<const MerkleTree*> trees = {&main_tree, &quot_tree};
+    if (cm.has_prep) trees.push_back(&prep_tree);
+    if (cm.has_perm) trees.push_back(&perm_tree);
+    std::map<uint32_t, std::vector<Ext>, std::greater<uint32_t>> ro;
+    std::map<uint32_t, Ext> apow;
+    for (size_t ri = 0; ri < rounds.size(); ri++) {
+        for (size_t mi = 0; mi < rounds[ri].size(); mi++) {
+            const MatOpen& mo = rounds[ri][mi];
+            const Mat& lde = *trees[ri]->mats[mi];
+            size_t N = lde.h;
+            if (log2_strict(N) != mo.log_h) throw std::runtime_error("oracle: round/tree mismatch");
+            if (!ro.count(mo.log_h)) {
+                ro[mo.log_h] = std::vector<Ext>(N, ext_zero());
+                apow[mo.log_h] = ext_one();
+            }
+            auto& acc = ro[mo.log_h];
+            Fp g = two_adic_gen(mo.log_h);
+            for (size_t pi = 0; pi < mo.points.size(); pi++) {
+                Ext ap0 = apow[mo.log_h];
+#pragma omp parallel for
+                for (size_t sidx = 0; sidx < N; sidx++) {
+                    Fp x = Fp{GEN} * fpow(g, bitrev((uint32_t)sidx, mo.log_h));
+                    Ext inv = einv(mo.points[pi] - x);
+                    Ext ap = ap0, sum = ext_zero();
+                    for (size_t c = 0; c < lde.w; c++) {
+                        sum = sum + ap * (mo.values[pi][c] - lde.at(sidx, c));
+                        ap = ap * alpha_fri;
+                    }
+                    acc[sidx] = acc[sidx] + sum * inv;
+                }
+                for (size_t c = 0; c < lde.w; c++) apow[mo.log_h] = apow[mo.log_h] * alpha_fri;
+            }
+        }
+    }
+    std::vector<uint32_t> in_heights;
+    for (auto& kv : ro) in_heights.push_back(kv.first);
+    std::vector<uint32_t> sched = arity_schedule(in_heights);
+    uint32_t log_max = in_heights[0];
+
+    // -- FRI commit phase --
+    std::vector<Ext> folded = ro[log_max];
+    std::vector<Mat> fri_mats(sched.size());
+    std::vector<MerkleTree> fri_trees(sched.size());
+    std::vector<Fp> commit_pow(sched.size());
+    uint32_t h = log_max;
+    for (size_t r = 0; r < sched.size(); r++) {
+        uint32_t k = sched[r];
+        size_t arity = (size_t)1 << k;
+        Mat& m = fri_mats[r];
+        m.h = folded.size() / arity;
+        m.w = arity * 4;
+        m.d.resize(m.h * m.w);
+        for (size_t i = 0; i < folded.size(); i++)
+            for (int c = 0; c < 4; c++) m.d[i * 4 + c] = folded[i].c[c];
+        fri_trees[r] = mmcs_commit({&m});
+        ch.observe_cap(fri_trees[r].cap());
+        commit_pow[r] = ch.grind(FRI.commit_pow_bits);
+        Ext beta = ch.sample_ext();
+        Ext b = beta;
+        for (uint32_t st = 0; st < k; st++) {
+            folded = fold_once(folded, b);
+            b = b * b;
+        }
+        h -= k;
+        if (ro.count(h) && h != log_max)
+            for (size_t i = 0; i < folded.size(); i++) folded[i] = folded[i] + b * ro[h][i];
+    }
+    // final polynomial: interpolate the bit-reversed folded evaluations over the (unshifted) subgroup
+    uint32_t log_final = FRI.log_blowup + FRI.log_final_poly_len;
+    if (h != log_final) throw std::runtime_error("oracle: schedule did not reach final height");
+    std::vector<Ext> nat(folded.size());
+    for (size_t i = 0; i < folded.size(); i++) nat[bitrev((uint32_t)i, log_final)] = folded[i];
+    ntt_inplace(nat, true);
+    size_t fpl = (size_t)1 << FRI.log_final_poly_len;
+    for (size_t i = fpl; i < nat.size(); i++)
+        if (!is_zero(nat[i])) throw std::runtime_error("oracle: final polynomial is not low degree");
+    std::vector<Ext> final_poly(nat.begin(), nat.begin() + fpl);
+    for (auto& c : final_poly) ch.observe_ext(c);
+    for (auto k : sched) ch.observe(mk(k));
+    Fp query_pow = ch.grind(FRI.query_pow_bits);
+
+    // -- proof blob --
+    Writer w;
+    size_t cap_n = (size_t)1 << CAP_HEIGHT;
+    w.u(MAGIC);
+    w.u((uint32_t)n_inst);
+    w.u(cm.has_perm);
+    w.u(cm.has_prep);
+    w.u((uint32_t)cap_n * 8);
+    for (auto& s : cm.insts) w.u(s.log_h);
+    w.cap(main_tree.cap());
+    if (cm.has_perm) w.cap(perm_tree.cap());
+    w.cap(quot_tree.cap());
+    for (size_t i = 0; i < n_inst; i++)
+        if (!cm.insts[i].lookups.empty()) w.e(terminals[i]);
+    write_opened(w, cm, ov);
+    w.u((uint32_t)sched.size());
+    for (auto k : sched) w.u(k);
+    for (auto& t : fri_trees) w.cap(t.cap());
+    for (auto p : commit_pow) w.f(p);
+    for (auto& c : final_poly) w.e(c);
+    w.f(query_pow);
+    for (uint32_t q = 0; q < FRI.num_queries; q++) {
+        size_t index = ch.sample_bits(log_max);
+        for (auto* t : trees) {
+            BatchOpening o = mmcs_open(*t, index >> (log_max - t->log_max_h));
+            for (auto& row : o.rows)
+                for (auto v : row) w.f(v);
+            for (auto& d : o.path) w.dg(d);
+        }
+        size_t idx = index;
+        for (size_t r = 0; r < sched.size(); r++) {
+            size_t arity = (size_t)1 << sched[r];
+            size_t row = idx >> sched[r], own = idx & (arity - 1);
+            for (size_t j = 0; j < arity; j++)
+                if (j != own)
+                    for (int c = 0; c < 4; c++) w.f(fri_mats[r].at(row, 4 * j + c));
+            BatchOpening o = mmcs_open(fri_trees[r], row);
+            for (auto& d : o.path) w.dg(d);
+            idx = row;
+        }
+    }
+    ProveOut po;
+    po.blob = std::move(w.w);
+    po.prep_cap = prep_cap;
+    return po;
+}
+
+// ------------------------------------------------------------------------------------------------
+// VERIFIER (restates recursion/src/verifier/batch_stark.rs:323-1024 + recursion/src/pcs/fri/verifier.rs).
+// Throws with a reason on rejection.
+// ------------------------------------------------------------------------------------------------
+void verify(const Common& cm, const std::vector<Digest>* prep_cap, const std::vector<std::vector<Fp>>& pubs,
+            const uint32_t* blob, size_t n_words) {
+    Reader r{blob, n_words};
+    const size_t n_inst = cm.insts.size();
+    size_t cap_n = (size_t)1 << CAP_HEIGHT;
+    if (r.u() != MAGIC) throw std::runtime_error("verify: bad magic");
+    if (r.u() != n_inst) throw std::runtime_error("verify: instance count");
+    if (r.u() != (uint32_t)cm.has_perm) throw std::runtime_error("verify: perm flag");
+    if (r.u() != (uint32_t)cm.has_prep) throw std::runtime_error("verify: prep flag");
+    if (r.u() != cap_n * 8) throw std::runtime_error("verify: cap size");
+    for (auto& s : cm.insts)
+        if (r.u() != s.log_h) throw std::runtime_error("verify: degree bits");
+    auto main_cap = r.cap(cap_n);
+    std::vector<Digest> perm_cap;
+    if (cm.has_perm) perm_cap = r.cap(cap_n);
+    auto quot_cap = r.cap(cap_n);
+    std::vector<Ext> terminals(n_inst, ext_zero());
+    for (size_t i = 0; i < n_inst; i++)
+        if (!cm.insts[i].lookups.empty()) terminals[i] = r.e();
+    std::vector<OpenedInst> ov = read_opened(r, cm);
+
+    Challenger ch;
+    transcript_head(ch, cm, main_cap, pubs, cm.has_prep ? prep_cap : nullptr);
+    std::vector<std::vector<Ext>> chal(n_inst);
+    if (cm.has_perm) {
+        Ext pa = ch.sample_ext();
+        Ext pb = ch.sample_ext();
+        chal = perm_challenges(cm.insts, pa, pb);
+        ch.observe_cap(perm_cap);
+        for (size_t i = 0; i < n_inst; i++)
+            if (!cm.insts[i].lookups.empty()) ch.observe_ext(terminals[i]);
+    }
+    Ext alpha = ch.sample_ext();
+    ch.observe_cap(quot_cap);
+    Ext zeta = ch.sample_ext();
+    std::vector<RoundOpen> rounds = build_rounds(cm, ov, zeta);
+    observe_openings(ch, rounds);
+    Ext alpha_fri = ch.sample_ext();
+
+    // FRI proof
+    uint32_t n_rounds = r.u();
+    if (n_rounds == 0 || n_rounds > 32) throw std::runtime_error("verify: FRI round count");
+    std::vector<uint32_t> sched(n_rounds);
+    for (auto& k : sched) k = r.u();
+    std::vector<std::vector<Digest>> fri_caps(n_rounds);
+    for (auto& c : fri_caps) c = r.cap(cap_n);
+    std::vector<Fp> commit_pow(n_rounds);
+    for (auto& p : commit_pow) p = r.f();
+    size_t fpl = (size_t)1 << FRI.log_final_poly_len;
+    std::vector<Ext> final_poly(fpl);
+    for (auto& c : final_poly) c = r.e();
+    Fp query_pow = r.f();
+
+    std::vector<Ext> betas(n_rounds);
+    for (uint32_t i = 0; i < n_rounds; i++) {
+        ch.observe_cap(fri_caps[i]);
+        if (!ch.check_witness(FRI.commit_pow_bits, commit_pow[i])) throw std::runtime_error("verify: commit PoW");
+        betas[i] = ch.sample_ext();
+    }
+    for (auto& c : final_poly) ch.observe_ext(c);
+    for (auto k : sched) ch.observe(mk(k));
+    if (!ch.check_witness(FRI.query_pow_bits, query_pow)) throw std::runtime_error("verify: query PoW");
+
+    // heights
+    std::vector<uint32_t> in_heights;
+    for (auto& rd : rounds)
+        for (auto& m : rd) in_heights.push_back(m.log_h);
+    std::sort(in_heights.begin(), in_heights.end(), std::greater<uint32_t>());
+    in_heights.erase(std::unique(in_heights.begin(), in_heights.end()), in_heights.end());
+    uint32_t log_max = in_heights[0];
+    uint32_t total = 0;
+    for (auto k : sched) total += k;
+    if (log_max != total + FRI.log_blowup + FRI.log_final_poly_len)
+        throw std::runtime_error("verify: log_arities do not match heights");
+    if (sched != arity_schedule(in_heights)) throw std::runtime_error("verify: arity schedule");
+
+    std::vector<const std::vector<Digest>*> caps = {&main_cap, &quot_cap};
+    if (cm.has_prep) caps.push_back(prep_cap);
+    if (cm.has_perm) caps.push_back(&perm_cap);
+    // widths per round/matrix
+    auto width_of = [&](size_t ri, size_t mi) { return rounds[ri][mi].values[0].size(); };
+
+    for (uint32_t q = 0; q < FRI.num_queries; q++) {
+        size_t index = ch.sample_bits(log_max);
+        std::map<uint32_t, Ext, std::greater<uint32_t>> ro;
+        std::map<uint32_t, Ext> apow;
+        for (size_t ri = 0; ri < rounds.size(); ri++) {
+            std::vector<size_t> heights;
+            uint32_t round_max = 0;
+            for (auto& m : rounds[ri]) {
+                heights.push_back((size_t)1 << m.log_h);
+                round_max = std::max(round_max, m.log_h);
+            }
+            std::vector<std::vector<Fp>> rows(rounds[ri].size());
+            for (size_t mi = 0; mi < rounds[ri].size(); mi++) {
+                rows[mi].resize(width_of(ri, mi));
+                for (auto& v : rows[mi]) v = r.f();
+            }
+            std::vector<Digest> path(round_max - CAP_HEIGHT);
+            for (auto& d : path) d = r.dg();
+            if (!mmcs_verify(*caps[ri], heights, index >> (log_max - round_max), rows, path))
+                throw std::runtime_error("verify: input MMCS path");
+            for (size_t mi = 0; mi < rounds[ri].size(); mi++) {
+                const MatOpen& mo = rounds[ri][mi];
+                size_t ridx = index >> (log_max - mo.log_h);
+                Fp x = Fp{GEN} * fpow(two_adic_gen(mo.log_h), bitrev((uint32_t)ridx, mo.log_h));
+                if (!ro.count(mo.log_h)) {
+                    ro[mo.log_h] = ext_zero();
+                    apow[mo.log_h] = ext_one();
+                }
+                for (size_t pi = 0; pi < mo.points.size(); pi++) {
+                    Ext inv = einv(mo.points[pi] - x);
+                    for (size_t c = 0; c < rows[mi].size(); c++) {
+                        ro[mo.log_h] = ro[mo.log_h] + apow[mo.log_h] * (mo.values[pi][c] - rows[mi][c]) * inv;
+                        apow[mo.log_h] = apow[mo.log_h] * alpha_fri;
+                    }
+                }
+            }
+        }
+        Ext folded = ro[log_max];
+        size_t idx = index;
+        uint32_t h = log_max;
+        for (uint32_t rd = 0; rd < n_rounds; rd++) {
+            uint32_t k = sched[rd];
+            size_t arity = (size_t)1 << k;
+            size_t row = idx >> k, own = idx & (arity - 1);
+            std::vector<Ext> evals(arity);
+            for (size_t j = 0; j < arity; j++) evals[j] = (j == own) ? folded : r.e();
+            std::vector<Digest> path(h - k - CAP_HEIGHT);
+            for (auto& d : path) d = r.dg();
+            std::vector<Fp> flat;
+            for (auto& e : evals)
+                for (int c = 0; c < 4; c++) flat.push_back(e.c[c]);
+            if (!mmcs_verify(fri_caps[rd], {(size_t)1 << (h - k)}, row, {flat}, path))
+                throw std::runtime_error("verify: FRI commit-phase MMCS path");
+            folded = fold_row(evals, row, h - k, betas[rd]);
+            h -= k;
+            if (ro.count(h)) {
+                Ext bp = betas[rd];
+                for (uint32_t st = 0; st < k; st++) bp = bp * bp;
+                folded = folded + bp * ro[h];
+            }
+            idx = row;
+        }
+        Fp xf = fpow(two_adic_gen(h), bitrev((uint32_t)idx, h));
+        if (!(horner(final_poly, lift(xf)) == folded)) throw std::runtime_error("verify: final polynomial mismatch");
+    }
+    if (r.i != r.n) throw std::runtime_error("verify: trailing words");
+
+    // AIR constraints at zeta (recursion/src/verifier/batch_stark.rs:886-1016)
+    Ext tsum = ext_zero();
+    for (size_t i = 0; i < n_inst; i++) {
+        const Inst& s = cm.insts[i];
+        size_t qc = (size_t)1 << s.log_qc;
+        uint32_t lq = s.log_h + s.log_qc;
+        Fp wq = two_adic_gen(lq);
+        // Q(zeta) = sum_i chunk_i(zeta) * prod_{j != i} Z_j(zeta)/Z_j(g_i)   (recursion/src/verifier/quotient.rs:11-60)
+        auto Zj = [&](size_t j, const Ext& x) {
+            Fp sh = Fp{GEN} * fpow(wq, j);
+            return epow(x * finv(sh), (uint64_t)1 << s.log_h) - Fp{1};
+        };
+        Ext Qz = ext_zero();
+        for (size_t c = 0; c < qc; c++) {
+            Ext zp = ext_one();
+            for (size_t j = 0; j < qc; j++)
+                if (j != c) zp = zp * Zj(j, zeta) * einv(Zj(j, lift(Fp{GEN} * fpow(wq, c))));
+            Ext chunk = ext_zero();
+            for (int k = 0; k < 4; k++) {
+                Ext basis = ext_zero();
+                basis.c[k] = Fp{1};
+                chunk = chunk + basis * ov[i].qchunks[c][k];
+            }
+            Qz = Qz + zp * chunk;
+        }
+        auto sel = selectors_at(zeta, s.log_h);
+        uint32_t aux = s.aux_w();
+        auto recompose = [&](const std::vector<Ext>& flat) {
+            std::vector<Ext> o(aux, ext_zero());
+            for (uint32_t c = 0; c < aux; c++)
+                for (int k = 0; k < 4; k++) {
+                    Ext basis = ext_zero();
+                    basis.c[k] = Fp{1};
+                    o[c] = o[c] + basis * flat[4 * c + k];
+                }
+            return o;
+        };
+        std::vector<Ext> pl, pn;
+        if (aux) {
+            pl = recompose(ov[i].perm_local);
+            pn = recompose(ov[i].perm_next);
+        }
+        RowCtx<Ext> rc;
+        std::vector<Ext> zeros(s.main_w, ext_zero());
+        rc.main[0] = ov[i].main_local.data();
+        rc.main[1] = s.uses_next ? ov[i].main_next.data() : zeros.data();
+        rc.prep[0] = ov[i].prep_local.data();
+        rc.prep[1] = ov[i].prep_next.data();
+        rc.perm[0] = pl.data();
+        rc.perm[1] = pn.data();
+        rc.pub = pubs[i].data();
+        rc.sel[0] = sel.is_first;
+        rc.sel[1] = sel.is_last;
+        rc.sel[2] = sel.is_transition;
+        rc.chal = chal[i].data();
+        rc.pval = &terminals[i];
+        std::vector<Ext> cons(s.cons.n_constraints, ext_zero());
+        run_program<Ext>(s.cons, rc, &cons, nullptr);
+        Ext folded = fold_constraints(cons, alpha);
+        if (!(folded * sel.inv_vanishing == Qz))
+            throw std::runtime_error("verify: constraint/quotient mismatch for instance " + std::to_string(i));
+        if (!s.lookups.empty()) tsum = tsum + terminals[i];
+    }
+    if (!is_zero(tsum)) throw std::runtime_error("verify: LogUp terminals do not sum to zero");
+}
+
+std::string g_err;
+bool g_init = false;
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C API (loaded with ctypes by tests/ and bench.py's reference arm).
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* orc_last_error(void) { return g_err.c_str(); }
+
+int orc_init(const p3r_field_desc* field, const p3r_poseidon2_consts* p2, const p3r_fri_params* fri) {
+    try {
+        P = field->p;
+        Wnr = field->w;
+        GEN = field->generator;
+        TWO_ADICITY = 0;
+        for (uint32_t t = P - 1; (t & 1) == 0; t >>= 1) TWO_ADICITY++;
+        R_INV = finv(mk((uint64_t)1 << 32));
+        if (p2->width != 16) throw std::runtime_error("oracle: only width 16");
+        P2.sbox = p2->sbox_degree;
+        P2.rf = p2->rounds_f;
+        P2.rp = p2->rounds_p;
+        P2.ext_rc.clear();
+        P2.int_rc.clear();
+        P2.diag.clear();
+        for (uint32_t i = 0; i < p2->rounds_f * 16; i++) P2.ext_rc.push_back(from_monty(p2->external_rc[i]));
+        for (uint32_t i = 0; i < p2->rounds_p; i++) P2.int_rc.push_back(from_monty(p2->internal_rc[i]));
+        for (uint32_t i = 0; i < 16; i++) P2.diag.push_back(from_monty(p2->internal_diag[i]));
+        FRI = *fri;
+        CAP_HEIGHT = fri->cap_height;
+        g_init = true;
+        return 0;
+    } catch (std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+#define ORC_GUARD(...)                                  \
+    try {                                                \
+        if (!g_init) throw std::runtime_error("oracle: orc_init not called"); \
+        __VA_ARGS__;                                     \
+        return 0;                                        \
+    } catch (std::exception & e) {                       \
+        g_err = e.what();                                \
+        return 1;                                        \
+    }
+
+int orc_poseidon2_permute(uint32_t* states, uint32_t n) {
+    ORC_GUARD({
+        for (uint32_t i = 0; i < n; i++) {
+            Fp s[16];
+            for (int k = 0; k < 16; k++) s[k] = from_monty(states[16 * i + k]);
+            poseidon2_permute(s);
+            for (int k = 0; k < 16; k++) states[16 * i + k] = to_monty(s[k]);
+        }
+    })
+}
+
+int orc_coset_lde(const p3r_matrix_u32* in, uint32_t log_blowup, uint32_t* out) {
+    ORC_GUARD({
+        Mat m = mat_from_abi(*in);
+        Mat o = coset_lde(m, log_blowup, Fp{1});
+        for (size_t i = 0; i < o.d.size(); i++) out[i] = to_monty(o.d[i]);
+    })
+}
+
+int orc_mmcs_commit(uint32_t n_mats, const p3r_matrix_u32* mats, uint32_t* cap_out) {
+    ORC_GUARD({
+        std::vector<Mat> ms;
+        for (uint32_t i = 0; i < n_mats; i++) ms.push_back(mat_from_abi(mats[i]));
+        std::vector<const Mat*> ptrs;
+        for (auto& m : ms) ptrs.push_back(&m);
+        MerkleTree t = mmcs_commit(ptrs);
+        size_t k = 0;
+        for (auto& d : t.cap())
+            for (int i = 0; i < 8; i++) cap_out[k++] = to_monty(d.d[i]);
+    })
+}
+
+// Open row `index` of an mmcs over `mats`, then verify it against the recomputed cap (self-check of the
+// open/verify pair; returns non-zero on mismatch).
+int orc_mmcs_open_verify(uint32_t n_mats, const p3r_matrix_u32* mats, uint32_t index) {
+    ORC_GUARD({
+        std::vector<Mat> ms;
+        for (uint32_t i = 0; i < n_mats; i++) ms.push_back(mat_from_abi(mats[i]));
+        std::vector<const Mat*> ptrs;
+        std::vector<size_t> heights;
+        for (auto& m : ms) {
+            ptrs.push_back(&m);
+            heights.push_back(m.h);
+        }
+        MerkleTree t = mmcs_commit(ptrs);
+        BatchOpening o = mmcs_open(t, index);
+        if (!mmcs_verify(t.cap(), heights, index, o.rows, o.path)) throw std::runtime_error("oracle: open/verify mismatch");
+    })
+}
+
+int orc_grind(const uint32_t state[16], const uint32_t* pending, uint32_t n_pending, uint32_t bits,
+              uint32_t* witness_out) {
+    ORC_GUARD({
+        Challenger c;
+        for (int i = 0; i < 16; i++) c.st[i] = from_monty(state[i]);
+        for (uint32_t i = 0; i < n_pending; i++) c.in.push_back(from_monty(pending[i]));
+        *witness_out = to_monty(c.grind(bits));
+    })
+}
+
+// Replays a list of challenger operations; used to test the product's host challenger against this one.
+// ops: 0 = observe(next input word), 1 = sample -> appended to out, 2 = sample_bits(arg) -> appended (raw int).
+int orc_challenger_script(const uint32_t* ops, uint32_t n_ops, const uint32_t* inputs, uint32_t* out,
+                          uint32_t* n_out) {
+    ORC_GUARD({
+        Challenger c;
+        uint32_t ii = 0, oi = 0;
+        for (uint32_t i = 0; i < n_ops; i++) {
+            uint32_t op = ops[2 * i], arg = ops[2 * i + 1];
+            if (op == 0) c.observe(from_monty(inputs[ii++]));
+            else if (op == 1) out[oi++] = to_monty(c.sample());
+            else out[oi++] = c.sample_bits(arg);
+        }
+        *n_out = oi;
+    })
+}
+
+int orc_prep_commit(uint32_t n_inst, const p3r_instance_desc* descs, const p3r_matrix_u32* prep, uint32_t* cap_out) {
+    ORC_GUARD({
+        std::vector<Mat> ldes;
+        for (uint32_t i = 0; i < n_inst; i++)
+            if (descs[i].prep_width) ldes.push_back(coset_lde(mat_from_abi(prep[i]), FRI.log_blowup, Fp{1}));
+        std::vector<const Mat*> ptrs;
+        for (auto& m : ldes) ptrs.push_back(&m);
+        if (ptrs.empty()) throw std::runtime_error("oracle: no preprocessed columns");
+        MerkleTree t = mmcs_commit(ptrs);
+        size_t k = 0;
+        for (auto& d : t.cap())
+            for (int i = 0; i < 8; i++) cap_out[k++] = to_monty(d.d[i]);
+    })
+}
+
+int orc_prove(uint32_t n_inst, const p3r_instance_desc* descs, const p3r_matrix_u32* prep,
+              const p3r_matrix_u32* traces, const uint32_t* const* public_values, uint32_t* proof_out,
+              size_t cap_words, size_t* n_words) {
+    ORC_GUARD({
+        Common cm = load_common(n_inst, descs);
+        std::vector<Mat> pm(n_inst), tm(n_inst);
+        std::vector<std::vector<Fp>> pubs(n_inst);
+        for (uint32_t i = 0; i < n_inst; i++) {
+            if (descs[i].prep_width) pm[i] = mat_from_abi(prep[i]);
+            tm[i] = mat_from_abi(traces[i]);
+            for (uint32_t k = 0; k < descs[i].n_public; k++) pubs[i].push_back(from_monty(public_values[i][k]));
+        }
+        ProveOut po = prove(cm, pm, tm, pubs);
+        *n_words = po.blob.size();
+        if (po.blob.size() > cap_words) throw std::runtime_error("oracle: proof buffer too small");
+        std::memcpy(proof_out, po.blob.data(), po.blob.size() * 4);
+    })
+}
+
+// prep_cap: 8<<cap_height Montgomery words or NULL when no instance has preprocessed columns.
+int orc_verify(uint32_t n_inst, const p3r_instance_desc* descs, const uint32_t* prep_cap,
+               const uint32_t* const* public_values, const uint32_t* proof, size_t n_words) {
+    ORC_GUARD({
+        Common cm = load_common(n_inst, descs);
+        std::vector<std::vector<Fp>> pubs(n_inst);
+        for (uint32_t i = 0; i < n_inst; i++)
+            for (uint32_t k = 0; k < descs[i].n_public; k++) pubs[i].push_back(from_monty(public_values[i][k]));
+        std::vector<Digest> pc;
+        if (cm.has_prep) {
+            if (!prep_cap) throw std::runtime_error("verify: missing preprocessed commitment");
+            pc.resize((size_t)1 << CAP_HEIGHT);
+            for (size_t d = 0; d < pc.size(); d++)
+                for (int k = 0; k < 8; k++) pc[d].d[k] = from_monty(prep_cap[8 * d + k]);
+        }
+        verify(cm, cm.has_prep ? &pc : nullptr, pubs, proof, n_words);
+    })
+}
+
+// Evaluate a constraint program on every row of (main, prep) in the trace domain with the given selectors
+// semantics (is_first = row 0, is_last = row n-1, is_transition = not last) and report the first violated
+// constraint: the analogue of p3's debug `check_constraints` (book/src/advanced_topics/debugging.md).
+// Programs with E_* perm/challenge inputs are not supported here (AIR-only check). Returns 0 when satisfied.
+int orc_check_constraints(const p3r_instance_desc* desc, const p3r_matrix_u32* prep, const p3r_matrix_u32* trace,
+                          const uint32_t* public_values, int64_t* bad_row, int64_t* bad_constraint) {
+    ORC_GUARD({
+        Inst s = load_inst(*desc);
+        Mat tm = mat_from_abi(*trace);
+        Mat pm;
+        if (s.prep_w) pm = mat_from_abi(*prep);
+        std::vector<Fp> pub;
+        for (uint32_t k = 0; k < s.n_pub; k++) pub.push_back(from_monty(public_values[k]));
+        *bad_row = -1;
+        *bad_constraint = -1;
+        size_t n = tm.h;
+        std::vector<Ext> zero_ch(2 * s.lookups.size() + 2, ext_zero());
+        std::vector<Ext> zperm(s.aux_w() + 1, ext_zero());
+        Ext zt = ext_zero();
+        for (size_t r = 0; r < n; r++) {
+            RowCtx<Fp> rc;
+            rc.main[0] = &tm.d[r * tm.w];
+            rc.main[1] = &tm.d[((r + 1) % n) * tm.w];
+            if (s.prep_w) {
+                rc.prep[0] = &pm.d[r * pm.w];
+                rc.prep[1] = &pm.d[((r + 1) % n) * pm.w];
+            }
+            rc.perm[0] = zperm.data();
+            rc.perm[1] = zperm.data();
+            rc.pub = pub.data();
+            rc.sel[0] = Fp{r == 0};
+            rc.sel[1] = Fp{r == n - 1};
+            rc.sel[2] = Fp{r != n - 1};
+            rc.chal = zero_ch.data();
+            rc.pval = &zt;
+            std::vector<Ext> cons(s.cons.n_constraints, ext_zero());
+            run_program<Fp>(s.cons, rc, &cons, nullptr);
+            for (size_t k = 0; k < cons.size(); k++)
+                if (!is_zero(cons[k])) {
+                    *bad_row = (int64_t)r;
+                    *bad_constraint = (int64_t)k;
+                    throw std::runtime_error("constraint violated");
+                }
+        }
+    })
+}
+
+}  // extern "C"

@@ -1,0 +1,151 @@
+"""ctypes mirror of include/p3r.h (data-format structs + marshalling helpers).
+
+Only the struct layouts live here; the product library loader is in `lib.py`. The CPU oracle under oracle/ reads the same
+structs (they are the wire format of the boundary), but it is loaded only by tests/ and bench.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .field import Field
+from .symbolic import OP_B_CONST, Program
+
+u32 = C.c_uint32
+u32p = C.POINTER(C.c_uint32)
+
+
+class FieldDesc(C.Structure):
+    _fields_ = [("field_id", u32), ("p", u32), ("w", u32), ("generator", u32)]
+
+
+class Poseidon2Consts(C.Structure):
+    _fields_ = [("width", u32), ("sbox_degree", u32), ("rounds_f", u32), ("rounds_p", u32),
+                ("external_rc", u32p), ("internal_rc", u32p), ("internal_diag", u32p)]
+
+
+class FriParams(C.Structure):
+    _fields_ = [("log_blowup", u32), ("log_final_poly_len", u32), ("max_log_arity", u32), ("num_queries", u32),
+                ("commit_pow_bits", u32), ("query_pow_bits", u32), ("cap_height", u32)]
+
+
+class MatrixU32(C.Structure):
+    _fields_ = [("data", u32p), ("height", u32), ("width", u32)]
+
+
+class Insn(C.Structure):
+    _fields_ = [("op", u32), ("dst", u32), ("a", u32), ("b", u32)]
+
+
+class ProgramC(C.Structure):
+    _fields_ = [("insns", C.POINTER(Insn)), ("n_insns", u32), ("n_base_slots", u32), ("n_ext_slots", u32),
+                ("ext_consts", u32p), ("n_ext_consts", u32), ("n_constraints", u32), ("n_outputs", u32)]
+
+
+class InteractionC(C.Structure):
+    _fields_ = [("mult_out", u32), ("elem_out_first", u32), ("n_elems", u32)]
+
+
+class LookupC(C.Structure):
+    _fields_ = [("bus", u32), ("first_interaction", u32), ("n_interactions", u32)]
+
+
+class InstanceDesc(C.Structure):
+    _fields_ = [("log_height", u32), ("main_width", u32), ("prep_width", u32), ("n_public", u32),
+                ("log_quotient_chunks", u32), ("uses_next_row", u32),
+                ("constraints", ProgramC), ("lookup_inputs", ProgramC),
+                ("lookups", C.POINTER(LookupC)), ("n_lookups", u32),
+                ("interactions", C.POINTER(InteractionC)), ("n_interactions", u32)]
+
+
+def as_u32p(a: np.ndarray):
+    assert a.dtype == np.uint32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(u32p)
+
+
+class Marshal:
+    """Keeps numpy buffers alive for the lifetime of the ctypes structs that point into them."""
+
+    def __init__(self, field: Field):
+        self.field = field
+        self._keep = []
+
+    def keep(self, a):
+        self._keep.append(a)
+        return a
+
+    def u32(self, a) -> np.ndarray:
+        return self.keep(np.ascontiguousarray(a, dtype=np.uint32))
+
+    def matrix(self, canonical: np.ndarray | None) -> MatrixU32:
+        """canonical: (height, width) uint32 canonical residues -> Montgomery row-major."""
+        if canonical is None:
+            return MatrixU32(None, 0, 0)
+        m = self.u32(self.field.to_monty(canonical))
+        assert m.ndim == 2
+        return MatrixU32(as_u32p(m), m.shape[0], m.shape[1])
+
+    def matrix_monty(self, monty: np.ndarray) -> MatrixU32:
+        m = self.u32(monty)
+        return MatrixU32(as_u32p(m), m.shape[0], m.shape[1])
+
+    def program(self, prog: Program | None) -> ProgramC:
+        if prog is None:
+            return ProgramC(None, 0, 1, 1, None, 0, 0, 0)
+        ins = np.array(prog.insns, dtype=np.uint32).reshape(-1, 4).copy()
+        is_const = ins[:, 0] == OP_B_CONST
+        ins[is_const, 2] = self.field.to_monty(ins[is_const, 2])
+        ins = self.u32(ins)
+        ec = self.u32(self.field.to_monty(prog.ext_consts.reshape(-1))) if prog.ext_consts.size else self.u32(np.zeros(4))
+        return ProgramC(C.cast(as_u32p(ins), C.POINTER(Insn)), ins.shape[0], prog.n_base_slots, prog.n_ext_slots,
+                        as_u32p(ec), prog.ext_consts.shape[0], prog.n_constraints, prog.n_outputs)
+
+    def fri(self, d: dict) -> FriParams:
+        return FriParams(d["log_blowup"], d["log_final_poly_len"], d["max_log_arity"], d["num_queries"],
+                         d["commit_pow_bits"], d["query_pow_bits"], d["cap_height"])
+
+    def field_desc(self) -> FieldDesc:
+        f = self.field
+        return FieldDesc(f.field_id, f.p, f.w, f.generator)
+
+    def poseidon2(self, params) -> Poseidon2Consts:
+        f = self.field
+        e = self.u32(f.to_monty(params.external_rc))
+        i = self.u32(f.to_monty(params.internal_rc))
+        d = self.u32(f.to_monty(params.internal_diag))
+        return Poseidon2Consts(params.width, params.sbox_degree, params.rounds_f, params.rounds_p,
+                               as_u32p(e), as_u32p(i), as_u32p(d))
+
+    def instances(self, insts) -> C.Array:
+        """insts: list of air.AirInstance -> contiguous array of InstanceDesc."""
+        arr = (InstanceDesc * len(insts))()
+        for k, s in enumerate(insts):
+            lk = (LookupC * max(1, len(s.lookups)))()
+            for j, (bus, first, n) in enumerate(s.lookups):
+                lk[j] = LookupC(bus, first, n)
+            it = (InteractionC * max(1, len(s.interactions)))()
+            for j, (mo, ef, ne) in enumerate(s.interactions):
+                it[j] = InteractionC(mo, ef, ne)
+            self.keep(lk)
+            self.keep(it)
+            arr[k] = InstanceDesc(s.log_height, s.main_width, s.prep_width, s.n_public, s.log_quotient_chunks,
+                                  int(s.uses_next_row), self.program(s.constraints), self.program(s.lookup_inputs),
+                                  lk, len(s.lookups), it, len(s.interactions))
+        return self.keep(arr)
+
+    def matrices(self, mats) -> C.Array:
+        arr = (MatrixU32 * len(mats))()
+        for k, m in enumerate(mats):
+            arr[k] = self.matrix(m)
+        return self.keep(arr)
+
+    def public_values(self, pubs) -> C.Array:
+        arr = (u32p * len(pubs))()
+        for k, pv in enumerate(pubs):
+            if pv is None or len(pv) == 0:
+                arr[k] = None
+            else:
+                a = self.u32(self.field.to_monty(np.asarray(pv, dtype=np.uint32)))
+                arr[k] = as_u32p(a)
+        return self.keep(arr)

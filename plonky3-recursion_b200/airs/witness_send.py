@@ -1,0 +1,56 @@
+"""WitnessSendAir: the AIR behind ConstAir and PublicAir.
+
+Reference: /root/reference circuit-prover/src/air/public_air.rs:43-230 (WitnessSendAir), const_air.rs:52-158 (ConstAir is the
+single-lane case). Main trace: `lanes * D` value coordinates; preprocessed: per lane `[multiplicity, witness_idx]`
+(column_layout.rs WITNESS_LOOKUP_PREP_COL_MAP). No local constraints; one `WitnessChecks` send per lane
+`(witness_idx, value[0..D])` with the preprocessed multiplicity (public_air.rs:202-230).
+Shape goldens (air/shape_golden.rs:33-45): Const D4 -> (4, 2); Public D4 x 2 lanes -> (8, 4).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+PREP_LANE_WIDTH = 2  # [multiplicity, witness_idx]
+
+
+def widths(d: int, lanes: int = 1):
+    return lanes * d, lanes * PREP_LANE_WIDTH
+
+
+def make_eval(d: int, lanes: int = 1):
+    def eval_air(b):
+        for lane in range(lanes):
+            mult = b.prep(lane * PREP_LANE_WIDTH + 0)
+            idx = b.prep(lane * PREP_LANE_WIDTH + 1)
+            fields = [idx] + [b.main(lane * d + j) for j in range(d)]
+            b.push_interaction("WitnessChecks", fields, mult)
+
+    return eval_air
+
+
+def trace_to_matrix(values: np.ndarray, d: int, lanes: int, min_height: int) -> np.ndarray:
+    """values: (num_ops, d) canonical. Lane packing + zero padding to max(pow2, min_height)
+    (public_air.rs:128-170, const_air.rs:91-126)."""
+    values = np.asarray(values, dtype=np.uint32).reshape(-1, d)
+    num_ops = values.shape[0]
+    rows = -(-num_ops // lanes) if num_ops else 0
+    height = max(min_height, 1 << max(rows - 1, 0).bit_length())
+    out = np.zeros((height, lanes * d), dtype=np.uint32)
+    flat = out.reshape(height * lanes, d)
+    flat[:num_ops] = values
+    return out
+
+
+def preprocessed_matrix(mults: np.ndarray, idxs: np.ndarray, lanes: int, min_height: int) -> np.ndarray:
+    """Per op (multiplicity, D-scaled witness index), canonical; padding rows have multiplicity 0
+    (circuit-prover/src/common.rs:226-287)."""
+    mults = np.asarray(mults, dtype=np.uint32)
+    idxs = np.asarray(idxs, dtype=np.uint32)
+    num_ops = mults.shape[0]
+    rows = -(-num_ops // lanes) if num_ops else 0
+    height = max(min_height, 1 << max(rows - 1, 0).bit_length())
+    out = np.zeros((height, lanes * PREP_LANE_WIDTH), dtype=np.uint32)
+    flat = out.reshape(height * lanes, PREP_LANE_WIDTH)
+    flat[:num_ops, 0] = mults
+    flat[:num_ops, 1] = idxs
+    return out
