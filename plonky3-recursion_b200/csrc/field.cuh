@@ -1,0 +1,189 @@
+// field.cuh — Montgomery 31-bit field + degree-4 binomial extension for sm_100a (K1 in SURVEY.md §2.3).
+//
+// Replaces p3-monty-31's MontyField31 and p3-field's BinomialExtensionField<F,4> (binomial multiplication restated at
+// /root/reference circuit-prover/src/air/alu_air.rs:715-733). All values are Montgomery residues x*2^32 mod P kept in
+// [0, P). 31-bit modular integer work on the IMAD pipe: no tensor cores.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define P3R_HD __host__ __device__ __forceinline__
+#else
+#define P3R_HD inline
+#endif
+
+namespace p3r {
+
+// Compile-time field parameters. MU = P^{-1} mod 2^32; R = 2^32 mod P; R2 = 2^64 mod P.
+struct KoalaBear {
+    static constexpr uint32_t P = 0x7f000001u;
+    static constexpr uint32_t MU = 0x81000001u;
+    static constexpr uint32_t R = 0x01fffffeu;
+    static constexpr uint32_t R2 = 0x17f7efe4u;
+    static constexpr uint32_t TWO_ADICITY = 24;
+    static constexpr int SBOX = 3;
+    static constexpr int ROUNDS_P = 20;
+};
+struct BabyBear {
+    static constexpr uint32_t P = 0x78000001u;
+    static constexpr uint32_t MU = 0x88000001u;
+    static constexpr uint32_t R = 0x0ffffffeu;
+    static constexpr uint32_t R2 = 0x45dddde3u;
+    static constexpr uint32_t TWO_ADICITY = 27;
+    static constexpr int SBOX = 7;
+    static constexpr int ROUNDS_P = 13;
+};
+
+template <class F>
+P3R_HD uint32_t fadd(uint32_t a, uint32_t b) {
+    uint32_t s = a + b;
+    return s >= F::P ? s - F::P : s;
+}
+template <class F>
+P3R_HD uint32_t fsub(uint32_t a, uint32_t b) {
+    uint32_t d = a - b;
+    return a < b ? d + F::P : d;
+}
+template <class F>
+P3R_HD uint32_t fneg(uint32_t a) {
+    return a ? F::P - a : 0u;
+}
+// Montgomery product: (a*b - m*P) / 2^32 with m = lo(a*b)*MU; result in [0,P).
+template <class F>
+P3R_HD uint32_t fmul(uint32_t a, uint32_t b) {
+    uint64_t t = (uint64_t)a * b;
+    uint32_t m = (uint32_t)t * F::MU;
+    uint32_t u = (uint32_t)(((uint64_t)m * F::P) >> 32);
+    uint32_t hi = (uint32_t)(t >> 32);
+    uint32_t r = hi - u;
+    return hi < u ? r + F::P : r;
+}
+// Reduce a 64-bit accumulator of Montgomery products (value < 2^64) to a Montgomery residue of acc / 2^32.
+template <class F>
+P3R_HD uint32_t fred64(uint64_t t) {
+    uint32_t m = (uint32_t)t * F::MU;
+    uint32_t u = (uint32_t)(((uint64_t)m * F::P) >> 32);
+    uint32_t hi = (uint32_t)(t >> 32);
+    // hi may be >= P here (t up to 2^64): bring into range first
+    uint32_t r = hi - u;
+    if (hi < u) r += F::P;  // r in (-P, 2^32): after wrap fix r in [0, 2^32 - ?]
+    // r < 2^32 - may still exceed P up to 2 times (hi < 2^32 ~ 2.02 P)
+    if (r >= F::P) r -= F::P;
+    if (r >= F::P) r -= F::P;
+    return r;
+}
+template <class F>
+P3R_HD uint32_t to_monty(uint32_t canonical) {
+    return fmul<F>(canonical % F::P, F::R2);
+}
+template <class F>
+P3R_HD uint32_t from_monty(uint32_t m) {
+    return fmul<F>(m, 1u);
+}
+template <class F>
+P3R_HD uint32_t fpow(uint32_t a, uint64_t e) {
+    uint32_t r = F::R;
+    while (e) {
+        if (e & 1) r = fmul<F>(r, a);
+        a = fmul<F>(a, a);
+        e >>= 1;
+    }
+    return r;
+}
+template <class F>
+P3R_HD uint32_t finv(uint32_t a) {
+    return fpow<F>(a, (uint64_t)F::P - 2);
+}
+
+// ---- degree-4 binomial extension, x^4 = W (W passed in Montgomery form) ----
+struct Ext4 {
+    uint32_t c[4];
+};
+P3R_HD Ext4 ext_zero() { return Ext4{{0, 0, 0, 0}}; }
+template <class F>
+P3R_HD Ext4 ext_one() {
+    return Ext4{{F::R, 0, 0, 0}};
+}
+template <class F>
+P3R_HD Ext4 ext_lift(uint32_t a) {
+    return Ext4{{a, 0, 0, 0}};
+}
+template <class F>
+P3R_HD Ext4 eadd(const Ext4& a, const Ext4& b) {
+    return Ext4{{fadd<F>(a.c[0], b.c[0]), fadd<F>(a.c[1], b.c[1]), fadd<F>(a.c[2], b.c[2]), fadd<F>(a.c[3], b.c[3])}};
+}
+template <class F>
+P3R_HD Ext4 esub(const Ext4& a, const Ext4& b) {
+    return Ext4{{fsub<F>(a.c[0], b.c[0]), fsub<F>(a.c[1], b.c[1]), fsub<F>(a.c[2], b.c[2]), fsub<F>(a.c[3], b.c[3])}};
+}
+template <class F>
+P3R_HD Ext4 eneg(const Ext4& a) {
+    return Ext4{{fneg<F>(a.c[0]), fneg<F>(a.c[1]), fneg<F>(a.c[2]), fneg<F>(a.c[3])}};
+}
+template <class F>
+P3R_HD Ext4 emul_base(const Ext4& a, uint32_t b) {
+    return Ext4{{fmul<F>(a.c[0], b), fmul<F>(a.c[1], b), fmul<F>(a.c[2], b), fmul<F>(a.c[3], b)}};
+}
+template <class F>
+P3R_HD Ext4 eadd_base(const Ext4& a, uint32_t b) {
+    return Ext4{{fadd<F>(a.c[0], b), a.c[1], a.c[2], a.c[3]}};
+}
+template <class F>
+P3R_HD Ext4 esub_base(const Ext4& a, uint32_t b) {
+    return Ext4{{fsub<F>(a.c[0], b), a.c[1], a.c[2], a.c[3]}};
+}
+// Schoolbook product with delayed reduction: each output coefficient accumulates <= 4 products (< 2^62 each, sum < 2^64),
+// the x^4 = W wrap-around terms are reduced once and multiplied by W.
+template <class F>
+P3R_HD Ext4 emul(const Ext4& a, const Ext4& b, uint32_t w) {
+    uint64_t lo0 = (uint64_t)a.c[0] * b.c[0];
+    uint64_t lo1 = (uint64_t)a.c[0] * b.c[1] + (uint64_t)a.c[1] * b.c[0];
+    uint64_t lo2 = (uint64_t)a.c[0] * b.c[2] + (uint64_t)a.c[1] * b.c[1] + (uint64_t)a.c[2] * b.c[0];
+    uint64_t lo3 = (uint64_t)a.c[0] * b.c[3] + (uint64_t)a.c[1] * b.c[2] + (uint64_t)a.c[2] * b.c[1] + (uint64_t)a.c[3] * b.c[0];
+    uint64_t hi0 = (uint64_t)a.c[1] * b.c[3] + (uint64_t)a.c[2] * b.c[2] + (uint64_t)a.c[3] * b.c[1];
+    uint64_t hi1 = (uint64_t)a.c[2] * b.c[3] + (uint64_t)a.c[3] * b.c[2];
+    uint64_t hi2 = (uint64_t)a.c[3] * b.c[3];
+    Ext4 r;
+    r.c[0] = fadd<F>(fred64<F>(lo0), fmul<F>(fred64<F>(hi0), w));
+    r.c[1] = fadd<F>(fred64<F>(lo1), fmul<F>(fred64<F>(hi1), w));
+    r.c[2] = fadd<F>(fred64<F>(lo2), fmul<F>(fred64<F>(hi2), w));
+    r.c[3] = fred64<F>(lo3);
+    return r;
+}
+// Inverse via the tower F -> F(y = x^2) -> F(x): a*(A - Bx) = A^2 - y*B^2 =: n0 + n1*y, 1/(n0+n1 y) = (n0 - n1 y)/(n0^2 - W n1^2).
+template <class F>
+P3R_HD Ext4 einv(const Ext4& a, uint32_t w) {
+    uint32_t a0 = a.c[0], a1 = a.c[1], a2 = a.c[2], a3 = a.c[3];
+    uint32_t a1a3 = fmul<F>(a1, a3);
+    uint32_t n0 = fsub<F>(fadd<F>(fmul<F>(a0, a0), fmul<F>(w, fmul<F>(a2, a2))), fmul<F>(w, fadd<F>(a1a3, a1a3)));
+    uint32_t a0a2 = fmul<F>(a0, a2);
+    uint32_t n1 = fsub<F>(fadd<F>(a0a2, a0a2), fadd<F>(fmul<F>(a1, a1), fmul<F>(w, fmul<F>(a3, a3))));
+    uint32_t d = fsub<F>(fmul<F>(n0, n0), fmul<F>(w, fmul<F>(n1, n1)));
+    uint32_t di = finv<F>(d);
+    uint32_t m0 = fmul<F>(n0, di), m1 = fneg<F>(fmul<F>(n1, di));
+    Ext4 conj{{a0, fneg<F>(a1), a2, fneg<F>(a3)}};
+    Ext4 m{{m0, 0, m1, 0}};
+    return emul<F>(conj, m, w);
+}
+template <class F>
+P3R_HD Ext4 epow(Ext4 a, uint64_t e, uint32_t w) {
+    Ext4 r = ext_one<F>();
+    while (e) {
+        if (e & 1) r = emul<F>(r, a, w);
+        a = emul<F>(a, a, w);
+        e >>= 1;
+    }
+    return r;
+}
+
+P3R_HD uint32_t bitrev32(uint32_t x, uint32_t bits) {
+#if defined(__CUDA_ARCH__)
+    return bits ? (__brev(x) >> (32 - bits)) : 0u;
+#else
+    uint32_t r = 0;
+    for (uint32_t i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
+    return r;
+#endif
+}
+
+}  // namespace p3r

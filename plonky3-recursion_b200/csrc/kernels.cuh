@@ -1,0 +1,860 @@
+// kernels.cuh — all device kernels of the B200 batch-STARK prover (sm_100a, hand-written; INT32/IMAD pipe, no tensor cores).
+//
+// Device data layout (DESIGN.md "Data layout in HBM"): every committed matrix lives COLUMN-MAJOR in HBM (column c of a
+// matrix of height H is the contiguous run d[c*H .. c*H+H)), LDE rows in bit-reversed order (p3's storage convention,
+// /root/reference recursion/src/pcs/fri/verifier.rs:921-976). With one thread per row every kernel below reads 128-byte
+// coalesced column segments. Extension-field vectors of the FRI phase are AoS (one uint4 per element).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/p3r.h"
+#include "field.cuh"
+#include "poseidon2.cuh"
+
+namespace p3r {
+
+// omega_T^e from the half table tw[k] = omega_T^k (k < T/2), T = 2^logT.
+template <class F>
+__device__ __forceinline__ uint32_t root_pow(const uint32_t* __restrict__ tw, uint32_t logT, uint64_t e) {
+    uint32_t T = 1u << logT, x = (uint32_t)e & (T - 1), half = T >> 1;
+    return x >= half ? fneg<F>(__ldg(tw + (x - half))) : __ldg(tw + x);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Setup kernels
+// ------------------------------------------------------------------------------------------------
+// tw[k] = w^k for k < n, w given (Montgomery); two-level so each thread does O(log) work.
+template <class F>
+__global__ void k_powers(uint32_t* out, uint32_t n, uint32_t w, uint32_t first) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = fmul<F>(first, fpow<F>(w, i));
+}
+
+// Row-major (h x w) -> column-major (w x h) through a 32x33 shared tile (coalesced on both sides).
+__global__ void k_transpose_in(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t h, uint32_t w) {
+    __shared__ uint32_t tile[32][33];
+    uint32_t c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (uint32_t dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        uint32_t r = r0 + dy, c = c0 + threadIdx.x;
+        if (r < h && c < w) tile[dy][threadIdx.x] = in[(size_t)r * w + c];
+    }
+    __syncthreads();
+    for (uint32_t dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        uint32_t c = c0 + dy, r = r0 + threadIdx.x;
+        if (r < h && c < w) out[(size_t)c * h + r] = tile[threadIdx.x][dy];
+    }
+}
+// Column-major (w x h) -> row-major (h x w); used only by the isolated p3r_coset_lde entry point.
+__global__ void k_transpose_out(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t h, uint32_t w) {
+    __shared__ uint32_t tile[32][33];
+    uint32_t c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (uint32_t dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        uint32_t c = c0 + dy, r = r0 + threadIdx.x;
+        if (r < h && c < w) tile[dy][threadIdx.x] = in[(size_t)c * h + r];
+    }
+    __syncthreads();
+    for (uint32_t dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        uint32_t r = r0 + dy, c = c0 + threadIdx.x;
+        if (r < h && c < w) out[(size_t)r * w + c] = tile[threadIdx.x][dy];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: batched coset LDE = radix-2 NTT passes over shared-memory tiles.
+// A pass executes butterfly stages [s0, s0+r) of a size-2^log_n transform on every column (grid.y) and, for forward passes,
+// every output coset (grid.z). Stage s pairs i and i + 2^s with twiddle omega_{2^{s+1}}^{i mod 2^s}.
+//   inverse  : decimation-in-frequency, stages descending, natural in -> bit-reversed out, inverse twiddles (no 1/n here);
+//   forward  : decimation-in-time, stages ascending, bit-reversed in -> natural out; the first pass multiplies coefficient k
+//              by (shift_j^k / n), the last pass stores to bit-reversed positions inside coset block j.
+// Tile = 2^r butterfly rows (stride 2^s0) x 2^log_cw consecutive elements; s0 == 0 tiles are contiguous runs.
+// ------------------------------------------------------------------------------------------------
+struct NttPass {
+    const uint32_t* src;
+    uint32_t* dst;
+    uint64_t src_col_stride, dst_col_stride;  // elements between columns
+    uint64_t dst_coset_stride;                // elements between coset blocks in dst (forward)
+    uint32_t log_n, s0, r, log_cw;
+    uint32_t forward;        // 0 = inverse DIF, 1 = forward DIT
+    uint32_t first, last;    // first / last pass of the transform
+    uint32_t log_blowup;     // forward: number of coset blocks = 2^log_blowup
+    uint32_t use_g;          // scale by GENERATOR^k (trace-like input domain H_n) or not (input domain already shifted by GENERATOR)
+    uint32_t rot;            // extra root-of-unity rotation exponent (mod N) applied per coefficient index
+    uint32_t n_inv;          // 1/n (Montgomery), used when use_g == 0
+    const uint32_t* tw;      // half table of omega_T
+    uint32_t logT;
+    const uint32_t* g_lo;    // g^k / n = g_lo[k & 1023] * g_hi[k >> 10]
+    const uint32_t* g_hi;
+};
+
+template <class F>
+__global__ void __launch_bounds__(256) k_ntt_pass(NttPass a) {
+    extern __shared__ uint32_t sm[];
+    const uint32_t R = 1u << a.r, CW = 1u << a.log_cw, S = 1u << a.s0;
+    const uint32_t CWP = CW >= 32 ? CW + 1 : CW;  // padded row stride: conflict-free bit-reversed stores
+    const uint32_t col = blockIdx.y, coset = blockIdx.z;
+    const uint32_t m0 = blockIdx.x * CW;
+    const uint32_t n = 1u << a.log_n;
+    const uint32_t* src = a.src + (size_t)col * a.src_col_stride;
+    if (a.forward && !a.first) src += (size_t)coset * a.dst_coset_stride;  // in-place chain lives in the coset block
+    uint32_t* dst = a.dst + (size_t)col * a.dst_col_stride + (size_t)coset * (a.forward ? a.dst_coset_stride : 0);
+    const uint32_t total = R * CW;
+
+    // ---- load ----
+    const bool t_fastest = (S < CW);  // contiguous tiles (s0 == 0)
+    const uint32_t rj = bitrev32(coset, a.log_blowup);
+    const uint32_t logN = a.log_n + a.log_blowup;
+    for (uint32_t idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        uint32_t t, mm;
+        if (t_fastest) {
+            t = idx & (R - 1);
+            mm = idx >> a.r;
+        } else {
+            mm = idx & (CW - 1);
+            t = idx >> a.log_cw;
+        }
+        uint32_t m = m0 + mm, lo = m & (S - 1), hi = m >> a.s0;
+        uint32_t gi = ((hi << a.r) + t) * S + lo;
+        uint32_t v = src[gi];
+        if (a.forward && a.first) {
+            uint32_t k = bitrev32(gi, a.log_n);  // coefficient index held at position gi
+            uint32_t sc = a.use_g ? fmul<F>(__ldg(a.g_lo + (k & 1023)), __ldg(a.g_hi + (k >> 10))) : a.n_inv;
+            uint64_t e = ((uint64_t)(rj + a.rot) * k) & ((1ull << logN) - 1);
+            sc = fmul<F>(sc, root_pow<F>(a.tw, a.logT, e << (a.logT - logN)));
+            v = fmul<F>(v, sc);
+        }
+        sm[t * CWP + mm] = v;
+    }
+    __syncthreads();
+
+    // ---- butterflies ----
+    const uint32_t nb = total >> 1;
+    for (uint32_t step = 0; step < a.r; step++) {
+        const uint32_t j = a.forward ? step : (a.r - 1 - step);
+        const uint32_t half = 1u << j, s = a.s0 + j;
+        const uint32_t tsh = a.logT - s - 1;
+        for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) {
+            uint32_t mm, tp;
+            if (t_fastest) {
+                tp = b & ((R >> 1) - 1);
+                mm = b >> (a.r - 1);
+            } else {
+                mm = b & (CW - 1);
+                tp = b >> a.log_cw;
+            }
+            uint32_t tlo = tp & (half - 1);
+            uint32_t t = ((tp >> j) << (j + 1)) | tlo;
+            uint32_t lo = (m0 + mm) & (S - 1);
+            uint32_t e = (tlo * S + lo) << tsh;  // < T/2
+            uint32_t w = __ldg(a.tw + e);
+            if (!a.forward && e) w = fneg<F>(__ldg(a.tw + ((1u << (a.logT - 1)) - e)));  // omega^{-e} = -omega^{T/2-e}
+            uint32_t i0 = t * CWP + mm, i1 = i0 + half * CWP;
+            uint32_t x = sm[i0], y = sm[i1];
+            if (a.forward) {
+                y = fmul<F>(y, w);
+                sm[i0] = fadd<F>(x, y);
+                sm[i1] = fsub<F>(x, y);
+            } else {
+                sm[i0] = fadd<F>(x, y);
+                sm[i1] = fmul<F>(fsub<F>(x, y), w);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- store ----
+    if (a.forward && a.last) {
+        // natural index i = (hi*R + t)*S + lo with hi == 0 (s0 + r == log_n)  ->  bitrev(i) = bitrev_s0(lo)*R + bitrev_r(t)
+        for (uint32_t idx = threadIdx.x; idx < total; idx += blockDim.x) {
+            uint32_t tt = idx & (R - 1), mm = idx >> a.r;
+            uint32_t lo = m0 + mm;
+            uint32_t pos = bitrev32(lo, a.s0) * R + tt;
+            dst[pos] = sm[bitrev32(tt, a.r) * CWP + mm];
+        }
+    } else {
+        for (uint32_t idx = threadIdx.x; idx < total; idx += blockDim.x) {
+            uint32_t t, mm;
+            if (t_fastest) {
+                t = idx & (R - 1);
+                mm = idx >> a.r;
+            } else {
+                mm = idx & (CW - 1);
+                t = idx >> a.log_cw;
+            }
+            uint32_t m = m0 + mm, lo = m & (S - 1), hi = m >> a.s0;
+            dst[((hi << a.r) + t) * S + lo] = sm[t * CWP + mm];
+        }
+    }
+    (void)n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: Poseidon2 sponge over rows + 2-to-1 compression tree (MerkleTreeMmcs).
+// ------------------------------------------------------------------------------------------------
+// colptr[i] = pointer to column i (already offset to this height's matrix), column-major; one thread per row.
+template <class F>
+__global__ void __launch_bounds__(128) k_hash_rows(const uint32_t* const* __restrict__ colptr, uint32_t ncols, uint32_t n_rows,
+                                                    uint32_t* __restrict__ out) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    uint32_t st[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) st[i] = 0;
+    for (uint32_t c0 = 0; c0 < ncols; c0 += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (c0 + k < ncols) st[k] = __ldg(colptr[c0 + k] + r);
+        poseidon2_permute<F>(st);
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + (size_t)r * 8);
+    o[0] = make_uint4(st[0], st[1], st[2], st[3]);
+    o[1] = make_uint4(st[4], st[5], st[6], st[7]);
+}
+// Rows of a row-major matrix of `w` words (ExtensionMmcs rows of the FRI commit phase, recursion/src/pcs/mmcs.rs:434-441).
+template <class F>
+__global__ void __launch_bounds__(128) k_hash_rows_rowmajor(const uint32_t* __restrict__ data, uint32_t w, uint32_t n_rows,
+                                                             uint32_t* __restrict__ out) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    uint32_t st[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) st[i] = 0;
+    const uint32_t* row = data + (size_t)r * w;
+    for (uint32_t c0 = 0; c0 < w; c0 += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (c0 + k < w) st[k] = row[c0 + k];
+        poseidon2_permute<F>(st);
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + (size_t)r * 8);
+    o[0] = make_uint4(st[0], st[1], st[2], st[3]);
+    o[1] = make_uint4(st[4], st[5], st[6], st[7]);
+}
+// next[i] = compress(prev[2i], prev[2i+1]); if inj_cols > 0 additionally next[i] = compress(next[i], hash(injected row i)).
+template <class F>
+__global__ void __launch_bounds__(128) k_compress(const uint32_t* __restrict__ prev, uint32_t* __restrict__ next, uint32_t n_next,
+                                                   const uint32_t* const* __restrict__ inj_colptr, uint32_t inj_cols) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_next) return;
+    uint32_t st[16];
+    const uint4* p = reinterpret_cast<const uint4*>(prev + (size_t)i * 16);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint4 v = p[q];
+        st[4 * q] = v.x;
+        st[4 * q + 1] = v.y;
+        st[4 * q + 2] = v.z;
+        st[4 * q + 3] = v.w;
+    }
+    poseidon2_permute<F>(st);
+    if (inj_cols) {
+        uint32_t h[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) h[k] = 0;
+        for (uint32_t c0 = 0; c0 < inj_cols; c0 += 8) {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (c0 + k < inj_cols) h[k] = __ldg(inj_colptr[c0 + k] + i);
+            poseidon2_permute<F>(h);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) st[8 + k] = h[k];
+        poseidon2_permute<F>(st);
+    }
+    uint4* o = reinterpret_cast<uint4*>(next + (size_t)i * 8);
+    o[0] = make_uint4(st[0], st[1], st[2], st[3]);
+    o[1] = make_uint4(st[4], st[5], st[6], st[7]);
+}
+template <class F>
+__global__ void k_permute_states(uint32_t* states, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t st[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) st[k] = states[(size_t)i * 16 + k];
+    poseidon2_permute<F>(st);
+#pragma unroll
+    for (int k = 0; k < 16; k++) states[(size_t)i * 16 + k] = st[k];
+}
+
+// K12: DuplexChallenger::grind. Thread w tests witness `base + w` (canonical): absorb pending||w, zero-fill the rate,
+// tag the length into state[8], permute, sample = state[7] (pop from the back of the output buffer); accept when its low
+// `bits` canonical bits are zero (recursion/src/challenger/circuit.rs:97-156,409-430). atomicMin keeps the smallest.
+template <class F>
+__global__ void __launch_bounds__(128) k_grind(const uint32_t* __restrict__ state, const uint32_t* __restrict__ pending,
+                                                uint32_t n_pending, uint32_t bits, uint32_t base, uint32_t count,
+                                                uint32_t* __restrict__ best) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t w = base + i;
+    if (w >= F::P) return;
+    uint32_t st[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) st[k] = state[k];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        uint32_t v = 0;
+        if ((uint32_t)k < n_pending) v = pending[k];
+        else if ((uint32_t)k == n_pending) v = to_monty<F>(w);
+        st[k] = v;
+    }
+    st[8] = fadd<F>(st[8], to_monty<F>(n_pending + 1));
+    poseidon2_permute<F>(st);
+    uint32_t s = from_monty<F>(st[7]);
+    if ((s & ((1u << bits) - 1)) == 0) atomicMin(best, w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Constraint bytecode interpreter (format: include/p3r.h). One thread = one row; slots live in local memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int MAX_B_SLOTS = 192;
+constexpr int MAX_E_SLOTS = 24;
+
+struct RowSrc {
+    const uint32_t* main;   // column-major
+    const uint32_t* prep;
+    const uint32_t* perm;   // flattened base columns (4 per EF column)
+    uint64_t main_cs, prep_cs, perm_cs;  // column strides
+    uint32_t row[2];        // storage row of local / next
+    const uint32_t* pub;
+    uint32_t sel[3];
+    const Ext4* chal;
+    const Ext4* pval;
+    const Ext4* econst;
+};
+
+// Sink: called for ASSERT_B/ASSERT_E/OUT_B.
+template <class F, class Sink>
+__device__ __forceinline__ void run_program(const uint4* __restrict__ insns, uint32_t n_insns, const RowSrc& rs, uint32_t wnr,
+                                            Sink& sink) {
+    uint32_t B[MAX_B_SLOTS];
+    Ext4 E[MAX_E_SLOTS];
+    for (uint32_t pc = 0; pc < n_insns; pc++) {
+        uint4 in = __ldg(insns + pc);
+        uint32_t op = in.x, d = in.y, a = in.z, b = in.w;
+        switch (op) {
+            case P3R_OP_B_MAIN: B[d] = __ldg(rs.main + (size_t)a * rs.main_cs + rs.row[b]); break;
+            case P3R_OP_B_PREP: B[d] = __ldg(rs.prep + (size_t)a * rs.prep_cs + rs.row[b]); break;
+            case P3R_OP_B_PUB: B[d] = __ldg(rs.pub + a); break;
+            case P3R_OP_B_SEL: B[d] = rs.sel[a]; break;
+            case P3R_OP_B_CONST: B[d] = a; break;
+            case P3R_OP_B_ADD: B[d] = fadd<F>(B[a], B[b]); break;
+            case P3R_OP_B_SUB: B[d] = fsub<F>(B[a], B[b]); break;
+            case P3R_OP_B_MUL: B[d] = fmul<F>(B[a], B[b]); break;
+            case P3R_OP_B_NEG: B[d] = fneg<F>(B[a]); break;
+            case P3R_OP_E_PERM: {
+                const uint32_t* p = rs.perm + (size_t)(4 * a) * rs.perm_cs + rs.row[b];
+                Ext4 v;
+                v.c[0] = __ldg(p);
+                v.c[1] = __ldg(p + rs.perm_cs);
+                v.c[2] = __ldg(p + 2 * rs.perm_cs);
+                v.c[3] = __ldg(p + 3 * rs.perm_cs);
+                E[d] = v;
+                break;
+            }
+            case P3R_OP_E_CHAL: E[d] = rs.chal[a]; break;
+            case P3R_OP_E_PVAL: E[d] = rs.pval[a]; break;
+            case P3R_OP_E_CONST: E[d] = rs.econst[a]; break;
+            case P3R_OP_E_FROMB: E[d] = ext_lift<F>(B[a]); break;
+            case P3R_OP_E_ADD: E[d] = eadd<F>(E[a], E[b]); break;
+            case P3R_OP_E_SUB: E[d] = esub<F>(E[a], E[b]); break;
+            case P3R_OP_E_MUL: E[d] = emul<F>(E[a], E[b], wnr); break;
+            case P3R_OP_E_NEG: E[d] = eneg<F>(E[a]); break;
+            case P3R_OP_E_MULB: E[d] = emul_base<F>(E[a], B[b]); break;
+            case P3R_OP_E_ADDB: E[d] = eadd_base<F>(E[a], B[b]); break;
+            case P3R_OP_E_SUBB: E[d] = esub_base<F>(E[a], B[b]); break;
+            case P3R_OP_ASSERT_B: sink.assert_b(d, B[a]); break;
+            case P3R_OP_ASSERT_E: sink.assert_e(d, E[a]); break;
+            case P3R_OP_OUT_B: sink.out_b(d, B[a]); break;
+            default: break;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: LogUp permutation trace. Thread = trace row r (natural order, trace domain).
+// Writes the fraction columns (perm EF column c+1, flattened) and the row sum; k_logup_scan turns row sums into the
+// running accumulator column 0 and the terminal.
+// ------------------------------------------------------------------------------------------------
+constexpr int MAX_LK_OUTS = 160;
+constexpr int MAX_INTERACTIONS = 32;
+
+struct LogupArgs {
+    const uint4* insns;
+    uint32_t n_insns;
+    const uint32_t* main;
+    const uint32_t* prep;
+    const uint32_t* pub;
+    uint32_t log_n;
+    const p3r_lookup* lookups;
+    uint32_t n_lookups;
+    const p3r_interaction* inter;
+    const Ext4* chal;       // per lookup [prefix, beta]
+    const Ext4* beta_pows;  // beta^k, k < 8
+    uint32_t* perm;         // column-major flattened, (n_lookups+1)*4 columns of height n
+    Ext4* rowsum;           // n entries
+    uint32_t wnr;
+};
+struct OutSink {
+    uint32_t* outs;
+    __device__ __forceinline__ void assert_b(uint32_t, uint32_t) {}
+    __device__ __forceinline__ void assert_e(uint32_t, const Ext4&) {}
+    __device__ __forceinline__ void out_b(uint32_t i, uint32_t v) { outs[i] = v; }
+};
+template <class F>
+__global__ void __launch_bounds__(128) k_logup_rows(LogupArgs a) {
+    uint32_t n = 1u << a.log_n;
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    uint32_t outs[MAX_LK_OUTS];
+    RowSrc rs;
+    rs.main = a.main;
+    rs.prep = a.prep;
+    rs.perm = nullptr;
+    rs.main_cs = rs.prep_cs = n;
+    rs.perm_cs = 0;
+    rs.row[0] = r;
+    rs.row[1] = (r + 1) & (n - 1);
+    rs.pub = a.pub;
+    rs.sel[0] = (r == 0) ? F::R : 0;
+    rs.sel[1] = (r == n - 1) ? F::R : 0;
+    rs.sel[2] = (r != n - 1) ? F::R : 0;
+    rs.chal = a.chal;
+    rs.pval = nullptr;
+    rs.econst = nullptr;
+    OutSink sink{outs};
+    run_program<F>(a.insns, a.n_insns, rs, a.wnr, sink);
+
+    // denominators of all interactions, then one batched inversion (Montgomery's trick)
+    Ext4 den[MAX_INTERACTIONS], pre[MAX_INTERACTIONS];
+    uint32_t nint = 0;
+    for (uint32_t c = 0; c < a.n_lookups; c++) {
+        p3r_lookup l = a.lookups[c];
+        Ext4 prefix = a.chal[2 * c];
+        for (uint32_t j = 0; j < l.n_interactions; j++) {
+            p3r_interaction it = a.inter[l.first_interaction + j];
+            Ext4 d = prefix;
+            for (uint32_t k = 0; k < it.n_elems; k++) d = eadd<F>(d, emul_base<F>(a.beta_pows[k], outs[it.elem_out_first + k]));
+            den[nint++] = d;
+        }
+    }
+    Ext4 acc = ext_one<F>();
+    for (uint32_t i = 0; i < nint; i++) {
+        pre[i] = acc;
+        acc = emul<F>(acc, den[i], a.wnr);
+    }
+    Ext4 inv = einv<F>(acc, a.wnr);
+    for (uint32_t i = nint; i-- > 0;) {
+        Ext4 di = emul<F>(inv, pre[i], a.wnr);
+        inv = emul<F>(inv, den[i], a.wnr);
+        den[i] = di;  // now 1/den[i]
+    }
+    Ext4 total = ext_zero();
+    uint32_t q = 0;
+    for (uint32_t c = 0; c < a.n_lookups; c++) {
+        p3r_lookup l = a.lookups[c];
+        Ext4 frac = ext_zero();
+        for (uint32_t j = 0; j < l.n_interactions; j++, q++) {
+            p3r_interaction it = a.inter[l.first_interaction + j];
+            frac = eadd<F>(frac, emul_base<F>(den[q], outs[it.mult_out]));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) a.perm[(size_t)(4 * (c + 1) + k) * n + r] = frac.c[k];
+        total = eadd<F>(total, frac);
+    }
+    a.rowsum[r] = total;
+}
+// Exclusive prefix sum of rowsum into perm columns 0..3 and the terminal; single CTA (n*16 bytes is tiny).
+template <class F>
+__global__ void __launch_bounds__(1024) k_logup_scan(const Ext4* __restrict__ rowsum, uint32_t log_n, uint32_t* __restrict__ perm,
+                                                      Ext4* __restrict__ terminal) {
+    __shared__ Ext4 part[1024];
+    uint32_t n = 1u << log_n, T = blockDim.x;
+    uint32_t per = (n + T - 1) / T;
+    uint32_t lo = threadIdx.x * per, hi = min(lo + per, n);
+    Ext4 s = ext_zero();
+    for (uint32_t i = lo; i < hi; i++) s = eadd<F>(s, rowsum[i]);
+    part[threadIdx.x] = s;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over T partials
+    for (uint32_t off = 1; off < T; off <<= 1) {
+        Ext4 v = part[threadIdx.x];
+        if (threadIdx.x >= off) v = eadd<F>(v, part[threadIdx.x - off]);
+        __syncthreads();
+        part[threadIdx.x] = v;
+        __syncthreads();
+    }
+    Ext4 acc = threadIdx.x ? part[threadIdx.x - 1] : ext_zero();
+    for (uint32_t i = lo; i < hi; i++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) perm[(size_t)k * n + i] = acc.c[k];
+        acc = eadd<F>(acc, rowsum[i]);
+    }
+    if (threadIdx.x == T - 1) *terminal = part[T - 1];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: quotient evaluation. Thread = storage row s of the quotient domain (first n*qc rows of the bit-reversed LDE);
+// natural index i = bitrev(s), next row = i + qc. Selectors follow p3's selectors_on_coset (trace domain shift 1):
+// Z_H(x) = x^n - 1, is_first = Z_H/(x-1), is_last = Z_H/(x - g^-1), is_transition = x - g^-1, inv_vanishing = 1/Z_H.
+// Folding: sum_k alpha^{N-1-k} * c_k  ==  Horner acc = acc*alpha + c (recursion/src/traits/air.rs:170-181).
+// Output: natural-order chunk matrices: chunk (i mod qc), row (i div qc), 4 base columns each (split_evals).
+// ------------------------------------------------------------------------------------------------
+struct QuotientArgs {
+    const uint4* insns;
+    uint32_t n_insns;
+    const uint32_t* main;
+    const uint32_t* prep;
+    const uint32_t* perm;
+    const uint32_t* pub;
+    uint32_t log_n, log_qc, log_blowup;
+    const uint32_t* sel;        // 3 arrays of NQ (storage order): is_first, is_last, is_transition
+    const uint32_t* inv_van;    // qc entries: 1/Z_H on coset class (i mod qc)
+    const Ext4* chal;
+    const Ext4* pval;
+    const Ext4* econst;
+    const Ext4* alpha_pows;     // alpha^{N-1-k} at index k
+    uint32_t* chunks;           // qc matrices, each 4 columns x n rows, column-major: [(c*4 + k)*n + r]
+    uint32_t wnr;
+};
+template <class F>
+struct FoldSink {
+    const Ext4* ap;
+    uint32_t wnr;
+    Ext4 acc;
+    __device__ __forceinline__ void assert_b(uint32_t k, uint32_t v) { acc = eadd<F>(acc, emul_base<F>(ap[k], v)); }
+    __device__ __forceinline__ void assert_e(uint32_t k, const Ext4& v) { acc = eadd<F>(acc, emul<F>(ap[k], v, wnr)); }
+    __device__ __forceinline__ void out_b(uint32_t, uint32_t) {}
+};
+template <class F>
+__global__ void __launch_bounds__(128) k_quotient(QuotientArgs a) {
+    const uint32_t lq = a.log_n + a.log_qc, NQ = 1u << lq, n = 1u << a.log_n;
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= NQ) return;
+    uint32_t i = bitrev32(s, lq);
+    uint32_t inext = (i + (1u << a.log_qc)) & (NQ - 1);
+    RowSrc rs;
+    rs.main = a.main;
+    rs.prep = a.prep;
+    rs.perm = a.perm;
+    rs.main_cs = rs.prep_cs = rs.perm_cs = (uint64_t)n << a.log_blowup;
+    rs.row[0] = s;
+    rs.row[1] = bitrev32(inext, lq);
+    rs.pub = a.pub;
+    rs.sel[0] = a.sel[s];
+    rs.sel[1] = a.sel[NQ + s];
+    rs.sel[2] = a.sel[2 * NQ + s];
+    rs.chal = a.chal;
+    rs.pval = a.pval;
+    rs.econst = a.econst;
+    FoldSink<F> sink{a.alpha_pows, a.wnr, ext_zero()};
+    run_program<F>(a.insns, a.n_insns, rs, a.wnr, sink);
+    Ext4 q = emul_base<F>(sink.acc, a.inv_van[i & ((1u << a.log_qc) - 1)]);
+    uint32_t c = i & ((1u << a.log_qc) - 1), r = i >> a.log_qc;
+#pragma unroll
+    for (int k = 0; k < 4; k++) a.chunks[((size_t)c * 4 + k) * n + r] = q.c[k];
+}
+// Selector arrays for (log_n, log_qc) in storage order + inv_vanishing per coset class.
+template <class F>
+__global__ void k_selectors(uint32_t* sel, uint32_t* inv_van, uint32_t log_n, uint32_t log_qc, uint32_t gen,
+                            const uint32_t* tw, uint32_t logT) {
+    const uint32_t lq = log_n + log_qc, NQ = 1u << lq;
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= NQ) return;
+    uint32_t i = bitrev32(s, lq);
+    uint32_t x = fmul<F>(gen, root_pow<F>(tw, logT, (uint64_t)i << (logT - lq)));
+    uint32_t ginv = root_pow<F>(tw, logT, ((uint64_t)1 << logT) - ((uint64_t)1 << (logT - log_n)));
+    uint32_t xn = x;
+    for (uint32_t k = 0; k < log_n; k++) xn = fmul<F>(xn, xn);
+    uint32_t z = fsub<F>(xn, F::R);
+    sel[s] = fmul<F>(z, finv<F>(fsub<F>(x, F::R)));
+    sel[NQ + s] = fmul<F>(z, finv<F>(fsub<F>(x, ginv)));
+    sel[2 * NQ + s] = fsub<F>(x, ginv);
+    if (i < (1u << log_qc)) inv_van[i] = finv<F>(z);
+}
+template <class F>
+__global__ void k_ext_powers_desc(Ext4* out, uint32_t n, Ext4 alpha, uint32_t wnr) {
+    // out[k] = alpha^{n-1-k}; n is small (number of constraints): one thread.
+    if (blockIdx.x || threadIdx.x) return;
+    Ext4 acc = ext_one<F>();
+    for (uint32_t k = n; k-- > 0;) {
+        out[k] = acc;
+        acc = emul<F>(acc, alpha, wnr);
+    }
+}
+template <class F>
+__global__ void k_ext_powers_asc(Ext4* out, uint32_t n, Ext4 alpha, uint32_t wnr) {
+    // out[k] = alpha^k, blocked so that n up to a few thousand stays cheap: thread t computes alpha^(t*64) then 64 steps.
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t lo = t * 64;
+    if (lo >= n) return;
+    Ext4 acc = epow<F>(alpha, lo, wnr);
+    for (uint32_t k = lo; k < min(lo + 64, n); k++) {
+        out[k] = acc;
+        acc = emul<F>(acc, alpha, wnr);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8: out-of-domain openings by barycentric evaluation over the source evaluations (n points of in_shift*H_n, natural
+// order): p(z) = ((u^n - 1)/n) * sum_i p_i * w^i / (u - w^i), u = z / in_shift.
+// ------------------------------------------------------------------------------------------------
+struct WeightJob {
+    Ext4 u;          // z / in_shift
+    uint32_t log_n;
+    uint32_t offset; // into the weights buffer (Ext4 units)
+};
+template <class F>
+__global__ void __launch_bounds__(256) k_bary_weights(const WeightJob* __restrict__ jobs, Ext4* __restrict__ weights,
+                                                       const uint32_t* tw, uint32_t logT, uint32_t wnr) {
+    WeightJob j = jobs[blockIdx.y];
+    uint32_t n = 1u << j.log_n;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t wi = root_pow<F>(tw, logT, (uint64_t)i << (logT - j.log_n));
+    Ext4 un = j.u;
+    for (uint32_t k = 0; k < j.log_n; k++) un = emul<F>(un, un, wnr);
+    Ext4 num = emul_base<F>(esub_base<F>(un, F::R), fmul<F>(wi, finv<F>(to_monty<F>(n))));
+    Ext4 den = esub_base<F>(j.u, wi);
+    weights[j.offset + i] = emul<F>(num, einv<F>(den, wnr), wnr);
+}
+struct DotJob {
+    const uint32_t* mat;   // column-major, height 2^log_n
+    uint32_t log_n, width;
+    uint32_t w_offset;     // weights
+    uint32_t out_offset;   // into opened values buffer (Ext4 units), width entries
+};
+constexpr uint32_t DOT_ROWS = 2048;  // rows per CTA
+constexpr uint32_t DOT_COLS = 8;     // columns per CTA
+// partial[job][chunk][col] ; grid = (max chunks, max col groups, jobs)
+template <class F>
+__global__ void __launch_bounds__(256) k_bary_dot(const DotJob* __restrict__ jobs, const Ext4* __restrict__ weights,
+                                                   Ext4* __restrict__ partial, uint32_t max_chunks, uint32_t max_width) {
+    DotJob j = jobs[blockIdx.z];
+    uint32_t n = 1u << j.log_n;
+    uint32_t r0 = blockIdx.x * DOT_ROWS;
+    uint32_t c0 = blockIdx.y * DOT_COLS;
+    if (r0 >= n || c0 >= j.width) return;
+    __shared__ Ext4 red[8];
+    const Ext4* w = weights + j.w_offset;
+    for (uint32_t c = c0; c < min(c0 + DOT_COLS, j.width); c++) {
+        const uint32_t* col = j.mat + (size_t)c * n;
+        uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;  // 64-bit accumulators of Montgomery products
+        uint32_t cnt = 0;
+        Ext4 acc = ext_zero();
+        for (uint32_t r = r0 + threadIdx.x; r < min(r0 + DOT_ROWS, n); r += blockDim.x) {
+            uint32_t v = __ldg(col + r);
+            Ext4 wr = w[r];
+            a0 += (uint64_t)v * wr.c[0];
+            a1 += (uint64_t)v * wr.c[1];
+            a2 += (uint64_t)v * wr.c[2];
+            a3 += (uint64_t)v * wr.c[3];
+            if (++cnt == 4) {  // 4 products < 2^64
+                acc = eadd<F>(acc, Ext4{{fred64<F>(a0), fred64<F>(a1), fred64<F>(a2), fred64<F>(a3)}});
+                a0 = a1 = a2 = a3 = 0;
+                cnt = 0;
+            }
+        }
+        acc = eadd<F>(acc, Ext4{{fred64<F>(a0), fred64<F>(a1), fred64<F>(a2), fred64<F>(a3)}});
+        // block reduce
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t v = acc.c[k];
+            for (int off = 16; off > 0; off >>= 1) v = fadd<F>(v, __shfl_down_sync(0xffffffffu, v, off));
+            acc.c[k] = v;
+        }
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            Ext4 t = red[0];
+            for (uint32_t q = 1; q < blockDim.x / 32; q++) t = eadd<F>(t, red[q]);
+            partial[((size_t)blockIdx.z * max_chunks + blockIdx.x) * max_width + c] = t;
+        }
+        __syncthreads();
+    }
+}
+template <class F>
+__global__ void k_bary_reduce(const DotJob* __restrict__ jobs, const Ext4* __restrict__ partial, Ext4* __restrict__ opened,
+                              uint32_t max_chunks, uint32_t max_width) {
+    DotJob j = jobs[blockIdx.y];
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= j.width) return;
+    uint32_t n = 1u << j.log_n;
+    uint32_t chunks = (n + DOT_ROWS - 1) / DOT_ROWS;
+    Ext4 t = ext_zero();
+    for (uint32_t q = 0; q < chunks; q++) t = eadd<F>(t, partial[((size_t)blockIdx.y * max_chunks + q) * max_width + c]);
+    opened[j.out_offset + c] = t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K9: reduced openings per LDE height. For storage row s at log-height h (x = GEN * w_h^{bitrev(s)}):
+//   ro[s] += sum over (matrix m, point j):  alpha^{off_{m,j}} * (P_{m,j} - R_m(s)) / (z_j - x),
+//   R_m(s) = sum_k alpha^k * lde_m[k][s],   P_{m,j} = sum_k alpha^k * opened_{m,j}[k].
+// ------------------------------------------------------------------------------------------------
+struct RoMat {
+    const uint32_t* lde;     // column-major, height 2^log_h
+    uint32_t width;
+    uint32_t n_points;       // 1 or 2 (point 0 = zeta, point 1 = zeta*g)
+    uint32_t opened_off[2];  // Ext4 offset of the opened values of each point
+    uint32_t alpha_off[2];   // exponent offset alpha^{off}
+};
+template <class F>
+__global__ void k_ro_prepare(const RoMat* __restrict__ mats, uint32_t n_mats, const Ext4* __restrict__ opened,
+                             const Ext4* __restrict__ apow, Ext4* __restrict__ coef /* [mat][2]: alpha^off * P */, uint32_t wnr) {
+    // one warp-free thread per (matrix, point): widths are a few hundred at most
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_mats * 2) return;
+    RoMat m = mats[t >> 1];
+    uint32_t j = t & 1;
+    if (j >= m.n_points) return;
+    Ext4 acc = ext_zero();
+    for (uint32_t k = 0; k < m.width; k++) acc = eadd<F>(acc, emul<F>(apow[k], opened[m.opened_off[j] + k], wnr));
+    coef[t] = emul<F>(acc, apow[m.alpha_off[j]], wnr);
+}
+struct RoArgs {
+    const RoMat* mats;
+    uint32_t n_mats;
+    uint32_t log_h;
+    const Ext4* apow;       // alpha^k
+    const Ext4* coef;       // alpha^off * P per (mat, point)
+    Ext4 z[2];              // zeta, zeta*g for this height
+    uint32_t gen;
+    const uint32_t* tw;
+    uint32_t logT;
+    Ext4* ro;               // 2^log_h entries (overwritten)
+    uint32_t wnr;
+};
+template <class F>
+__global__ void __launch_bounds__(128) k_reduced_openings(RoArgs a) {
+    uint32_t N = 1u << a.log_h;
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= N) return;
+    uint32_t x = fmul<F>(a.gen, root_pow<F>(a.tw, a.logT, (uint64_t)bitrev32(s, a.log_h) << (a.logT - a.log_h)));
+    Ext4 inv0 = einv<F>(esub_base<F>(a.z[0], x), a.wnr);
+    Ext4 inv1 = einv<F>(esub_base<F>(a.z[1], x), a.wnr);
+    Ext4 acc = ext_zero();
+    for (uint32_t mi = 0; mi < a.n_mats; mi++) {
+        RoMat m = a.mats[mi];
+        Ext4 R = ext_zero();
+        const uint32_t* p = m.lde + s;
+        for (uint32_t k = 0; k < m.width; k++) R = eadd<F>(R, emul_base<F>(a.apow[k], __ldg(p + (size_t)k * N)));
+        for (uint32_t j = 0; j < m.n_points; j++) {
+            // alpha^off * (P - R) = coef - alpha^off * R
+            Ext4 t = esub<F>(a.coef[2 * mi + j], emul<F>(a.apow[m.alpha_off[j]], R, a.wnr));
+            acc = eadd<F>(acc, emul<F>(t, j ? inv1 : inv0, a.wnr));
+        }
+    }
+    a.ro[s] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K10: FRI fold of a bit-reversed EF vector by arity 2^k (k sequential arity-2 folds with beta, beta^2, ...) and roll-in
+// of the reduced opening of the folded height (recursion/src/pcs/fri/verifier.rs:564-585,772-777).
+// fold(e0,e1) at x0 = w_L^{bitrev(i)}: (e0+e1)/2 + beta*(e0-e1)/(2*x0).
+// ------------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128) k_fri_fold(const Ext4* __restrict__ in, Ext4* __restrict__ out, uint32_t log_len,
+                                                   uint32_t log_arity, Ext4 beta, const Ext4* __restrict__ roll, uint32_t inv2,
+                                                   const uint32_t* tw, uint32_t logT, uint32_t wnr) {
+    uint32_t out_len = 1u << (log_len - log_arity);
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= out_len) return;
+    Ext4 v[16];
+    uint32_t arity = 1u << log_arity;
+    for (uint32_t j = 0; j < arity; j++) v[j] = in[(size_t)i * arity + j];
+    Ext4 b = beta;
+    for (uint32_t step = 0; step < log_arity; step++) {
+        uint32_t lg = log_len - step;          // log length of the vector being folded
+        uint32_t half = arity >> (step + 1);   // outputs this thread produces at this step
+        for (uint32_t j = 0; j < half; j++) {
+            uint32_t gi = i * half + j;        // index in the folded vector (length 2^(lg-1))
+            uint32_t e = bitrev32(gi, lg - 1);
+            // 1/x0 = w_{2^lg}^{-e}
+            uint32_t xinv = root_pow<F>(tw, logT, (((uint64_t)1 << lg) - e) << (logT - lg));
+            Ext4 e0 = v[2 * j], e1 = v[2 * j + 1];
+            Ext4 sum = eadd<F>(e0, e1);
+            Ext4 dif = emul_base<F>(esub<F>(e0, e1), xinv);
+            v[j] = emul_base<F>(eadd<F>(sum, emul<F>(b, dif, wnr)), inv2);
+        }
+        b = emul<F>(b, b, wnr);
+    }
+    Ext4 r = v[0];
+    if (roll) r = eadd<F>(r, emul<F>(b, roll[i], wnr));
+    out[i] = r;
+}
+// Final polynomial: coefficients of the degree < 2^log_fpl interpolant of the folded evaluations (first 2^log_fpl storage
+// entries = the size-2^log_fpl subgroup in bit-reversed order). Naive O(n^2) inverse DFT: n <= 64.
+template <class F>
+__global__ void k_final_poly(const Ext4* __restrict__ folded, Ext4* __restrict__ coeffs, uint32_t log_fpl, const uint32_t* tw,
+                             uint32_t logT) {
+    uint32_t n = 1u << log_fpl;
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    Ext4 acc = ext_zero();
+    for (uint32_t i = 0; i < n; i++) {
+        Ext4 v = folded[bitrev32(i, log_fpl)];  // evaluation at w_n^i
+        uint64_t e = ((uint64_t)n - ((uint64_t)i * k) % n) % n;
+        acc = eadd<F>(acc, emul_base<F>(v, root_pow<F>(tw, logT, e << (logT - log_fpl))));
+    }
+    coeffs[k] = emul_base<F>(acc, finv<F>(to_monty<F>(n)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K11: query openings. Static gather plan per session: for every (query-independent) segment either
+//   kind 0: matrix row  — `width` words from a column-major matrix at row (index >> shift)
+//   kind 1: merkle path — `depth` sibling digests of tree `layers` for leaf (index >> shift)
+//   kind 2: FRI siblings — (arity-1) EF values of row (index >> shift >> log_arity) of a row-major EF matrix
+// ------------------------------------------------------------------------------------------------
+struct GatherSeg {
+    uint32_t kind;
+    const uint32_t* base;     // matrix / digest layers / EF vector
+    uint32_t log_h;           // matrix: log height; path: log leaves; fri: log length of the vector
+    uint32_t width;           // matrix width; path depth; fri: log_arity
+    uint32_t shift;           // index >> shift
+    uint32_t out_off;         // word offset within one query's blob
+};
+__global__ void __launch_bounds__(256) k_query_gather(const GatherSeg* __restrict__ segs, uint32_t n_segs,
+                                                       const uint32_t* __restrict__ indices, uint32_t words_per_query,
+                                                       uint32_t* __restrict__ out) {
+    uint32_t q = blockIdx.x;
+    uint32_t index = indices[q];
+    uint32_t* o = out + (size_t)q * words_per_query;
+    for (uint32_t si = blockIdx.y; si < n_segs; si += gridDim.y) {
+        GatherSeg g = segs[si];
+        uint32_t idx = index >> g.shift;
+        if (g.kind == 0) {
+            size_t H = (size_t)1 << g.log_h;
+            for (uint32_t c = threadIdx.x; c < g.width; c += blockDim.x) o[g.out_off + c] = g.base[(size_t)c * H + idx];
+        } else if (g.kind == 1) {
+            // layers are stored back to back: level l (2^(log_h-l) digests) at digest offset 2^(log_h+1) - 2^(log_h-l+1)
+            for (uint32_t t = threadIdx.x; t < g.width * 8; t += blockDim.x) {
+                uint32_t l = t >> 3, k = t & 7;
+                size_t lvl_off = ((size_t)2 << g.log_h) - ((size_t)2 << (g.log_h - l));
+                size_t node = (idx >> l) ^ 1;
+                o[g.out_off + t] = g.base[(lvl_off + node) * 8 + k];
+            }
+        } else {
+            uint32_t arity = 1u << g.width;
+            uint32_t row = idx >> g.width, own = idx & (arity - 1);
+            for (uint32_t t = threadIdx.x; t < (arity - 1) * 4; t += blockDim.x) {
+                uint32_t j = t >> 2, k = t & 3;
+                uint32_t src = j < own ? j : j + 1;
+                o[g.out_off + t] = g.base[((size_t)row * arity + src) * 4 + k];
+            }
+        }
+    }
+}
+
+// Synthetic data for the isolated commit benchmark: splitmix64(seed + index) reduced mod P.
+template <class F>
+__global__ void k_fill_random(uint32_t* out, size_t n, uint64_t seed) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (i + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    out[i] = (uint32_t)(z % F::P);
+}
+
+}  // namespace p3r

@@ -1,0 +1,1782 @@
+// p3r.cu — host side of libp3r_b200.so: context, device arena, LDE planner, MMCS commit, the phase-stepped proving
+// session behind include/p3r.h, the host DuplexChallenger and the one-shot p3r_prove (host mirror of
+// BatchStarkProver::prove, /root/reference circuit-prover/src/batch_stark_prover.rs:1275-1642 -> p3_batch_stark::prove_batch).
+// No CPU fallback: every compute entry point runs CUDA kernels from kernels.cuh or fails.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace p3r;
+
+#define CUDA_TRY(x)                                                                              \
+    do {                                                                                         \
+        cudaError_t e_ = (x);                                                                    \
+        if (e_ != cudaSuccess) {                                                                 \
+            set_err(ctx, std::string(#x) + ": " + cudaGetErrorString(e_));                       \
+            return P3R_ERR_CUDA;                                                                 \
+        }                                                                                        \
+    } while (0)
+#define TRY(x)                   \
+    do {                         \
+        int rc_ = (x);           \
+        if (rc_ != P3R_OK) return rc_; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+struct Slab {
+    char* base = nullptr;
+    size_t size = 0, used = 0;
+};
+struct Arena {  // bump allocator over cudaMalloc'd slabs; reset() keeps the slabs for the next session
+    std::vector<Slab> slabs;
+    size_t cur = 0;
+    void reset() {
+        for (auto& s : slabs) s.used = 0;
+        cur = 0;
+    }
+    void* alloc(size_t bytes) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        for (; cur < slabs.size(); cur++) {
+            Slab& s = slabs[cur];
+            if (s.used + bytes <= s.size) {
+                void* p = s.base + s.used;
+                s.used += bytes;
+                return p;
+            }
+        }
+        Slab s;
+        s.size = std::max(bytes, (size_t)256 << 20);
+        if (cudaMalloc(&s.base, s.size) != cudaSuccess) return nullptr;
+        s.used = bytes;
+        slabs.push_back(s);
+        cur = slabs.size() - 1;
+        return s.base;
+    }
+    void destroy() {
+        for (auto& s : slabs) cudaFree(s.base);
+        slabs.clear();
+    }
+};
+struct GTable {
+    uint32_t *lo = nullptr, *hi = nullptr;
+};
+
+struct p3r_ctx {
+    int device = 0;
+    int field_id = 0;
+    p3r_field_desc field{};
+    p3r_fri_params fri{};
+    Poseidon2Consts p2{};
+    uint32_t w_m = 0, gen_m = 0, inv2_m = 0;  // Montgomery
+    cudaStream_t stream = nullptr;
+    uint32_t* tw = nullptr;
+    uint32_t logT = 0;
+    std::map<uint32_t, GTable> gtables;
+    Arena arena;
+    // pinned staging for small uploads/downloads
+    char* pin = nullptr;
+    size_t pin_size = 0, pin_used = 0;
+    char* dstage = nullptr;  // device mirror for small uploads
+    size_t dstage_size = 0;
+    std::string err;
+    uint64_t launches = 0;
+    std::vector<std::pair<std::string, float>> phase_times;
+    std::string phase_names_blob;
+};
+static void set_err(p3r_ctx* ctx, const std::string& s) {
+    if (ctx) ctx->err = s;
+}
+static void set_err(const p3r_ctx* ctx, const std::string& s) { set_err(const_cast<p3r_ctx*>(ctx), s); }
+
+#define LAUNCH_CHECK()                                                   \
+    do {                                                                 \
+        ctx->launches++;                                                 \
+        cudaError_t e_ = cudaGetLastError();                             \
+        if (e_ != cudaSuccess) {                                         \
+            set_err(ctx, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
+            return P3R_ERR_CUDA;                                         \
+        }                                                                \
+    } while (0)
+
+template <class T>
+static T* arena_alloc(p3r_ctx* ctx, size_t count) {
+    return reinterpret_cast<T*>(ctx->arena.alloc(count * sizeof(T)));
+}
+// Copy a small host blob to the device through the pinned staging area (valid until the next session begins).
+static void* upload_small(p3r_ctx* ctx, const void* src, size_t bytes) {
+    size_t b = (bytes + 255) & ~(size_t)255;
+    if (ctx->pin_used + b > ctx->pin_size) return nullptr;
+    char* h = ctx->pin + ctx->pin_used;
+    char* d = ctx->dstage + ctx->pin_used;
+    ctx->pin_used += b;
+    std::memcpy(h, src, bytes);
+    if (cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return nullptr;
+    return d;
+}
+template <class T>
+static T* upload_vec(p3r_ctx* ctx, const std::vector<T>& v) {
+    if (v.empty()) return reinterpret_cast<T*>(ctx->dstage);
+    return reinterpret_cast<T*>(upload_small(ctx, v.data(), v.size() * sizeof(T)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-side descriptions
+// ------------------------------------------------------------------------------------------------
+struct MatRef {  // column-major device matrix
+    const uint32_t* d = nullptr;
+    uint32_t log_h = 0, w = 0;
+};
+struct Tree {
+    uint32_t log_max_h = 0;
+    uint32_t* digests = nullptr;  // layers back to back, level l at digest offset 2^(log_max_h+1) - 2^(log_max_h-l+1)
+    std::vector<MatRef> mats;     // commit order
+    size_t level_off(uint32_t l) const { return ((size_t)2 << log_max_h) - ((size_t)2 << (log_max_h - l)); }
+};
+struct InstDev {
+    uint32_t log_h = 0, main_w = 0, prep_w = 0, n_pub = 0, log_qc = 0, uses_next = 0;
+    uint4* cons = nullptr;
+    uint32_t n_cons_insns = 0, n_constraints = 0;
+    Ext4* cons_econst = nullptr;
+    uint4* lk = nullptr;
+    uint32_t n_lk_insns = 0, n_lk_outs = 0;
+    std::vector<p3r_lookup> lookups;
+    std::vector<p3r_interaction> inter;
+    p3r_lookup* d_lookups = nullptr;
+    p3r_interaction* d_inter = nullptr;
+    uint32_t* prep_trace = nullptr;  // natural order, column-major
+    uint32_t* prep_lde = nullptr;
+    uint32_t* sel = nullptr;
+    uint32_t* inv_van = nullptr;
+    uint32_t aux_w() const { return lookups.empty() ? 0 : (uint32_t)lookups.size() + 1; }
+};
+struct p3r_prep {
+    p3r_ctx* ctx = nullptr;
+    std::vector<InstDev> inst;
+    std::vector<void*> owned;  // cudaMalloc'd
+    Tree prep_tree;
+    bool has_prep = false, has_perm = false;
+    uint32_t max_msg_w = 1, n_buses = 0;
+    std::vector<uint32_t> prep_cap;  // host copy, Montgomery
+};
+
+enum Phase { PH_BEGIN = 0, PH_MAIN, PH_PERM, PH_QUOT, PH_OPEN, PH_FRI };
+
+struct FriRound {
+    uint32_t log_arity = 0, log_len = 0;  // length of the vector committed in this round
+    Ext4* vec = nullptr;                  // committed vector (bit-reversed EF, AoS) = row-major matrix arity*4 wide
+    Tree tree;
+};
+struct p3r_session {
+    p3r_ctx* ctx = nullptr;
+    const p3r_prep* prep = nullptr;
+    int phase = PH_BEGIN;
+    std::vector<uint32_t*> trace, main_lde, perm, perm_lde, chunks, chunk_lde, d_pub;
+    uint32_t* scratch_coef = nullptr;   // LDE coefficient scratch
+    uint32_t* scratch_tmp = nullptr;    // LDE multi-pass scratch
+    Tree main_tree, perm_tree, quot_tree;
+    Ext4* d_chal = nullptr;             // per instance block of [prefix, beta] pairs
+    std::vector<uint32_t> chal_off;
+    Ext4* d_terminals = nullptr;        // one per instance
+    Ext4* d_opened = nullptr;
+    size_t n_opened = 0;                // Ext4 count
+    std::vector<uint32_t> opened_host;  // Montgomery words
+    Ext4 zeta{};
+    // FRI
+    std::vector<uint32_t> heights;      // distinct LDE log heights, descending
+    std::map<uint32_t, Ext4*> ro;
+    std::vector<FriRound> rounds;
+    Ext4* final_vec = nullptr;
+    uint32_t log_max = 0;
+    // openings bookkeeping: for every (round, matrix) the offsets of its opened values in d_opened
+    struct OpenRef {
+        uint32_t inst, kind;  // kind 0 main, 1 quotient chunk, 2 prep, 3 perm
+        uint32_t chunk;
+        uint32_t off[2];
+        uint32_t n_points;
+        uint32_t width;
+    };
+    std::vector<std::vector<OpenRef>> open_rounds;  // [main, quot, prep?, perm?]
+};
+
+// ------------------------------------------------------------------------------------------------
+// Host DuplexChallenger — product code, Montgomery arithmetic, shares nothing with oracle/.
+// ------------------------------------------------------------------------------------------------
+template <class F>
+struct HostChallenger {
+    const Poseidon2Consts* k;
+    uint32_t st[16];
+    uint32_t in[8], out[8];
+    int n_in = 0, n_out = 0;
+    explicit HostChallenger(const Poseidon2Consts* k_) : k(k_) { std::memset(st, 0, sizeof st); }
+    void duplex() {
+        for (int i = 0; i < n_in; i++) st[i] = in[i];
+        if (n_in > 0) {
+            for (int i = n_in; i < 8; i++) st[i] = 0;
+            st[8] = fadd<F>(st[8], to_monty<F>((uint32_t)n_in));
+        }
+        n_in = 0;
+        poseidon2_permute_with<F>(st, *k);
+        for (int i = 0; i < 8; i++) out[i] = st[i];
+        n_out = 8;
+    }
+    void observe(uint32_t v) {
+        n_out = 0;
+        in[n_in++] = v;
+        if (n_in == 8) duplex();
+    }
+    void observe_words(const uint32_t* v, size_t n) {
+        for (size_t i = 0; i < n; i++) observe(v[i]);
+    }
+    void observe_lifted(uint32_t canonical) {  // observe_base_as_algebra_element
+        observe(to_monty<F>(canonical));
+        observe(0);
+        observe(0);
+        observe(0);
+    }
+    uint32_t sample() {
+        if (n_in > 0 || n_out == 0) duplex();
+        return out[--n_out];
+    }
+    void sample_ext(uint32_t e[4]) {
+        for (int i = 0; i < 4; i++) e[i] = sample();
+    }
+    uint32_t sample_bits(uint32_t bits) { return from_monty<F>(sample()) & ((1u << bits) - 1); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+template <class F>
+static int ensure_twiddles(p3r_ctx* ctx, uint32_t logT) {
+    if (logT < 12) logT = 12;
+    if (ctx->tw && ctx->logT >= logT) return P3R_OK;
+    if (logT > F::TWO_ADICITY) {
+        set_err(ctx, "domain exceeds the field's two-adicity");
+        return P3R_ERR_INVALID_ARG;
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ctx->tw) cudaFree(ctx->tw);
+    ctx->tw = nullptr;
+    size_t half = (size_t)1 << (logT - 1);
+    CUDA_TRY(cudaMalloc(&ctx->tw, half * 4));
+    uint32_t gen = ctx->gen_m;
+    uint32_t w = fpow<F>(gen, ((uint64_t)F::P - 1) >> logT);
+    k_powers<F><<<(unsigned)((half + 255) / 256), 256, 0, ctx->stream>>>(ctx->tw, (uint32_t)half, w, F::R);
+    LAUNCH_CHECK();
+    ctx->logT = logT;
+    for (auto& kv : ctx->gtables) {  // tables do not depend on logT, keep them
+        (void)kv;
+    }
+    return P3R_OK;
+}
+template <class F>
+static int get_gtable(p3r_ctx* ctx, uint32_t log_n, GTable* out) {
+    auto it = ctx->gtables.find(log_n);
+    if (it != ctx->gtables.end()) {
+        *out = it->second;
+        return P3R_OK;
+    }
+    GTable t;
+    uint32_t n_hi = log_n > 10 ? (1u << (log_n - 10)) : 1;
+    CUDA_TRY(cudaMalloc(&t.lo, 1024 * 4));
+    CUDA_TRY(cudaMalloc(&t.hi, n_hi * 4));
+    uint32_t n_inv = finv<F>(to_monty<F>(1u << log_n));
+    uint32_t g = ctx->gen_m;
+    k_powers<F><<<4, 256, 0, ctx->stream>>>(t.lo, 1024, g, n_inv);
+    LAUNCH_CHECK();
+    k_powers<F><<<(n_hi + 255) / 256, 256, 0, ctx->stream>>>(t.hi, n_hi, fpow<F>(g, 1024), F::R);
+    LAUNCH_CHECK();
+    ctx->gtables[log_n] = t;
+    *out = t;
+    return P3R_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 host planner: batched coset LDE of `w` columns (natural order, column-major, height n) into dst
+// (column-major, height N = n << log_blowup, rows bit-reversed). in_shift = GENERATOR^(1-use_g) * w_N^{-rot}... see NttPass.
+// scratch_coef: n*w words; scratch_tmp: N*w words (only touched when log_n > TILE_LOG).
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t TILE_LOG = 13;
+struct PassPlan {
+    uint32_t s0, r, log_cw;
+};
+static std::vector<PassPlan> plan_passes(uint32_t log_n) {
+    std::vector<PassPlan> p;
+    if (log_n <= TILE_LOG) {
+        p.push_back({0, log_n, 0});
+        return p;
+    }
+    // contiguous first chunk, then strided chunks of <= 8 stages (tile rows <= 256, >= 32 consecutive elements per row)
+    uint32_t rest = log_n;
+    uint32_t n_strided = (log_n - TILE_LOG + 7) / 8;
+    uint32_t strided_total = log_n - std::min(log_n, TILE_LOG);
+    // balance: last chunk at least 5 stages so bit-reversed stores form >=128-byte runs
+    std::vector<uint32_t> chunks;
+    uint32_t first = log_n - strided_total;
+    if (strided_total < 5) {
+        first -= (5 - strided_total);
+        strided_total = 5;
+        n_strided = 1;
+    }
+    chunks.push_back(first);
+    for (uint32_t i = 0; i < n_strided; i++) {
+        uint32_t c = strided_total / (n_strided - i);
+        chunks.push_back(c);
+        strided_total -= c;
+    }
+    uint32_t s0 = 0;
+    for (size_t i = 0; i < chunks.size(); i++) {
+        uint32_t r = chunks[i];
+        uint32_t log_cw = (i == 0) ? (TILE_LOG - r) : std::min(s0, TILE_LOG - r);
+        if (i == 0) log_cw = std::min(log_cw, log_n - r);
+        p.push_back({s0, r, log_cw});
+        s0 += r;
+    }
+    (void)rest;
+    return p;
+}
+template <class F>
+static int launch_pass(p3r_ctx* ctx, NttPass a, uint32_t n_cols, uint32_t n_cosets) {
+    uint32_t R = 1u << a.r, CW = 1u << a.log_cw;
+    uint32_t CWP = CW >= 32 ? CW + 1 : CW;
+    size_t smem = (size_t)R * CWP * 4;
+    static bool attr_set[2] = {false, false};
+    int fid = FieldId<F>::value;
+    if (!attr_set[fid]) {
+        cudaFuncSetAttribute(k_ntt_pass<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr_set[fid] = true;
+    }
+    uint32_t tiles = (1u << a.log_n) / (R * CW);
+    dim3 grid(tiles, n_cols, n_cosets);
+    k_ntt_pass<F><<<grid, 256, smem, ctx->stream>>>(a);
+    LAUNCH_CHECK();
+    return P3R_OK;
+}
+template <class F>
+static int coset_lde(p3r_ctx* ctx, const uint32_t* src, uint32_t* dst, uint32_t log_n, uint32_t w, uint32_t log_blowup,
+                     bool use_g, uint32_t rot, uint32_t* scratch_coef, uint32_t* scratch_tmp) {
+    if (w == 0) return P3R_OK;
+    uint32_t logN = log_n + log_blowup;
+    TRY(ensure_twiddles<F>(ctx, logN));
+    GTable gt;
+    TRY(get_gtable<F>(ctx, log_n, &gt));
+    size_t n = (size_t)1 << log_n, N = (size_t)1 << logN;
+    auto plan = plan_passes(log_n);
+    NttPass a{};
+    a.log_n = log_n;
+    a.tw = ctx->tw;
+    a.logT = ctx->logT;
+    a.g_lo = gt.lo;
+    a.g_hi = gt.hi;
+    a.use_g = use_g;
+    a.rot = rot;
+    a.n_inv = finv<F>(to_monty<F>(1u << log_n));
+    a.log_blowup = log_blowup;
+    // inverse: DIF, stages descending => passes in reverse plan order
+    for (size_t pi = plan.size(); pi-- > 0;) {
+        NttPass b = a;
+        b.forward = 0;
+        b.first = (pi == plan.size() - 1);
+        b.last = (pi == 0);
+        b.s0 = plan[pi].s0;
+        b.r = plan[pi].r;
+        b.log_cw = plan[pi].log_cw;
+        b.src = b.first ? src : scratch_coef;
+        b.dst = scratch_coef;
+        b.src_col_stride = b.dst_col_stride = n;
+        b.dst_coset_stride = 0;
+        TRY(launch_pass<F>(ctx, b, w, 1));
+    }
+    // forward: DIT, stages ascending, all cosets in grid.z
+    for (size_t pi = 0; pi < plan.size(); pi++) {
+        NttPass b = a;
+        b.forward = 1;
+        b.first = (pi == 0);
+        b.last = (pi == plan.size() - 1);
+        b.s0 = plan[pi].s0;
+        b.r = plan[pi].r;
+        b.log_cw = plan[pi].log_cw;
+        bool single = plan.size() == 1;
+        b.src = b.first ? scratch_coef : scratch_tmp;
+        b.dst = (b.last || single) ? dst : scratch_tmp;
+        b.src_col_stride = b.first ? n : N;
+        b.dst_col_stride = N;
+        b.dst_coset_stride = n;
+        TRY(launch_pass<F>(ctx, b, w, 1u << log_blowup));
+    }
+    return P3R_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5 host: MerkleTreeMmcs::commit over column-major device matrices (mixed heights).
+// ------------------------------------------------------------------------------------------------
+template <class F>
+static int commit_tree(p3r_ctx* ctx, const std::vector<MatRef>& mats, Tree* t, uint32_t* digests) {
+    t->mats = mats;
+    uint32_t lmax = 0;
+    for (auto& m : mats) lmax = std::max(lmax, m.log_h);
+    t->log_max_h = lmax;
+    t->digests = digests;
+    const uint32_t cap = ctx->fri.cap_height;
+    if (lmax < cap) {
+        set_err(ctx, "matrix shorter than the Merkle cap");
+        return P3R_ERR_INVALID_ARG;
+    }
+    auto cols_at = [&](uint32_t lh) {
+        std::vector<const uint32_t*> v;
+        for (auto& m : mats)
+            if (m.log_h == lh)
+                for (uint32_t c = 0; c < m.w; c++) v.push_back(m.d + ((size_t)c << m.log_h));
+        return v;
+    };
+    auto top = cols_at(lmax);
+    const uint32_t* const* d_cols = upload_vec(ctx, top);
+    if (!d_cols) {
+        set_err(ctx, "staging exhausted");
+        return P3R_ERR_OOM;
+    }
+    uint32_t rows = 1u << lmax;
+    k_hash_rows<F><<<(rows + 127) / 128, 128, 0, ctx->stream>>>(d_cols, (uint32_t)top.size(), rows, digests);
+    LAUNCH_CHECK();
+    for (uint32_t l = 1; lmax - l + 1 > cap; l++) {
+        uint32_t n_next = 1u << (lmax - l);
+        auto inj = cols_at(lmax - l);
+        const uint32_t* const* d_inj = nullptr;
+        if (!inj.empty()) {
+            d_inj = upload_vec(ctx, inj);
+            if (!d_inj) {
+                set_err(ctx, "staging exhausted");
+                return P3R_ERR_OOM;
+            }
+        }
+        k_compress<F><<<(n_next + 127) / 128, 128, 0, ctx->stream>>>(digests + t->level_off(l - 1) * 8,
+                                                                      digests + t->level_off(l) * 8, n_next, d_inj,
+                                                                      (uint32_t)inj.size());
+        LAUNCH_CHECK();
+    }
+    return P3R_OK;
+}
+static size_t tree_digest_words(uint32_t log_max_h) { return ((size_t)2 << log_max_h) * 8; }
+static int read_cap(p3r_ctx* ctx, const Tree& t, uint32_t* cap_out) {
+    uint32_t cap = ctx->fri.cap_height;
+    uint32_t l = t.log_max_h - cap;
+    CUDA_TRY(cudaMemcpyAsync(cap_out, t.digests + t.level_off(l) * 8, ((size_t)8 << cap) * 4, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return P3R_OK;
+}
+
+// Upload a row-major host matrix and transpose to column-major device memory.
+static int upload_matrix(p3r_ctx* ctx, const p3r_matrix_u32& m, uint32_t* d_rowmajor_scratch, uint32_t* d_colmajor) {
+    size_t words = (size_t)m.height * m.width;
+    if (!words) return P3R_OK;
+    CUDA_TRY(cudaMemcpyAsync(d_rowmajor_scratch, m.data, words * 4, cudaMemcpyHostToDevice, ctx->stream));
+    dim3 grid((m.width + 31) / 32, (m.height + 31) / 32), block(32, 8);
+    k_transpose_in<<<grid, block, 0, ctx->stream>>>(d_rowmajor_scratch, d_colmajor, m.height, m.width);
+    LAUNCH_CHECK();
+    return P3R_OK;
+}
+
+static bool is_pow2(uint32_t x) { return x && !(x & (x - 1)); }
+static uint32_t ilog2(uint32_t x) {
+    uint32_t l = 0;
+    while ((1u << l) < x) l++;
+    return l;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prep
+// ------------------------------------------------------------------------------------------------
+template <class F>
+static int prep_commit_impl(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_desc* descs, const p3r_matrix_u32* prep,
+                            p3r_prep** out, uint32_t* cap_out, uint32_t* has_prep_out) {
+    auto* pp = new p3r_prep();
+    pp->ctx = ctx;
+    auto fail = [&](int rc) {
+        for (void* p : pp->owned) cudaFree(p);
+        delete pp;
+        return rc;
+    };
+    auto dmalloc = [&](size_t bytes) -> void* {
+        void* p = nullptr;
+        if (cudaMalloc(&p, std::max<size_t>(bytes, 16)) != cudaSuccess) return nullptr;
+        pp->owned.push_back(p);
+        return p;
+    };
+    ctx->arena.reset();
+    ctx->pin_used = 0;
+    const uint32_t lb = ctx->fri.log_blowup;
+    uint32_t max_logN = 0;
+    for (uint32_t i = 0; i < n_inst; i++) max_logN = std::max(max_logN, descs[i].log_height + lb);
+    {
+        int rc = ensure_twiddles<F>(ctx, max_logN);
+        if (rc) return fail(rc);
+    }
+    for (uint32_t i = 0; i < n_inst; i++) {
+        const p3r_instance_desc& d = descs[i];
+        InstDev s;
+        s.log_h = d.log_height;
+        s.main_w = d.main_width;
+        s.prep_w = d.prep_width;
+        s.n_pub = d.n_public;
+        s.log_qc = d.log_quotient_chunks;
+        s.uses_next = d.uses_next_row;
+        if (d.log_quotient_chunks > lb) {
+            set_err(ctx, "log_quotient_chunks exceeds log_blowup");
+            return fail(P3R_ERR_INVALID_ARG);
+        }
+        if (d.constraints.n_base_slots > (uint32_t)MAX_B_SLOTS || d.constraints.n_ext_slots > (uint32_t)MAX_E_SLOTS ||
+            d.lookup_inputs.n_base_slots > (uint32_t)MAX_B_SLOTS || d.lookup_inputs.n_outputs > (uint32_t)MAX_LK_OUTS ||
+            d.n_interactions > (uint32_t)MAX_INTERACTIONS) {
+            set_err(ctx, "program exceeds interpreter limits (slots/outputs/interactions)");
+            return fail(P3R_ERR_UNSUPPORTED);
+        }
+        auto up = [&](const void* src, size_t bytes) -> void* {
+            void* p = dmalloc(bytes);
+            if (p && bytes) cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+            return p;
+        };
+        s.n_cons_insns = d.constraints.n_insns;
+        s.n_constraints = d.constraints.n_constraints;
+        s.cons = (uint4*)up(d.constraints.insns, (size_t)d.constraints.n_insns * 16);
+        s.cons_econst = (Ext4*)up(d.constraints.ext_consts, (size_t)d.constraints.n_ext_consts * 16);
+        s.n_lk_insns = d.lookup_inputs.n_insns;
+        s.n_lk_outs = d.lookup_inputs.n_outputs;
+        s.lk = (uint4*)up(d.lookup_inputs.insns, (size_t)d.lookup_inputs.n_insns * 16);
+        s.lookups.assign(d.lookups, d.lookups + d.n_lookups);
+        s.inter.assign(d.interactions, d.interactions + d.n_interactions);
+        s.d_lookups = (p3r_lookup*)up(d.lookups, (size_t)d.n_lookups * sizeof(p3r_lookup));
+        s.d_inter = (p3r_interaction*)up(d.interactions, (size_t)d.n_interactions * sizeof(p3r_interaction));
+        if (!s.cons || !s.cons_econst || !s.lk || !s.d_lookups || !s.d_inter) {
+            set_err(ctx, "device allocation failed");
+            return fail(P3R_ERR_OOM);
+        }
+        for (auto& it : s.inter) pp->max_msg_w = std::max(pp->max_msg_w, it.n_elems);
+        for (auto& l : s.lookups) pp->n_buses = std::max(pp->n_buses, l.bus + 1);
+        if (pp->max_msg_w > 8) {
+            set_err(ctx, "lookup tuples wider than 8 are not supported");
+            return fail(P3R_ERR_UNSUPPORTED);
+        }
+        if (!s.lookups.empty()) pp->has_perm = true;
+        // selectors on the quotient domain
+        uint32_t NQ = 1u << (s.log_h + s.log_qc);
+        s.sel = (uint32_t*)dmalloc((size_t)3 * NQ * 4);
+        s.inv_van = (uint32_t*)dmalloc(((size_t)4 << s.log_qc));
+        if (!s.sel || !s.inv_van) return fail(P3R_ERR_OOM);
+        k_selectors<F><<<(NQ + 255) / 256, 256, 0, ctx->stream>>>(s.sel, s.inv_van, s.log_h, s.log_qc, ctx->gen_m, ctx->tw,
+                                                                  ctx->logT);
+        ctx->launches++;
+        if (s.prep_w) {
+            if (!prep || !prep[i].data || prep[i].height != (1u << s.log_h) || prep[i].width != s.prep_w) {
+                set_err(ctx, "preprocessed matrix shape mismatch");
+                return fail(P3R_ERR_INVALID_ARG);
+            }
+            pp->has_prep = true;
+            size_t n = (size_t)1 << s.log_h;
+            s.prep_trace = (uint32_t*)dmalloc(n * s.prep_w * 4);
+            s.prep_lde = (uint32_t*)dmalloc((n << lb) * s.prep_w * 4);
+            uint32_t* rm = arena_alloc<uint32_t>(ctx, n * s.prep_w);
+            uint32_t* coef = arena_alloc<uint32_t>(ctx, n * s.prep_w);
+            uint32_t* tmp = s.log_h > TILE_LOG ? arena_alloc<uint32_t>(ctx, (n << lb) * s.prep_w) : nullptr;
+            if (!s.prep_trace || !s.prep_lde || !rm || !coef || (s.log_h > TILE_LOG && !tmp)) return fail(P3R_ERR_OOM);
+            int rc = upload_matrix(ctx, prep[i], rm, s.prep_trace);
+            if (rc) return fail(rc);
+            rc = coset_lde<F>(ctx, s.prep_trace, s.prep_lde, s.log_h, s.prep_w, lb, true, 0, coef, tmp);
+            if (rc) return fail(rc);
+        }
+        pp->inst.push_back(std::move(s));
+    }
+    if (pp->has_prep) {
+        std::vector<MatRef> mats;
+        uint32_t lmax = 0;
+        for (auto& s : pp->inst)
+            if (s.prep_w) {
+                mats.push_back({s.prep_lde, s.log_h + lb, s.prep_w});
+                lmax = std::max(lmax, s.log_h + lb);
+            }
+        uint32_t* dg = (uint32_t*)dmalloc(tree_digest_words(lmax) * 4);
+        if (!dg) return fail(P3R_ERR_OOM);
+        int rc = commit_tree<F>(ctx, mats, &pp->prep_tree, dg);
+        if (rc) return fail(rc);
+        pp->prep_cap.resize((size_t)8 << ctx->fri.cap_height);
+        rc = read_cap(ctx, pp->prep_tree, pp->prep_cap.data());
+        if (rc) return fail(rc);
+        if (cap_out) std::memcpy(cap_out, pp->prep_cap.data(), pp->prep_cap.size() * 4);
+    }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        set_err(ctx, "prep: stream sync failed");
+        return fail(P3R_ERR_CUDA);
+    }
+    if (has_prep_out) *has_prep_out = pp->has_prep;
+    *out = pp;
+    return P3R_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// session phases
+// ------------------------------------------------------------------------------------------------
+template <class F>
+static int prove_begin_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces,
+                            const uint32_t* const* public_values, p3r_session** out) {
+    ctx->arena.reset();
+    ctx->pin_used = 0;
+    auto* s = new p3r_session();
+    s->ctx = ctx;
+    s->prep = prep;
+    const uint32_t lb = ctx->fri.log_blowup;
+    size_t n_inst = prep->inst.size();
+    s->trace.assign(n_inst, nullptr);
+    s->main_lde.assign(n_inst, nullptr);
+    s->perm.assign(n_inst, nullptr);
+    s->perm_lde.assign(n_inst, nullptr);
+    s->chunks.assign(n_inst, nullptr);
+    s->chunk_lde.assign(n_inst, nullptr);
+    s->d_pub.assign(n_inst, nullptr);
+    size_t max_rm = 0, max_coef = 0, max_tmp = 0;
+    for (size_t i = 0; i < n_inst; i++) {
+        const InstDev& d = prep->inst[i];
+        if (traces[i].height != (1u << d.log_h) || traces[i].width != d.main_w || !traces[i].data) {
+            set_err(ctx, "trace shape mismatch for instance " + std::to_string(i));
+            delete s;
+            return P3R_ERR_INVALID_ARG;
+        }
+        size_t n = (size_t)1 << d.log_h;
+        size_t wmax = std::max<size_t>({d.main_w, (size_t)d.aux_w() * 4, (size_t)4 << d.log_qc});
+        max_rm = std::max(max_rm, n * d.main_w);
+        max_coef = std::max(max_coef, n * wmax);
+        if (d.log_h > TILE_LOG) max_tmp = std::max(max_tmp, (n << lb) * wmax);
+    }
+    uint32_t* rm = arena_alloc<uint32_t>(ctx, max_rm);
+    s->scratch_coef = arena_alloc<uint32_t>(ctx, max_coef);
+    s->scratch_tmp = max_tmp ? arena_alloc<uint32_t>(ctx, max_tmp) : nullptr;
+    if (!rm || !s->scratch_coef || (max_tmp && !s->scratch_tmp)) {
+        set_err(ctx, "device allocation failed");
+        delete s;
+        return P3R_ERR_OOM;
+    }
+    for (size_t i = 0; i < n_inst; i++) {
+        const InstDev& d = prep->inst[i];
+        size_t n = (size_t)1 << d.log_h;
+        s->trace[i] = arena_alloc<uint32_t>(ctx, n * d.main_w);
+        s->main_lde[i] = arena_alloc<uint32_t>(ctx, (n << lb) * d.main_w);
+        if (!s->trace[i] || !s->main_lde[i]) {
+            set_err(ctx, "device allocation failed");
+            delete s;
+            return P3R_ERR_OOM;
+        }
+        int rc = upload_matrix(ctx, traces[i], rm, s->trace[i]);
+        if (rc) {
+            delete s;
+            return rc;
+        }
+        if (d.n_pub) {
+            s->d_pub[i] = (uint32_t*)upload_small(ctx, public_values[i], (size_t)d.n_pub * 4);
+        } else {
+            s->d_pub[i] = reinterpret_cast<uint32_t*>(ctx->dstage);
+        }
+    }
+    *out = s;
+    return P3R_OK;
+}
+
+template <class F>
+static int commit_main_impl(p3r_session* s, uint32_t* cap_out) {
+    p3r_ctx* ctx = s->ctx;
+    if (s->phase != PH_BEGIN) {
+        set_err(ctx, "commit_main: wrong phase");
+        return P3R_ERR_STATE;
+    }
+    const uint32_t lb = ctx->fri.log_blowup;
+    std::vector<MatRef> mats;
+    uint32_t lmax = 0;
+    for (size_t i = 0; i < s->prep->inst.size(); i++) {
+        const InstDev& d = s->prep->inst[i];
+        TRY(coset_lde<F>(ctx, s->trace[i], s->main_lde[i], d.log_h, d.main_w, lb, true, 0, s->scratch_coef, s->scratch_tmp));
+        mats.push_back({s->main_lde[i], d.log_h + lb, d.main_w});
+        lmax = std::max(lmax, d.log_h + lb);
+    }
+    uint32_t* dg = arena_alloc<uint32_t>(ctx, tree_digest_words(lmax));
+    if (!dg) return P3R_ERR_OOM;
+    TRY(commit_tree<F>(ctx, mats, &s->main_tree, dg));
+    TRY(read_cap(ctx, s->main_tree, cap_out));
+    s->phase = PH_MAIN;
+    return P3R_OK;
+}
+
+template <class F>
+static int commit_perm_impl(p3r_session* s, const uint32_t alpha[4], const uint32_t beta[4], uint32_t* cap_out,
+                            uint32_t* terminals_out) {
+    p3r_ctx* ctx = s->ctx;
+    if (s->phase != PH_MAIN) {
+        set_err(ctx, "commit_perm: wrong phase");
+        return P3R_ERR_STATE;
+    }
+    const p3r_prep* pp = s->prep;
+    size_t n_inst = pp->inst.size();
+    s->d_terminals = arena_alloc<Ext4>(ctx, n_inst);
+    s->chal_off.assign(n_inst, 0);
+    if (!pp->has_perm) {
+        s->d_chal = reinterpret_cast<Ext4*>(ctx->dstage);
+        s->phase = PH_PERM;
+        return P3R_OK;
+    }
+    const uint32_t lb = ctx->fri.log_blowup, wnr = ctx->w_m;
+    Ext4 a, b;
+    std::memcpy(a.c, alpha, 16);
+    std::memcpy(b.c, beta, 16);
+    // challenge layout (recursion/src/verifier/batch_stark.rs:1086-1110): gamma = beta^W, prefix[bus] = alpha + (bus+1)*gamma
+    Ext4 gamma = b;
+    for (uint32_t i = 1; i < pp->max_msg_w; i++) gamma = emul<F>(gamma, b, wnr);
+    std::vector<Ext4> prefix(pp->n_buses);
+    Ext4 pr = a;
+    for (uint32_t i = 0; i < pp->n_buses; i++) {
+        pr = eadd<F>(pr, gamma);
+        prefix[i] = pr;
+    }
+    std::vector<Ext4> chal;
+    for (size_t i = 0; i < n_inst; i++) {
+        s->chal_off[i] = (uint32_t)chal.size();
+        for (auto& l : pp->inst[i].lookups) {
+            chal.push_back(prefix[l.bus]);
+            chal.push_back(b);
+        }
+    }
+    std::vector<Ext4> bp(8);
+    bp[0] = ext_one<F>();
+    for (int k = 1; k < 8; k++) bp[k] = emul<F>(bp[k - 1], b, wnr);
+    s->d_chal = upload_vec(ctx, chal);
+    Ext4* d_bp = upload_vec(ctx, bp);
+    if (!s->d_chal || !d_bp || !s->d_terminals) return P3R_ERR_OOM;
+    std::vector<MatRef> mats;
+    uint32_t lmax = 0;
+    for (size_t i = 0; i < n_inst; i++) {
+        const InstDev& d = pp->inst[i];
+        if (d.lookups.empty()) continue;
+        size_t n = (size_t)1 << d.log_h;
+        uint32_t pw = d.aux_w() * 4;
+        s->perm[i] = arena_alloc<uint32_t>(ctx, n * pw);
+        s->perm_lde[i] = arena_alloc<uint32_t>(ctx, (n << lb) * pw);
+        Ext4* rowsum = arena_alloc<Ext4>(ctx, n);
+        if (!s->perm[i] || !s->perm_lde[i] || !rowsum) return P3R_ERR_OOM;
+        LogupArgs la{};
+        la.insns = d.lk;
+        la.n_insns = d.n_lk_insns;
+        la.main = s->trace[i];
+        la.prep = d.prep_trace;
+        la.pub = s->d_pub[i];
+        la.log_n = d.log_h;
+        la.lookups = d.d_lookups;
+        la.n_lookups = (uint32_t)d.lookups.size();
+        la.inter = d.d_inter;
+        la.chal = s->d_chal + s->chal_off[i];
+        la.beta_pows = d_bp;
+        la.perm = s->perm[i];
+        la.rowsum = rowsum;
+        la.wnr = wnr;
+        k_logup_rows<F><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(la);
+        LAUNCH_CHECK();
+        k_logup_scan<F><<<1, 1024, 0, ctx->stream>>>(rowsum, d.log_h, s->perm[i], s->d_terminals + i);
+        LAUNCH_CHECK();
+        TRY(coset_lde<F>(ctx, s->perm[i], s->perm_lde[i], d.log_h, pw, lb, true, 0, s->scratch_coef, s->scratch_tmp));
+        mats.push_back({s->perm_lde[i], d.log_h + lb, pw});
+        lmax = std::max(lmax, d.log_h + lb);
+    }
+    uint32_t* dg = arena_alloc<uint32_t>(ctx, tree_digest_words(lmax));
+    if (!dg) return P3R_ERR_OOM;
+    TRY(commit_tree<F>(ctx, mats, &s->perm_tree, dg));
+    // terminals of instances with lookups, in order
+    std::vector<Ext4> term(n_inst);
+    CUDA_TRY(cudaMemcpyAsync(term.data(), s->d_terminals, n_inst * sizeof(Ext4), cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(read_cap(ctx, s->perm_tree, cap_out));
+    size_t k = 0;
+    for (size_t i = 0; i < n_inst; i++)
+        if (!pp->inst[i].lookups.empty()) {
+            std::memcpy(terminals_out + 4 * k, term[i].c, 16);
+            k++;
+        }
+    s->phase = PH_PERM;
+    return P3R_OK;
+}
+
+template <class F>
+static int commit_quotient_impl(p3r_session* s, const uint32_t alpha[4], uint32_t* cap_out) {
+    p3r_ctx* ctx = s->ctx;
+    if (s->phase != PH_PERM) {
+        set_err(ctx, "commit_quotient: wrong phase");
+        return P3R_ERR_STATE;
+    }
+    const p3r_prep* pp = s->prep;
+    const uint32_t lb = ctx->fri.log_blowup, wnr = ctx->w_m;
+    Ext4 al;
+    std::memcpy(al.c, alpha, 16);
+    std::vector<MatRef> mats;
+    uint32_t lmax = 0;
+    for (size_t i = 0; i < pp->inst.size(); i++) {
+        const InstDev& d = pp->inst[i];
+        size_t n = (size_t)1 << d.log_h;
+        uint32_t qc = 1u << d.log_qc;
+        s->chunks[i] = arena_alloc<uint32_t>(ctx, n * 4 * qc);
+        s->chunk_lde[i] = arena_alloc<uint32_t>(ctx, (n << lb) * 4 * qc);
+        Ext4* ap = arena_alloc<Ext4>(ctx, std::max<uint32_t>(d.n_constraints, 1));
+        if (!s->chunks[i] || !s->chunk_lde[i] || !ap) return P3R_ERR_OOM;
+        k_ext_powers_desc<F><<<1, 32, 0, ctx->stream>>>(ap, d.n_constraints, al, wnr);
+        LAUNCH_CHECK();
+        QuotientArgs qa{};
+        qa.insns = d.cons;
+        qa.n_insns = d.n_cons_insns;
+        qa.main = s->main_lde[i];
+        qa.prep = d.prep_lde;
+        qa.perm = s->perm_lde[i];
+        qa.pub = s->d_pub[i];
+        qa.log_n = d.log_h;
+        qa.log_qc = d.log_qc;
+        qa.log_blowup = lb;
+        qa.sel = d.sel;
+        qa.inv_van = d.inv_van;
+        qa.chal = s->d_chal + s->chal_off[i];
+        qa.pval = s->d_terminals + i;
+        qa.econst = d.cons_econst;
+        qa.alpha_pows = ap;
+        qa.chunks = s->chunks[i];
+        qa.wnr = wnr;
+        uint32_t NQ = (uint32_t)(n << d.log_qc);
+        k_quotient<F><<<(NQ + 127) / 128, 128, 0, ctx->stream>>>(qa);
+        LAUNCH_CHECK();
+        // chunk c lives on the coset GENERATOR * w_NQ^c * H_n: LDE without the GENERATOR factor, rotated by -c*(N/NQ)
+        uint32_t logN = d.log_h + lb;
+        for (uint32_t c = 0; c < qc; c++) {
+            uint32_t rot = (uint32_t)((((uint64_t)1 << logN) - ((uint64_t)c << (lb - d.log_qc))) & (((uint64_t)1 << logN) - 1));
+            uint32_t* src = s->chunks[i] + (size_t)c * 4 * n;
+            uint32_t* dst = s->chunk_lde[i] + (size_t)c * 4 * (n << lb);
+            TRY(coset_lde<F>(ctx, src, dst, d.log_h, 4, lb, false, rot, s->scratch_coef, s->scratch_tmp));
+            mats.push_back({dst, logN, 4});
+        }
+        lmax = std::max(lmax, logN);
+    }
+    uint32_t* dg = arena_alloc<uint32_t>(ctx, tree_digest_words(lmax));
+    if (!dg) return P3R_ERR_OOM;
+    TRY(commit_tree<F>(ctx, mats, &s->quot_tree, dg));
+    TRY(read_cap(ctx, s->quot_tree, cap_out));
+    s->phase = PH_QUOT;
+    return P3R_OK;
+}
+
+// Opened-value layout per instance: see include/p3r.h p3r_open.
+template <class F>
+static int open_impl(p3r_session* s, const uint32_t zeta_w[4], uint32_t* opened_out, size_t cap_words, size_t* n_words) {
+    p3r_ctx* ctx = s->ctx;
+    if (s->phase != PH_QUOT) {
+        set_err(ctx, "open: wrong phase");
+        return P3R_ERR_STATE;
+    }
+    const p3r_prep* pp = s->prep;
+    const uint32_t wnr = ctx->w_m;
+    size_t n_inst = pp->inst.size();
+    Ext4 zeta;
+    std::memcpy(zeta.c, zeta_w, 16);
+    s->zeta = zeta;
+    // host-side small field helpers for the points
+    std::vector<WeightJob> wjobs;
+    std::vector<DotJob> djobs;
+    uint32_t w_off = 0, o_off = 0, max_n_log = 0, max_w = 1;
+    s->open_rounds.assign(4, {});
+    std::vector<std::vector<p3r_session::OpenRef>> refs(4);
+    for (size_t i = 0; i < n_inst; i++) {
+        const InstDev& d = pp->inst[i];
+        uint32_t n = 1u << d.log_h;
+        max_n_log = std::max(max_n_log, d.log_h);
+        // g_n = w_n ; zeta*g
+        uint32_t gn = fpow<F>(ctx->gen_m, ((uint64_t)F::P - 1) >> d.log_h);
+        Ext4 znext = emul_base<F>(zeta, gn);
+        uint32_t wz = w_off;
+        wjobs.push_back({zeta, d.log_h, wz});
+        w_off += n;
+        uint32_t wzn = w_off;
+        wjobs.push_back({znext, d.log_h, wzn});
+        w_off += n;
+        auto add = [&](const uint32_t* mat, uint32_t width, uint32_t woff) {
+            djobs.push_back({mat, d.log_h, width, woff, o_off});
+            uint32_t o = o_off;
+            o_off += width;
+            max_w = std::max(max_w, width);
+            return o;
+        };
+        p3r_session::OpenRef m{(uint32_t)i, 0, 0, {0, 0}, 1, d.main_w};
+        m.off[0] = add(s->trace[i], d.main_w, wz);
+        if (d.uses_next) {
+            m.off[1] = add(s->trace[i], d.main_w, wzn);
+            m.n_points = 2;
+        }
+        refs[0].push_back(m);
+        if (d.prep_w) {
+            p3r_session::OpenRef p{(uint32_t)i, 2, 0, {0, 0}, 2, d.prep_w};
+            p.off[0] = add(d.prep_trace, d.prep_w, wz);
+            p.off[1] = add(d.prep_trace, d.prep_w, wzn);
+            refs[2].push_back(p);
+        }
+        if (!d.lookups.empty()) {
+            uint32_t pw = d.aux_w() * 4;
+            p3r_session::OpenRef p{(uint32_t)i, 3, 0, {0, 0}, 2, pw};
+            p.off[0] = add(s->perm[i], pw, wz);
+            p.off[1] = add(s->perm[i], pw, wzn);
+            refs[3].push_back(p);
+        }
+        // quotient chunk c: source evaluations on shift_c * H_n, shift_c = GENERATOR * w_NQ^c => u = zeta / shift_c
+        uint32_t lq = d.log_h + d.log_qc;
+        uint32_t wq = fpow<F>(ctx->gen_m, ((uint64_t)F::P - 1) >> lq);
+        for (uint32_t c = 0; c < (1u << d.log_qc); c++) {
+            uint32_t shift = fmul<F>(ctx->gen_m, fpow<F>(wq, c));
+            Ext4 u = emul_base<F>(zeta, finv<F>(shift));
+            uint32_t wc = w_off;
+            wjobs.push_back({u, d.log_h, wc});
+            w_off += n;
+            p3r_session::OpenRef q{(uint32_t)i, 1, c, {0, 0}, 1, 4};
+            q.off[0] = add(s->chunks[i] + (size_t)c * 4 * n, 4, wc);
+            refs[1].push_back(q);
+        }
+    }
+    s->open_rounds = refs;
+    s->n_opened = o_off;
+    Ext4* d_w = arena_alloc<Ext4>(ctx, w_off);
+    s->d_opened = arena_alloc<Ext4>(ctx, o_off);
+    uint32_t max_chunks = ((1u << max_n_log) + DOT_ROWS - 1) / DOT_ROWS;
+    Ext4* partial = arena_alloc<Ext4>(ctx, djobs.size() * (size_t)max_chunks * max_w);
+    WeightJob* d_wj = upload_vec(ctx, wjobs);
+    DotJob* d_dj = upload_vec(ctx, djobs);
+    if (!d_w || !s->d_opened || !partial || !d_wj || !d_dj) return P3R_ERR_OOM;
+    {
+        dim3 grid(((1u << max_n_log) + 255) / 256, (unsigned)wjobs.size());
+        k_bary_weights<F><<<grid, 256, 0, ctx->stream>>>(d_wj, d_w, ctx->tw, ctx->logT, wnr);
+        LAUNCH_CHECK();
+    }
+    {
+        dim3 grid(max_chunks, (max_w + DOT_COLS - 1) / DOT_COLS, (unsigned)djobs.size());
+        k_bary_dot<F><<<grid, 256, 0, ctx->stream>>>(d_dj, d_w, partial, max_chunks, max_w);
+        LAUNCH_CHECK();
+        dim3 g2((max_w + 127) / 128, (unsigned)djobs.size());
+        k_bary_reduce<F><<<g2, 128, 0, ctx->stream>>>(d_dj, partial, s->d_opened, max_chunks, max_w);
+        LAUNCH_CHECK();
+    }
+    // download; re-order into the per-instance ABI layout
+    std::vector<Ext4> host(o_off);
+    CUDA_TRY(cudaMemcpyAsync(host.data(), s->d_opened, (size_t)o_off * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    std::vector<uint32_t> outw;
+    outw.reserve((size_t)o_off * 4);
+    auto push = [&](uint32_t off, uint32_t width) {
+        for (uint32_t k = 0; k < width; k++)
+            for (int c = 0; c < 4; c++) outw.push_back(host[off + k].c[c]);
+    };
+    for (size_t i = 0; i < n_inst; i++) {
+        for (int kind : {0, 2, 3, 1})  // main, prep, perm, quotient chunks
+            for (auto& r : refs[kind])
+                if (r.inst == i)
+                    for (uint32_t p = 0; p < r.n_points; p++) push(r.off[p], r.width);
+    }
+    s->opened_host = outw;
+    *n_words = outw.size();
+    if (outw.size() > cap_words) {
+        set_err(ctx, "open: output buffer too small");
+        return P3R_ERR_BUFFER;
+    }
+    std::memcpy(opened_out, outw.data(), outw.size() * 4);
+    s->phase = PH_OPEN;
+    return P3R_OK;
+}
+
+static std::vector<uint32_t> arity_schedule(const p3r_fri_params& fri, const std::vector<uint32_t>& heights_desc, bool* ok) {
+    std::vector<uint32_t> sched;
+    uint32_t log_final = fri.log_blowup + fri.log_final_poly_len;
+    uint32_t h = heights_desc[0];
+    size_t next = 1;
+    *ok = true;
+    while (h > log_final) {
+        uint32_t k = std::min(fri.max_log_arity, h - log_final);
+        if (next < heights_desc.size()) k = std::min(k, h - heights_desc[next]);
+        if (k == 0) {
+            *ok = false;
+            return sched;
+        }
+        h -= k;
+        if (next < heights_desc.size() && heights_desc[next] == h) next++;
+        sched.push_back(k);
+    }
+    if (next != heights_desc.size()) *ok = false;
+    return sched;
+}
+
+template <class F>
+static int fri_begin_impl(p3r_session* s, const uint32_t alpha_w[4], uint32_t* n_rounds_out, uint32_t* log_arities_out) {
+    p3r_ctx* ctx = s->ctx;
+    if (s->phase != PH_OPEN) {
+        set_err(ctx, "fri_begin: wrong phase");
+        return P3R_ERR_STATE;
+    }
+    const p3r_prep* pp = s->prep;
+    const uint32_t lb = ctx->fri.log_blowup, wnr = ctx->w_m;
+    Ext4 alpha;
+    std::memcpy(alpha.c, alpha_w, 16);
+    // group (round, matrix, point) by LDE height in commit order; running alpha exponent per height
+    struct HGroup {
+        std::vector<RoMat> mats;
+        uint32_t alpha_count = 0;
+        uint32_t log_n = 0;
+    };
+    std::map<uint32_t, HGroup, std::greater<uint32_t>> groups;
+    uint32_t max_exp = 1;
+    for (int kind : {0, 1, 2, 3}) {  // rounds in commit order [main, quotient, preprocessed, permutation]
+        for (auto& r : s->open_rounds[kind]) {
+            const InstDev& d = pp->inst[r.inst];
+            uint32_t lh = d.log_h + lb;
+            HGroup& g = groups[lh];
+            g.log_n = d.log_h;
+            RoMat m{};
+            size_t N = (size_t)1 << lh;
+            switch (kind) {
+                case 0: m.lde = s->main_lde[r.inst]; break;
+                case 1: m.lde = s->chunk_lde[r.inst] + (size_t)r.chunk * 4 * N; break;
+                case 2: m.lde = d.prep_lde; break;
+                default: m.lde = s->perm_lde[r.inst]; break;
+            }
+            m.width = r.width;
+            m.n_points = r.n_points;
+            for (uint32_t p = 0; p < r.n_points; p++) {
+                m.opened_off[p] = r.off[p];
+                m.alpha_off[p] = g.alpha_count;
+                g.alpha_count += r.width;
+            }
+            g.mats.push_back(m);
+            max_exp = std::max(max_exp, g.alpha_count + 1);
+        }
+    }
+    Ext4* apow = arena_alloc<Ext4>(ctx, max_exp);
+    if (!apow) return P3R_ERR_OOM;
+    k_ext_powers_asc<F><<<(max_exp / 64 + 128) / 128, 128, 0, ctx->stream>>>(apow, max_exp, alpha, wnr);
+    LAUNCH_CHECK();
+    s->heights.clear();
+    s->ro.clear();
+    for (auto& kv : groups) {
+        uint32_t lh = kv.first;
+        HGroup& g = kv.second;
+        s->heights.push_back(lh);
+        RoMat* d_m = upload_vec(ctx, g.mats);
+        Ext4* coef = arena_alloc<Ext4>(ctx, g.mats.size() * 2);
+        Ext4* ro = arena_alloc<Ext4>(ctx, (size_t)1 << lh);
+        if (!d_m || !coef || !ro) return P3R_ERR_OOM;
+        uint32_t nm = (uint32_t)g.mats.size();
+        k_ro_prepare<F><<<(nm * 2 + 63) / 64, 64, 0, ctx->stream>>>(d_m, nm, s->d_opened, apow, coef, wnr);
+        LAUNCH_CHECK();
+        RoArgs ra{};
+        ra.mats = d_m;
+        ra.n_mats = nm;
+        ra.log_h = lh;
+        ra.apow = apow;
+        ra.coef = coef;
+        ra.z[0] = s->zeta;
+        ra.z[1] = emul_base<F>(s->zeta, fpow<F>(ctx->gen_m, ((uint64_t)F::P - 1) >> g.log_n));
+        ra.gen = ctx->gen_m;
+        ra.tw = ctx->tw;
+        ra.logT = ctx->logT;
+        ra.ro = ro;
+        ra.wnr = wnr;
+        uint32_t N = 1u << lh;
+        k_reduced_openings<F><<<(N + 127) / 128, 128, 0, ctx->stream>>>(ra);
+        LAUNCH_CHECK();
+        s->ro[lh] = ro;
+    }
+    bool ok = false;
+    std::vector<uint32_t> sched = arity_schedule(ctx->fri, s->heights, &ok);
+    if (!ok || sched.empty() || sched.size() > 32) {
+        set_err(ctx, "fri_begin: table heights incompatible with log_final_poly_len/log_blowup");
+        return P3R_ERR_INVALID_ARG;
+    }
+    s->log_max = s->heights[0];
+    s->rounds.clear();
+    uint32_t h = s->log_max;
+    for (size_t r = 0; r < sched.size(); r++) {
+        FriRound fr;
+        fr.log_arity = sched[r];
+        fr.log_len = h;
+        fr.vec = (r == 0) ? s->ro[h] : arena_alloc<Ext4>(ctx, (size_t)1 << h);
+        if (!fr.vec) return P3R_ERR_OOM;
+        h -= sched[r];
+        s->rounds.push_back(fr);
+        log_arities_out[r] = sched[r];
+    }
+    s->final_vec = arena_alloc<Ext4>(ctx, (size_t)1 << h);
+    if (!s->final_vec) return P3R_ERR_OOM;
+    *n_rounds_out = (uint32_t)sched.size();
+    s->phase = PH_FRI;
+    return P3R_OK;
+}
+
+template <class F>
+static int fri_commit_impl(p3r_session* s, uint32_t round, uint32_t* cap_out) {
+    p3r_ctx* ctx = s->ctx;
+    if (s->phase != PH_FRI || round >= s->rounds.size()) {
+        set_err(ctx, "fri_commit: wrong phase/round");
+        return P3R_ERR_STATE;
+    }
+    FriRound& fr = s->rounds[round];
+    uint32_t log_rows = fr.log_len - fr.log_arity;
+    if (log_rows < ctx->fri.cap_height) {
+        set_err(ctx, "fri_commit: folded height below the Merkle cap");
+        return P3R_ERR_INVALID_ARG;
+    }
+    uint32_t* dg = arena_alloc<uint32_t>(ctx, tree_digest_words(log_rows));
+    if (!dg) return P3R_ERR_OOM;
+    fr.tree.log_max_h = log_rows;
+    fr.tree.digests = dg;
+    uint32_t rows = 1u << log_rows, w = 4u << fr.log_arity;
+    k_hash_rows_rowmajor<F><<<(rows + 127) / 128, 128, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(fr.vec), w, rows, dg);
+    LAUNCH_CHECK();
+    for (uint32_t l = 1; log_rows - l + 1 > ctx->fri.cap_height; l++) {
+        uint32_t n_next = 1u << (log_rows - l);
+        k_compress<F><<<(n_next + 127) / 128, 128, 0, ctx->stream>>>(dg + fr.tree.level_off(l - 1) * 8,
+                                                                      dg + fr.tree.level_off(l) * 8, n_next, nullptr, 0);
+        LAUNCH_CHECK();
+    }
+    return read_cap(ctx, fr.tree, cap_out);
+}
+
+template <class F>
+static int fri_fold_impl(p3r_session* s, uint32_t round, const uint32_t beta_w[4]) {
+    p3r_ctx* ctx = s->ctx;
+    if (s->phase != PH_FRI || round >= s->rounds.size()) {
+        set_err(ctx, "fri_fold: wrong phase/round");
+        return P3R_ERR_STATE;
+    }
+    FriRound& fr = s->rounds[round];
+    Ext4 beta;
+    std::memcpy(beta.c, beta_w, 16);
+    uint32_t out_log = fr.log_len - fr.log_arity;
+    Ext4* out = (round + 1 < s->rounds.size()) ? s->rounds[round + 1].vec : s->final_vec;
+    const Ext4* roll = nullptr;
+    auto it = s->ro.find(out_log);
+    if (it != s->ro.end() && out_log != s->log_max) roll = it->second;
+    uint32_t n_out = 1u << out_log;
+    k_fri_fold<F><<<(n_out + 127) / 128, 128, 0, ctx->stream>>>(fr.vec, out, fr.log_len, fr.log_arity, beta, roll, ctx->inv2_m,
+                                                                ctx->tw, ctx->logT, ctx->w_m);
+    LAUNCH_CHECK();
+    return P3R_OK;
+}
+
+template <class F>
+static int fri_final_poly_impl(p3r_session* s, uint32_t* coeffs_out) {
+    p3r_ctx* ctx = s->ctx;
+    if (s->phase != PH_FRI) {
+        set_err(ctx, "fri_final_poly: wrong phase");
+        return P3R_ERR_STATE;
+    }
+    uint32_t lf = ctx->fri.log_final_poly_len, n = 1u << lf;
+    Ext4* d_c = arena_alloc<Ext4>(ctx, n);
+    if (!d_c) return P3R_ERR_OOM;
+    k_final_poly<F><<<(n + 63) / 64, 64, 0, ctx->stream>>>(s->final_vec, d_c, lf, ctx->tw, ctx->logT);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(coeffs_out, d_c, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return P3R_OK;
+}
+
+static int fri_query_impl(p3r_session* s, const uint32_t* indices, uint32_t nq, uint32_t* out, size_t cap_words,
+                          size_t* n_words) {
+    p3r_ctx* ctx = s->ctx;
+    if (s->phase != PH_FRI) {
+        set_err(ctx, "fri_query: wrong phase");
+        return P3R_ERR_STATE;
+    }
+    const uint32_t cap = ctx->fri.cap_height;
+    std::vector<GatherSeg> segs;
+    uint32_t off = 0;
+    std::vector<const Tree*> trees = {&s->main_tree, &s->quot_tree};
+    if (s->prep->has_prep) trees.push_back(&s->prep->prep_tree);
+    if (s->prep->has_perm) trees.push_back(&s->perm_tree);
+    for (const Tree* t : trees) {
+        uint32_t tshift = s->log_max - t->log_max_h;
+        for (auto& m : t->mats) {
+            segs.push_back({0, m.d, m.log_h, m.w, tshift + (t->log_max_h - m.log_h), off});
+            off += m.w;
+        }
+        uint32_t depth = t->log_max_h - cap;
+        segs.push_back({1, t->digests, t->log_max_h, depth, tshift, off});
+        off += depth * 8;
+    }
+    uint32_t consumed = 0;
+    for (auto& fr : s->rounds) {
+        uint32_t arity = 1u << fr.log_arity;
+        segs.push_back({2, reinterpret_cast<const uint32_t*>(fr.vec), fr.log_len, fr.log_arity, consumed, off});
+        off += (arity - 1) * 4;
+        uint32_t log_rows = fr.log_len - fr.log_arity;
+        uint32_t depth = log_rows - cap;
+        segs.push_back({1, fr.tree.digests, log_rows, depth, consumed + fr.log_arity, off});
+        off += depth * 8;
+        consumed += fr.log_arity;
+    }
+    size_t total = (size_t)off * nq;
+    *n_words = total;
+    if (total > cap_words) {
+        set_err(ctx, "fri_query: output buffer too small");
+        return P3R_ERR_BUFFER;
+    }
+    GatherSeg* d_segs = upload_vec(ctx, segs);
+    uint32_t* d_idx = (uint32_t*)upload_small(ctx, indices, (size_t)nq * 4);
+    uint32_t* d_out = arena_alloc<uint32_t>(ctx, total);
+    if (!d_segs || !d_idx || !d_out) return P3R_ERR_OOM;
+    dim3 grid(nq, 8);
+    k_query_gather<<<grid, 256, 0, ctx->stream>>>(d_segs, (uint32_t)segs.size(), d_idx, off, d_out);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(out, d_out, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return P3R_OK;
+}
+
+template <class F>
+static int grind_impl(p3r_ctx* ctx, const uint32_t state[16], const uint32_t* pending, uint32_t n_pending, uint32_t bits,
+                      uint32_t* witness_out) {
+    if (bits == 0) {
+        *witness_out = 0;
+        return P3R_OK;
+    }
+    if (n_pending >= 8 || bits > 30) {
+        set_err(ctx, "grind: bad arguments");
+        return P3R_ERR_INVALID_ARG;
+    }
+    uint32_t host[16 + 8 + 1];
+    std::memcpy(host, state, 64);
+    std::memset(host + 16, 0, 32);
+    if (n_pending) std::memcpy(host + 16, pending, (size_t)n_pending * 4);
+    host[24] = 0xffffffffu;
+    uint32_t* d = (uint32_t*)upload_small(ctx, host, sizeof host);
+    if (!d) {  // staging may be exhausted outside a session: fall back to a private buffer
+        ctx->pin_used = 0;
+        d = (uint32_t*)upload_small(ctx, host, sizeof host);
+        if (!d) return P3R_ERR_OOM;
+    }
+    uint32_t batch = std::max(1u << 16, 4u << bits);
+    for (uint64_t base = 0; base < F::P; base += batch) {
+        k_grind<F><<<(batch + 127) / 128, 128, 0, ctx->stream>>>(d, d + 16, n_pending, bits, (uint32_t)base, batch, d + 24);
+        LAUNCH_CHECK();
+        uint32_t best;
+        CUDA_TRY(cudaMemcpyAsync(&best, d + 24, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (best != 0xffffffffu) {
+            *witness_out = to_monty<F>(best);
+            return P3R_OK;
+        }
+    }
+    set_err(ctx, "grind: no witness");
+    return P3R_ERR_POW;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One-shot prove: host transcript (SURVEY.md A1/A2/A7 order) over the phases. Blob layout: DESIGN.md "Proof blob".
+// ------------------------------------------------------------------------------------------------
+struct PhaseTimer {
+    p3r_ctx* ctx;
+    std::vector<cudaEvent_t> ev;
+    std::vector<std::string> names;
+    explicit PhaseTimer(p3r_ctx* c) : ctx(c) { mark("start"); }
+    void mark(const char* name) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, ctx->stream);
+        ev.push_back(e);
+        names.push_back(name);
+    }
+    void finish() {
+        cudaEventSynchronize(ev.back());
+        ctx->phase_times.clear();
+        for (size_t i = 1; i < ev.size(); i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            ctx->phase_times.push_back({names[i], ms});
+        }
+        for (auto e : ev) cudaEventDestroy(e);
+        ev.clear();
+    }
+};
+
+template <class F>
+static int challenger_grind(p3r_ctx* ctx, HostChallenger<F>& ch, uint32_t bits, uint32_t* witness) {
+    if (bits == 0) {
+        *witness = 0;
+        return P3R_OK;
+    }
+    TRY(grind_impl<F>(ctx, ch.st, ch.in, (uint32_t)ch.n_in, bits, witness));
+    ch.observe(*witness);
+    if (ch.sample_bits(bits) != 0) {
+        set_err(ctx, "grind: device witness rejected by host transcript");
+        return P3R_ERR_POW;
+    }
+    return P3R_OK;
+}
+
+template <class F>
+static int prove_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, const uint32_t* const* public_values,
+                      uint32_t* proof_out, size_t cap_words, size_t* n_words) {
+    p3r_session* s = nullptr;
+    TRY(prove_begin_impl<F>(ctx, prep, traces, public_values, &s));
+    struct Guard {
+        p3r_session* s;
+        ~Guard() { delete s; }
+    } guard{s};
+    PhaseTimer pt(ctx);
+    const size_t n_inst = prep->inst.size();
+    const size_t capw = (size_t)8 << ctx->fri.cap_height;
+    std::vector<uint32_t> blob;
+    auto put = [&](const uint32_t* p, size_t n) { blob.insert(blob.end(), p, p + n); };
+    HostChallenger<F> ch(&ctx->p2);
+
+    std::vector<uint32_t> main_cap(capw), perm_cap(capw), quot_cap(capw);
+    TRY(commit_main_impl<F>(s, main_cap.data()));
+    pt.mark("commit_main");
+    ch.observe_lifted((uint32_t)n_inst);
+    for (auto& d : prep->inst) {
+        ch.observe_lifted(d.log_h);
+        ch.observe_lifted(d.log_h);
+        ch.observe_lifted(d.main_w);
+        ch.observe_lifted(1u << d.log_qc);
+    }
+    ch.observe_words(main_cap.data(), capw);
+    for (size_t i = 0; i < n_inst; i++)
+        if (prep->inst[i].n_pub) ch.observe_words(public_values[i], prep->inst[i].n_pub);
+    for (auto& d : prep->inst) ch.observe_lifted(d.prep_w);
+    if (prep->has_prep) ch.observe_words(prep->prep_cap.data(), capw);
+
+    size_t n_perm_inst = 0;
+    for (auto& d : prep->inst) n_perm_inst += !d.lookups.empty();
+    std::vector<uint32_t> terminals(4 * std::max<size_t>(n_perm_inst, 1));
+    uint32_t pa[4] = {0, 0, 0, 0}, pb[4] = {0, 0, 0, 0};
+    if (prep->has_perm) {
+        ch.sample_ext(pa);
+        ch.sample_ext(pb);
+    }
+    TRY(commit_perm_impl<F>(s, pa, pb, perm_cap.data(), terminals.data()));
+    pt.mark("commit_perm");
+    if (prep->has_perm) {
+        ch.observe_words(perm_cap.data(), capw);
+        ch.observe_words(terminals.data(), 4 * n_perm_inst);
+    }
+    uint32_t alpha[4];
+    ch.sample_ext(alpha);
+    TRY(commit_quotient_impl<F>(s, alpha, quot_cap.data()));
+    pt.mark("commit_quotient");
+    ch.observe_words(quot_cap.data(), capw);
+    uint32_t zeta[4];
+    ch.sample_ext(zeta);
+
+    size_t n_open = 0;
+    {
+        size_t need = 0;
+        for (auto& d : prep->inst)
+            need += 4 * ((size_t)d.main_w * 2 + (size_t)d.prep_w * 2 + (size_t)d.aux_w() * 8 + ((size_t)4 << d.log_qc));
+        std::vector<uint32_t> tmp(need);
+        TRY(open_impl<F>(s, zeta, tmp.data(), tmp.size(), &n_open));
+    }
+    pt.mark("open");
+    // observe in round order [main, quotient, preprocessed, permutation] (recursion/src/generation.rs:474-485)
+    {
+        std::vector<Ext4> dummy;
+        // opened_host is per instance; rebuild round order from the refs (offsets into the device order = download order)
+        // Simpler: walk the per-instance blob with a cursor table.
+        std::vector<size_t> base(n_inst);
+        size_t cur = 0;
+        for (size_t i = 0; i < n_inst; i++) {
+            base[i] = cur;
+            const InstDev& d = prep->inst[i];
+            cur += 4 * ((size_t)d.main_w * (1 + (d.uses_next ? 1 : 0)) + (size_t)d.prep_w * 2 + (size_t)d.aux_w() * 8 +
+                        ((size_t)4 << d.log_qc));
+        }
+        const uint32_t* ov = s->opened_host.data();
+        for (size_t i = 0; i < n_inst; i++) {  // main: local (+ next)
+            const InstDev& d = prep->inst[i];
+            ch.observe_words(ov + base[i], 4 * (size_t)d.main_w * (1 + (d.uses_next ? 1 : 0)));
+        }
+        for (size_t i = 0; i < n_inst; i++) {  // quotient chunks
+            const InstDev& d = prep->inst[i];
+            size_t off = base[i] + 4 * ((size_t)d.main_w * (1 + (d.uses_next ? 1 : 0)) + (size_t)d.prep_w * 2 + (size_t)d.aux_w() * 8);
+            ch.observe_words(ov + off, 4 * ((size_t)4 << d.log_qc));
+        }
+        for (size_t i = 0; i < n_inst; i++) {  // preprocessed
+            const InstDev& d = prep->inst[i];
+            if (!d.prep_w) continue;
+            size_t off = base[i] + 4 * ((size_t)d.main_w * (1 + (d.uses_next ? 1 : 0)));
+            ch.observe_words(ov + off, 4 * (size_t)d.prep_w * 2);
+        }
+        for (size_t i = 0; i < n_inst; i++) {  // permutation
+            const InstDev& d = prep->inst[i];
+            if (d.lookups.empty()) continue;
+            size_t off = base[i] + 4 * ((size_t)d.main_w * (1 + (d.uses_next ? 1 : 0)) + (size_t)d.prep_w * 2);
+            ch.observe_words(ov + off, 4 * (size_t)d.aux_w() * 8);
+        }
+    }
+    uint32_t alpha_fri[4];
+    ch.sample_ext(alpha_fri);
+    uint32_t n_rounds = 0, log_arities[32];
+    TRY(fri_begin_impl<F>(s, alpha_fri, &n_rounds, log_arities));
+    pt.mark("fri_reduce");
+    std::vector<uint32_t> fri_caps(n_rounds * capw), commit_pow(n_rounds);
+    for (uint32_t r = 0; r < n_rounds; r++) {
+        TRY(fri_commit_impl<F>(s, r, fri_caps.data() + r * capw));
+        ch.observe_words(fri_caps.data() + r * capw, capw);
+        TRY(challenger_grind<F>(ctx, ch, ctx->fri.commit_pow_bits, &commit_pow[r]));
+        uint32_t beta[4];
+        ch.sample_ext(beta);
+        TRY(fri_fold_impl<F>(s, r, beta));
+    }
+    std::vector<uint32_t> final_poly((size_t)4 << ctx->fri.log_final_poly_len);
+    TRY(fri_final_poly_impl<F>(s, final_poly.data()));
+    pt.mark("fri_commit_phase");
+    ch.observe_words(final_poly.data(), final_poly.size());
+    for (uint32_t r = 0; r < n_rounds; r++) ch.observe(to_monty<F>(log_arities[r]));
+    uint32_t query_pow = 0;
+    TRY(challenger_grind<F>(ctx, ch, ctx->fri.query_pow_bits, &query_pow));
+    pt.mark("grind");
+    std::vector<uint32_t> indices(ctx->fri.num_queries);
+    for (auto& ix : indices) ix = ch.sample_bits(s->log_max);
+
+    uint32_t hdr[5] = {0x50335250u, (uint32_t)n_inst, (uint32_t)prep->has_perm, (uint32_t)prep->has_prep, (uint32_t)capw};
+    put(hdr, 5);
+    for (auto& d : prep->inst) blob.push_back(d.log_h);
+    put(main_cap.data(), capw);
+    if (prep->has_perm) put(perm_cap.data(), capw);
+    put(quot_cap.data(), capw);
+    if (prep->has_perm) put(terminals.data(), 4 * n_perm_inst);
+    put(s->opened_host.data(), s->opened_host.size());
+    blob.push_back(n_rounds);
+    put(log_arities, n_rounds);
+    put(fri_caps.data(), fri_caps.size());
+    put(commit_pow.data(), n_rounds);
+    put(final_poly.data(), final_poly.size());
+    blob.push_back(query_pow);
+    size_t head = blob.size();
+    size_t qwords = 0;
+    // query the size first with a zero-capacity call
+    {
+        int rc = fri_query_impl(s, indices.data(), (uint32_t)indices.size(), nullptr, 0, &qwords);
+        if (rc != P3R_ERR_BUFFER && rc != P3R_OK) return rc;
+    }
+    *n_words = head + qwords;
+    if (*n_words > cap_words) {
+        set_err(ctx, "prove: proof buffer too small");
+        return P3R_ERR_BUFFER;
+    }
+    std::memcpy(proof_out, blob.data(), head * 4);
+    TRY(fri_query_impl(s, indices.data(), (uint32_t)indices.size(), proof_out + head, cap_words - head, &qwords));
+    pt.mark("query");
+    pt.finish();
+    return P3R_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// isolated entry points
+// ------------------------------------------------------------------------------------------------
+template <class F>
+static int coset_lde_host_impl(p3r_ctx* ctx, const p3r_matrix_u32* in, uint32_t log_blowup, uint32_t* out) {
+    if (!is_pow2(in->height) || !in->width) {
+        set_err(ctx, "coset_lde: height must be a power of two");
+        return P3R_ERR_INVALID_ARG;
+    }
+    ctx->arena.reset();
+    ctx->pin_used = 0;
+    uint32_t log_n = ilog2(in->height);
+    size_t n = in->height, N = n << log_blowup, w = in->width;
+    uint32_t* rm = arena_alloc<uint32_t>(ctx, N * w);
+    uint32_t* cm = arena_alloc<uint32_t>(ctx, n * w);
+    uint32_t* coef = arena_alloc<uint32_t>(ctx, n * w);
+    uint32_t* lde = arena_alloc<uint32_t>(ctx, N * w);
+    uint32_t* tmp = log_n > TILE_LOG ? arena_alloc<uint32_t>(ctx, N * w) : nullptr;
+    if (!rm || !cm || !coef || !lde || (log_n > TILE_LOG && !tmp)) return P3R_ERR_OOM;
+    TRY(upload_matrix(ctx, *in, rm, cm));
+    TRY(coset_lde<F>(ctx, cm, lde, log_n, (uint32_t)w, log_blowup, true, 0, coef, tmp));
+    dim3 grid((unsigned)((w + 31) / 32), (unsigned)((N + 31) / 32)), block(32, 8);
+    k_transpose_out<<<grid, block, 0, ctx->stream>>>(lde, rm, (uint32_t)N, (uint32_t)w);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(out, rm, N * w * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return P3R_OK;
+}
+template <class F>
+static int mmcs_commit_host_impl(p3r_ctx* ctx, uint32_t n_mats, const p3r_matrix_u32* mats, uint32_t* cap_out) {
+    ctx->arena.reset();
+    ctx->pin_used = 0;
+    std::vector<MatRef> refs;
+    uint32_t lmax = 0;
+    for (uint32_t i = 0; i < n_mats; i++) {
+        if (!is_pow2(mats[i].height) || !mats[i].width) {
+            set_err(ctx, "mmcs_commit: heights must be powers of two");
+            return P3R_ERR_INVALID_ARG;
+        }
+        size_t words = (size_t)mats[i].height * mats[i].width;
+        uint32_t* rm = arena_alloc<uint32_t>(ctx, words);
+        uint32_t* cm = arena_alloc<uint32_t>(ctx, words);
+        if (!rm || !cm) return P3R_ERR_OOM;
+        TRY(upload_matrix(ctx, mats[i], rm, cm));
+        refs.push_back({cm, ilog2(mats[i].height), mats[i].width});
+        lmax = std::max(lmax, refs.back().log_h);
+    }
+    uint32_t* dg = arena_alloc<uint32_t>(ctx, tree_digest_words(lmax));
+    if (!dg) return P3R_ERR_OOM;
+    Tree t;
+    TRY(commit_tree<F>(ctx, refs, &t, dg));
+    return read_cap(ctx, t, cap_out);
+}
+template <class F>
+static int permute_host_impl(p3r_ctx* ctx, uint32_t* states, uint32_t n) {
+    ctx->arena.reset();
+    uint32_t* d = arena_alloc<uint32_t>(ctx, (size_t)n * 16);
+    if (!d) return P3R_ERR_OOM;
+    CUDA_TRY(cudaMemcpyAsync(d, states, (size_t)n * 64, cudaMemcpyHostToDevice, ctx->stream));
+    k_permute_states<F><<<(n + 127) / 128, 128, 0, ctx->stream>>>(d, n);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(states, d, (size_t)n * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return P3R_OK;
+}
+template <class F>
+static int bench_commit_impl(p3r_ctx* ctx, uint32_t log_height, uint32_t width, uint32_t iters, uint64_t seed, float* ms_out) {
+    ctx->arena.reset();
+    ctx->pin_used = 0;
+    const uint32_t lb = ctx->fri.log_blowup;
+    size_t n = (size_t)1 << log_height, N = n << lb, w = width;
+    uint32_t* cm = arena_alloc<uint32_t>(ctx, n * w);
+    uint32_t* coef = arena_alloc<uint32_t>(ctx, n * w);
+    uint32_t* lde = arena_alloc<uint32_t>(ctx, N * w);
+    uint32_t* tmp = log_height > TILE_LOG ? arena_alloc<uint32_t>(ctx, N * w) : nullptr;
+    uint32_t* dg = arena_alloc<uint32_t>(ctx, tree_digest_words(log_height + lb));
+    if (!cm || !coef || !lde || !dg || (log_height > TILE_LOG && !tmp)) return P3R_ERR_OOM;
+    k_fill_random<F><<<(unsigned)((n * w + 255) / 256), 256, 0, ctx->stream>>>(cm, n * w, seed);
+    LAUNCH_CHECK();
+    TRY(coset_lde<F>(ctx, cm, lde, log_height, width, lb, true, 0, coef, tmp));  // warm-up (tables, attributes)
+    cudaEvent_t e0, e1, e2;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventCreate(&e2);
+    float t_lde = 0, t_tree = 0;
+    for (uint32_t it = 0; it < iters; it++) {
+        size_t pin_mark = ctx->pin_used;
+        cudaEventRecord(e0, ctx->stream);
+        TRY(coset_lde<F>(ctx, cm, lde, log_height, width, lb, true, 0, coef, tmp));
+        cudaEventRecord(e1, ctx->stream);
+        Tree t;
+        TRY(commit_tree<F>(ctx, {{lde, log_height + lb, width}}, &t, dg));
+        cudaEventRecord(e2, ctx->stream);
+        CUDA_TRY(cudaEventSynchronize(e2));
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, e0, e1);
+        cudaEventElapsedTime(&b, e1, e2);
+        t_lde += a;
+        t_tree += b;
+        ctx->pin_used = pin_mark;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    ms_out[0] = t_lde / iters;
+    ms_out[1] = t_tree / iters;
+    ms_out[2] = 0;
+    return P3R_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+#define DISPATCH(ctx, call)                          \
+    ((ctx)->field_id == P3R_FIELD_KOALABEAR ? [&] {  \
+        using F = KoalaBear;                         \
+        return call;                                 \
+    }()                                              \
+                                            : [&] {  \
+                                                  using F = BabyBear; \
+                                                  return call;        \
+                                              }())
+
+static thread_local std::string g_noctx_err;
+
+extern "C" {
+
+uint32_t p3r_abi_version(void) { return 1; }
+const char* p3r_build_info(void) { return "libp3r_b200 sm_100a; fields: koala-bear, baby-bear; ext degree 4; poseidon2 width 16"; }
+
+int p3r_ctx_create(int device, const p3r_field_desc* field, const p3r_poseidon2_consts* p2, const p3r_fri_params* fri,
+                   p3r_ctx** out) {
+    if (!field || !p2 || !fri || !out) return P3R_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) {
+        g_noctx_err = "no usable CUDA device (this library has no CPU fallback)";
+        cudaGetLastError();
+        return P3R_ERR_CUDA;
+    }
+    uint32_t want_p = field->field_id == P3R_FIELD_KOALABEAR ? KoalaBear::P : BabyBear::P;
+    if (field->field_id > 1 || field->p != want_p) return P3R_ERR_UNSUPPORTED;
+    uint32_t rp = field->field_id == P3R_FIELD_KOALABEAR ? KoalaBear::ROUNDS_P : BabyBear::ROUNDS_P;
+    uint32_t sb = field->field_id == P3R_FIELD_KOALABEAR ? KoalaBear::SBOX : BabyBear::SBOX;
+    if (p2->width != 16 || p2->rounds_f != 8 || p2->rounds_p != rp || p2->sbox_degree != sb) return P3R_ERR_UNSUPPORTED;
+    if (fri->max_log_arity < 1 || fri->max_log_arity > 4 || fri->log_blowup < 1 || fri->log_final_poly_len > 6 ||
+        fri->query_pow_bits > 30 || fri->commit_pow_bits > 30)
+        return P3R_ERR_INVALID_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return P3R_ERR_CUDA;
+    auto* ctx = new p3r_ctx();
+    ctx->device = device;
+    ctx->field_id = (int)field->field_id;
+    ctx->field = *field;
+    ctx->fri = *fri;
+    std::memcpy(ctx->p2.ext_rc, p2->external_rc, 8 * 16 * 4);
+    std::memset(ctx->p2.int_rc, 0, sizeof ctx->p2.int_rc);
+    std::memcpy(ctx->p2.int_rc, p2->internal_rc, rp * 4);
+    std::memcpy(ctx->p2.diag, p2->internal_diag, 16 * 4);
+    if (ctx->field_id == 0) {
+        ctx->w_m = to_monty<KoalaBear>(field->w);
+        ctx->gen_m = to_monty<KoalaBear>(field->generator);
+        ctx->inv2_m = finv<KoalaBear>(to_monty<KoalaBear>(2));
+    } else {
+        ctx->w_m = to_monty<BabyBear>(field->w);
+        ctx->gen_m = to_monty<BabyBear>(field->generator);
+        ctx->inv2_m = finv<BabyBear>(to_monty<BabyBear>(2));
+    }
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ctx->pin_size = ctx->dstage_size = (size_t)8 << 20;
+    ok = ok && cudaHostAlloc((void**)&ctx->pin, ctx->pin_size, cudaHostAllocDefault) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&ctx->dstage, ctx->dstage_size) == cudaSuccess;
+    ok = ok && cudaMemcpyToSymbol(c_p2, &ctx->p2, sizeof(Poseidon2Consts), (size_t)ctx->field_id * sizeof(Poseidon2Consts)) ==
+                   cudaSuccess;
+    if (!ok) {
+        g_noctx_err = std::string("ctx_create: ") + cudaGetErrorString(cudaGetLastError());
+        delete ctx;
+        return P3R_ERR_CUDA;
+    }
+    *out = ctx;
+    return P3R_OK;
+}
+void p3r_ctx_destroy(p3r_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->arena.destroy();
+    for (auto& kv : ctx->gtables) {
+        cudaFree(kv.second.lo);
+        cudaFree(kv.second.hi);
+    }
+    if (ctx->tw) cudaFree(ctx->tw);
+    if (ctx->pin) cudaFreeHost(ctx->pin);
+    if (ctx->dstage) cudaFree(ctx->dstage);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+const char* p3r_last_error(const p3r_ctx* ctx) { return ctx ? ctx->err.c_str() : g_noctx_err.c_str(); }
+
+int p3r_prep_commit(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_desc* descs, const p3r_matrix_u32* prep, p3r_prep** out,
+                    uint32_t* cap_out, uint32_t* has_prep_out) {
+    if (!ctx || !descs || !out || n_inst == 0) return P3R_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    return DISPATCH(ctx, prep_commit_impl<F>(ctx, n_inst, descs, prep, out, cap_out, has_prep_out));
+}
+void p3r_prep_free(p3r_prep* prep) {
+    if (!prep) return;
+    cudaSetDevice(prep->ctx->device);
+    cudaStreamSynchronize(prep->ctx->stream);
+    for (void* p : prep->owned) cudaFree(p);
+    delete prep;
+}
+int p3r_prove_begin(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, const uint32_t* const* public_values,
+                    p3r_session** out) {
+    if (!ctx || !prep || !traces || !out) return P3R_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    return DISPATCH(ctx, prove_begin_impl<F>(ctx, prep, traces, public_values, out));
+}
+int p3r_commit_main(p3r_session* s, uint32_t* cap_out) {
+    if (!s || !cap_out) return P3R_ERR_INVALID_ARG;
+    return DISPATCH(s->ctx, commit_main_impl<F>(s, cap_out));
+}
+int p3r_commit_perm(p3r_session* s, const uint32_t alpha[4], const uint32_t beta[4], uint32_t* cap_out, uint32_t* terminals_out) {
+    if (!s) return P3R_ERR_INVALID_ARG;
+    return DISPATCH(s->ctx, commit_perm_impl<F>(s, alpha, beta, cap_out, terminals_out));
+}
+int p3r_commit_quotient(p3r_session* s, const uint32_t alpha[4], uint32_t* cap_out) {
+    if (!s || !cap_out) return P3R_ERR_INVALID_ARG;
+    return DISPATCH(s->ctx, commit_quotient_impl<F>(s, alpha, cap_out));
+}
+int p3r_open(p3r_session* s, const uint32_t zeta[4], uint32_t* opened_out, size_t cap_words, size_t* n_words) {
+    if (!s || !n_words) return P3R_ERR_INVALID_ARG;
+    return DISPATCH(s->ctx, open_impl<F>(s, zeta, opened_out, cap_words, n_words));
+}
+int p3r_fri_begin(p3r_session* s, const uint32_t alpha_fri[4], uint32_t* n_rounds_out, uint32_t* log_arities_out) {
+    if (!s || !n_rounds_out || !log_arities_out) return P3R_ERR_INVALID_ARG;
+    return DISPATCH(s->ctx, fri_begin_impl<F>(s, alpha_fri, n_rounds_out, log_arities_out));
+}
+int p3r_fri_commit(p3r_session* s, uint32_t round, uint32_t* cap_out) {
+    if (!s || !cap_out) return P3R_ERR_INVALID_ARG;
+    return DISPATCH(s->ctx, fri_commit_impl<F>(s, round, cap_out));
+}
+int p3r_fri_fold(p3r_session* s, uint32_t round, const uint32_t beta[4]) {
+    if (!s) return P3R_ERR_INVALID_ARG;
+    return DISPATCH(s->ctx, fri_fold_impl<F>(s, round, beta));
+}
+int p3r_fri_final_poly(p3r_session* s, uint32_t* coeffs_out) {
+    if (!s || !coeffs_out) return P3R_ERR_INVALID_ARG;
+    return DISPATCH(s->ctx, fri_final_poly_impl<F>(s, coeffs_out));
+}
+int p3r_fri_query(p3r_session* s, const uint32_t* indices, uint32_t n, uint32_t* out, size_t cap_words, size_t* n_words) {
+    if (!s || !indices || !n_words) return P3R_ERR_INVALID_ARG;
+    return fri_query_impl(s, indices, n, out, cap_words, n_words);
+}
+void p3r_session_free(p3r_session* s) {
+    if (!s) return;
+    cudaStreamSynchronize(s->ctx->stream);
+    delete s;
+}
+int p3r_grind(p3r_ctx* ctx, const uint32_t state[16], const uint32_t* pending, uint32_t n_pending, uint32_t bits,
+              uint32_t* witness_out) {
+    if (!ctx || !state || !witness_out) return P3R_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    return DISPATCH(ctx, grind_impl<F>(ctx, state, pending, n_pending, bits, witness_out));
+}
+int p3r_prove(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, const uint32_t* const* public_values,
+              uint32_t* proof_out, size_t cap_words, size_t* n_words) {
+    if (!ctx || !prep || !traces || !n_words) return P3R_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    return DISPATCH(ctx, prove_impl<F>(ctx, prep, traces, public_values, proof_out, cap_words, n_words));
+}
+int p3r_coset_lde(p3r_ctx* ctx, const p3r_matrix_u32* in, uint32_t log_blowup, uint32_t* out) {
+    if (!ctx || !in || !out) return P3R_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    return DISPATCH(ctx, coset_lde_host_impl<F>(ctx, in, log_blowup, out));
+}
+int p3r_mmcs_commit(p3r_ctx* ctx, uint32_t n_mats, const p3r_matrix_u32* mats, uint32_t* cap_out) {
+    if (!ctx || !mats || !cap_out || !n_mats) return P3R_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    return DISPATCH(ctx, mmcs_commit_host_impl<F>(ctx, n_mats, mats, cap_out));
+}
+int p3r_poseidon2_permute(p3r_ctx* ctx, uint32_t* states, uint32_t n) {
+    if (!ctx || !states) return P3R_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    return DISPATCH(ctx, permute_host_impl<F>(ctx, states, n));
+}
+int p3r_bench_commit(p3r_ctx* ctx, uint32_t log_height, uint32_t width, uint32_t iters, uint64_t seed, float* times_ms_out) {
+    if (!ctx || !times_ms_out || !iters) return P3R_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    return DISPATCH(ctx, bench_commit_impl<F>(ctx, log_height, width, iters, seed, times_ms_out));
+}
+int p3r_last_phase_times(p3r_ctx* ctx, const char** names_out, float* ms_out, uint32_t cap, uint32_t* n_out) {
+    if (!ctx || !n_out) return P3R_ERR_INVALID_ARG;
+    ctx->phase_names_blob.clear();
+    uint32_t n = 0;
+    for (auto& kv : ctx->phase_times) {
+        if (n < cap && ms_out) ms_out[n] = kv.second;
+        ctx->phase_names_blob += kv.first;
+        ctx->phase_names_blob.push_back('\0');
+        n++;
+    }
+    ctx->phase_names_blob.push_back('\0');
+    if (names_out) *names_out = ctx->phase_names_blob.c_str();
+    *n_out = n;
+    return P3R_OK;
+}
+uint64_t p3r_launch_count(const p3r_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

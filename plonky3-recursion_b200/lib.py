@@ -1,0 +1,216 @@
+"""ctypes binding of libp3r_b200.so (include/p3r.h) — the product path. Fails loudly when the CUDA library or a GPU is
+missing; there is no CPU fallback and nothing here touches oracle/.
+
+Host-side mirror of the reference interface for this path:
+  `ProverData.from_airs_and_degrees`  <->  ProverData::from_airs_and_degrees (/root/reference recursion/src/recursion.rs:376)
+  `BatchStarkProver.prove_all_tables` <->  BatchStarkProver::prove_all_tables (circuit-prover/src/batch_stark_prover.rs:1203-1222)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import abi
+from .field import get_field
+from .poseidon2_params import Poseidon2Params
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libp3r_b200.so")
+
+DEFAULT_FRI = dict(log_blowup=2, log_final_poly_len=5, max_log_arity=2, num_queries=54, commit_pow_bits=0,
+                   query_pow_bits=15, cap_height=0)  # /root/reference recursion/examples/recursive_fibonacci.rs:71-132
+
+
+class P3RError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"p3r error {code}: {msg}")
+        self.code = code
+
+
+def build(force: bool = False) -> str:
+    """Compile csrc/ for sm_100a into libp3r_b200.so (in-tree)."""
+    srcs = [os.path.join(_HERE, "csrc", f) for f in ("p3r.cu", "kernels.cuh", "field.cuh", "poseidon2.cuh")]
+    srcs.append(os.path.join(_HERE, "..", "include", "p3r.h"))
+    stale = not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc"), "-s"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise P3RError(-1, f"{_LIB_PATH} not built: run __graft_entry__.build() (no CPU fallback exists)")
+        lib = C.CDLL(_LIB_PATH)
+        lib.p3r_last_error.restype = C.c_char_p
+        lib.p3r_last_error.argtypes = [C.c_void_p]
+        lib.p3r_build_info.restype = C.c_char_p
+        lib.p3r_launch_count.restype = C.c_uint64
+        lib.p3r_launch_count.argtypes = [C.c_void_p]
+        lib.p3r_abi_version.restype = C.c_uint32
+        for name in ("p3r_ctx_destroy", "p3r_prep_free", "p3r_session_free"):
+            getattr(lib, name).restype = None
+            getattr(lib, name).argtypes = [C.c_void_p]
+        _lib = lib
+    return _lib
+
+
+EXPORTS = ["p3r_abi_version", "p3r_build_info", "p3r_ctx_create", "p3r_ctx_destroy", "p3r_last_error", "p3r_prep_commit",
+           "p3r_prep_free", "p3r_prove_begin", "p3r_commit_main", "p3r_commit_perm", "p3r_commit_quotient", "p3r_open",
+           "p3r_fri_begin", "p3r_fri_commit", "p3r_fri_fold", "p3r_fri_final_poly", "p3r_fri_query", "p3r_session_free",
+           "p3r_grind", "p3r_prove", "p3r_coset_lde", "p3r_mmcs_commit", "p3r_poseidon2_permute", "p3r_bench_commit",
+           "p3r_last_phase_times", "p3r_launch_count"]
+
+
+class Context:
+    """p3r_ctx: one prover context on one CUDA device (replaces building StarkConfig/MyPcs,
+    recursion/examples/common/mod.rs:464-486)."""
+
+    def __init__(self, field="koala-bear", fri: dict | None = None, device: int = 0, poseidon2: Poseidon2Params | None = None):
+        self.lib = load()
+        self.field = get_field(field)
+        self.fri = dict(DEFAULT_FRI if fri is None else fri)
+        self.p2 = poseidon2 or Poseidon2Params(self.field.field_id)
+        self._m = abi.Marshal(self.field)
+        fd, pc, fp = self._m.field_desc(), self._m.poseidon2(self.p2), self._m.fri(self.fri)
+        h = C.c_void_p()
+        rc = self.lib.p3r_ctx_create(device, C.byref(fd), C.byref(pc), C.byref(fp), C.byref(h))
+        if rc != 0:
+            raise P3RError(rc, self.lib.p3r_last_error(None).decode() or "p3r_ctx_create failed")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.p3r_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise P3RError(rc, self.lib.p3r_last_error(self.h).decode())
+
+    @property
+    def cap_words(self):
+        return 8 << self.fri["cap_height"]
+
+    def launch_count(self) -> int:
+        return int(self.lib.p3r_launch_count(self.h))
+
+    # ---- isolated kernels -------------------------------------------------------------------------
+    def poseidon2_permute(self, states_canonical: np.ndarray) -> np.ndarray:
+        s = np.ascontiguousarray(self.field.to_monty(states_canonical).reshape(-1, 16))
+        self._check(self.lib.p3r_poseidon2_permute(self.h, abi.as_u32p(s), s.shape[0]))
+        return self.field.from_monty(s)
+
+    def coset_lde(self, mat_canonical: np.ndarray, log_blowup: int) -> np.ndarray:
+        m = abi.Marshal(self.field)
+        mm = m.matrix(mat_canonical)
+        out = np.zeros((mat_canonical.shape[0] << log_blowup, mat_canonical.shape[1]), dtype=np.uint32)
+        self._check(self.lib.p3r_coset_lde(self.h, C.byref(mm), log_blowup, abi.as_u32p(out)))
+        return self.field.from_monty(out)
+
+    def mmcs_commit(self, mats_canonical) -> np.ndarray:
+        m = abi.Marshal(self.field)
+        arr = m.matrices(mats_canonical)
+        cap = np.zeros(self.cap_words, dtype=np.uint32)
+        self._check(self.lib.p3r_mmcs_commit(self.h, len(mats_canonical), arr, abi.as_u32p(cap)))
+        return cap
+
+    def grind(self, state_monty, pending_monty, bits) -> int:
+        st = np.ascontiguousarray(state_monty, dtype=np.uint32)
+        pe = np.ascontiguousarray(pending_monty, dtype=np.uint32)
+        w = C.c_uint32(0)
+        self._check(self.lib.p3r_grind(self.h, abi.as_u32p(st), abi.as_u32p(pe) if pe.size else None, pe.size, bits, C.byref(w)))
+        return w.value
+
+    def bench_commit(self, log_height: int, width: int, iters: int = 5, seed: int = 0xB200):
+        t = (C.c_float * 3)()
+        self._check(self.lib.p3r_bench_commit(self.h, log_height, width, iters, C.c_uint64(seed), t))
+        return {"lde_ms": t[0], "merkle_ms": t[1]}
+
+    def last_phase_times(self) -> dict:
+        names = C.c_char_p()
+        ms = (C.c_float * 32)()
+        n = C.c_uint32(0)
+        self._check(self.lib.p3r_last_phase_times(self.h, C.byref(names), ms, 32, C.byref(n)))
+        raw = C.string_at(names, 1024).split(b"\0")
+        return {raw[i].decode(): float(ms[i]) for i in range(n.value)}
+
+
+class ProverData:
+    """Device-resident preprocessed commitment + compiled AIR programs for one circuit shape
+    (p3r_prep; ProverData::from_airs_and_degrees)."""
+
+    def __init__(self, ctx: Context, insts, prep_mats, handle, cap, has_prep):
+        self.ctx, self.insts, self.prep_mats, self.h = ctx, insts, prep_mats, handle
+        self.preprocessed_commitment = cap if has_prep else None  # Montgomery words
+
+    @classmethod
+    def from_airs_and_degrees(cls, ctx: Context, insts, prep_mats):
+        """insts: list[air.AirInstance]; prep_mats: list of canonical (h, w) uint32 arrays or None per instance."""
+        m = abi.Marshal(ctx.field)
+        descs = m.instances(insts)
+        pm = m.matrices(prep_mats)
+        cap = np.zeros(ctx.cap_words, dtype=np.uint32)
+        has_prep = C.c_uint32(0)
+        h = C.c_void_p()
+        ctx._check(ctx.lib.p3r_prep_commit(ctx.h, len(insts), descs, pm, C.byref(h), abi.as_u32p(cap), C.byref(has_prep)))
+        return cls(ctx, insts, prep_mats, h, cap, bool(has_prep.value))
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.p3r_prep_free(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class TraceBatch:
+    """Traces marshalled once (Montgomery, row-major) so repeated proofs do not pay the numpy conversion."""
+
+    def __init__(self, ctx: Context, traces, pubs):
+        self.m = abi.Marshal(ctx.field)
+        self.tm = self.m.matrices(traces)
+        self.pv = self.m.public_values(pubs)
+        self.h2d_bytes = int(sum(int(t.size) * 4 for t in traces))
+
+
+class BatchStarkProver:
+    """Mirror of BatchStarkProver<SC> (circuit-prover/src/batch_stark_prover.rs:685-697)."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self._buf = np.zeros(1 << 22, dtype=np.uint32)
+
+    def prove_all_tables(self, traces, prover_data: ProverData, public_values=None) -> np.ndarray:
+        """traces: list of canonical (h, w) uint32 matrices in instance order, or a TraceBatch.
+        Returns the flat proof blob (DESIGN.md "Proof blob")."""
+        ctx = self.ctx
+        if not isinstance(traces, TraceBatch):
+            pubs = public_values if public_values is not None else [None] * len(traces)
+            traces = TraceBatch(ctx, traces, pubs)
+        n = C.c_size_t(0)
+        rc = ctx.lib.p3r_prove(ctx.h, prover_data.h, traces.tm, traces.pv, abi.as_u32p(self._buf), C.c_size_t(self._buf.size),
+                               C.byref(n))
+        if rc == 6 and n.value > self._buf.size:  # P3R_ERR_BUFFER: grow once
+            self._buf = np.zeros(n.value, dtype=np.uint32)
+            rc = ctx.lib.p3r_prove(ctx.h, prover_data.h, traces.tm, traces.pv, abi.as_u32p(self._buf),
+                                   C.c_size_t(self._buf.size), C.byref(n))
+        ctx._check(rc)
+        return self._buf[: n.value].copy()
