@@ -17,11 +17,14 @@ def widths(d: int, lanes: int = 1):
     return lanes * d, lanes * PREP_LANE_WIDTH
 
 
-def make_eval(d: int, lanes: int = 1):
+def make_eval(d: int, lanes: int = 1, idx_first: bool = False):
+    """idx_first=False: [multiplicity, witness_idx] (Const/Public, column_layout.rs); idx_first=True: [output_idx, out_mult]
+    (RecomposeAir without coefficient lookups, circuit-prover/src/air/recompose_air.rs:150-175)."""
+
     def eval_air(b):
         for lane in range(lanes):
-            mult = b.prep(lane * PREP_LANE_WIDTH + 0)
-            idx = b.prep(lane * PREP_LANE_WIDTH + 1)
+            mult = b.prep(lane * PREP_LANE_WIDTH + (1 if idx_first else 0))
+            idx = b.prep(lane * PREP_LANE_WIDTH + (0 if idx_first else 1))
             fields = [idx] + [b.main(lane * d + j) for j in range(d)]
             b.push_interaction("WitnessChecks", fields, mult)
 
@@ -41,7 +44,7 @@ def trace_to_matrix(values: np.ndarray, d: int, lanes: int, min_height: int) -> 
     return out
 
 
-def preprocessed_matrix(mults: np.ndarray, idxs: np.ndarray, lanes: int, min_height: int) -> np.ndarray:
+def preprocessed_matrix(mults: np.ndarray, idxs: np.ndarray, lanes: int, min_height: int, idx_first: bool = False) -> np.ndarray:
     """Per op (multiplicity, D-scaled witness index), canonical; padding rows have multiplicity 0
     (circuit-prover/src/common.rs:226-287)."""
     mults = np.asarray(mults, dtype=np.uint32)
@@ -51,6 +54,6 @@ def preprocessed_matrix(mults: np.ndarray, idxs: np.ndarray, lanes: int, min_hei
     height = max(min_height, 1 << max(rows - 1, 0).bit_length())
     out = np.zeros((height, lanes * PREP_LANE_WIDTH), dtype=np.uint32)
     flat = out.reshape(height * lanes, PREP_LANE_WIDTH)
-    flat[:num_ops, 0] = mults
-    flat[:num_ops, 1] = idxs
+    flat[:num_ops, 1 if idx_first else 0] = mults
+    flat[:num_ops, 0 if idx_first else 1] = idxs
     return out
