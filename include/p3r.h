@@ -34,6 +34,7 @@ extern "C" {
 typedef struct p3r_ctx p3r_ctx;
 typedef struct p3r_prep p3r_prep;
 typedef struct p3r_session p3r_session;
+typedef struct p3r_traces p3r_traces;
 
 typedef enum {
     P3R_OK = 0,
@@ -245,6 +246,17 @@ int p3r_grind(p3r_ctx* ctx, const uint32_t state[16], const uint32_t* pending, u
 int p3r_prove(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces,
               const uint32_t* const* public_values, uint32_t* proof_out, size_t cap_words, size_t* n_words);
 
+/* Device-resident traces: upload (and transpose to the column-major device layout) once, prove many times. This is the
+ * path a caller uses when the trace builders already ran on the device or when the same traces are proved repeatedly;
+ * bench.py uses it for the device-resident `value` next to the host-buffer `e2e` number. */
+int p3r_traces_upload(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, p3r_traces** out);
+void p3r_traces_free(p3r_traces* t);
+int p3r_prove_resident(p3r_ctx* ctx, const p3r_prep* prep, const p3r_traces* traces, const uint32_t* const* public_values,
+                       uint32_t* proof_out, size_t cap_words, size_t* n_words);
+/* Pinned host memory for trace/proof buffers (cudaHostAlloc); plain malloc'd buffers also work, just slower to copy. */
+void* p3r_host_alloc(size_t bytes);
+void p3r_host_free(void* p);
+
 /* ---- isolated kernels (LDE + Merkle + FRI-fold sweep). Host pointers. ---- */
 /* Coset LDE of a row-major height x width matrix -> row-major (height<<log_blowup) x width, rows bit-reversed
  * (TwoAdicFriPcs::commit -> Radix2DitParallel::coset_lde_batch, circuit-prover/src/config.rs:17,131). */
@@ -261,6 +273,19 @@ int p3r_bench_commit(p3r_ctx* ctx, uint32_t log_height, uint32_t width, uint32_t
 /* Per-session device timings (CUDA events on the session stream) of the last one-shot p3r_prove:
  * names_out receives a pointer to a static NUL-separated list; ms_out up to cap entries. */
 int p3r_last_phase_times(p3r_ctx* ctx, const char** names_out, float* ms_out, uint32_t cap, uint32_t* n_out);
+/* CUDA-event stopwatch on the ctx stream (the stream every kernel of this ctx is launched on): start synchronises the
+ * stream and records; stop records, synchronises and returns the elapsed device milliseconds. */
+int p3r_timer_start(p3r_ctx* ctx);
+int p3r_timer_stop(p3r_ctx* ctx, float* ms_out);
+
+/* Per-kernel-class device timing. p3r_set_kernel_timing enables CUDA-event pairs (on the ctx stream) around every launch
+ * group of the classes in `class_mask` (bit k = class k); p3r_kernel_stats returns, per class, the accumulated milliseconds
+ * (only for enabled classes), launch counts and ALGORITHMIC bytes (DESIGN.md "Kernels") since the last reset.
+ * Classes: 0 ntt_lde, 1 hash_rows, 2 compress, 3 logup, 4 quotient, 5 open, 6 reduced_openings, 7 fri_fold, 8 transpose, 9 misc. */
+int p3r_set_kernel_timing(p3r_ctx* ctx, uint32_t class_mask);
+int p3r_reset_kernel_stats(p3r_ctx* ctx);
+int p3r_kernel_stats(p3r_ctx* ctx, const char** names_out, double* ms_out, uint64_t* launches_out, uint64_t* bytes_out,
+                     uint32_t cap, uint32_t* n_out);
 /* Number of kernel launches issued by this ctx since creation (for bench.py's gpu_launches). */
 uint64_t p3r_launch_count(const p3r_ctx* ctx);
 

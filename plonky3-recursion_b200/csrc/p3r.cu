@@ -66,7 +66,22 @@ struct GTable {
     uint32_t *lo = nullptr, *hi = nullptr;
 };
 
+enum KClass { KC_NTT = 0, KC_HASH, KC_COMPRESS, KC_LOGUP, KC_QUOTIENT, KC_OPEN, KC_REDUCE, KC_FOLD, KC_TRANSPOSE, KC_MISC, KC_COUNT };
+static const char* const KCLASS_NAMES[KC_COUNT] = {"ntt_lde", "hash_rows", "compress", "logup", "quotient", "open", "reduced_openings",
+                                                   "fri_fold", "transpose", "misc"};
+struct KernelStats {
+    double ms[KC_COUNT] = {0};
+    uint64_t launches[KC_COUNT] = {0};
+    uint64_t bytes[KC_COUNT] = {0};  // algorithmic bytes (DESIGN.md "Kernels")
+};
+
 struct p3r_ctx {
+    cudaEvent_t timer_ev[2] = {nullptr, nullptr};
+    uint32_t time_mask = 0;  // bit per KClass: record CUDA events around launches of that class
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    std::vector<std::pair<int, size_t>> ev_pending;  // (class, index of start event)
+    KernelStats kstats;
     int device = 0;
     int field_id = 0;
     p3r_field_desc field{};
@@ -93,6 +108,11 @@ static void set_err(p3r_ctx* ctx, const std::string& s) {
 }
 static void set_err(const p3r_ctx* ctx, const std::string& s) { set_err(const_cast<p3r_ctx*>(ctx), s); }
 
+#define LAUNCH_CHECK_C(cls)                                              \
+    do {                                                                 \
+        ctx->kstats.launches[cls]++;                                     \
+        LAUNCH_CHECK();                                                  \
+    } while (0)
 #define LAUNCH_CHECK()                                                   \
     do {                                                                 \
         ctx->launches++;                                                 \
@@ -102,6 +122,42 @@ static void set_err(const p3r_ctx* ctx, const std::string& s) { set_err(const_ca
             return P3R_ERR_CUDA;                                         \
         }                                                                \
     } while (0)
+
+// Scoped CUDA-event pair around the launches issued while it is alive (only when the class is enabled in time_mask).
+struct KT {
+    p3r_ctx* ctx;
+    int cls;
+    bool on;
+    KT(p3r_ctx* c, int k, uint64_t algo_bytes = 0) : ctx(c), cls(k) {
+        ctx->kstats.bytes[k] += algo_bytes;
+        on = (ctx->time_mask >> k) & 1u;
+        if (!on) return;
+        if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
+            for (int i = 0; i < 256; i++) {
+                cudaEvent_t e;
+                cudaEventCreate(&e);
+                ctx->ev_pool.push_back(e);
+            }
+        }
+        ctx->ev_pending.push_back({k, ctx->ev_used});
+        cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream);
+        ctx->ev_used += 2;
+    }
+    ~KT() {
+        if (on) cudaEventRecord(ctx->ev_pool[ctx->ev_pending.back().second + 1], ctx->stream);
+    }
+};
+static void kstats_collect(p3r_ctx* ctx) {
+    if (ctx->ev_pending.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& pr : ctx->ev_pending) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev_pool[pr.second], ctx->ev_pool[pr.second + 1]);
+        ctx->kstats.ms[pr.first] += ms;
+    }
+    ctx->ev_pending.clear();
+    ctx->ev_used = 0;
+}
 
 template <class T>
 static T* arena_alloc(p3r_ctx* ctx, size_t count) {
@@ -162,6 +218,11 @@ struct p3r_prep {
     bool has_prep = false, has_perm = false;
     uint32_t max_msg_w = 1, n_buses = 0;
     std::vector<uint32_t> prep_cap;  // host copy, Montgomery
+};
+
+struct p3r_traces {  // device-resident column-major copies of one layer's traces
+    p3r_ctx* ctx = nullptr;
+    std::vector<uint32_t*> d;
 };
 
 enum Phase { PH_BEGIN = 0, PH_MAIN, PH_PERM, PH_QUOT, PH_OPEN, PH_FRI };
@@ -354,7 +415,7 @@ static int launch_pass(p3r_ctx* ctx, NttPass a, uint32_t n_cols, uint32_t n_cose
     uint32_t tiles = (1u << a.log_n) / (R * CW);
     dim3 grid(tiles, n_cols, n_cosets);
     k_ntt_pass<F><<<grid, 256, smem, ctx->stream>>>(a);
-    LAUNCH_CHECK();
+    LAUNCH_CHECK_C(KC_NTT);
     return P3R_OK;
 }
 template <class F>
@@ -366,6 +427,7 @@ static int coset_lde(p3r_ctx* ctx, const uint32_t* src, uint32_t* dst, uint32_t 
     GTable gt;
     TRY(get_gtable<F>(ctx, log_n, &gt));
     size_t n = (size_t)1 << log_n, N = (size_t)1 << logN;
+    KT kt(ctx, KC_NTT, 4ull * (n + N) * w);  // algorithmic bytes: read the trace once, write the LDE once
     auto plan = plan_passes(log_n);
     NttPass a{};
     a.log_n = log_n;
@@ -441,8 +503,12 @@ static int commit_tree(p3r_ctx* ctx, const std::vector<MatRef>& mats, Tree* t, u
         return P3R_ERR_OOM;
     }
     uint32_t rows = 1u << lmax;
-    k_hash_rows<F><<<(rows + 127) / 128, 128, 0, ctx->stream>>>(d_cols, (uint32_t)top.size(), rows, digests);
-    LAUNCH_CHECK();
+    {
+        KT kt(ctx, KC_HASH, (uint64_t)rows * (4ull * top.size() + 32));
+        k_hash_rows<F><<<(rows + 127) / 128, 128, 0, ctx->stream>>>(d_cols, (uint32_t)top.size(), rows, digests);
+        LAUNCH_CHECK_C(KC_HASH);
+    }
+    KT kt_tree(ctx, KC_COMPRESS, 96ull * rows);
     for (uint32_t l = 1; lmax - l + 1 > cap; l++) {
         uint32_t n_next = 1u << (lmax - l);
         auto inj = cols_at(lmax - l);
@@ -457,7 +523,8 @@ static int commit_tree(p3r_ctx* ctx, const std::vector<MatRef>& mats, Tree* t, u
         k_compress<F><<<(n_next + 127) / 128, 128, 0, ctx->stream>>>(digests + t->level_off(l - 1) * 8,
                                                                       digests + t->level_off(l) * 8, n_next, d_inj,
                                                                       (uint32_t)inj.size());
-        LAUNCH_CHECK();
+        ctx->kstats.bytes[KC_COMPRESS] += 4ull * inj.size() * n_next;
+        LAUNCH_CHECK_C(KC_COMPRESS);
     }
     return P3R_OK;
 }
@@ -477,8 +544,11 @@ static int upload_matrix(p3r_ctx* ctx, const p3r_matrix_u32& m, uint32_t* d_rowm
     if (!words) return P3R_OK;
     CUDA_TRY(cudaMemcpyAsync(d_rowmajor_scratch, m.data, words * 4, cudaMemcpyHostToDevice, ctx->stream));
     dim3 grid((m.width + 31) / 32, (m.height + 31) / 32), block(32, 8);
-    k_transpose_in<<<grid, block, 0, ctx->stream>>>(d_rowmajor_scratch, d_colmajor, m.height, m.width);
-    LAUNCH_CHECK();
+    {
+        KT kt(ctx, KC_TRANSPOSE, 8ull * words);
+        k_transpose_in<<<grid, block, 0, ctx->stream>>>(d_rowmajor_scratch, d_colmajor, m.height, m.width);
+        LAUNCH_CHECK_C(KC_TRANSPOSE);
+    }
     return P3R_OK;
 }
 
@@ -622,7 +692,7 @@ static int prep_commit_impl(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_de
 // ------------------------------------------------------------------------------------------------
 template <class F>
 static int prove_begin_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces,
-                            const uint32_t* const* public_values, p3r_session** out) {
+                            const uint32_t* const* public_values, p3r_session** out, const p3r_traces* resident = nullptr) {
     ctx->arena.reset();
     ctx->pin_used = 0;
     auto* s = new p3r_session();
@@ -640,7 +710,7 @@ static int prove_begin_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix
     size_t max_rm = 0, max_coef = 0, max_tmp = 0;
     for (size_t i = 0; i < n_inst; i++) {
         const InstDev& d = prep->inst[i];
-        if (traces[i].height != (1u << d.log_h) || traces[i].width != d.main_w || !traces[i].data) {
+        if (!resident && (traces[i].height != (1u << d.log_h) || traces[i].width != d.main_w || !traces[i].data)) {
             set_err(ctx, "trace shape mismatch for instance " + std::to_string(i));
             delete s;
             return P3R_ERR_INVALID_ARG;
@@ -662,17 +732,19 @@ static int prove_begin_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix
     for (size_t i = 0; i < n_inst; i++) {
         const InstDev& d = prep->inst[i];
         size_t n = (size_t)1 << d.log_h;
-        s->trace[i] = arena_alloc<uint32_t>(ctx, n * d.main_w);
+        s->trace[i] = resident ? resident->d[i] : arena_alloc<uint32_t>(ctx, n * d.main_w);
         s->main_lde[i] = arena_alloc<uint32_t>(ctx, (n << lb) * d.main_w);
         if (!s->trace[i] || !s->main_lde[i]) {
             set_err(ctx, "device allocation failed");
             delete s;
             return P3R_ERR_OOM;
         }
-        int rc = upload_matrix(ctx, traces[i], rm, s->trace[i]);
-        if (rc) {
-            delete s;
-            return rc;
+        if (!resident) {
+            int rc = upload_matrix(ctx, traces[i], rm, s->trace[i]);
+            if (rc) {
+                delete s;
+                return rc;
+            }
         }
         if (d.n_pub) {
             s->d_pub[i] = (uint32_t*)upload_small(ctx, public_values[i], (size_t)d.n_pub * 4);
@@ -778,10 +850,13 @@ static int commit_perm_impl(p3r_session* s, const uint32_t alpha[4], const uint3
         la.perm = s->perm[i];
         la.rowsum = rowsum;
         la.wnr = wnr;
-        k_logup_rows<F><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(la);
-        LAUNCH_CHECK();
-        k_logup_scan<F><<<1, 1024, 0, ctx->stream>>>(rowsum, d.log_h, s->perm[i], s->d_terminals + i);
-        LAUNCH_CHECK();
+        {
+            KT kt(ctx, KC_LOGUP, (uint64_t)n * 4 * (d.main_w + d.prep_w + pw));
+            k_logup_rows<F><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(la);
+            LAUNCH_CHECK_C(KC_LOGUP);
+            k_logup_scan<F><<<1, 1024, 0, ctx->stream>>>(rowsum, d.log_h, s->perm[i], s->d_terminals + i);
+            LAUNCH_CHECK_C(KC_LOGUP);
+        }
         TRY(coset_lde<F>(ctx, s->perm[i], s->perm_lde[i], d.log_h, pw, lb, true, 0, s->scratch_coef, s->scratch_tmp));
         mats.push_back({s->perm_lde[i], d.log_h + lb, pw});
         lmax = std::max(lmax, d.log_h + lb);
@@ -845,8 +920,11 @@ static int commit_quotient_impl(p3r_session* s, const uint32_t alpha[4], uint32_
         qa.chunks = s->chunks[i];
         qa.wnr = wnr;
         uint32_t NQ = (uint32_t)(n << d.log_qc);
-        k_quotient<F><<<(NQ + 127) / 128, 128, 0, ctx->stream>>>(qa);
-        LAUNCH_CHECK();
+        {
+            KT kt(ctx, KC_QUOTIENT, (uint64_t)NQ * (8ull * (d.main_w + d.prep_w + d.aux_w() * 4) + 16));
+            k_quotient<F><<<(NQ + 127) / 128, 128, 0, ctx->stream>>>(qa);
+            LAUNCH_CHECK_C(KC_QUOTIENT);
+        }
         // chunk c lives on the coset GENERATOR * w_NQ^c * H_n: LDE without the GENERATOR factor, rotated by -c*(N/NQ)
         uint32_t logN = d.log_h + lb;
         for (uint32_t c = 0; c < qc; c++) {
@@ -949,6 +1027,7 @@ static int open_impl(p3r_session* s, const uint32_t zeta_w[4], uint32_t* opened_
     WeightJob* d_wj = upload_vec(ctx, wjobs);
     DotJob* d_dj = upload_vec(ctx, djobs);
     if (!d_w || !s->d_opened || !partial || !d_wj || !d_dj) return P3R_ERR_OOM;
+    KT kt_open(ctx, KC_OPEN);
     {
         dim3 grid(((1u << max_n_log) + 255) / 256, (unsigned)wjobs.size());
         k_bary_weights<F><<<grid, 256, 0, ctx->stream>>>(d_wj, d_w, ctx->tw, ctx->logT, wnr);
@@ -1085,8 +1164,13 @@ static int fri_begin_impl(p3r_session* s, const uint32_t alpha_w[4], uint32_t* n
         ra.ro = ro;
         ra.wnr = wnr;
         uint32_t N = 1u << lh;
-        k_reduced_openings<F><<<(N + 127) / 128, 128, 0, ctx->stream>>>(ra);
-        LAUNCH_CHECK();
+        {
+            uint64_t wsum = 0;
+            for (auto& m : g.mats) wsum += m.width;
+            KT kt(ctx, KC_REDUCE, (uint64_t)N * (4 * wsum + 16));
+            k_reduced_openings<F><<<(N + 127) / 128, 128, 0, ctx->stream>>>(ra);
+            LAUNCH_CHECK_C(KC_REDUCE);
+        }
         s->ro[lh] = ro;
     }
     bool ok = false;
@@ -1133,13 +1217,17 @@ static int fri_commit_impl(p3r_session* s, uint32_t round, uint32_t* cap_out) {
     fr.tree.log_max_h = log_rows;
     fr.tree.digests = dg;
     uint32_t rows = 1u << log_rows, w = 4u << fr.log_arity;
-    k_hash_rows_rowmajor<F><<<(rows + 127) / 128, 128, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(fr.vec), w, rows, dg);
-    LAUNCH_CHECK();
+    {
+        KT kt(ctx, KC_HASH, (uint64_t)rows * (4ull * w + 32));
+        k_hash_rows_rowmajor<F><<<(rows + 127) / 128, 128, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(fr.vec), w, rows, dg);
+        LAUNCH_CHECK_C(KC_HASH);
+    }
+    KT kt_tree(ctx, KC_COMPRESS, 96ull * rows);
     for (uint32_t l = 1; log_rows - l + 1 > ctx->fri.cap_height; l++) {
         uint32_t n_next = 1u << (log_rows - l);
         k_compress<F><<<(n_next + 127) / 128, 128, 0, ctx->stream>>>(dg + fr.tree.level_off(l - 1) * 8,
                                                                       dg + fr.tree.level_off(l) * 8, n_next, nullptr, 0);
-        LAUNCH_CHECK();
+        LAUNCH_CHECK_C(KC_COMPRESS);
     }
     return read_cap(ctx, fr.tree, cap_out);
 }
@@ -1160,9 +1248,11 @@ static int fri_fold_impl(p3r_session* s, uint32_t round, const uint32_t beta_w[4
     auto it = s->ro.find(out_log);
     if (it != s->ro.end() && out_log != s->log_max) roll = it->second;
     uint32_t n_out = 1u << out_log;
+    KT kt(ctx, KC_FOLD);
     k_fri_fold<F><<<(n_out + 127) / 128, 128, 0, ctx->stream>>>(fr.vec, out, fr.log_len, fr.log_arity, beta, roll, ctx->inv2_m,
                                                                 ctx->tw, ctx->logT, ctx->w_m);
-    LAUNCH_CHECK();
+    ctx->kstats.bytes[KC_FOLD] += 16ull * (((size_t)1 << fr.log_len) + n_out);
+    LAUNCH_CHECK_C(KC_FOLD);
     return P3R_OK;
 }
 
@@ -1318,9 +1408,9 @@ static int challenger_grind(p3r_ctx* ctx, HostChallenger<F>& ch, uint32_t bits, 
 
 template <class F>
 static int prove_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, const uint32_t* const* public_values,
-                      uint32_t* proof_out, size_t cap_words, size_t* n_words) {
+                      uint32_t* proof_out, size_t cap_words, size_t* n_words, const p3r_traces* resident = nullptr) {
     p3r_session* s = nullptr;
-    TRY(prove_begin_impl<F>(ctx, prep, traces, public_values, &s));
+    TRY(prove_begin_impl<F>(ctx, prep, traces, public_values, &s, resident));
     struct Guard {
         p3r_session* s;
         ~Guard() { delete s; }
@@ -1470,6 +1560,7 @@ static int prove_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* 
     TRY(fri_query_impl(s, indices.data(), (uint32_t)indices.size(), proof_out + head, cap_words - head, &qwords));
     pt.mark("query");
     pt.finish();
+    kstats_collect(ctx);
     return P3R_OK;
 }
 
@@ -1577,6 +1668,7 @@ static int bench_commit_impl(p3r_ctx* ctx, uint32_t log_height, uint32_t width, 
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaEventDestroy(e2);
+    kstats_collect(ctx);
     ms_out[0] = t_lde / iters;
     ms_out[1] = t_tree / iters;
     ms_out[2] = 0;
@@ -1662,6 +1754,7 @@ void p3r_ctx_destroy(p3r_ctx* ctx) {
         cudaFree(kv.second.lo);
         cudaFree(kv.second.hi);
     }
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->tw) cudaFree(ctx->tw);
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->dstage) cudaFree(ctx->dstage);
@@ -1741,6 +1834,100 @@ int p3r_prove(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, 
     if (!ctx || !prep || !traces || !n_words) return P3R_ERR_INVALID_ARG;
     cudaSetDevice(ctx->device);
     return DISPATCH(ctx, prove_impl<F>(ctx, prep, traces, public_values, proof_out, cap_words, n_words));
+}
+int p3r_traces_upload(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, p3r_traces** out) {
+    if (!ctx || !prep || !traces || !out) return P3R_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    auto* t = new p3r_traces();
+    t->ctx = ctx;
+    ctx->arena.reset();
+    for (size_t i = 0; i < prep->inst.size(); i++) {
+        const InstDev& d = prep->inst[i];
+        if (traces[i].height != (1u << d.log_h) || traces[i].width != d.main_w || !traces[i].data) {
+            set_err(ctx, "traces_upload: shape mismatch");
+            p3r_traces_free(t);
+            return P3R_ERR_INVALID_ARG;
+        }
+        size_t words = (size_t)traces[i].height * traces[i].width;
+        uint32_t* dm = nullptr;
+        uint32_t* rm = arena_alloc<uint32_t>(ctx, words);
+        if (!rm || cudaMalloc(&dm, words * 4) != cudaSuccess) {
+            p3r_traces_free(t);
+            return P3R_ERR_OOM;
+        }
+        t->d.push_back(dm);
+        int rc = upload_matrix(ctx, traces[i], rm, dm);
+        if (rc) {
+            p3r_traces_free(t);
+            return rc;
+        }
+    }
+    cudaStreamSynchronize(ctx->stream);
+    *out = t;
+    return P3R_OK;
+}
+void p3r_traces_free(p3r_traces* t) {
+    if (!t) return;
+    cudaStreamSynchronize(t->ctx->stream);
+    for (auto* p : t->d) cudaFree(p);
+    delete t;
+}
+int p3r_prove_resident(p3r_ctx* ctx, const p3r_prep* prep, const p3r_traces* traces, const uint32_t* const* public_values,
+                       uint32_t* proof_out, size_t cap_words, size_t* n_words) {
+    if (!ctx || !prep || !traces || !n_words || traces->d.size() != prep->inst.size()) return P3R_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    return DISPATCH(ctx, prove_impl<F>(ctx, prep, nullptr, public_values, proof_out, cap_words, n_words, traces));
+}
+int p3r_timer_start(p3r_ctx* ctx) {
+    if (!ctx) return P3R_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    if (!ctx->timer_ev[0]) {
+        cudaEventCreate(&ctx->timer_ev[0]);
+        cudaEventCreate(&ctx->timer_ev[1]);
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaEventRecord(ctx->timer_ev[0], ctx->stream));
+    return P3R_OK;
+}
+int p3r_timer_stop(p3r_ctx* ctx, float* ms_out) {
+    if (!ctx || !ms_out || !ctx->timer_ev[0]) return P3R_ERR_INVALID_ARG;
+    CUDA_TRY(cudaEventRecord(ctx->timer_ev[1], ctx->stream));
+    CUDA_TRY(cudaEventSynchronize(ctx->timer_ev[1]));
+    CUDA_TRY(cudaEventElapsedTime(ms_out, ctx->timer_ev[0], ctx->timer_ev[1]));
+    return P3R_OK;
+}
+void* p3r_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void p3r_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+int p3r_set_kernel_timing(p3r_ctx* ctx, uint32_t class_mask) {
+    if (!ctx) return P3R_ERR_INVALID_ARG;
+    kstats_collect(ctx);
+    ctx->time_mask = class_mask;
+    return P3R_OK;
+}
+int p3r_reset_kernel_stats(p3r_ctx* ctx) {
+    if (!ctx) return P3R_ERR_INVALID_ARG;
+    kstats_collect(ctx);
+    ctx->kstats = KernelStats();
+    return P3R_OK;
+}
+int p3r_kernel_stats(p3r_ctx* ctx, const char** names_out, double* ms_out, uint64_t* launches_out, uint64_t* bytes_out,
+                     uint32_t cap, uint32_t* n_out) {
+    if (!ctx || !n_out) return P3R_ERR_INVALID_ARG;
+    kstats_collect(ctx);
+    for (uint32_t k = 0; k < KC_COUNT && k < cap; k++) {
+        if (names_out) names_out[k] = KCLASS_NAMES[k];
+        if (ms_out) ms_out[k] = ctx->kstats.ms[k];
+        if (launches_out) launches_out[k] = ctx->kstats.launches[k];
+        if (bytes_out) bytes_out[k] = ctx->kstats.bytes[k];
+    }
+    *n_out = KC_COUNT;
+    return P3R_OK;
 }
 int p3r_coset_lde(p3r_ctx* ctx, const p3r_matrix_u32* in, uint32_t log_blowup, uint32_t* out) {
     if (!ctx || !in || !out) return P3R_ERR_INVALID_ARG;

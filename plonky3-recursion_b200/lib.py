@@ -55,7 +55,11 @@ def load():
         lib.p3r_launch_count.restype = C.c_uint64
         lib.p3r_launch_count.argtypes = [C.c_void_p]
         lib.p3r_abi_version.restype = C.c_uint32
-        for name in ("p3r_ctx_destroy", "p3r_prep_free", "p3r_session_free"):
+        lib.p3r_host_alloc.restype = C.c_void_p
+        lib.p3r_host_alloc.argtypes = [C.c_size_t]
+        lib.p3r_host_free.restype = None
+        lib.p3r_host_free.argtypes = [C.c_void_p]
+        for name in ("p3r_ctx_destroy", "p3r_prep_free", "p3r_session_free", "p3r_traces_free"):
             getattr(lib, name).restype = None
             getattr(lib, name).argtypes = [C.c_void_p]
         _lib = lib
@@ -66,7 +70,12 @@ EXPORTS = ["p3r_abi_version", "p3r_build_info", "p3r_ctx_create", "p3r_ctx_destr
            "p3r_prep_free", "p3r_prove_begin", "p3r_commit_main", "p3r_commit_perm", "p3r_commit_quotient", "p3r_open",
            "p3r_fri_begin", "p3r_fri_commit", "p3r_fri_fold", "p3r_fri_final_poly", "p3r_fri_query", "p3r_session_free",
            "p3r_grind", "p3r_prove", "p3r_coset_lde", "p3r_mmcs_commit", "p3r_poseidon2_permute", "p3r_bench_commit",
-           "p3r_last_phase_times", "p3r_launch_count"]
+           "p3r_last_phase_times", "p3r_launch_count", "p3r_traces_upload", "p3r_traces_free", "p3r_prove_resident",
+           "p3r_host_alloc", "p3r_host_free", "p3r_timer_start", "p3r_timer_stop", "p3r_set_kernel_timing",
+           "p3r_reset_kernel_stats", "p3r_kernel_stats"]
+
+KERNEL_CLASSES = ["ntt_lde", "hash_rows", "compress", "logup", "quotient", "open", "reduced_openings", "fri_fold", "transpose",
+                  "misc"]
 
 
 class Context:
@@ -140,6 +149,42 @@ class Context:
         self._check(self.lib.p3r_bench_commit(self.h, log_height, width, iters, C.c_uint64(seed), t))
         return {"lde_ms": t[0], "merkle_ms": t[1]}
 
+    def timer_start(self):
+        self._check(self.lib.p3r_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float(0)
+        self._check(self.lib.p3r_timer_stop(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def set_kernel_timing(self, classes):
+        mask = 0
+        for c in classes:
+            mask |= 1 << KERNEL_CLASSES.index(c)
+        self._check(self.lib.p3r_set_kernel_timing(self.h, mask))
+
+    def reset_kernel_stats(self):
+        self._check(self.lib.p3r_reset_kernel_stats(self.h))
+
+    def kernel_stats(self) -> dict:
+        n = len(KERNEL_CLASSES)
+        ms, la, by = (C.c_double * n)(), (C.c_uint64 * n)(), (C.c_uint64 * n)()
+        cnt = C.c_uint32(0)
+        self._check(self.lib.p3r_kernel_stats(self.h, None, ms, la, by, n, C.byref(cnt)))
+        return {KERNEL_CLASSES[k]: {"ms": float(ms[k]), "launches": int(la[k]), "bytes": int(by[k])} for k in range(n)}
+
+    def pinned_empty(self, shape, dtype=np.uint32) -> np.ndarray:
+        """numpy view of cudaHostAlloc'd memory (kept alive by the returned array's base object)."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = self.lib.p3r_host_alloc(C.c_size_t(max(nbytes, 16)))
+        if not ptr:
+            raise P3RError(3, "p3r_host_alloc failed")
+        buf = (C.c_uint8 * max(nbytes, 16)).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(ptr)
+        return arr
+
     def last_phase_times(self) -> dict:
         names = C.c_char_p()
         ms = (C.c_float * 32)()
@@ -182,21 +227,56 @@ class ProverData:
 
 
 class TraceBatch:
-    """Traces marshalled once (Montgomery, row-major) so repeated proofs do not pay the numpy conversion."""
+    """Traces marshalled once (Montgomery, row-major) so repeated proofs do not pay the numpy conversion.
+    pinned=True places the Montgomery matrices in cudaHostAlloc'd memory (the e2e path of bench.py)."""
 
-    def __init__(self, ctx: Context, traces, pubs):
+    def __init__(self, ctx: Context, traces, pubs, pinned: bool = False):
+        self.ctx = ctx
         self.m = abi.Marshal(ctx.field)
-        self.tm = self.m.matrices(traces)
+        if pinned:
+            arr = (abi.MatrixU32 * len(traces))()
+            self._bufs = []
+            for k, t in enumerate(traces):
+                buf = ctx.pinned_empty(t.shape)
+                buf[...] = ctx.field.to_monty(t)
+                self._bufs.append(buf)
+                arr[k] = abi.MatrixU32(abi.as_u32p(buf), t.shape[0], t.shape[1])
+            self.tm = arr
+        else:
+            self.tm = self.m.matrices(traces)
         self.pv = self.m.public_values(pubs)
         self.h2d_bytes = int(sum(int(t.size) * 4 for t in traces))
+        self.resident = None
+
+    def upload(self, prover_data):
+        """Make the traces device-resident (p3r_traces_upload)."""
+        h = C.c_void_p()
+        self.ctx._check(self.ctx.lib.p3r_traces_upload(self.ctx.h, prover_data.h, self.tm, C.byref(h)))
+        self.resident = h
+        return self
+
+    def close(self):
+        if self.resident is not None and self.ctx.h:
+            self.ctx.lib.p3r_traces_free(self.resident)
+        self.resident = None
 
 
 class BatchStarkProver:
     """Mirror of BatchStarkProver<SC> (circuit-prover/src/batch_stark_prover.rs:685-697)."""
 
-    def __init__(self, ctx: Context):
+    def __init__(self, ctx: Context, pinned_output: bool = False):
         self.ctx = ctx
-        self._buf = np.zeros(1 << 22, dtype=np.uint32)
+        self._buf = ctx.pinned_empty((1 << 22,)) if pinned_output else np.zeros(1 << 22, dtype=np.uint32)
+        self.last_proof_words = 0
+
+    def prove_resident(self, traces: "TraceBatch", prover_data: ProverData, copy: bool = True):
+        """Prove from device-resident traces (TraceBatch.upload)."""
+        ctx = self.ctx
+        n = C.c_size_t(0)
+        ctx._check(ctx.lib.p3r_prove_resident(ctx.h, prover_data.h, traces.resident, traces.pv, abi.as_u32p(self._buf),
+                                              C.c_size_t(self._buf.size), C.byref(n)))
+        self.last_proof_words = n.value
+        return self._buf[: n.value].copy() if copy else self._buf[: n.value]
 
     def prove_all_tables(self, traces, prover_data: ProverData, public_values=None) -> np.ndarray:
         """traces: list of canonical (h, w) uint32 matrices in instance order, or a TraceBatch.
@@ -213,4 +293,5 @@ class BatchStarkProver:
             rc = ctx.lib.p3r_prove(ctx.h, prover_data.h, traces.tm, traces.pv, abi.as_u32p(self._buf),
                                    C.c_size_t(self._buf.size), C.byref(n))
         ctx._check(rc)
+        self.last_proof_words = n.value
         return self._buf[: n.value].copy()

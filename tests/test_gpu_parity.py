@@ -72,3 +72,24 @@ def test_full_proof_bit_identical_and_verifies(pair):
     assert diff.size == 0, f"first differing word {diff[:5]} of {proof.size}"
     orc.verify(insts, pd.preprocessed_commitment, pubs, proof)
     pd.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_recursion_layer_tables_bit_identical(pair, seed):
+    """Const/Public/ALU(3 lanes, k=4)/Poseidon2/Recompose with the WitnessChecks LogUp bus, mixed heights."""
+    wl = importlib.import_module("plonky3-recursion_b200.workload")
+    ctx, orc = pair
+    L = wl.synthetic_layer(ctx.field, seed, n_const=20, n_public=70, n_alu=400, n_perms=90, n_recompose=10, min_height=32)
+    pd = lib.ProverData.from_airs_and_degrees(ctx, L.insts, L.preps)
+    proof = lib.BatchStarkProver(ctx).prove_all_tables(L.traces, pd, L.pubs)
+    want = orc.prove(L.insts, L.preps, L.traces, L.pubs)
+    assert proof.size == want.size
+    diff = np.nonzero(proof != want)[0]
+    assert diff.size == 0, f"first differing word {diff[:5]} of {proof.size}"
+    orc.verify(L.insts, pd.preprocessed_commitment, L.pubs, proof)
+    # tampering with any opened value or commitment must be rejected
+    bad = proof.copy()
+    bad[30] ^= 1
+    with pytest.raises(RuntimeError):
+        orc.verify(L.insts, pd.preprocessed_commitment, L.pubs, bad)
+    pd.close()
