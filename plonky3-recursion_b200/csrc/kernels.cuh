@@ -61,13 +61,16 @@ __global__ void k_transpose_out(const uint32_t* __restrict__ in, uint32_t* __res
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4: batched coset LDE = radix-2 NTT passes over shared-memory tiles.
+// K4: batched coset LDE = radix-2 NTT passes over shared-memory tiles, butterflies done in REGISTERS in groups of up to
+// three stages (radix-8): one shared-memory round trip and one barrier per group instead of per stage.
 // A pass executes butterfly stages [s0, s0+r) of a size-2^log_n transform on every column (grid.y) and, for forward passes,
 // every output coset (grid.z). Stage s pairs i and i + 2^s with twiddle omega_{2^{s+1}}^{i mod 2^s}.
 //   inverse  : decimation-in-frequency, stages descending, natural in -> bit-reversed out, inverse twiddles (no 1/n here);
 //   forward  : decimation-in-time, stages ascending, bit-reversed in -> natural out; the first pass multiplies coefficient k
 //              by (shift_j^k / n), the last pass stores to bit-reversed positions inside coset block j.
 // Tile = 2^r butterfly rows (stride 2^s0) x 2^log_cw consecutive elements; s0 == 0 tiles are contiguous runs.
+// Twiddles: `tws` holds, for every stage s, the compact table omega_{2^{s+1}}^e (e < 2^s) at offset 2^s - 1, so the one
+// twiddle a thread loads per group is a coalesced read; the other twiddles of the group are W^2, W^4 and W times 4th/8th roots.
 // ------------------------------------------------------------------------------------------------
 struct NttPass {
     const uint32_t* src;
@@ -81,40 +84,158 @@ struct NttPass {
     uint32_t use_g;          // scale by GENERATOR^k (trace-like input domain H_n) or not (input domain already shifted by GENERATOR)
     uint32_t rot;            // extra root-of-unity rotation exponent (mod N) applied per coefficient index
     uint32_t n_inv;          // 1/n (Montgomery), used when use_g == 0
-    const uint32_t* tw;      // half table of omega_T
+    const uint32_t* tws;     // per-stage compact twiddle tables
+    const uint32_t* tw;      // half table of omega_T (for the coset scaling)
     uint32_t logT;
+    uint32_t r4, r8, r8_3;   // omega_4, omega_8, omega_8^3 (Montgomery)
     const uint32_t* g_lo;    // g^k / n = g_lo[k & 1023] * g_hi[k >> 10]
     const uint32_t* g_hi;
+    uint32_t n_tiles, n_cols, n_cosets;  // CTA decomposition of this job inside a multi-job launch
+    uint32_t cta_begin;                  // first flat CTA index of this job
 };
 
+// Butterflies of Q consecutive stages on the 2^Q register values v[k] (k = bits j..j+Q-1 of the tile row index).
+// W = twiddle of the group's top stage for this thread's (t_lo, column); q4/q8/q83 = 4th/8th roots (already inverted for DIF).
+template <class F, int Q, bool FWD>
+__device__ __forceinline__ void ntt_group(uint32_t (&v)[8], uint32_t W, uint32_t q4, uint32_t q8, uint32_t q83) {
+    uint32_t tw[3][4];
+    if (Q == 3) {
+        uint32_t W2 = fmul<F>(W, W);
+        tw[0][0] = fmul<F>(W2, W2);
+        tw[1][0] = W2;
+        tw[1][1] = fmul<F>(W2, q4);
+        tw[2][0] = W;
+        tw[2][1] = fmul<F>(W, q8);
+        tw[2][2] = fmul<F>(W, q4);
+        tw[2][3] = fmul<F>(W, q83);
+    } else if (Q == 2) {
+        tw[0][0] = fmul<F>(W, W);
+        tw[1][0] = W;
+        tw[1][1] = fmul<F>(W, q4);
+    } else {
+        tw[0][0] = W;
+    }
+#pragma unroll
+    for (int step = 0; step < Q; step++) {
+        const int u = FWD ? step : (Q - 1 - step);
+#pragma unroll
+        for (int k = 0; k < (1 << Q); k++) {
+            if (k & (1 << u)) continue;
+            const int k1 = k | (1 << u);
+            const uint32_t w = tw[u][k & ((1 << u) - 1)];
+            uint32_t x = v[k], y = v[k1];
+            if (FWD) {
+                y = fmul<F>(y, w);
+                v[k] = fadd<F>(x, y);
+                v[k1] = fsub<F>(x, y);
+            } else {
+                v[k] = fadd<F>(x, y);
+                v[k1] = fmul<F>(fsub<F>(x, y), w);
+            }
+        }
+    }
+}
+
+template <class F, int Q, bool FWD>
+__device__ __forceinline__ void ntt_group_pass(uint32_t* sm, const NttPass& a, uint32_t j, uint32_t m0, bool contig, uint32_t CWP) {
+    const uint32_t R = 1u << a.r, S = 1u << a.s0;
+    const uint32_t total = R << a.log_cw;
+    const uint32_t tasks = total >> Q;
+    const uint32_t s_top = a.s0 + j + Q - 1;
+    const uint32_t* tab = a.tws + ((1u << s_top) - 1);
+    const uint32_t q4 = FWD ? a.r4 : fneg<F>(a.r4);
+    const uint32_t q8 = FWD ? a.r8 : fneg<F>(a.r8_3);
+    const uint32_t q83 = FWD ? a.r8_3 : fneg<F>(a.r8);
+    for (uint32_t tau = threadIdx.x; tau < tasks; tau += blockDim.x) {
+        uint32_t mm, t_lo, t_hi;
+        if (contig) {
+            t_lo = tau & ((1u << j) - 1);
+            uint32_t rest = tau >> j;
+            uint32_t hi_cnt_log = a.r - j - Q;
+            t_hi = rest & ((1u << hi_cnt_log) - 1);
+            mm = rest >> hi_cnt_log;
+        } else {
+            mm = tau & ((1u << a.log_cw) - 1);
+            uint32_t rest = tau >> a.log_cw;
+            t_lo = rest & ((1u << j) - 1);
+            t_hi = rest >> j;
+        }
+        const uint32_t tbase = (t_hi << (j + Q)) | t_lo;
+        const uint32_t lo_g = contig ? 0u : ((m0 + mm) & (S - 1));
+        const uint32_t e = t_lo * S + lo_g;
+        uint32_t W;
+        if (FWD) W = __ldg(tab + e);
+        else W = e ? fneg<F>(__ldg(tab + ((1u << s_top) - e))) : F::R;
+        uint32_t v[8];
+        uint32_t idx[8];
+#pragma unroll
+        for (int k = 0; k < (1 << Q); k++) {
+            uint32_t t = tbase | ((uint32_t)k << j);
+            uint32_t x = contig ? (mm << a.r) + t : t * CWP + mm;
+            if (contig) x += x >> 5;
+            idx[k] = x;
+            v[k] = sm[x];
+        }
+        ntt_group<F, Q, FWD>(v, W, q4, q8, q83);
+#pragma unroll
+        for (int k = 0; k < (1 << Q); k++) sm[idx[k]] = v[k];
+    }
+}
+
+template <class F, bool FWD>
+__device__ __forceinline__ void ntt_tile_stages(uint32_t* sm, const NttPass& a, uint32_t m0, bool contig, uint32_t CWP) {
+    // forward: groups ascend from stage offset 0; inverse: groups descend from the top
+    uint32_t done = 0;
+    while (done < a.r) {
+        uint32_t q = a.r - done >= 3 ? 3 : a.r - done;
+        uint32_t j = FWD ? done : (a.r - done - q);
+        if (q == 3) ntt_group_pass<F, 3, FWD>(sm, a, j, m0, contig, CWP);
+        else if (q == 2) ntt_group_pass<F, 2, FWD>(sm, a, j, m0, contig, CWP);
+        else ntt_group_pass<F, 1, FWD>(sm, a, j, m0, contig, CWP);
+        done += q;
+        __syncthreads();
+    }
+}
+
+// One launch runs the same pass level of MANY LDE jobs (all tables of a commit round): flat grid, each CTA finds its job
+// through cta_begin. Keeps the number of dependent launches per commit at (inverse passes + forward passes).
 template <class F>
-__global__ void __launch_bounds__(256) k_ntt_pass(NttPass a) {
+__global__ void __launch_bounds__(512) k_ntt_pass(const NttPass* __restrict__ jobs, uint32_t n_jobs) {
     extern __shared__ uint32_t sm[];
+    __shared__ NttPass a;
+    {
+        uint32_t j = 0;
+        while (j + 1 < n_jobs && blockIdx.x >= jobs[j + 1].cta_begin) j++;
+        const uint32_t* srcw = reinterpret_cast<const uint32_t*>(jobs + j);
+        uint32_t* dstw = reinterpret_cast<uint32_t*>(&a);
+        for (uint32_t i = threadIdx.x; i < sizeof(NttPass) / 4; i += blockDim.x) dstw[i] = srcw[i];
+    }
+    __syncthreads();
+    const uint32_t local = blockIdx.x - a.cta_begin;
+    const uint32_t tile_id = local % a.n_tiles, col = (local / a.n_tiles) % a.n_cols, coset = local / (a.n_tiles * a.n_cols);
     const uint32_t R = 1u << a.r, CW = 1u << a.log_cw, S = 1u << a.s0;
-    const uint32_t CWP = CW >= 32 ? CW + 1 : CW;  // padded row stride: conflict-free bit-reversed stores
-    const uint32_t col = blockIdx.y, coset = blockIdx.z;
-    const uint32_t m0 = blockIdx.x * CW;
-    const uint32_t n = 1u << a.log_n;
+    const bool contig = (a.s0 == 0);          // tile = CW contiguous runs of R elements
+    const uint32_t CWP = CW + 1;              // strided layout: padded row stride
+    const uint32_t m0 = tile_id * CW;
     const uint32_t* src = a.src + (size_t)col * a.src_col_stride;
     if (a.forward && !a.first) src += (size_t)coset * a.dst_coset_stride;  // in-place chain lives in the coset block
     uint32_t* dst = a.dst + (size_t)col * a.dst_col_stride + (size_t)coset * (a.forward ? a.dst_coset_stride : 0);
     const uint32_t total = R * CW;
 
     // ---- load ----
-    const bool t_fastest = (S < CW);  // contiguous tiles (s0 == 0)
     const uint32_t rj = bitrev32(coset, a.log_blowup);
     const uint32_t logN = a.log_n + a.log_blowup;
     for (uint32_t idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        uint32_t t, mm;
-        if (t_fastest) {
-            t = idx & (R - 1);
-            mm = idx >> a.r;
+        uint32_t gi, x;
+        if (contig) {
+            gi = m0 * R + idx;  // (m0+mm)*R + t with idx = mm*R + t
+            x = idx + (idx >> 5);
         } else {
-            mm = idx & (CW - 1);
-            t = idx >> a.log_cw;
+            uint32_t mm = idx & (CW - 1), t = idx >> a.log_cw;
+            uint32_t m = m0 + mm, lo = m & (S - 1), hi = m >> a.s0;
+            gi = ((hi << a.r) + t) * S + lo;
+            x = t * CWP + mm;
         }
-        uint32_t m = m0 + mm, lo = m & (S - 1), hi = m >> a.s0;
-        uint32_t gi = ((hi << a.r) + t) * S + lo;
         uint32_t v = src[gi];
         if (a.forward && a.first) {
             uint32_t k = bitrev32(gi, a.log_n);  // coefficient index held at position gi
@@ -123,69 +244,54 @@ __global__ void __launch_bounds__(256) k_ntt_pass(NttPass a) {
             sc = fmul<F>(sc, root_pow<F>(a.tw, a.logT, e << (a.logT - logN)));
             v = fmul<F>(v, sc);
         }
-        sm[t * CWP + mm] = v;
+        sm[x] = v;
     }
     __syncthreads();
 
-    // ---- butterflies ----
-    const uint32_t nb = total >> 1;
-    for (uint32_t step = 0; step < a.r; step++) {
-        const uint32_t j = a.forward ? step : (a.r - 1 - step);
-        const uint32_t half = 1u << j, s = a.s0 + j;
-        const uint32_t tsh = a.logT - s - 1;
-        for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) {
-            uint32_t mm, tp;
-            if (t_fastest) {
-                tp = b & ((R >> 1) - 1);
-                mm = b >> (a.r - 1);
-            } else {
-                mm = b & (CW - 1);
-                tp = b >> a.log_cw;
-            }
-            uint32_t tlo = tp & (half - 1);
-            uint32_t t = ((tp >> j) << (j + 1)) | tlo;
-            uint32_t lo = (m0 + mm) & (S - 1);
-            uint32_t e = (tlo * S + lo) << tsh;  // < T/2
-            uint32_t w = __ldg(a.tw + e);
-            if (!a.forward && e) w = fneg<F>(__ldg(a.tw + ((1u << (a.logT - 1)) - e)));  // omega^{-e} = -omega^{T/2-e}
-            uint32_t i0 = t * CWP + mm, i1 = i0 + half * CWP;
-            uint32_t x = sm[i0], y = sm[i1];
-            if (a.forward) {
-                y = fmul<F>(y, w);
-                sm[i0] = fadd<F>(x, y);
-                sm[i1] = fsub<F>(x, y);
-            } else {
-                sm[i0] = fadd<F>(x, y);
-                sm[i1] = fmul<F>(fsub<F>(x, y), w);
-            }
-        }
-        __syncthreads();
-    }
+    if (a.forward) ntt_tile_stages<F, true>(sm, a, m0, contig, CWP);
+    else ntt_tile_stages<F, false>(sm, a, m0, contig, CWP);
 
     // ---- store ----
     if (a.forward && a.last) {
-        // natural index i = (hi*R + t)*S + lo with hi == 0 (s0 + r == log_n)  ->  bitrev(i) = bitrev_s0(lo)*R + bitrev_r(t)
+        // natural index i = t*S + lo (hi == 0 since s0 + r == log_n)  ->  bitrev(i) = bitrev_s0(lo)*R + bitrev_r(t)
         for (uint32_t idx = threadIdx.x; idx < total; idx += blockDim.x) {
             uint32_t tt = idx & (R - 1), mm = idx >> a.r;
-            uint32_t lo = m0 + mm;
-            uint32_t pos = bitrev32(lo, a.s0) * R + tt;
-            dst[pos] = sm[bitrev32(tt, a.r) * CWP + mm];
+            uint32_t tb = bitrev32(tt, a.r);
+            uint32_t x;
+            if (contig) {
+                x = (mm << a.r) + tb;
+                x += x >> 5;
+            } else {
+                x = tb * CWP + mm;
+            }
+            uint32_t pos = bitrev32(m0 + mm, a.s0) * R + tt;
+            dst[pos] = sm[x];
         }
     } else {
         for (uint32_t idx = threadIdx.x; idx < total; idx += blockDim.x) {
-            uint32_t t, mm;
-            if (t_fastest) {
-                t = idx & (R - 1);
-                mm = idx >> a.r;
+            uint32_t gi, x;
+            if (contig) {
+                gi = m0 * R + idx;
+                x = idx + (idx >> 5);
             } else {
-                mm = idx & (CW - 1);
-                t = idx >> a.log_cw;
+                uint32_t mm = idx & (CW - 1), t = idx >> a.log_cw;
+                uint32_t m = m0 + mm, lo = m & (S - 1), hi = m >> a.s0;
+                gi = ((hi << a.r) + t) * S + lo;
+                x = t * CWP + mm;
             }
-            uint32_t m = m0 + mm, lo = m & (S - 1), hi = m >> a.s0;
-            dst[((hi << a.r) + t) * S + lo] = sm[t * CWP + mm];
+            dst[gi] = sm[x];
         }
     }
-    (void)n;
+}
+
+// tws[(2^s - 1) + e] = omega_{2^{s+1}}^e for s < logT, e < 2^s  (w_T = primitive 2^logT-th root, Montgomery).
+template <class F>
+__global__ void k_stage_twiddles(uint32_t* tws, uint32_t logT, uint32_t w_T) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // linear index into tws, < 2^logT - 1
+    if (i >= (1u << logT) - 1) return;
+    uint32_t s = 31 - __clz(i + 1);
+    uint32_t e = i + 1 - (1u << s);
+    tws[i] = fpow<F>(w_T, (uint64_t)e << (logT - s - 1));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -264,6 +370,106 @@ __global__ void __launch_bounds__(128) k_compress(const uint32_t* __restrict__ p
     uint4* o = reinterpret_cast<uint4*>(next + (size_t)i * 8);
     o[0] = make_uint4(st[0], st[1], st[2], st[3]);
     o[1] = make_uint4(st[4], st[5], st[6], st[7]);
+}
+// ---- cooperative (16 lanes per permutation) Merkle kernels for the small levels -----------------------------------------
+// One half-warp = one node. hash of an injected / leaf row: lanes 0..7 absorb 8 columns per permutation.
+template <class F>
+__device__ __forceinline__ uint32_t coop_hash_cols(const uint32_t* const* __restrict__ colptr, uint32_t ncols, uint32_t row,
+                                                   uint32_t lane, const P2Lane& c) {
+    const uint32_t l16 = lane & 15u;
+    uint32_t x = 0;
+    for (uint32_t c0 = 0; c0 < ncols; c0 += 8) {
+        if (l16 < 8 && c0 + l16 < ncols) x = __ldg(colptr[c0 + l16] + row);
+        x = p2_coop_permute<F>(x, lane, c);
+    }
+    return x;
+}
+// compress(left, right) (+ optional injection) for node i, state distributed over the half-warp; returns lane value.
+template <class F>
+__device__ __forceinline__ uint32_t coop_node(const uint32_t* __restrict__ prev, uint32_t i, const uint32_t* const* inj,
+                                              uint32_t inj_cols, uint32_t lane, const P2Lane& c) {
+    const uint32_t l16 = lane & 15u;
+    uint32_t x = prev[(size_t)i * 16 + l16];  // left digest (8 words) then right digest (8 words)
+    x = p2_coop_permute<F>(x, lane, c);
+    if (inj_cols) {
+        uint32_t h = coop_hash_cols<F>(inj, inj_cols, i, lane, c);
+        uint32_t hs = __shfl_sync(0xffffffffu, h, (lane & ~15u) | (l16 & 7u));  // lanes 8..15 take h[0..8)
+        x = l16 < 8 ? x : hs;
+        x = p2_coop_permute<F>(x, lane, c);
+    }
+    return x;
+}
+template <class F>
+__global__ void __launch_bounds__(256) k_compress_coop(const uint32_t* __restrict__ prev, uint32_t* __restrict__ next,
+                                                        uint32_t n_next, const uint32_t* const* __restrict__ inj_colptr,
+                                                        uint32_t inj_cols, const Poseidon2Consts* __restrict__ gk) {
+    const uint32_t lane = threadIdx.x & 31u, l16 = lane & 15u;
+    const P2Lane c = p2_lane_consts<F>(gk, l16);
+    uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    bool live = i < n_next;
+    uint32_t x = coop_node<F>(prev, live ? i : 0, inj_colptr, inj_cols, lane, c);
+    if (live && l16 < 8) next[(size_t)i * 8 + l16] = x;
+}
+// Leaf level of a row-major matrix of w words per row (FRI commit-phase matrices), one half-warp per row.
+template <class F>
+__global__ void __launch_bounds__(256) k_hash_rows_rowmajor_coop(const uint32_t* __restrict__ data, uint32_t w, uint32_t n_rows,
+                                                                  uint32_t* __restrict__ out, const Poseidon2Consts* __restrict__ gk) {
+    const uint32_t lane = threadIdx.x & 31u, l16 = lane & 15u;
+    const P2Lane c = p2_lane_consts<F>(gk, l16);
+    uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    bool live = r < n_rows;
+    const uint32_t* row = data + (size_t)(live ? r : 0) * w;
+    uint32_t x = 0;
+    for (uint32_t c0 = 0; c0 < w; c0 += 8) {
+        if (l16 < 8 && c0 + l16 < w) x = row[c0 + l16];
+        x = p2_coop_permute<F>(x, lane, c);
+    }
+    if (live && l16 < 8) out[(size_t)r * 8 + l16] = x;
+}
+// Leaf level of column-major matrices, one half-warp per row (small heights only: loads are one word per column).
+template <class F>
+__global__ void __launch_bounds__(256) k_hash_rows_coop(const uint32_t* const* __restrict__ colptr, uint32_t ncols, uint32_t n_rows,
+                                                         uint32_t* __restrict__ out, const Poseidon2Consts* __restrict__ gk) {
+    const uint32_t lane = threadIdx.x & 31u, l16 = lane & 15u;
+    const P2Lane c = p2_lane_consts<F>(gk, l16);
+    uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    bool live = r < n_rows;
+    uint32_t x = coop_hash_cols<F>(colptr, ncols, live ? r : 0, lane, c);
+    if (live && l16 < 8) out[(size_t)r * 8 + l16] = x;
+}
+// Tail of a Merkle tree in ONE launch: a single 1024-thread CTA (64 cooperative permutations at a time) walks the levels
+// with at most TAIL_NODES nodes, one barrier per level, instead of one latency-bound launch per level.
+// Level l (2^(log_max_h - l) digests) lives at digest offset 2^(log_max_h+1) - 2^(log_max_h-l+1).
+struct TreeTail {
+    uint32_t* digests;
+    uint32_t log_max_h;
+    uint32_t first_level, last_level;
+    const uint32_t* const* inj_colptr[24];  // indexed by (level - first_level); nullptr = no injected matrices at that level
+    uint32_t inj_cols[24];
+};
+template <class F>
+__global__ void __launch_bounds__(1024) k_tree_tail(TreeTail a, const Poseidon2Consts* __restrict__ gk) {
+    const uint32_t lane = threadIdx.x & 31u, l16 = lane & 15u;
+    const P2Lane c = p2_lane_consts<F>(gk, l16);
+    const uint32_t per_pass = blockDim.x >> 4;
+    for (uint32_t l = a.first_level; l <= a.last_level; l++) {
+        uint32_t n_next = 1u << (a.log_max_h - l);
+        const uint32_t* prev = a.digests + (((size_t)2 << a.log_max_h) - ((size_t)2 << (a.log_max_h - (l - 1)))) * 8;
+        uint32_t* next = a.digests + (((size_t)2 << a.log_max_h) - ((size_t)2 << (a.log_max_h - l))) * 8;
+        const uint32_t* const* inj = a.inj_colptr[l - a.first_level];
+        uint32_t inj_cols = a.inj_cols[l - a.first_level];
+        for (uint32_t base = 0; base < n_next; base += per_pass) {
+            uint32_t i = base + (threadIdx.x >> 4);
+            bool live = i < n_next;
+            // whole warps with no live node skip (both half-warps dead); a warp with one live half runs both
+            uint32_t any = __ballot_sync(0xffffffffu, live);
+            if (any) {
+                uint32_t x = coop_node<F>(prev, live ? i : 0, inj, inj_cols, lane, c);
+                if (live && l16 < 8) next[(size_t)i * 8 + l16] = x;
+            }
+        }
+        __syncthreads();
+    }
 }
 template <class F>
 __global__ void k_permute_states(uint32_t* states, uint32_t n) {
@@ -464,33 +670,59 @@ __global__ void __launch_bounds__(128) k_logup_rows(LogupArgs a) {
     }
     a.rowsum[r] = total;
 }
-// Exclusive prefix sum of rowsum into perm columns 0..3 and the terminal; single CTA (n*16 bytes is tiny).
+// Exclusive prefix sum of rowsum into perm columns 0..3 and the terminal, in two small launches:
+// (1) one partial sum per 256-row chunk, (2) every chunk adds the partials before it and scans its own rows.
+constexpr uint32_t SCAN_CHUNK = 256;
 template <class F>
-__global__ void __launch_bounds__(1024) k_logup_scan(const Ext4* __restrict__ rowsum, uint32_t log_n, uint32_t* __restrict__ perm,
-                                                      Ext4* __restrict__ terminal) {
-    __shared__ Ext4 part[1024];
-    uint32_t n = 1u << log_n, T = blockDim.x;
-    uint32_t per = (n + T - 1) / T;
-    uint32_t lo = threadIdx.x * per, hi = min(lo + per, n);
-    Ext4 s = ext_zero();
-    for (uint32_t i = lo; i < hi; i++) s = eadd<F>(s, rowsum[i]);
-    part[threadIdx.x] = s;
-    __syncthreads();
-    // Hillis-Steele inclusive scan over T partials
-    for (uint32_t off = 1; off < T; off <<= 1) {
-        Ext4 v = part[threadIdx.x];
-        if (threadIdx.x >= off) v = eadd<F>(v, part[threadIdx.x - off]);
-        __syncthreads();
-        part[threadIdx.x] = v;
-        __syncthreads();
-    }
-    Ext4 acc = threadIdx.x ? part[threadIdx.x - 1] : ext_zero();
-    for (uint32_t i = lo; i < hi; i++) {
+__device__ __forceinline__ Ext4 block_sum_256(Ext4 v, Ext4* red) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) perm[(size_t)k * n + i] = acc.c[k];
-        acc = eadd<F>(acc, rowsum[i]);
+    for (int k = 0; k < 4; k++) {
+        uint32_t x = v.c[k];
+        for (int off = 16; off > 0; off >>= 1) x = fadd<F>(x, __shfl_down_sync(0xffffffffu, x, off));
+        v.c[k] = x;
     }
-    if (threadIdx.x == T - 1) *terminal = part[T - 1];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    Ext4 t = red[0];
+    for (uint32_t q = 1; q < blockDim.x / 32; q++) t = eadd<F>(t, red[q]);
+    __syncthreads();
+    return t;
+}
+template <class F>
+__global__ void __launch_bounds__(256) k_logup_chunk_sums(const Ext4* __restrict__ rowsum, uint32_t n, Ext4* __restrict__ chunk_sum) {
+    __shared__ Ext4 red[8];
+    uint32_t r = blockIdx.x * SCAN_CHUNK + threadIdx.x;
+    Ext4 v = r < n ? rowsum[r] : ext_zero();
+    Ext4 t = block_sum_256<F>(v, red);
+    if (threadIdx.x == 0) chunk_sum[blockIdx.x] = t;
+}
+template <class F>
+__global__ void __launch_bounds__(256) k_logup_scan_apply(const Ext4* __restrict__ rowsum, const Ext4* __restrict__ chunk_sum,
+                                                           uint32_t n, uint32_t* __restrict__ perm, Ext4* __restrict__ terminal) {
+    __shared__ Ext4 red[8];
+    __shared__ Ext4 buf[SCAN_CHUNK];
+    // prefix over earlier chunks
+    Ext4 pre = ext_zero();
+    for (uint32_t c = threadIdx.x; c < blockIdx.x; c += blockDim.x) pre = eadd<F>(pre, chunk_sum[c]);
+    pre = block_sum_256<F>(pre, red);
+    uint32_t r = blockIdx.x * SCAN_CHUNK + threadIdx.x;
+    Ext4 own = r < n ? rowsum[r] : ext_zero();
+    buf[threadIdx.x] = own;
+    __syncthreads();
+    for (uint32_t off = 1; off < SCAN_CHUNK; off <<= 1) {  // Hillis-Steele inclusive scan
+        Ext4 v = buf[threadIdx.x];
+        if (threadIdx.x >= off) v = eadd<F>(v, buf[threadIdx.x - off]);
+        __syncthreads();
+        buf[threadIdx.x] = v;
+        __syncthreads();
+    }
+    Ext4 incl = eadd<F>(pre, buf[threadIdx.x]);
+    Ext4 excl = esub<F>(incl, own);
+    if (r < n) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) perm[(size_t)k * n + r] = excl.c[k];
+        if (r == n - 1) *terminal = incl;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

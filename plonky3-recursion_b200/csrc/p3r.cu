@@ -89,8 +89,11 @@ struct p3r_ctx {
     Poseidon2Consts p2{};
     uint32_t w_m = 0, gen_m = 0, inv2_m = 0;  // Montgomery
     cudaStream_t stream = nullptr;
-    uint32_t* tw = nullptr;
+    uint32_t* tws = nullptr;  // per-stage compact twiddle tables, 2^logT - 1 entries
+    uint32_t* tw = nullptr;   // = tws + 2^(logT-1) - 1: half table of omega_T
     uint32_t logT = 0;
+    uint32_t r4 = 0, r8 = 0, r8_3 = 0;
+    Poseidon2Consts* d_p2 = nullptr;  // global-memory copy of the Poseidon2 constants (per-lane reads of the cooperative kernels)
     std::map<uint32_t, GTable> gtables;
     Arena arena;
     // pinned staging for small uploads/downloads
@@ -321,15 +324,19 @@ static int ensure_twiddles(p3r_ctx* ctx, uint32_t logT) {
         return P3R_ERR_INVALID_ARG;
     }
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    if (ctx->tw) cudaFree(ctx->tw);
-    ctx->tw = nullptr;
-    size_t half = (size_t)1 << (logT - 1);
-    CUDA_TRY(cudaMalloc(&ctx->tw, half * 4));
+    if (ctx->tws) cudaFree(ctx->tws);
+    ctx->tws = ctx->tw = nullptr;
+    size_t count = ((size_t)1 << logT) - 1;
+    CUDA_TRY(cudaMalloc(&ctx->tws, (count + 1) * 4));
     uint32_t gen = ctx->gen_m;
     uint32_t w = fpow<F>(gen, ((uint64_t)F::P - 1) >> logT);
-    k_powers<F><<<(unsigned)((half + 255) / 256), 256, 0, ctx->stream>>>(ctx->tw, (uint32_t)half, w, F::R);
+    k_stage_twiddles<F><<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(ctx->tws, logT, w);
     LAUNCH_CHECK();
+    ctx->tw = ctx->tws + (((size_t)1 << (logT - 1)) - 1);
     ctx->logT = logT;
+    ctx->r4 = fpow<F>(w, (uint64_t)1 << (logT - 2));
+    ctx->r8 = fpow<F>(w, (uint64_t)1 << (logT - 3));
+    ctx->r8_3 = fpow<F>(w, (uint64_t)3 << (logT - 3));
     for (auto& kv : ctx->gtables) {  // tables do not depend on logT, keep them
         (void)kv;
     }
@@ -363,6 +370,8 @@ static int get_gtable(p3r_ctx* ctx, uint32_t log_n, GTable* out) {
 // scratch_coef: n*w words; scratch_tmp: N*w words (only touched when log_n > TILE_LOG).
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t TILE_LOG = 13;
+constexpr uint32_t TAIL_NODES = 128;       // Merkle levels with at most this many nodes are produced by one k_tree_tail launch
+constexpr uint32_t COOP_MAX_NODES = 1u << 15;  // levels up to this size use the 16-lanes-per-permutation kernels
 struct PassPlan {
     uint32_t s0, r, log_cw;
 };
@@ -401,77 +410,135 @@ static std::vector<PassPlan> plan_passes(uint32_t log_n) {
     (void)rest;
     return p;
 }
+struct LdeJob {
+    const uint32_t* src;   // natural order, column-major, height n
+    uint32_t* dst;         // column-major, height n << log_blowup, bit-reversed rows
+    uint32_t log_n, w;
+    bool use_g;
+    uint32_t rot;
+    uint32_t* coef;        // n*w words of scratch
+    uint32_t* tmp;         // (n << log_blowup)*w words of scratch, only when log_n > TILE_LOG
+};
 template <class F>
-static int launch_pass(p3r_ctx* ctx, NttPass a, uint32_t n_cols, uint32_t n_cosets) {
-    uint32_t R = 1u << a.r, CW = 1u << a.log_cw;
-    uint32_t CWP = CW >= 32 ? CW + 1 : CW;
-    size_t smem = (size_t)R * CWP * 4;
+static int launch_pass_level(p3r_ctx* ctx, std::vector<NttPass>& passes) {
+    if (passes.empty()) return P3R_OK;
+    size_t smem = 0;
+    uint32_t cta = 0;
+    for (auto& a : passes) {
+        uint32_t R = 1u << a.r, CW = 1u << a.log_cw;
+        size_t total = (size_t)R * CW;
+        smem = std::max(smem, (a.s0 == 0 ? total + (total >> 5) + 1 : (size_t)R * (CW + 1)) * 4);
+        a.n_tiles = (1u << a.log_n) / (R * CW);
+        a.cta_begin = cta;
+        cta += a.n_tiles * a.n_cols * a.n_cosets;
+    }
     static bool attr_set[2] = {false, false};
     int fid = FieldId<F>::value;
     if (!attr_set[fid]) {
         cudaFuncSetAttribute(k_ntt_pass<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         attr_set[fid] = true;
     }
-    uint32_t tiles = (1u << a.log_n) / (R * CW);
-    dim3 grid(tiles, n_cols, n_cosets);
-    k_ntt_pass<F><<<grid, 256, smem, ctx->stream>>>(a);
+    NttPass* d_jobs = upload_vec(ctx, passes);
+    if (!d_jobs) {
+        set_err(ctx, "staging exhausted");
+        return P3R_ERR_OOM;
+    }
+    k_ntt_pass<F><<<cta, 512, smem, ctx->stream>>>(d_jobs, (uint32_t)passes.size());
     LAUNCH_CHECK_C(KC_NTT);
+    return P3R_OK;
+}
+// Batched coset LDE of several matrices (all tables of one commit round): the same pass level of every job shares a launch.
+template <class F>
+static int coset_lde_batch(p3r_ctx* ctx, const std::vector<LdeJob>& jobs, uint32_t log_blowup) {
+    if (jobs.empty()) return P3R_OK;
+    uint32_t max_logN = 0;
+    uint64_t bytes = 0;
+    for (auto& j : jobs) {
+        max_logN = std::max(max_logN, j.log_n + log_blowup);
+        bytes += 4ull * (((size_t)1 << j.log_n) + ((size_t)1 << (j.log_n + log_blowup))) * j.w;
+    }
+    TRY(ensure_twiddles<F>(ctx, max_logN));
+    KT kt(ctx, KC_NTT, bytes);  // algorithmic bytes: read every trace once, write every LDE once
+    std::vector<std::vector<PassPlan>> plans;
+    std::vector<NttPass> base;
+    size_t max_passes = 0;
+    for (auto& j : jobs) {
+        GTable gt;
+        TRY(get_gtable<F>(ctx, j.log_n, &gt));
+        NttPass a{};
+        a.log_n = j.log_n;
+        a.tw = ctx->tw;
+        a.tws = ctx->tws;
+        a.logT = ctx->logT;
+        a.r4 = ctx->r4;
+        a.r8 = ctx->r8;
+        a.r8_3 = ctx->r8_3;
+        a.g_lo = gt.lo;
+        a.g_hi = gt.hi;
+        a.use_g = j.use_g;
+        a.rot = j.rot;
+        a.n_inv = finv<F>(to_monty<F>(1u << j.log_n));
+        a.log_blowup = log_blowup;
+        a.n_cols = j.w;
+        base.push_back(a);
+        plans.push_back(plan_passes(j.log_n));
+        max_passes = std::max(max_passes, plans.back().size());
+    }
+    // inverse: DIF, stages descending => every job walks its plan from the last pass to the first
+    for (size_t lvl = 0; lvl < max_passes; lvl++) {
+        std::vector<NttPass> level;
+        for (size_t q = 0; q < jobs.size(); q++) {
+            auto& plan = plans[q];
+            if (lvl >= plan.size()) continue;
+            size_t pi = plan.size() - 1 - lvl;
+            size_t n = (size_t)1 << jobs[q].log_n;
+            NttPass b = base[q];
+            b.forward = 0;
+            b.first = (lvl == 0);
+            b.last = (pi == 0);
+            b.s0 = plan[pi].s0;
+            b.r = plan[pi].r;
+            b.log_cw = plan[pi].log_cw;
+            b.src = b.first ? jobs[q].src : jobs[q].coef;
+            b.dst = jobs[q].coef;
+            b.src_col_stride = b.dst_col_stride = n;
+            b.dst_coset_stride = 0;
+            b.n_cosets = 1;
+            level.push_back(b);
+        }
+        TRY(launch_pass_level<F>(ctx, level));
+    }
+    // forward: DIT, stages ascending, all cosets of all jobs in one launch per level
+    for (size_t lvl = 0; lvl < max_passes; lvl++) {
+        std::vector<NttPass> level;
+        for (size_t q = 0; q < jobs.size(); q++) {
+            auto& plan = plans[q];
+            if (lvl >= plan.size()) continue;
+            size_t n = (size_t)1 << jobs[q].log_n, N = n << log_blowup;
+            NttPass b = base[q];
+            b.forward = 1;
+            b.first = (lvl == 0);
+            b.last = (lvl == plan.size() - 1);
+            b.s0 = plan[lvl].s0;
+            b.r = plan[lvl].r;
+            b.log_cw = plan[lvl].log_cw;
+            b.src = b.first ? jobs[q].coef : jobs[q].tmp;
+            b.dst = b.last ? jobs[q].dst : jobs[q].tmp;
+            b.src_col_stride = b.first ? n : N;
+            b.dst_col_stride = N;
+            b.dst_coset_stride = n;
+            b.n_cosets = 1u << log_blowup;
+            level.push_back(b);
+        }
+        TRY(launch_pass_level<F>(ctx, level));
+    }
     return P3R_OK;
 }
 template <class F>
 static int coset_lde(p3r_ctx* ctx, const uint32_t* src, uint32_t* dst, uint32_t log_n, uint32_t w, uint32_t log_blowup,
                      bool use_g, uint32_t rot, uint32_t* scratch_coef, uint32_t* scratch_tmp) {
     if (w == 0) return P3R_OK;
-    uint32_t logN = log_n + log_blowup;
-    TRY(ensure_twiddles<F>(ctx, logN));
-    GTable gt;
-    TRY(get_gtable<F>(ctx, log_n, &gt));
-    size_t n = (size_t)1 << log_n, N = (size_t)1 << logN;
-    KT kt(ctx, KC_NTT, 4ull * (n + N) * w);  // algorithmic bytes: read the trace once, write the LDE once
-    auto plan = plan_passes(log_n);
-    NttPass a{};
-    a.log_n = log_n;
-    a.tw = ctx->tw;
-    a.logT = ctx->logT;
-    a.g_lo = gt.lo;
-    a.g_hi = gt.hi;
-    a.use_g = use_g;
-    a.rot = rot;
-    a.n_inv = finv<F>(to_monty<F>(1u << log_n));
-    a.log_blowup = log_blowup;
-    // inverse: DIF, stages descending => passes in reverse plan order
-    for (size_t pi = plan.size(); pi-- > 0;) {
-        NttPass b = a;
-        b.forward = 0;
-        b.first = (pi == plan.size() - 1);
-        b.last = (pi == 0);
-        b.s0 = plan[pi].s0;
-        b.r = plan[pi].r;
-        b.log_cw = plan[pi].log_cw;
-        b.src = b.first ? src : scratch_coef;
-        b.dst = scratch_coef;
-        b.src_col_stride = b.dst_col_stride = n;
-        b.dst_coset_stride = 0;
-        TRY(launch_pass<F>(ctx, b, w, 1));
-    }
-    // forward: DIT, stages ascending, all cosets in grid.z
-    for (size_t pi = 0; pi < plan.size(); pi++) {
-        NttPass b = a;
-        b.forward = 1;
-        b.first = (pi == 0);
-        b.last = (pi == plan.size() - 1);
-        b.s0 = plan[pi].s0;
-        b.r = plan[pi].r;
-        b.log_cw = plan[pi].log_cw;
-        bool single = plan.size() == 1;
-        b.src = b.first ? scratch_coef : scratch_tmp;
-        b.dst = (b.last || single) ? dst : scratch_tmp;
-        b.src_col_stride = b.first ? n : N;
-        b.dst_col_stride = N;
-        b.dst_coset_stride = n;
-        TRY(launch_pass<F>(ctx, b, w, 1u << log_blowup));
-    }
-    return P3R_OK;
+    return coset_lde_batch<F>(ctx, {LdeJob{src, dst, log_n, w, use_g, rot, scratch_coef, scratch_tmp}}, log_blowup);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -505,11 +572,17 @@ static int commit_tree(p3r_ctx* ctx, const std::vector<MatRef>& mats, Tree* t, u
     uint32_t rows = 1u << lmax;
     {
         KT kt(ctx, KC_HASH, (uint64_t)rows * (4ull * top.size() + 32));
-        k_hash_rows<F><<<(rows + 127) / 128, 128, 0, ctx->stream>>>(d_cols, (uint32_t)top.size(), rows, digests);
+        if (rows <= 4096)
+            k_hash_rows_coop<F><<<(rows * 16 + 255) / 256, 256, 0, ctx->stream>>>(d_cols, (uint32_t)top.size(), rows, digests, ctx->d_p2);
+        else
+            k_hash_rows<F><<<(rows + 127) / 128, 128, 0, ctx->stream>>>(d_cols, (uint32_t)top.size(), rows, digests);
         LAUNCH_CHECK_C(KC_HASH);
     }
     KT kt_tree(ctx, KC_COMPRESS, 96ull * rows);
-    for (uint32_t l = 1; lmax - l + 1 > cap; l++) {
+    const uint32_t last_level = lmax - cap;
+    TreeTail tail{};
+    bool in_tail = false;
+    for (uint32_t l = 1; l <= last_level; l++) {
         uint32_t n_next = 1u << (lmax - l);
         auto inj = cols_at(lmax - l);
         const uint32_t* const* d_inj = nullptr;
@@ -520,10 +593,32 @@ static int commit_tree(p3r_ctx* ctx, const std::vector<MatRef>& mats, Tree* t, u
                 return P3R_ERR_OOM;
             }
         }
-        k_compress<F><<<(n_next + 127) / 128, 128, 0, ctx->stream>>>(digests + t->level_off(l - 1) * 8,
-                                                                      digests + t->level_off(l) * 8, n_next, d_inj,
-                                                                      (uint32_t)inj.size());
         ctx->kstats.bytes[KC_COMPRESS] += 4ull * inj.size() * n_next;
+        if (n_next <= TAIL_NODES && last_level - l < 24) {
+            if (!in_tail) {
+                in_tail = true;
+                tail.digests = digests;
+                tail.log_max_h = lmax;
+                tail.first_level = l;
+                tail.last_level = last_level;
+            }
+            tail.inj_colptr[l - tail.first_level] = d_inj;
+            tail.inj_cols[l - tail.first_level] = (uint32_t)inj.size();
+            continue;
+        }
+        if (n_next <= COOP_MAX_NODES && inj.size() <= 16)
+            k_compress_coop<F><<<(n_next * 16 + 255) / 256, 256, 0, ctx->stream>>>(digests + t->level_off(l - 1) * 8,
+                                                                                   digests + t->level_off(l) * 8, n_next, d_inj,
+                                                                                   (uint32_t)inj.size(), ctx->d_p2);
+        else
+            k_compress<F><<<(n_next + 127) / 128, 128, 0, ctx->stream>>>(digests + t->level_off(l - 1) * 8,
+                                                                          digests + t->level_off(l) * 8, n_next, d_inj,
+                                                                          (uint32_t)inj.size());
+        LAUNCH_CHECK_C(KC_COMPRESS);
+    }
+    if (in_tail) {
+        uint32_t n_first = 1u << (lmax - tail.first_level);
+        k_tree_tail<F><<<1, std::max(32u, std::min(n_first * 16, 1024u)), 0, ctx->stream>>>(tail, ctx->d_p2);
         LAUNCH_CHECK_C(KC_COMPRESS);
     }
     return P3R_OK;
@@ -707,7 +802,7 @@ static int prove_begin_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix
     s->chunks.assign(n_inst, nullptr);
     s->chunk_lde.assign(n_inst, nullptr);
     s->d_pub.assign(n_inst, nullptr);
-    size_t max_rm = 0, max_coef = 0, max_tmp = 0;
+    size_t max_rm = 0;
     for (size_t i = 0; i < n_inst; i++) {
         const InstDev& d = prep->inst[i];
         if (!resident && (traces[i].height != (1u << d.log_h) || traces[i].width != d.main_w || !traces[i].data)) {
@@ -716,15 +811,10 @@ static int prove_begin_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix
             return P3R_ERR_INVALID_ARG;
         }
         size_t n = (size_t)1 << d.log_h;
-        size_t wmax = std::max<size_t>({d.main_w, (size_t)d.aux_w() * 4, (size_t)4 << d.log_qc});
         max_rm = std::max(max_rm, n * d.main_w);
-        max_coef = std::max(max_coef, n * wmax);
-        if (d.log_h > TILE_LOG) max_tmp = std::max(max_tmp, (n << lb) * wmax);
     }
-    uint32_t* rm = arena_alloc<uint32_t>(ctx, max_rm);
-    s->scratch_coef = arena_alloc<uint32_t>(ctx, max_coef);
-    s->scratch_tmp = max_tmp ? arena_alloc<uint32_t>(ctx, max_tmp) : nullptr;
-    if (!rm || !s->scratch_coef || (max_tmp && !s->scratch_tmp)) {
+    uint32_t* rm = resident ? reinterpret_cast<uint32_t*>(ctx->dstage) : arena_alloc<uint32_t>(ctx, max_rm);
+    if (!rm) {
         set_err(ctx, "device allocation failed");
         delete s;
         return P3R_ERR_OOM;
@@ -766,12 +856,18 @@ static int commit_main_impl(p3r_session* s, uint32_t* cap_out) {
     const uint32_t lb = ctx->fri.log_blowup;
     std::vector<MatRef> mats;
     uint32_t lmax = 0;
+    std::vector<LdeJob> jobs;
     for (size_t i = 0; i < s->prep->inst.size(); i++) {
         const InstDev& d = s->prep->inst[i];
-        TRY(coset_lde<F>(ctx, s->trace[i], s->main_lde[i], d.log_h, d.main_w, lb, true, 0, s->scratch_coef, s->scratch_tmp));
+        size_t n = (size_t)1 << d.log_h;
+        uint32_t* coef = arena_alloc<uint32_t>(ctx, n * d.main_w);
+        uint32_t* tmp = d.log_h > TILE_LOG ? arena_alloc<uint32_t>(ctx, (n << lb) * d.main_w) : nullptr;
+        if (!coef || (d.log_h > TILE_LOG && !tmp)) return P3R_ERR_OOM;
+        jobs.push_back({s->trace[i], s->main_lde[i], d.log_h, d.main_w, true, 0, coef, tmp});
         mats.push_back({s->main_lde[i], d.log_h + lb, d.main_w});
         lmax = std::max(lmax, d.log_h + lb);
     }
+    TRY(coset_lde_batch<F>(ctx, jobs, lb));
     uint32_t* dg = arena_alloc<uint32_t>(ctx, tree_digest_words(lmax));
     if (!dg) return P3R_ERR_OOM;
     TRY(commit_tree<F>(ctx, mats, &s->main_tree, dg));
@@ -825,6 +921,7 @@ static int commit_perm_impl(p3r_session* s, const uint32_t alpha[4], const uint3
     Ext4* d_bp = upload_vec(ctx, bp);
     if (!s->d_chal || !d_bp || !s->d_terminals) return P3R_ERR_OOM;
     std::vector<MatRef> mats;
+    std::vector<LdeJob> jobs;
     uint32_t lmax = 0;
     for (size_t i = 0; i < n_inst; i++) {
         const InstDev& d = pp->inst[i];
@@ -854,13 +951,22 @@ static int commit_perm_impl(p3r_session* s, const uint32_t alpha[4], const uint3
             KT kt(ctx, KC_LOGUP, (uint64_t)n * 4 * (d.main_w + d.prep_w + pw));
             k_logup_rows<F><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(la);
             LAUNCH_CHECK_C(KC_LOGUP);
-            k_logup_scan<F><<<1, 1024, 0, ctx->stream>>>(rowsum, d.log_h, s->perm[i], s->d_terminals + i);
+            uint32_t n_chunks = (uint32_t)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
+            Ext4* chunk_sum = arena_alloc<Ext4>(ctx, n_chunks);
+            if (!chunk_sum) return P3R_ERR_OOM;
+            k_logup_chunk_sums<F><<<n_chunks, 256, 0, ctx->stream>>>(rowsum, (uint32_t)n, chunk_sum);
+            LAUNCH_CHECK_C(KC_LOGUP);
+            k_logup_scan_apply<F><<<n_chunks, 256, 0, ctx->stream>>>(rowsum, chunk_sum, (uint32_t)n, s->perm[i], s->d_terminals + i);
             LAUNCH_CHECK_C(KC_LOGUP);
         }
-        TRY(coset_lde<F>(ctx, s->perm[i], s->perm_lde[i], d.log_h, pw, lb, true, 0, s->scratch_coef, s->scratch_tmp));
+        uint32_t* coef = arena_alloc<uint32_t>(ctx, n * pw);
+        uint32_t* tmp = d.log_h > TILE_LOG ? arena_alloc<uint32_t>(ctx, (n << lb) * pw) : nullptr;
+        if (!coef || (d.log_h > TILE_LOG && !tmp)) return P3R_ERR_OOM;
+        jobs.push_back({s->perm[i], s->perm_lde[i], d.log_h, pw, true, 0, coef, tmp});
         mats.push_back({s->perm_lde[i], d.log_h + lb, pw});
         lmax = std::max(lmax, d.log_h + lb);
     }
+    TRY(coset_lde_batch<F>(ctx, jobs, lb));
     uint32_t* dg = arena_alloc<uint32_t>(ctx, tree_digest_words(lmax));
     if (!dg) return P3R_ERR_OOM;
     TRY(commit_tree<F>(ctx, mats, &s->perm_tree, dg));
@@ -890,6 +996,7 @@ static int commit_quotient_impl(p3r_session* s, const uint32_t alpha[4], uint32_
     Ext4 al;
     std::memcpy(al.c, alpha, 16);
     std::vector<MatRef> mats;
+    std::vector<LdeJob> jobs;
     uint32_t lmax = 0;
     for (size_t i = 0; i < pp->inst.size(); i++) {
         const InstDev& d = pp->inst[i];
@@ -931,11 +1038,15 @@ static int commit_quotient_impl(p3r_session* s, const uint32_t alpha[4], uint32_
             uint32_t rot = (uint32_t)((((uint64_t)1 << logN) - ((uint64_t)c << (lb - d.log_qc))) & (((uint64_t)1 << logN) - 1));
             uint32_t* src = s->chunks[i] + (size_t)c * 4 * n;
             uint32_t* dst = s->chunk_lde[i] + (size_t)c * 4 * (n << lb);
-            TRY(coset_lde<F>(ctx, src, dst, d.log_h, 4, lb, false, rot, s->scratch_coef, s->scratch_tmp));
+            uint32_t* coef = arena_alloc<uint32_t>(ctx, n * 4);
+            uint32_t* tmp = d.log_h > TILE_LOG ? arena_alloc<uint32_t>(ctx, (n << lb) * 4) : nullptr;
+            if (!coef || (d.log_h > TILE_LOG && !tmp)) return P3R_ERR_OOM;
+            jobs.push_back({src, dst, d.log_h, 4, false, rot, coef, tmp});
             mats.push_back({dst, logN, 4});
         }
         lmax = std::max(lmax, logN);
     }
+    TRY(coset_lde_batch<F>(ctx, jobs, lb));
     uint32_t* dg = arena_alloc<uint32_t>(ctx, tree_digest_words(lmax));
     if (!dg) return P3R_ERR_OOM;
     TRY(commit_tree<F>(ctx, mats, &s->quot_tree, dg));
@@ -1219,15 +1330,44 @@ static int fri_commit_impl(p3r_session* s, uint32_t round, uint32_t* cap_out) {
     uint32_t rows = 1u << log_rows, w = 4u << fr.log_arity;
     {
         KT kt(ctx, KC_HASH, (uint64_t)rows * (4ull * w + 32));
-        k_hash_rows_rowmajor<F><<<(rows + 127) / 128, 128, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(fr.vec), w, rows, dg);
+        if (rows <= COOP_MAX_NODES)
+            k_hash_rows_rowmajor_coop<F><<<(rows * 16 + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(fr.vec), w,
+                                                                                           rows, dg, ctx->d_p2);
+        else
+            k_hash_rows_rowmajor<F><<<(rows + 127) / 128, 128, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(fr.vec), w, rows, dg);
         LAUNCH_CHECK_C(KC_HASH);
     }
     KT kt_tree(ctx, KC_COMPRESS, 96ull * rows);
-    for (uint32_t l = 1; log_rows - l + 1 > ctx->fri.cap_height; l++) {
-        uint32_t n_next = 1u << (log_rows - l);
-        k_compress<F><<<(n_next + 127) / 128, 128, 0, ctx->stream>>>(dg + fr.tree.level_off(l - 1) * 8,
-                                                                      dg + fr.tree.level_off(l) * 8, n_next, nullptr, 0);
-        LAUNCH_CHECK_C(KC_COMPRESS);
+    {
+        const uint32_t last_level = log_rows - ctx->fri.cap_height;
+        TreeTail tail{};
+        bool in_tail = false;
+        for (uint32_t l = 1; l <= last_level; l++) {
+            uint32_t n_next = 1u << (log_rows - l);
+            if (n_next <= TAIL_NODES && last_level - l < 24) {
+                if (!in_tail) {
+                    in_tail = true;
+                    tail.digests = dg;
+                    tail.log_max_h = log_rows;
+                    tail.first_level = l;
+                    tail.last_level = last_level;
+                }
+                continue;
+            }
+            if (n_next <= COOP_MAX_NODES)
+                k_compress_coop<F><<<(n_next * 16 + 255) / 256, 256, 0, ctx->stream>>>(dg + fr.tree.level_off(l - 1) * 8,
+                                                                                       dg + fr.tree.level_off(l) * 8, n_next, nullptr, 0,
+                                                                                       ctx->d_p2);
+            else
+                k_compress<F><<<(n_next + 127) / 128, 128, 0, ctx->stream>>>(dg + fr.tree.level_off(l - 1) * 8,
+                                                                              dg + fr.tree.level_off(l) * 8, n_next, nullptr, 0);
+            LAUNCH_CHECK_C(KC_COMPRESS);
+        }
+        if (in_tail) {
+            uint32_t n_first = 1u << (log_rows - tail.first_level);
+            k_tree_tail<F><<<1, std::max(32u, std::min(n_first * 16, 1024u)), 0, ctx->stream>>>(tail, ctx->d_p2);
+            LAUNCH_CHECK_C(KC_COMPRESS);
+        }
     }
     return read_cap(ctx, fr.tree, cap_out);
 }
@@ -1735,6 +1875,8 @@ int p3r_ctx_create(int device, const p3r_field_desc* field, const p3r_poseidon2_
     ctx->pin_size = ctx->dstage_size = (size_t)8 << 20;
     ok = ok && cudaHostAlloc((void**)&ctx->pin, ctx->pin_size, cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&ctx->dstage, ctx->dstage_size) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&ctx->d_p2, sizeof(Poseidon2Consts)) == cudaSuccess;
+    ok = ok && cudaMemcpy(ctx->d_p2, &ctx->p2, sizeof(Poseidon2Consts), cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMemcpyToSymbol(c_p2, &ctx->p2, sizeof(Poseidon2Consts), (size_t)ctx->field_id * sizeof(Poseidon2Consts)) ==
                    cudaSuccess;
     if (!ok) {
@@ -1755,7 +1897,8 @@ void p3r_ctx_destroy(p3r_ctx* ctx) {
         cudaFree(kv.second.hi);
     }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
-    if (ctx->tw) cudaFree(ctx->tw);
+    if (ctx->tws) cudaFree(ctx->tws);
+    if (ctx->d_p2) cudaFree(ctx->d_p2);
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->dstage) cudaFree(ctx->dstage);
     cudaStreamDestroy(ctx->stream);
