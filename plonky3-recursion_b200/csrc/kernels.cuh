@@ -34,7 +34,7 @@ __global__ void k_powers(uint32_t* out, uint32_t n, uint32_t w, uint32_t first) 
 // Row-major (h x w) -> column-major (w x h) through a 32x33 shared tile (coalesced on both sides).
 __global__ void k_transpose_in(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t h, uint32_t w) {
     __shared__ uint32_t tile[32][33];
-    uint32_t c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    uint32_t c0 = blockIdx.y * 32, r0 = blockIdx.x * 32;  // rows on grid.x (no 65535 limit)
     for (uint32_t dy = threadIdx.y; dy < 32; dy += blockDim.y) {
         uint32_t r = r0 + dy, c = c0 + threadIdx.x;
         if (r < h && c < w) tile[dy][threadIdx.x] = in[(size_t)r * w + c];
@@ -48,7 +48,7 @@ __global__ void k_transpose_in(const uint32_t* __restrict__ in, uint32_t* __rest
 // Column-major (w x h) -> row-major (h x w); used only by the isolated p3r_coset_lde entry point.
 __global__ void k_transpose_out(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t h, uint32_t w) {
     __shared__ uint32_t tile[32][33];
-    uint32_t c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    uint32_t c0 = blockIdx.y * 32, r0 = blockIdx.x * 32;  // rows on grid.x (no 65535 limit)
     for (uint32_t dy = threadIdx.y; dy < 32; dy += blockDim.y) {
         uint32_t c = c0 + dy, r = r0 + threadIdx.x;
         if (r < h && c < w) tile[dy][threadIdx.x] = in[(size_t)c * h + r];

@@ -638,7 +638,7 @@ static int upload_matrix(p3r_ctx* ctx, const p3r_matrix_u32& m, uint32_t* d_rowm
     size_t words = (size_t)m.height * m.width;
     if (!words) return P3R_OK;
     CUDA_TRY(cudaMemcpyAsync(d_rowmajor_scratch, m.data, words * 4, cudaMemcpyHostToDevice, ctx->stream));
-    dim3 grid((m.width + 31) / 32, (m.height + 31) / 32), block(32, 8);
+    dim3 grid((m.height + 31) / 32, (m.width + 31) / 32), block(32, 8);
     {
         KT kt(ctx, KC_TRANSPOSE, 8ull * words);
         k_transpose_in<<<grid, block, 0, ctx->stream>>>(d_rowmajor_scratch, d_colmajor, m.height, m.width);
@@ -1725,7 +1725,7 @@ static int coset_lde_host_impl(p3r_ctx* ctx, const p3r_matrix_u32* in, uint32_t 
     if (!rm || !cm || !coef || !lde || (log_n > TILE_LOG && !tmp)) return P3R_ERR_OOM;
     TRY(upload_matrix(ctx, *in, rm, cm));
     TRY(coset_lde<F>(ctx, cm, lde, log_n, (uint32_t)w, log_blowup, true, 0, coef, tmp));
-    dim3 grid((unsigned)((w + 31) / 32), (unsigned)((N + 31) / 32)), block(32, 8);
+    dim3 grid((unsigned)((N + 31) / 32), (unsigned)((w + 31) / 32)), block(32, 8);
     k_transpose_out<<<grid, block, 0, ctx->stream>>>(lde, rm, (uint32_t)N, (uint32_t)w);
     LAUNCH_CHECK();
     CUDA_TRY(cudaMemcpyAsync(out, rm, N * w * 4, cudaMemcpyDeviceToHost, ctx->stream));

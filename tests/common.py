@@ -34,3 +34,50 @@ def send_receive_system(F, rng, n_ops=40, log_ha=6, log_hb=5, d=4):
     tB = ws.trace_to_matrix(vals, d, 2, 1 << log_hb)
     pB = ws.preprocessed_matrix(np.full(n_ops, F.p - 1), idx, 2, 1 << log_hb)
     return [A, B], [pA, pB], [tA, tB], [None, None]
+
+
+class PyChallenger:
+    """DuplexChallenger<F, Perm, 16, 8> in plain Python/numpy, the transcript a Rust host would own when it
+    drives the phase-stepped C ABI. Values are canonical."""
+
+    def __init__(self, F):
+        self.F = F
+        self.prm = p2mod.Poseidon2Params(F.field_id)
+        self.state = [0] * 16
+        self.inp, self.out = [], []
+
+    def _duplex(self):
+        n = len(self.inp)
+        for i, v in enumerate(self.inp):
+            self.state[i] = v
+        if n:
+            for i in range(n, 8):
+                self.state[i] = 0
+            self.state[8] = (self.state[8] + n) % self.F.p
+        self.inp = []
+        self.state = [int(x) for x in self.prm.permute(np.array(self.state, dtype=np.uint64)[None])[0]]
+        self.out = list(self.state[:8])
+
+    def observe(self, v):
+        self.out = []
+        self.inp.append(int(v) % self.F.p)
+        if len(self.inp) == 8:
+            self._duplex()
+
+    def observe_many(self, vs):
+        for v in vs:
+            self.observe(v)
+
+    def observe_lifted(self, v):
+        self.observe_many([v, 0, 0, 0])
+
+    def sample(self):
+        if self.inp or not self.out:
+            self._duplex()
+        return self.out.pop()
+
+    def sample_ext(self):
+        return [self.sample() for _ in range(4)]
+
+    def sample_bits(self, bits):
+        return self.sample() & ((1 << bits) - 1)

@@ -1,0 +1,54 @@
+"""The C-ABI library loads and exports every symbol include/p3r.h declares; without a GPU it fails loudly (no fallback)."""
+import importlib
+import os
+import re
+
+import pytest
+
+lib = importlib.import_module("plonky3-recursion_b200.lib")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "p3r.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(p3r_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    l = lib.load()
+    names = header_functions()
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(l, n)]
+    assert not missing, f"declared in include/p3r.h but not exported: {missing}"
+    assert sorted(lib.EXPORTS) == names, "lib.EXPORTS and include/p3r.h disagree"
+    assert l.p3r_abi_version() == 1
+    assert b"sm_100a" in l.p3r_build_info()
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback_without_gpu():
+    with pytest.raises(lib.P3RError) as e:
+        lib.Context("koala-bear")
+    assert "no usable CUDA device" in str(e.value) or e.value.code == 2
+
+
+def test_product_never_imports_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py may touch oracle/ (grep of the product package)."""
+    pkg = os.path.join(ROOT, "plonky3-recursion_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                if re.search(r"oracle_py|liboracle|orc_[a-z_]+\(", text):
+                    offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders

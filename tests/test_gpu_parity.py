@@ -93,3 +93,208 @@ def test_recursion_layer_tables_bit_identical(pair, seed):
     with pytest.raises(RuntimeError):
         orc.verify(L.insts, pd.preprocessed_commitment, L.pubs, bad)
     pd.close()
+
+
+def _fib_system(F, log_n=6):
+    fib = importlib.import_module("plonky3-recursion_b200.airs.fibonacci")
+    air_mod = importlib.import_module("plonky3-recursion_b200.air")
+    t, pubs = fib.trace(F.p, log_n)
+    inst = air_mod.build_instance("fib", fib.eval_air, F.p, log_n, 2, 0, 3, air_mod.BusRegistry())
+    return [inst], [None], [t], [pubs]
+
+
+def test_fibonacci_public_values_no_lookups_no_prep(pair):
+    ctx, orc = pair
+    insts, preps, traces, pubs = _fib_system(ctx.field)
+    pd = lib.ProverData.from_airs_and_degrees(ctx, insts, preps)
+    assert pd.preprocessed_commitment is None
+    proof = lib.BatchStarkProver(ctx).prove_all_tables(traces, pd, pubs)
+    assert np.array_equal(proof, orc.prove(insts, preps, traces, pubs))
+    orc.verify(insts, None, pubs, proof)
+    # an invalid witness still yields a proof, which the verifier rejects (same behaviour as the CPU path)
+    bad = traces[0].copy()
+    bad[10, 1] = (int(bad[10, 1]) + 1) % ctx.field.p
+    bad_proof = lib.BatchStarkProver(ctx).prove_all_tables([bad], pd, pubs)
+    with pytest.raises(RuntimeError):
+        orc.verify(insts, None, pubs, bad_proof)
+    pd.close()
+
+
+@pytest.mark.parametrize("fri", [
+    dict(SMALL_FRI, cap_height=2),
+    dict(SMALL_FRI, max_log_arity=1),
+    dict(SMALL_FRI, max_log_arity=3, log_final_poly_len=0),
+    dict(SMALL_FRI, commit_pow_bits=3, query_pow_bits=0),
+    dict(SMALL_FRI, log_blowup=1, num_queries=10),
+    dict(SMALL_FRI, log_blowup=3, log_final_poly_len=1),
+    dict(lib.DEFAULT_FRI),
+])
+def test_fri_parameter_variants_bit_identical(fri):
+    wl = importlib.import_module("plonky3-recursion_b200.workload")
+    ctx = lib.Context("koala-bear", fri)
+    orc = make_oracle("koala-bear", fri)
+    mh = 256 if fri["log_final_poly_len"] == 5 else 64
+    L = wl.synthetic_layer(ctx.field, 4, n_const=10, n_public=20, n_alu=120, n_perms=30, n_recompose=5, min_height=mh)
+    fi, fp, ft, fpub = _fib_system(ctx.field, 9)
+    insts, preps, traces, pubs = L.insts + fi, L.preps + fp, L.traces + ft, L.pubs + fpub
+    pd = lib.ProverData.from_airs_and_degrees(ctx, insts, preps)
+    proof = lib.BatchStarkProver(ctx).prove_all_tables(traces, pd, pubs)
+    want = orc.prove(insts, preps, traces, pubs)
+    assert proof.size == want.size and np.array_equal(proof, want)
+    orc.verify(insts, pd.preprocessed_commitment, pubs, proof)
+    pd.close()
+    ctx.close()
+
+
+def test_resident_and_pinned_paths_give_the_same_proof(pair):
+    wl = importlib.import_module("plonky3-recursion_b200.workload")
+    ctx, orc = pair
+    L = wl.synthetic_layer(ctx.field, 11, n_const=10, n_public=40, n_alu=300, n_perms=60, n_recompose=5, min_height=32)
+    pd = lib.ProverData.from_airs_and_degrees(ctx, L.insts, L.preps)
+    prover = lib.BatchStarkProver(ctx, pinned_output=True)
+    a = prover.prove_all_tables(L.traces, pd, L.pubs)
+    b = prover.prove_all_tables(lib.TraceBatch(ctx, L.traces, L.pubs, pinned=True), pd)
+    tb = lib.TraceBatch(ctx, L.traces, L.pubs).upload(pd)
+    c = prover.prove_resident(tb, pd)
+    c2 = prover.prove_resident(tb, pd)  # idempotent: the session must not modify resident traces
+    assert np.array_equal(a, b) and np.array_equal(a, c) and np.array_equal(a, c2)
+    assert np.array_equal(a, orc.prove(L.insts, L.preps, L.traces, L.pubs))
+    tb.close()
+    pd.close()
+
+
+def test_phase_stepped_abi_with_external_transcript(pair):
+    """Drive p3r_prove_begin .. p3r_fri_query the way the Rust GpuBatchStarkProver would, with the Fiat-Shamir transcript
+    owned by the caller (tests/common.PyChallenger); the assembled proof must equal the oracle's and p3r_prove's."""
+    import ctypes as C
+    from common import PyChallenger
+    abi = importlib.import_module("plonky3-recursion_b200.abi")
+    wl = importlib.import_module("plonky3-recursion_b200.workload")
+    ctx, orc = pair
+    F, l, fri = ctx.field, ctx.lib, ctx.fri
+    L = wl.synthetic_layer(F, 21, n_const=10, n_public=30, n_alu=150, n_perms=40, n_recompose=5, min_height=32)
+    pd = lib.ProverData.from_airs_and_degrees(ctx, L.insts, L.preps)
+    tb = lib.TraceBatch(ctx, L.traces, L.pubs)
+    sess = C.c_void_p()
+    ctx._check(l.p3r_prove_begin(ctx.h, pd.h, tb.tm, tb.pv, C.byref(sess)))
+    capw = ctx.cap_words
+    mont = lambda xs: np.ascontiguousarray(F.to_monty(np.array(xs, dtype=np.uint32)))
+    canon = lambda a: [int(x) for x in F.from_monty(a)]
+    ch = PyChallenger(F)
+    buf = lambda n: np.zeros(n, dtype=np.uint32)
+    main_cap = buf(capw)
+    ctx._check(l.p3r_commit_main(sess, abi.as_u32p(main_cap)))
+    # a phase called out of order is refused (P3R_ERR_STATE = 4)
+    assert l.p3r_commit_quotient(sess, abi.as_u32p(mont([1, 0, 0, 0])), abi.as_u32p(buf(capw))) == 4
+    ch.observe_lifted(len(L.insts))
+    for s in L.insts:
+        for v in (s.log_height, s.log_height, s.main_width, 1 << s.log_quotient_chunks):
+            ch.observe_lifted(v)
+    ch.observe_many(canon(main_cap))
+    for s in L.insts:
+        ch.observe_lifted(s.prep_width)
+    ch.observe_many(canon(pd.preprocessed_commitment))
+    pa, pb = ch.sample_ext(), ch.sample_ext()
+    n_perm = sum(1 for s in L.insts if s.lookups)
+    perm_cap, terms = buf(capw), buf(4 * n_perm)
+    ctx._check(l.p3r_commit_perm(sess, abi.as_u32p(mont(pa)), abi.as_u32p(mont(pb)), abi.as_u32p(perm_cap), abi.as_u32p(terms)))
+    ch.observe_many(canon(perm_cap))
+    ch.observe_many(canon(terms))
+    alpha = ch.sample_ext()
+    quot_cap = buf(capw)
+    ctx._check(l.p3r_commit_quotient(sess, abi.as_u32p(mont(alpha)), abi.as_u32p(quot_cap)))
+    ch.observe_many(canon(quot_cap))
+    zeta = ch.sample_ext()
+    opened, n_open = buf(1 << 16), C.c_size_t(0)
+    ctx._check(l.p3r_open(sess, abi.as_u32p(mont(zeta)), abi.as_u32p(opened), C.c_size_t(opened.size), C.byref(n_open)))
+    opened = opened[: n_open.value]
+    # observe in round order [main, quotient, preprocessed, permutation]; the blob is per instance
+    # [main_local, main_next?, prep_local, prep_next, perm_local, perm_next, quotient chunks]
+    segs, cur = [], 0
+    for s in L.insts:
+        m = 4 * s.main_width * (2 if s.uses_next_row else 1)
+        pr = 4 * s.prep_width * 2
+        pe = 4 * s.aux_width * 4 * 2
+        q = 4 * (4 << s.log_quotient_chunks)
+        segs.append((cur, m, pr, pe, q))
+        cur += m + pr + pe + q
+    assert cur == opened.size
+    oc = canon(opened)
+    for (o, m, pr, pe, q) in segs:
+        ch.observe_many(oc[o:o + m])
+    for (o, m, pr, pe, q) in segs:
+        ch.observe_many(oc[o + m + pr + pe:o + m + pr + pe + q])
+    for (o, m, pr, pe, q) in segs:
+        ch.observe_many(oc[o + m:o + m + pr])
+    for (o, m, pr, pe, q) in segs:
+        ch.observe_many(oc[o + m + pr:o + m + pr + pe])
+    alpha_fri = ch.sample_ext()
+    n_rounds, arities = C.c_uint32(0), buf(32)
+    ctx._check(l.p3r_fri_begin(sess, abi.as_u32p(mont(alpha_fri)), C.byref(n_rounds), abi.as_u32p(arities)))
+    R = n_rounds.value
+    fri_caps, commit_pow = [], []
+    for r in range(R):
+        cap = buf(capw)
+        ctx._check(l.p3r_fri_commit(sess, r, abi.as_u32p(cap)))
+        fri_caps.append(cap)
+        ch.observe_many(canon(cap))
+        commit_pow.append(0)  # commit_pow_bits == 0: no-op on the transcript
+        beta = ch.sample_ext()
+        ctx._check(l.p3r_fri_fold(sess, r, abi.as_u32p(mont(beta))))
+    final = buf(4 << fri["log_final_poly_len"])
+    ctx._check(l.p3r_fri_final_poly(sess, abi.as_u32p(final)))
+    ch.observe_many(canon(final))
+    for r in range(R):
+        ch.observe(int(arities[r]))
+    w = ctx.grind(mont(ch.state), mont(ch.inp) if ch.inp else np.zeros(0, dtype=np.uint32), fri["query_pow_bits"])
+    w_canon = canon(np.array([w], dtype=np.uint32))[0]
+    ch.observe(w_canon)
+    assert ch.sample_bits(fri["query_pow_bits"]) == 0
+    log_max = max(s.log_height for s in L.insts) + fri["log_blowup"]
+    idx = np.array([ch.sample_bits(log_max) for _ in range(fri["num_queries"])], dtype=np.uint32)
+    qbuf, nq = buf(1 << 20), C.c_size_t(0)
+    ctx._check(l.p3r_fri_query(sess, abi.as_u32p(idx), idx.size, abi.as_u32p(qbuf), C.c_size_t(qbuf.size), C.byref(nq)))
+    l.p3r_session_free(sess)
+    blob = np.concatenate([
+        np.array([0x50335250, len(L.insts), 1, 1, capw] + [s.log_height for s in L.insts], dtype=np.uint32),
+        main_cap, perm_cap, quot_cap, terms, opened, np.array([R], dtype=np.uint32), arities[:R], *fri_caps,
+        np.array(commit_pow, dtype=np.uint32), final, np.array([w], dtype=np.uint32), qbuf[: nq.value]])
+    want = orc.prove(L.insts, L.preps, L.traces, L.pubs)
+    assert blob.size == want.size and np.array_equal(blob, want)
+    assert np.array_equal(blob, lib.BatchStarkProver(ctx).prove_all_tables(tb, pd))
+    pd.close()
+
+
+@pytest.mark.parametrize("log_n,width", [(18, 3), (20, 2)])
+def test_large_lde_properties(pair, log_n, width):
+    """Sizes the oracle cannot reach in seconds: check size-independent properties instead. The first n rows of the
+    bit-reversed LDE are the evaluations on the coset GENERATOR*H_n (so interpolating them must reproduce the input after
+    shifting back), and the LDE is linear."""
+    ctx, orc = pair
+    F = ctx.field
+    rng = np.random.default_rng(log_n)
+    a = F.rand(rng, (1 << log_n, width))
+    b = F.rand(rng, (1 << log_n, width))
+    s = ((a.astype(np.uint64) + b) % F.p).astype(np.uint32)
+    la, lb_, ls = ctx.coset_lde(a, 1), ctx.coset_lde(b, 1), ctx.coset_lde(s, 1)
+    assert np.array_equal(ls, ((la.astype(np.uint64) + lb_) % F.p).astype(np.uint32))
+    # a constant column extends to the same constant; the column x -> x (identity on H_n) extends to GENERATOR*w_N^bitrev(r)
+    n, N = 1 << log_n, 1 << (log_n + 1)
+    w = F.two_adic_generator(log_n)
+    # build the subgroup H_n iteratively in numpy (object-free): powers via cumulative products in chunks
+    pw = np.ones(n, dtype=np.uint64)
+    step = 1
+    base = w
+    while step < n:
+        pw[step:2 * step] = pw[:step] * np.uint64(base) % np.uint64(F.p)
+        base = base * base % F.p
+        step *= 2
+    # pw currently holds w^(bit-reversed-like enumeration)?  it holds w^i for i in natural order:
+    # pw[step + j] = pw[j] * w^(step)  requires base = w^step: base starts at w = w^1 and squares -> w^step. OK.
+    ident = np.stack([pw.astype(np.uint32), np.full(n, 7, dtype=np.uint32)], axis=1)
+    lde = ctx.coset_lde(ident, 1)
+    assert (lde[:, 1] == 7).all()
+    wN = F.two_adic_generator(log_n + 1)
+    for r in (0, 1, 2, 12345 % N, N - 1):
+        rev = int(format(r, f"0{log_n + 1}b")[::-1], 2)
+        assert int(lde[rev, 0]) == F.generator * pow(wN, r, F.p) % F.p

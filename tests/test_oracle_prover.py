@@ -1,0 +1,109 @@
+"""CPU oracle prover <-> verifier: round trips over the proof shapes and FRI parameter variants the reference exercises
+(circuit-prover/src/batch_stark_prover/tests.rs, recursion/tests/fri.rs), plus rejection of tampered proofs and of
+invalid witnesses. These run without a GPU; the GPU suite repeats the same systems through the C ABI bit-for-bit."""
+import importlib
+
+import numpy as np
+import pytest
+
+from common import SMALL_FRI, air_mod, field_mod, make_oracle, send_receive_system, ws
+
+fib = importlib.import_module("plonky3-recursion_b200.airs.fibonacci")
+wl = importlib.import_module("plonky3-recursion_b200.workload")
+
+
+def fib_system(F, log_n=6):
+    t, pubs = fib.trace(F.p, log_n)
+    inst = air_mod.build_instance("fib", fib.eval_air, F.p, log_n, 2, 0, 3, air_mod.BusRegistry())
+    return [inst], [None], [t], [pubs]
+
+
+@pytest.mark.parametrize("field", ["koala-bear", "baby-bear"])
+def test_send_receive_roundtrip_and_tamper(field):
+    orc = make_oracle(field)
+    rng = np.random.default_rng(1)
+    insts, preps, traces, pubs = send_receive_system(orc.field, rng)
+    proof = orc.prove(insts, preps, traces, pubs)
+    cap = orc.prep_commit(insts, preps)
+    orc.verify(insts, cap, pubs, proof)
+    assert np.array_equal(proof, orc.prove(insts, preps, traces, pubs))  # deterministic (smallest PoW witness)
+    # header, commitments, terminals, opened values, FRI caps, final polynomial, PoW witness, query data
+    for pos in (1, 9, 17, 30, 33, 60, 200, proof.size // 2, proof.size - 5):
+        bad = proof.copy()
+        bad[pos] = (int(bad[pos]) + 1) % orc.field.p
+        with pytest.raises(RuntimeError):
+            orc.verify(insts, cap, pubs, bad)
+    with pytest.raises(RuntimeError):
+        orc.verify(insts, cap, pubs, proof[:-1])
+    wrong_cap = cap.copy()
+    wrong_cap[0] ^= 1
+    with pytest.raises(RuntimeError):
+        orc.verify(insts, wrong_cap, pubs, proof)
+
+
+def test_unbalanced_bus_is_rejected():
+    orc = make_oracle("koala-bear")
+    rng = np.random.default_rng(2)
+    insts, preps, traces, pubs = send_receive_system(orc.field, rng)
+    preps[0] = preps[0].copy()
+    preps[0][3, 0] = 2  # creator claims two reads, only one reader exists
+    proof = orc.prove(insts, preps, traces, pubs)
+    with pytest.raises(RuntimeError, match="terminals"):
+        orc.verify(insts, orc.prep_commit(insts, preps), pubs, proof)
+    # a reader looking up a value nobody created is also caught
+    insts, preps, traces, pubs = send_receive_system(orc.field, rng)
+    traces[1] = traces[1].copy()
+    traces[1][0, 0] = (int(traces[1][0, 0]) + 1) % orc.field.p
+    proof = orc.prove(insts, preps, traces, pubs)
+    with pytest.raises(RuntimeError, match="terminals"):
+        orc.verify(insts, orc.prep_commit(insts, preps), pubs, proof)
+
+
+@pytest.mark.parametrize("field", ["koala-bear", "baby-bear"])
+def test_fibonacci_public_values_no_lookups_no_prep(field):
+    orc = make_oracle(field)
+    insts, preps, traces, pubs = fib_system(orc.field)
+    assert insts[0].log_quotient_chunks == 0 and not insts[0].lookups and insts[0].uses_next_row
+    proof = orc.prove(insts, preps, traces, pubs)
+    assert proof[2] == 0 and proof[3] == 0  # no permutation / preprocessed commitments in the proof
+    orc.verify(insts, None, pubs, proof)
+    wrong = [pubs[0].copy()]
+    wrong[0][2] = (int(wrong[0][2]) + 1) % orc.field.p
+    with pytest.raises(RuntimeError):
+        orc.verify(insts, None, wrong, proof)
+    # an invalid witness yields a proof the verifier rejects: constraints(zeta)/Z_H(zeta) != Q(zeta)
+    bad = traces[0].copy()
+    bad[10, 1] = (int(bad[10, 1]) + 1) % orc.field.p
+    bad_proof = orc.prove(insts, preps, [bad], pubs)
+    with pytest.raises(RuntimeError, match="constraint/quotient"):
+        orc.verify(insts, None, pubs, bad_proof)
+
+
+@pytest.mark.parametrize("fri", [
+    dict(SMALL_FRI, cap_height=2),
+    dict(SMALL_FRI, max_log_arity=1),
+    dict(SMALL_FRI, max_log_arity=3, log_final_poly_len=0),
+    dict(SMALL_FRI, commit_pow_bits=3, query_pow_bits=0),
+    dict(SMALL_FRI, log_blowup=1, num_queries=10),
+    dict(SMALL_FRI, log_blowup=3, log_final_poly_len=1),
+])
+def test_fri_parameter_variants(fri):
+    orc = make_oracle("koala-bear", fri)
+    L = wl.synthetic_layer(orc.field, 4, n_const=10, n_public=20, n_alu=120, n_perms=30, n_recompose=5, min_height=64)
+    proof = orc.prove(L.insts, L.preps, L.traces, L.pubs)
+    orc.verify(L.insts, orc.prep_commit(L.insts, L.preps), L.pubs, proof)
+    n_inst = len(L.insts)
+    cap_words = 8 << fri["cap_height"]
+    assert proof[1] == n_inst and proof[4] == cap_words
+
+
+def test_layer_with_public_values_and_mixed_heights():
+    """Fibonacci (public values, no lookups) next to the 5 recursion tables: instances with and without lookups /
+    preprocessed columns / next-row openings in one batch."""
+    orc = make_oracle("baby-bear")
+    F = orc.field
+    L = wl.synthetic_layer(F, 6, n_const=10, n_public=20, n_alu=100, n_perms=30, n_recompose=5, min_height=32)
+    fi, fp, ft, fpub = fib_system(F, 7)
+    insts, preps, traces, pubs = L.insts + fi, L.preps + fp, L.traces + ft, L.pubs + fpub
+    proof = orc.prove(insts, preps, traces, pubs)
+    orc.verify(insts, orc.prep_commit(insts, preps), pubs, proof)
