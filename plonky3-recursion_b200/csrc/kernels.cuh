@@ -32,7 +32,7 @@ __global__ void k_powers(uint32_t* out, uint32_t n, uint32_t w, uint32_t first) 
 }
 
 // Row-major (h x w) -> column-major (w x h) through a 32x33 shared tile (coalesced on both sides).
-__global__ void k_transpose_in(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t h, uint32_t w) {
+static __global__ void k_transpose_in(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t h, uint32_t w) {
     __shared__ uint32_t tile[32][33];
     uint32_t c0 = blockIdx.y * 32, r0 = blockIdx.x * 32;  // rows on grid.x (no 65535 limit)
     for (uint32_t dy = threadIdx.y; dy < 32; dy += blockDim.y) {
@@ -46,7 +46,7 @@ __global__ void k_transpose_in(const uint32_t* __restrict__ in, uint32_t* __rest
     }
 }
 // Column-major (w x h) -> row-major (h x w); used only by the isolated p3r_coset_lde entry point.
-__global__ void k_transpose_out(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t h, uint32_t w) {
+static __global__ void k_transpose_out(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t h, uint32_t w) {
     __shared__ uint32_t tile[32][33];
     uint32_t c0 = blockIdx.y * 32, r0 = blockIdx.x * 32;  // rows on grid.x (no 65535 limit)
     for (uint32_t dy = threadIdx.y; dy < 32; dy += blockDim.y) {
@@ -1045,7 +1045,7 @@ struct GatherSeg {
     uint32_t shift;           // index >> shift
     uint32_t out_off;         // word offset within one query's blob
 };
-__global__ void __launch_bounds__(256) k_query_gather(const GatherSeg* __restrict__ segs, uint32_t n_segs,
+static __global__ void __launch_bounds__(256) k_query_gather(const GatherSeg* __restrict__ segs, uint32_t n_segs,
                                                        const uint32_t* __restrict__ indices, uint32_t words_per_query,
                                                        uint32_t* __restrict__ out) {
     uint32_t q = blockIdx.x;

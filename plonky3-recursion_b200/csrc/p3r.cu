@@ -3,6 +3,7 @@
 // BatchStarkProver::prove, /root/reference circuit-prover/src/batch_stark_prover.rs:1275-1642 -> p3_batch_stark::prove_batch).
 // No CPU fallback: every compute entry point runs CUDA kernels from kernels.cuh or fails.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -10,6 +11,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "spec.h"
 
 using namespace p3r;
 
@@ -76,6 +78,7 @@ struct KernelStats {
 };
 
 struct p3r_ctx {
+    bool use_spec = true;  // p3r_set_specialization
     cudaEvent_t timer_ev[2] = {nullptr, nullptr};
     uint32_t time_mask = 0;  // bit per KClass: record CUDA events around launches of that class
     std::vector<cudaEvent_t> ev_pool;
@@ -211,6 +214,7 @@ struct InstDev {
     uint32_t* prep_lde = nullptr;
     uint32_t* sel = nullptr;
     uint32_t* inv_van = nullptr;
+    SpecQuotientKernel spec = nullptr;  // build-time specialised quotient kernel whose program hash matches, if any
     uint32_t aux_w() const { return lookups.empty() ? 0 : (uint32_t)lookups.size() + 1; }
 };
 struct p3r_prep {
@@ -276,8 +280,11 @@ struct HostChallenger {
     uint32_t st[16];
     uint32_t in[8], out[8];
     int n_in = 0, n_out = 0;
+    double host_ms = 0;  // wall time spent in host permutations
+    uint32_t n_perms = 0;
     explicit HostChallenger(const Poseidon2Consts* k_) : k(k_) { std::memset(st, 0, sizeof st); }
     void duplex() {
+        auto t0 = std::chrono::steady_clock::now();
         for (int i = 0; i < n_in; i++) st[i] = in[i];
         if (n_in > 0) {
             for (int i = n_in; i < 8; i++) st[i] = 0;
@@ -287,6 +294,8 @@ struct HostChallenger {
         poseidon2_permute_with<F>(st, *k);
         for (int i = 0; i < 8; i++) out[i] = st[i];
         n_out = 8;
+        n_perms++;
+        host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
     void observe(uint32_t v) {
         n_out = 0;
@@ -706,6 +715,19 @@ static int prep_commit_impl(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_de
             if (p && bytes) cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
             return p;
         };
+        {
+            // FNV-1a over the instruction words: selects a build-time specialised quotient kernel (specialized_gen.cuh)
+            uint64_t h = 0xCBF29CE484222325ull;
+            const uint8_t* bytes = reinterpret_cast<const uint8_t*>(d.constraints.insns);
+            for (size_t k = 0; k < (size_t)d.constraints.n_insns * 16; k++) {
+                h ^= bytes[k];
+                h *= 0x100000001B3ull;
+            }
+            size_t n_spec = 0;
+            const SpecEntry* reg = p3r_spec_registry(&n_spec);
+            for (size_t q = 0; q < n_spec; q++)
+                if (reg[q].hash == h && reg[q].field_id == ctx->field_id && reg[q].n_insns == d.constraints.n_insns) s.spec = reg[q].fn;
+        }
         s.n_cons_insns = d.constraints.n_insns;
         s.n_constraints = d.constraints.n_constraints;
         s.cons = (uint4*)up(d.constraints.insns, (size_t)d.constraints.n_insns * 16);
@@ -1029,7 +1051,10 @@ static int commit_quotient_impl(p3r_session* s, const uint32_t alpha[4], uint32_
         uint32_t NQ = (uint32_t)(n << d.log_qc);
         {
             KT kt(ctx, KC_QUOTIENT, (uint64_t)NQ * (8ull * (d.main_w + d.prep_w + d.aux_w() * 4) + 16));
-            k_quotient<F><<<(NQ + 127) / 128, 128, 0, ctx->stream>>>(qa);
+            if (d.spec && ctx->use_spec)
+                p3r_spec_launch(d.spec, qa, (NQ + 127) / 128, 128, ctx->stream);
+            else
+                k_quotient<F><<<(NQ + 127) / 128, 128, 0, ctx->stream>>>(qa);
             LAUNCH_CHECK_C(KC_QUOTIENT);
         }
         // chunk c lives on the coset GENERATOR * w_NQ^c * H_n: LDE without the GENERATOR factor, rotated by -c*(N/NQ)
@@ -1700,6 +1725,8 @@ static int prove_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* 
     TRY(fri_query_impl(s, indices.data(), (uint32_t)indices.size(), proof_out + head, cap_words - head, &qwords));
     pt.mark("query");
     pt.finish();
+    ctx->phase_times.push_back({"host_challenger", (float)ch.host_ms});
+    ctx->phase_times.push_back({"host_perms", (float)ch.n_perms});
     kstats_collect(ctx);
     return P3R_OK;
 }
@@ -2020,6 +2047,11 @@ int p3r_prove_resident(p3r_ctx* ctx, const p3r_prep* prep, const p3r_traces* tra
     if (!ctx || !prep || !traces || !n_words || traces->d.size() != prep->inst.size()) return P3R_ERR_INVALID_ARG;
     cudaSetDevice(ctx->device);
     return DISPATCH(ctx, prove_impl<F>(ctx, prep, nullptr, public_values, proof_out, cap_words, n_words, traces));
+}
+int p3r_set_specialization(p3r_ctx* ctx, int enable) {
+    if (!ctx) return P3R_ERR_INVALID_ARG;
+    ctx->use_spec = enable != 0;
+    return P3R_OK;
 }
 int p3r_timer_start(p3r_ctx* ctx) {
     if (!ctx) return P3R_ERR_INVALID_ARG;

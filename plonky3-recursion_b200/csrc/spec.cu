@@ -1,0 +1,12 @@
+// spec.cu — separate translation unit for the generated straight-line quotient kernels (slow to compile, rarely changes).
+#include "spec.h"
+#include "specialized_gen.cuh"
+namespace p3r {
+const SpecEntry* p3r_spec_registry(size_t* n) {
+    *n = sizeof(SPEC_QUOTIENT) / sizeof(SPEC_QUOTIENT[0]);
+    return SPEC_QUOTIENT;
+}
+void p3r_spec_launch(SpecQuotientKernel fn, const QuotientArgs& a, unsigned grid, unsigned block, cudaStream_t stream) {
+    fn<<<grid, block, 0, stream>>>(a);
+}
+}  // namespace p3r

@@ -1,0 +1,14 @@
+// spec.h — registry of build-time specialised quotient kernels (defined in spec.cu from specialized_gen.cuh).
+#pragma once
+#include "kernels.cuh"
+namespace p3r {
+typedef void (*SpecQuotientKernel)(QuotientArgs);
+struct SpecEntry {
+    uint64_t hash;      // FNV-1a over the Montgomery-encoded instruction words of the constraint program
+    int field_id;
+    uint32_t n_insns;
+    SpecQuotientKernel fn;
+};
+const SpecEntry* p3r_spec_registry(size_t* n);
+void p3r_spec_launch(SpecQuotientKernel fn, const QuotientArgs& a, unsigned grid, unsigned block, cudaStream_t stream);
+}  // namespace p3r

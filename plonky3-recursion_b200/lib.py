@@ -32,7 +32,7 @@ class P3RError(RuntimeError):
 
 def build(force: bool = False) -> str:
     """Compile csrc/ for sm_100a into libp3r_b200.so (in-tree)."""
-    srcs = [os.path.join(_HERE, "csrc", f) for f in ("p3r.cu", "kernels.cuh", "field.cuh", "poseidon2.cuh")]
+    srcs = [os.path.join(_HERE, "csrc", f) for f in ("p3r.cu", "spec.cu", "spec.h", "kernels.cuh", "field.cuh", "poseidon2.cuh", "specialized_gen.cuh")]
     srcs.append(os.path.join(_HERE, "..", "include", "p3r.h"))
     stale = not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in srcs)
     if force or stale:
@@ -72,7 +72,7 @@ EXPORTS = ["p3r_abi_version", "p3r_build_info", "p3r_ctx_create", "p3r_ctx_destr
            "p3r_grind", "p3r_prove", "p3r_coset_lde", "p3r_mmcs_commit", "p3r_poseidon2_permute", "p3r_bench_commit",
            "p3r_last_phase_times", "p3r_launch_count", "p3r_traces_upload", "p3r_traces_free", "p3r_prove_resident",
            "p3r_host_alloc", "p3r_host_free", "p3r_timer_start", "p3r_timer_stop", "p3r_set_kernel_timing",
-           "p3r_reset_kernel_stats", "p3r_kernel_stats"]
+           "p3r_reset_kernel_stats", "p3r_kernel_stats", "p3r_set_specialization"]
 
 KERNEL_CLASSES = ["ntt_lde", "hash_rows", "compress", "logup", "quotient", "open", "reduced_openings", "fri_fold", "transpose",
                   "misc"]
@@ -148,6 +148,9 @@ class Context:
         t = (C.c_float * 3)()
         self._check(self.lib.p3r_bench_commit(self.h, log_height, width, iters, C.c_uint64(seed), t))
         return {"lde_ms": t[0], "merkle_ms": t[1]}
+
+    def set_specialization(self, enable: bool):
+        self._check(self.lib.p3r_set_specialization(self.h, int(enable)))
 
     def timer_start(self):
         self._check(self.lib.p3r_timer_start(self.h))

@@ -171,3 +171,27 @@ def test_bytecode_lowering_matches_direct_evaluation():
     want = next(((r, k) for r in range(height) for k, val in enumerate(direct(r)) if val), None)
     assert res == want
     assert inst.constraints.n_constraints == 3 and inst.constraints.n_base_slots < 12
+
+
+def test_specialized_kernels_are_current():
+    """csrc/specialized_gen.cuh must have been generated from the current AIR programs (otherwise the library silently
+    falls back to the interpreter)."""
+    import os
+    import re
+    gen = importlib.import_module("scripts.gen_specialized") if False else None
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_specialized", os.path.join(root, "scripts", "gen_specialized.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    text = open(os.path.join(root, "plonky3-recursion_b200", "csrc", "specialized_gen.cuh")).read()
+    have = set(re.findall(r"\{0x([0-9a-f]{16})ull, (\d), (\d+)u,", text))
+    for fname in ("koala-bear", "baby-bear"):
+        F = field_mod.get_field(fname)
+        prm = p2mod.Poseidon2Params(F.field_id)
+        buses = air_mod.BusRegistry()
+        aw, apw = alu.widths(4, 3, 4)
+        for inst in (air_mod.build_instance("alu", alu.make_eval(4, 3, 4, F.w), F.p, 8, aw, apw, 0, buses),
+                     air_mod.build_instance("p2", p2air.make_eval(prm), F.p, 8, *p2air.widths(prm), 0, buses)):
+            ins = g.monty_insns(F, inst.constraints)
+            assert (f"{g.fnv1a(ins):016x}", str(F.field_id), str(ins.shape[0])) in have, (fname, inst.name)

@@ -298,3 +298,21 @@ def test_large_lde_properties(pair, log_n, width):
     for r in (0, 1, 2, 12345 % N, N - 1):
         rev = int(format(r, f"0{log_n + 1}b")[::-1], 2)
         assert int(lde[rev, 0]) == F.generator * pow(wN, r, F.p) % F.p
+
+
+def test_specialized_and_interpreted_quotient_agree(pair):
+    """The build-time specialised quotient kernels (ALU / Poseidon2 programs) and the bytecode interpreter must produce the
+    same proof; both equal the oracle's."""
+    wl = importlib.import_module("plonky3-recursion_b200.workload")
+    ctx, orc = pair
+    L = wl.synthetic_layer(ctx.field, 31, n_const=10, n_public=40, n_alu=300, n_perms=60, n_recompose=5, min_height=32)
+    pd = lib.ProverData.from_airs_and_degrees(ctx, L.insts, L.preps)
+    prover = lib.BatchStarkProver(ctx)
+    ctx.set_specialization(True)
+    a = prover.prove_all_tables(L.traces, pd, L.pubs)
+    ctx.set_specialization(False)
+    b = prover.prove_all_tables(L.traces, pd, L.pubs)
+    ctx.set_specialization(True)
+    assert np.array_equal(a, b)
+    assert np.array_equal(a, orc.prove(L.insts, L.preps, L.traces, L.pubs))
+    pd.close()
