@@ -36,27 +36,29 @@ struct BabyBear {
 
 template <class F>
 P3R_HD uint32_t fadd(uint32_t a, uint32_t b) {
-    uint32_t s = a + b;
-    return s >= F::P ? s - F::P : s;
+    uint32_t s = a + b, s2 = s - F::P;
+    return s2 < s ? s2 : s;  // unsigned min(s, s - P)
 }
 template <class F>
 P3R_HD uint32_t fsub(uint32_t a, uint32_t b) {
-    uint32_t d = a - b;
-    return a < b ? d + F::P : d;
+    uint32_t d = a - b, d2 = d + F::P;
+    return d2 < d ? d2 : d;  // a >= b: d < P <= d + P (no wrap) -> d; a < b: d wrapped (>= 2^32 - P), d + P wraps to the answer
 }
 template <class F>
 P3R_HD uint32_t fneg(uint32_t a) {
     return a ? F::P - a : 0u;
 }
-// Montgomery product: (a*b - m*P) / 2^32 with m = lo(a*b)*MU; result in [0,P).
+// Montgomery product in the "positive" form: m = lo(a*b) * (-P^-1), (a*b + m*P) has a zero low word, so the result is the
+// high word of ONE multiply-add (IMAD.WIDE with a 64-bit addend) and lies in [0, 2P): 5 SASS instructions
+// (IMAD.WIDE, IMAD, IMAD.WIDE, IADD, VIMNMX) instead of 7 for the subtractive form with its 64-bit compare.
 template <class F>
 P3R_HD uint32_t fmul(uint32_t a, uint32_t b) {
     uint64_t t = (uint64_t)a * b;
-    uint32_t m = (uint32_t)t * F::MU;
-    uint32_t u = (uint32_t)(((uint64_t)m * F::P) >> 32);
-    uint32_t hi = (uint32_t)(t >> 32);
-    uint32_t r = hi - u;
-    return hi < u ? r + F::P : r;
+    uint32_t m = (uint32_t)t * (0u - F::MU);
+    uint64_t u = (uint64_t)m * F::P + t;  // < 2^63, low 32 bits are zero
+    uint32_t r = (uint32_t)(u >> 32);     // < 2P
+    uint32_t r2 = r - F::P;
+    return r2 < r ? r2 : r;               // min(r, r - P) as unsigned: r - P wraps above r exactly when r < P
 }
 // Reduce a 64-bit accumulator of Montgomery products (value < 2^64) to a Montgomery residue of acc / 2^32.
 template <class F>
