@@ -173,6 +173,17 @@ typedef struct {
     uint32_t n_interactions;
 } p3r_instance_desc;
 
+/* Operation list of the Poseidon2 table (the fields of `Poseidon2CircuitRow`, circuit/src/ops/poseidon2_perm/trace.rs:94-124,
+ * that determine the MAIN trace; new_start / merkle_path are read from the committed preprocessed columns). When given for an
+ * instance instead of a matrix, the library fills the full round-state trace on the device
+ * (replaces Poseidon2CircuitAir::generate_trace_rows, poseidon2-circuit-air/src/air.rs:280-520). */
+typedef struct {
+    uint32_t n_ops;
+    const uint32_t* input_values;      /* n_ops * 16 Montgomery words                                  */
+    const uint8_t* mmcs_bit;           /* n_ops                                                        */
+    const uint32_t* mmcs_index_sum;    /* n_ops Montgomery words (value where the accumulator restarts) */
+} p3r_poseidon2_ops;
+
 /* ---------------------------------------------------------------------------------------------- */
 
 /* Library/ABI version and a description of the build (arch, fields). */
@@ -245,6 +256,15 @@ int p3r_grind(p3r_ctx* ctx, const uint32_t state[16], const uint32_t* pending, u
  * blob described in DESIGN.md §"Proof blob". */
 int p3r_prove(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces,
               const uint32_t* const* public_values, uint32_t* proof_out, size_t cap_words, size_t* n_words);
+
+/* Variants taking, per instance, either a matrix (p2_ops[i] == NULL) or a Poseidon2 operation list (p2_ops[i] != NULL, the
+ * matrix entry is ignored): the Poseidon2 table is then generated on the device. `p2_ops` itself may be NULL. */
+int p3r_prove_ex(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, const p3r_poseidon2_ops* const* p2_ops,
+                 const uint32_t* const* public_values, uint32_t* proof_out, size_t cap_words, size_t* n_words);
+int p3r_traces_upload_ex(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces,
+                         const p3r_poseidon2_ops* const* p2_ops, p3r_traces** out);
+/* Debug/parity helper: download the (row-major) main trace of instance `inst` from device-resident traces. */
+int p3r_traces_download(p3r_ctx* ctx, const p3r_prep* prep, const p3r_traces* traces, uint32_t inst, uint32_t* out);
 
 /* Device-resident traces: upload (and transpose to the column-major device layout) once, prove many times. This is the
  * path a caller uses when the trace builders already ran on the device or when the same traces are proved repeatedly;

@@ -43,6 +43,10 @@ class ProgramC(C.Structure):
                 ("ext_consts", u32p), ("n_ext_consts", u32), ("n_constraints", u32), ("n_outputs", u32)]
 
 
+class Poseidon2OpsC(C.Structure):
+    _fields_ = [("n_ops", u32), ("input_values", u32p), ("mmcs_bit", C.POINTER(C.c_uint8)), ("mmcs_index_sum", u32p)]
+
+
 class InteractionC(C.Structure):
     _fields_ = [("mult_out", u32), ("elem_out_first", u32), ("n_elems", u32)]
 
@@ -138,6 +142,18 @@ class Marshal:
         arr = (MatrixU32 * len(mats))()
         for k, m in enumerate(mats):
             arr[k] = self.matrix(m)
+        return self.keep(arr)
+
+    def poseidon2_ops(self, ops_by_instance: dict, n_inst: int):
+        """{instance index: airs.poseidon2.Poseidon2Ops} -> array of n_inst pointers to p3r_poseidon2_ops (NULL = matrix)."""
+        arr = (C.POINTER(Poseidon2OpsC) * n_inst)()
+        for i, ops in ops_by_instance.items():
+            iv = self.u32(self.field.to_monty(ops.input_values.reshape(-1)))
+            bit = self.keep(np.ascontiguousarray(ops.mmcs_bit, dtype=np.uint8))
+            sm = self.u32(self.field.to_monty(ops.mmcs_index_sum))
+            st = Poseidon2OpsC(ops.n, as_u32p(iv), bit.ctypes.data_as(C.POINTER(C.c_uint8)), as_u32p(sm))
+            self.keep(st)
+            arr[i] = C.pointer(st)
         return self.keep(arr)
 
     def public_values(self, pubs) -> C.Array:

@@ -1077,6 +1077,87 @@ static __global__ void __launch_bounds__(256) k_query_gather(const GatherSeg* __
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K3: Poseidon2 table fill (Poseidon2CircuitAir::generate_trace_rows, /root/reference poseidon2-circuit-air/src/air.rs:280-520
+// -> p3_poseidon2_air::generate_trace_rows_for_perm [P3-EXT]). One thread per table row: runs the permutation and stores
+// every committed round value straight into the column-major device trace:
+//   inputs[16] | 4 x (sbox regs[16*R], post[16]) | P x (sbox reg[R], post_sbox) | 4 x (sbox regs, post) | mmcs_bit | mmcs_index_sum
+// with R = 1 register (x^3) for the degree-7 S-box, 0 for degree 3. Rows >= n_ops are the padding rows: real permutations of
+// the zero state (batch_stark_prover/poseidon2.rs:1121-1140). The index accumulator (pass 1 of the reference, sequential) is
+// recomputed per row by walking back to the start of its Merkle chain: acc = 2*acc + bit on chained Merkle rows.
+// ------------------------------------------------------------------------------------------------
+struct P2FillArgs {
+    const uint32_t* inputs;        // n_ops x 16, row-major, Montgomery
+    const uint8_t* mmcs_bit;       // n_ops
+    const uint32_t* idx_sum;       // n_ops: op.mmcs_index_sum (used where the accumulator restarts), Montgomery
+    const uint32_t* new_start;     // preprocessed column (device, natural order, height H): non-zero = chain start
+    const uint32_t* merkle_path;   // preprocessed column
+    uint32_t n_ops, log_h;
+    uint32_t* out;                 // column-major main trace, height H
+};
+template <class F>
+__global__ void __launch_bounds__(128) k_poseidon2_table_fill(P2FillArgs a) {
+    const uint32_t H = 1u << a.log_h;
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= H) return;
+    const Poseidon2Consts& k = c_p2[FieldId<F>::value];
+    constexpr int R = (F::SBOX == 7) ? 1 : 0;
+    uint32_t s[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = r < a.n_ops ? a.inputs[(size_t)r * 16 + i] : 0u;
+    uint32_t* out = a.out + r;
+    uint32_t col = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) out[(size_t)(col++) * H] = s[i];
+    external_linear<F>(s);
+    auto full_round = [&](int rr) {
+        uint32_t reg[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            uint32_t x = fadd<F>(s[i], k.ext_rc[16 * rr + i]);
+            uint32_t x3 = fmul<F>(fmul<F>(x, x), x);
+            reg[i] = x3;
+            s[i] = R ? fmul<F>(fmul<F>(x3, x3), x) : x3;
+        }
+        if (R) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) out[(size_t)(col++) * H] = reg[i];
+        }
+        external_linear<F>(s);
+#pragma unroll
+        for (int i = 0; i < 16; i++) out[(size_t)(col++) * H] = s[i];
+    };
+#pragma unroll 1
+    for (int rr = 0; rr < 4; rr++) full_round(rr);
+#pragma unroll 1
+    for (int rr = 0; rr < F::ROUNDS_P; rr++) {
+        uint32_t x = fadd<F>(s[0], k.int_rc[rr]);
+        uint32_t x3 = fmul<F>(fmul<F>(x, x), x);
+        uint32_t y = R ? fmul<F>(fmul<F>(x3, x3), x) : x3;
+        if (R) out[(size_t)(col++) * H] = x3;
+        out[(size_t)(col++) * H] = y;
+        s[0] = y;
+        uint32_t sum = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) sum = fadd<F>(sum, s[i]);
+#pragma unroll
+        for (int i = 0; i < 16; i++) s[i] = fadd<F>(sum, fmul<F>(k.diag[i], s[i]));
+    }
+#pragma unroll 1
+    for (int rr = 4; rr < 8; rr++) full_round(rr);
+    // circuit columns
+    uint32_t bit = 0, acc = 0;
+    if (r < a.n_ops) {
+        bit = a.mmcs_bit[r] ? F::R : 0u;
+        uint32_t t = r;
+        while (t > 0 && a.merkle_path[t] != 0 && a.new_start[t] == 0) t--;
+        acc = a.idx_sum[t];
+        for (uint32_t u = t + 1; u <= r; u++) acc = fadd<F>(fadd<F>(acc, acc), a.mmcs_bit[u] ? F::R : 0u);
+    }
+    out[(size_t)(col++) * H] = bit;
+    out[(size_t)(col++) * H] = acc;
+}
+
 // Synthetic data for the isolated commit benchmark: splitmix64(seed + index) reduced mod P.
 template <class F>
 __global__ void k_fill_random(uint32_t* out, size_t n, uint64_t seed) {

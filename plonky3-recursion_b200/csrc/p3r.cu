@@ -656,6 +656,40 @@ static int upload_matrix(p3r_ctx* ctx, const p3r_matrix_u32& m, uint32_t* d_rowm
     return P3R_OK;
 }
 
+// K3 host: generate the Poseidon2 table of instance `d` on the device from its operation list.
+template <class F>
+static int fill_poseidon2_table(p3r_ctx* ctx, const InstDev& d, const p3r_poseidon2_ops& ops, uint32_t* d_colmajor) {
+    const uint32_t H = 1u << d.log_h;
+    constexpr uint32_t R = (F::SBOX == 7) ? 1 : 0;
+    const uint32_t width = 16 + 8 * (16 * R + 16) + F::ROUNDS_P * (R + 1) + 2;
+    if (d.main_w != width || d.prep_w != 24 || !d.prep_trace || ops.n_ops > H || !ops.input_values || !ops.mmcs_bit ||
+        !ops.mmcs_index_sum) {
+        set_err(ctx, "poseidon2 ops given for an instance that is not a Poseidon2 table of this field");
+        return P3R_ERR_INVALID_ARG;
+    }
+    size_t n = ops.n_ops;
+    uint32_t* d_in = arena_alloc<uint32_t>(ctx, std::max<size_t>(n * 16, 4));
+    uint32_t* d_sum = arena_alloc<uint32_t>(ctx, std::max<size_t>(n, 4));
+    uint8_t* d_bit = arena_alloc<uint8_t>(ctx, std::max<size_t>(n, 16));
+    if (!d_in || !d_sum || !d_bit) return P3R_ERR_OOM;
+    CUDA_TRY(cudaMemcpyAsync(d_in, ops.input_values, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_sum, ops.mmcs_index_sum, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_bit, ops.mmcs_bit, n, cudaMemcpyHostToDevice, ctx->stream));
+    P2FillArgs a{};
+    a.inputs = d_in;
+    a.mmcs_bit = d_bit;
+    a.idx_sum = d_sum;
+    a.new_start = d.prep_trace + (size_t)22 * H;    // preprocessed tail: [.., mmcs_idx, mmcs_flag, new_start, merkle_path]
+    a.merkle_path = d.prep_trace + (size_t)23 * H;
+    a.n_ops = ops.n_ops;
+    a.log_h = d.log_h;
+    a.out = d_colmajor;
+    KT kt(ctx, KC_MISC, (uint64_t)H * width * 4);
+    k_poseidon2_table_fill<F><<<(H + 127) / 128, 128, 0, ctx->stream>>>(a);
+    LAUNCH_CHECK_C(KC_MISC);
+    return P3R_OK;
+}
+
 static bool is_pow2(uint32_t x) { return x && !(x & (x - 1)); }
 static uint32_t ilog2(uint32_t x) {
     uint32_t l = 0;
@@ -809,7 +843,8 @@ static int prep_commit_impl(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_de
 // ------------------------------------------------------------------------------------------------
 template <class F>
 static int prove_begin_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces,
-                            const uint32_t* const* public_values, p3r_session** out, const p3r_traces* resident = nullptr) {
+                            const uint32_t* const* public_values, p3r_session** out, const p3r_traces* resident = nullptr,
+                            const p3r_poseidon2_ops* const* p2_ops = nullptr) {
     ctx->arena.reset();
     ctx->pin_used = 0;
     auto* s = new p3r_session();
@@ -827,13 +862,14 @@ static int prove_begin_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix
     size_t max_rm = 0;
     for (size_t i = 0; i < n_inst; i++) {
         const InstDev& d = prep->inst[i];
-        if (!resident && (traces[i].height != (1u << d.log_h) || traces[i].width != d.main_w || !traces[i].data)) {
+        const bool from_ops = p2_ops && p2_ops[i];
+        if (!resident && !from_ops && (traces[i].height != (1u << d.log_h) || traces[i].width != d.main_w || !traces[i].data)) {
             set_err(ctx, "trace shape mismatch for instance " + std::to_string(i));
             delete s;
             return P3R_ERR_INVALID_ARG;
         }
         size_t n = (size_t)1 << d.log_h;
-        max_rm = std::max(max_rm, n * d.main_w);
+        if (!from_ops) max_rm = std::max(max_rm, n * d.main_w);
     }
     uint32_t* rm = resident ? reinterpret_cast<uint32_t*>(ctx->dstage) : arena_alloc<uint32_t>(ctx, max_rm);
     if (!rm) {
@@ -852,7 +888,8 @@ static int prove_begin_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix
             return P3R_ERR_OOM;
         }
         if (!resident) {
-            int rc = upload_matrix(ctx, traces[i], rm, s->trace[i]);
+            int rc = (p2_ops && p2_ops[i]) ? fill_poseidon2_table<F>(ctx, d, *p2_ops[i], s->trace[i])
+                                           : upload_matrix(ctx, traces[i], rm, s->trace[i]);
             if (rc) {
                 delete s;
                 return rc;
@@ -1573,9 +1610,10 @@ static int challenger_grind(p3r_ctx* ctx, HostChallenger<F>& ch, uint32_t bits, 
 
 template <class F>
 static int prove_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, const uint32_t* const* public_values,
-                      uint32_t* proof_out, size_t cap_words, size_t* n_words, const p3r_traces* resident = nullptr) {
+                      uint32_t* proof_out, size_t cap_words, size_t* n_words, const p3r_traces* resident = nullptr,
+                      const p3r_poseidon2_ops* const* p2_ops = nullptr) {
     p3r_session* s = nullptr;
-    TRY(prove_begin_impl<F>(ctx, prep, traces, public_values, &s, resident));
+    TRY(prove_begin_impl<F>(ctx, prep, traces, public_values, &s, resident, p2_ops));
     struct Guard {
         p3r_session* s;
         ~Guard() { delete s; }
@@ -2005,28 +2043,30 @@ int p3r_prove(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, 
     cudaSetDevice(ctx->device);
     return DISPATCH(ctx, prove_impl<F>(ctx, prep, traces, public_values, proof_out, cap_words, n_words));
 }
-int p3r_traces_upload(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, p3r_traces** out) {
-    if (!ctx || !prep || !traces || !out) return P3R_ERR_INVALID_ARG;
-    cudaSetDevice(ctx->device);
+}  // extern "C" (template below)
+template <class F>
+static int traces_upload_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces,
+                              const p3r_poseidon2_ops* const* p2_ops, p3r_traces** out) {
     auto* t = new p3r_traces();
     t->ctx = ctx;
     ctx->arena.reset();
     for (size_t i = 0; i < prep->inst.size(); i++) {
         const InstDev& d = prep->inst[i];
-        if (traces[i].height != (1u << d.log_h) || traces[i].width != d.main_w || !traces[i].data) {
+        const bool from_ops = p2_ops && p2_ops[i];
+        if (!from_ops && (traces[i].height != (1u << d.log_h) || traces[i].width != d.main_w || !traces[i].data)) {
             set_err(ctx, "traces_upload: shape mismatch");
             p3r_traces_free(t);
             return P3R_ERR_INVALID_ARG;
         }
-        size_t words = (size_t)traces[i].height * traces[i].width;
+        size_t words = ((size_t)1 << d.log_h) * d.main_w;
         uint32_t* dm = nullptr;
-        uint32_t* rm = arena_alloc<uint32_t>(ctx, words);
+        uint32_t* rm = from_ops ? reinterpret_cast<uint32_t*>(ctx->dstage) : arena_alloc<uint32_t>(ctx, words);
         if (!rm || cudaMalloc(&dm, words * 4) != cudaSuccess) {
             p3r_traces_free(t);
             return P3R_ERR_OOM;
         }
         t->d.push_back(dm);
-        int rc = upload_matrix(ctx, traces[i], rm, dm);
+        int rc = from_ops ? fill_poseidon2_table<F>(ctx, d, *p2_ops[i], dm) : upload_matrix(ctx, traces[i], rm, dm);
         if (rc) {
             p3r_traces_free(t);
             return rc;
@@ -2035,6 +2075,37 @@ int p3r_traces_upload(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* 
     cudaStreamSynchronize(ctx->stream);
     *out = t;
     return P3R_OK;
+}
+extern "C" {
+int p3r_traces_upload_ex(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, const p3r_poseidon2_ops* const* p2_ops,
+                         p3r_traces** out) {
+    if (!ctx || !prep || !traces || !out) return P3R_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    return DISPATCH(ctx, traces_upload_impl<F>(ctx, prep, traces, p2_ops, out));
+}
+int p3r_traces_upload(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, p3r_traces** out) {
+    return p3r_traces_upload_ex(ctx, prep, traces, nullptr, out);
+}
+int p3r_traces_download(p3r_ctx* ctx, const p3r_prep* prep, const p3r_traces* traces, uint32_t inst, uint32_t* out) {
+    if (!ctx || !prep || !traces || !out || inst >= prep->inst.size()) return P3R_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    const InstDev& d = prep->inst[inst];
+    uint32_t H = 1u << d.log_h;
+    ctx->arena.reset();
+    uint32_t* rm = arena_alloc<uint32_t>(ctx, (size_t)H * d.main_w);
+    if (!rm) return P3R_ERR_OOM;
+    dim3 grid((H + 31) / 32, (d.main_w + 31) / 32), block(32, 8);
+    k_transpose_out<<<grid, block, 0, ctx->stream>>>(traces->d[inst], rm, H, d.main_w);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(out, rm, (size_t)H * d.main_w * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return P3R_OK;
+}
+int p3r_prove_ex(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, const p3r_poseidon2_ops* const* p2_ops,
+                 const uint32_t* const* public_values, uint32_t* proof_out, size_t cap_words, size_t* n_words) {
+    if (!ctx || !prep || !traces || !n_words) return P3R_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    return DISPATCH(ctx, prove_impl<F>(ctx, prep, traces, public_values, proof_out, cap_words, n_words, nullptr, p2_ops));
 }
 void p3r_traces_free(p3r_traces* t) {
     if (!t) return;

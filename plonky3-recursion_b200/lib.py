@@ -72,7 +72,8 @@ EXPORTS = ["p3r_abi_version", "p3r_build_info", "p3r_ctx_create", "p3r_ctx_destr
            "p3r_grind", "p3r_prove", "p3r_coset_lde", "p3r_mmcs_commit", "p3r_poseidon2_permute", "p3r_bench_commit",
            "p3r_last_phase_times", "p3r_launch_count", "p3r_traces_upload", "p3r_traces_free", "p3r_prove_resident",
            "p3r_host_alloc", "p3r_host_free", "p3r_timer_start", "p3r_timer_stop", "p3r_set_kernel_timing",
-           "p3r_reset_kernel_stats", "p3r_kernel_stats", "p3r_set_specialization"]
+           "p3r_reset_kernel_stats", "p3r_kernel_stats", "p3r_set_specialization", "p3r_prove_ex", "p3r_traces_upload_ex",
+           "p3r_traces_download"]
 
 KERNEL_CLASSES = ["ntt_lde", "hash_rows", "compress", "logup", "quotient", "open", "reduced_openings", "fri_fold", "transpose",
                   "misc"]
@@ -233,13 +234,21 @@ class TraceBatch:
     """Traces marshalled once (Montgomery, row-major) so repeated proofs do not pay the numpy conversion.
     pinned=True places the Montgomery matrices in cudaHostAlloc'd memory (the e2e path of bench.py)."""
 
-    def __init__(self, ctx: Context, traces, pubs, pinned: bool = False):
+    def __init__(self, ctx: Context, traces, pubs, pinned: bool = False, p2_ops: dict | None = None):
+        """p2_ops: {instance index: Poseidon2Ops}; those instances' traces are generated on the device (K3) and their
+        entry in `traces` may be None."""
         self.ctx = ctx
         self.m = abi.Marshal(ctx.field)
+        self.p2 = self.m.poseidon2_ops(p2_ops, len(traces)) if p2_ops else None
+        skip = set(p2_ops or {})
+        traces = [None if k in skip else t for k, t in enumerate(traces)]
         if pinned:
             arr = (abi.MatrixU32 * len(traces))()
             self._bufs = []
             for k, t in enumerate(traces):
+                if t is None:
+                    arr[k] = abi.MatrixU32(None, 0, 0)
+                    continue
                 buf = ctx.pinned_empty(t.shape)
                 buf[...] = ctx.field.to_monty(t)
                 self._bufs.append(buf)
@@ -248,15 +257,24 @@ class TraceBatch:
         else:
             self.tm = self.m.matrices(traces)
         self.pv = self.m.public_values(pubs)
-        self.h2d_bytes = int(sum(int(t.size) * 4 for t in traces))
+        self.h2d_bytes = int(sum(int(t.size) * 4 for t in traces if t is not None))
+        if p2_ops:
+            self.h2d_bytes += int(sum(o.n * (64 + 4 + 1) for o in p2_ops.values()))
         self.resident = None
 
     def upload(self, prover_data):
         """Make the traces device-resident (p3r_traces_upload)."""
         h = C.c_void_p()
-        self.ctx._check(self.ctx.lib.p3r_traces_upload(self.ctx.h, prover_data.h, self.tm, C.byref(h)))
+        self.ctx._check(self.ctx.lib.p3r_traces_upload_ex(self.ctx.h, prover_data.h, self.tm, self.p2, C.byref(h)))
         self.resident = h
         return self
+
+    def download(self, prover_data, inst: int) -> np.ndarray:
+        """Main trace of instance `inst` as held on the device (canonical, row-major) — parity checks of the GPU table fill."""
+        s = prover_data.insts[inst]
+        out = np.zeros((1 << s.log_height, s.main_width), dtype=np.uint32)
+        self.ctx._check(self.ctx.lib.p3r_traces_download(self.ctx.h, prover_data.h, self.resident, inst, abi.as_u32p(out)))
+        return self.ctx.field.from_monty(out)
 
     def close(self):
         if self.resident is not None and self.ctx.h:
@@ -289,12 +307,12 @@ class BatchStarkProver:
             pubs = public_values if public_values is not None else [None] * len(traces)
             traces = TraceBatch(ctx, traces, pubs)
         n = C.c_size_t(0)
-        rc = ctx.lib.p3r_prove(ctx.h, prover_data.h, traces.tm, traces.pv, abi.as_u32p(self._buf), C.c_size_t(self._buf.size),
-                               C.byref(n))
+        rc = ctx.lib.p3r_prove_ex(ctx.h, prover_data.h, traces.tm, traces.p2, traces.pv, abi.as_u32p(self._buf),
+                                  C.c_size_t(self._buf.size), C.byref(n))
         if rc == 6 and n.value > self._buf.size:  # P3R_ERR_BUFFER: grow once
             self._buf = np.zeros(n.value, dtype=np.uint32)
-            rc = ctx.lib.p3r_prove(ctx.h, prover_data.h, traces.tm, traces.pv, abi.as_u32p(self._buf),
-                                   C.c_size_t(self._buf.size), C.byref(n))
+            rc = ctx.lib.p3r_prove_ex(ctx.h, prover_data.h, traces.tm, traces.p2, traces.pv, abi.as_u32p(self._buf),
+                                      C.c_size_t(self._buf.size), C.byref(n))
         ctx._check(rc)
         self.last_proof_words = n.value
         return self._buf[: n.value].copy()

@@ -222,6 +222,7 @@ class NpoTables:
                     ops.out_mult[i, k] = W.reads[r["out_ids"][k]]
             ops.mmcs_index_sum_idx[i] = r["mmcs_idx"]
             ops.mmcs_ctl_enabled[i] = r["mmcs_en"]
+        self.ops = ops
         tp2, pp2 = poseidon2.build_tables(params, ops, min_height)
         lh = lambda m: int(m.shape[0]).bit_length() - 1
         w2, pw2 = poseidon2.widths(params)
@@ -241,8 +242,9 @@ class NpoTables:
 
 
 class LayerWorkload:
-    def __init__(self, insts, preps, traces, pubs, shapes):
+    def __init__(self, insts, preps, traces, pubs, shapes, p2_ops=None):
         self.insts, self.preps, self.traces, self.pubs, self.shapes = insts, preps, traces, pubs, shapes
+        self.p2_ops = p2_ops or {}   # {instance index: Poseidon2Ops} for the GPU table-fill path
 
     @property
     def h2d_bytes(self):
@@ -288,11 +290,13 @@ def synthetic_layer(F: Field, seed: int, n_const: int, n_public: int, n_alu: int
         air.build_instance("alu", alu.make_eval(D, alu_lanes, horner_k, F.w), F.p, lh(ta), aw, apw, 0, buses),
     ]
     prep_mats, traces, pubs = [pc, pp, pa], [tc, tp, ta], [None, None, None]
+    p2_ops = {}
     if npo:
         ei, ep, et, epub = npo.finish(W, buses, min_height, recompose_lanes)
+        p2_ops = {len(insts): npo.ops}
         insts += ei
         prep_mats += ep
         traces += et
         pubs += epub
     shapes = [(s.name, t.shape[0], t.shape[1], 0 if pm is None else pm.shape[1]) for s, t, pm in zip(insts, traces, prep_mats)]
-    return LayerWorkload(insts, prep_mats, traces, pubs, shapes)
+    return LayerWorkload(insts, prep_mats, traces, pubs, shapes, p2_ops)

@@ -316,3 +316,25 @@ def test_specialized_and_interpreted_quotient_agree(pair):
     assert np.array_equal(a, b)
     assert np.array_equal(a, orc.prove(L.insts, L.preps, L.traces, L.pubs))
     pd.close()
+
+
+def test_gpu_poseidon2_table_fill_matches_reference_builder(pair):
+    """K3: the device-generated Poseidon2 table equals the host restatement of generate_trace_rows bit for bit (padding rows,
+    Merkle index accumulator, S-box registers for BabyBear), and proofs from ops == proofs from the uploaded matrix."""
+    wl = importlib.import_module("plonky3-recursion_b200.workload")
+    ctx, orc = pair
+    for seed, n_perms in ((41, 70), (42, 128), (43, 1)):
+        L = wl.synthetic_layer(ctx.field, seed, n_const=10, n_public=40, n_alu=200, n_perms=n_perms, n_recompose=5, min_height=32)
+        (idx, ops), = L.p2_ops.items()
+        pd = lib.ProverData.from_airs_and_degrees(ctx, L.insts, L.preps)
+        tb = lib.TraceBatch(ctx, L.traces, L.pubs, p2_ops=L.p2_ops).upload(pd)
+        got = tb.download(pd, idx)
+        assert got.shape == L.traces[idx].shape and np.array_equal(got, L.traces[idx])
+        prover = lib.BatchStarkProver(ctx)
+        from_ops = prover.prove_all_tables(lib.TraceBatch(ctx, L.traces, L.pubs, p2_ops=L.p2_ops), pd)
+        from_matrix = prover.prove_all_tables(L.traces, pd, L.pubs)
+        assert np.array_equal(from_ops, from_matrix)
+        assert np.array_equal(from_ops, prover.prove_resident(tb, pd))
+        assert np.array_equal(from_ops, orc.prove(L.insts, L.preps, L.traces, L.pubs))
+        tb.close()
+        pd.close()
