@@ -51,12 +51,22 @@ P3R_HD uint32_t fneg(uint32_t a) {
 // Montgomery product in the "positive" form: m = lo(a*b) * (-P^-1), (a*b + m*P) has a zero low word, so the result is the
 // high word of ONE multiply-add (IMAD.WIDE with a 64-bit addend) and lies in [0, 2P): 5 SASS instructions
 // (IMAD.WIDE, IMAD, IMAD.WIDE, IADD, VIMNMX) instead of 7 for the subtractive form with its 64-bit compare.
+// On the device the high word is taken with an explicit carry chain (mad.lo.cc / madc.hi): ptxas then emits exactly
+// IMAD.WIDE.U32, IMAD, IMAD.HI.U32 (64-bit addend), VIADDMNMX.U32 — 4 instructions. Written as a 64-bit C expression it
+// adds a dead "+ carry-out" IADD3/UMOV pair per product (checked with cuobjdump -sass, CUDA 12.9).
 template <class F>
 P3R_HD uint32_t fmul(uint32_t a, uint32_t b) {
     uint64_t t = (uint64_t)a * b;
     uint32_t m = (uint32_t)t * (0u - F::MU);
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("{ .reg .u32 l2;\n\tmad.lo.cc.u32 l2, %1, %2, %3;\n\tmadc.hi.u32 %0, %1, %2, %4; }"
+        : "=r"(r)
+        : "r"(m), "r"(F::P), "r"((uint32_t)t), "r"((uint32_t)(t >> 32)));
+#else
     uint64_t u = (uint64_t)m * F::P + t;  // < 2^63, low 32 bits are zero
     uint32_t r = (uint32_t)(u >> 32);     // < 2P
+#endif
     uint32_t r2 = r - F::P;
     return r2 < r ? r2 : r;               // min(r, r - P) as unsigned: r - P wraps above r exactly when r < P
 }

@@ -297,22 +297,35 @@ __global__ void k_stage_twiddles(uint32_t* tws, uint32_t logT, uint32_t w_T) {
 // ------------------------------------------------------------------------------------------------
 // K5: Poseidon2 sponge over rows + 2-to-1 compression tree (MerkleTreeMmcs).
 // ------------------------------------------------------------------------------------------------
-// colptr[i] = pointer to column i (already offset to this height's matrix), column-major; one thread per row.
+// Row digests of the matrices of EVERY height of one commit in a single launch (flat grid, each CTA finds its job through
+// cta_begin; jobs sorted by decreasing sponge length so the long rows start first). The tallest height's digests are level 0
+// of the tree, the others are the digests injected at their level. Hashing the injected rows here instead of inside the
+// level's compression kernel gives the whole commit's sponge work to one grid (1.5 waves for the recursion layer) instead of
+// a 2^16-thread launch running 23 dependent permutations per thread at 18 % occupancy.
+// colptr[i] = pointer to column i (column-major); one thread per row.
+struct HashJob {
+    const uint32_t* const* colptr;
+    uint32_t ncols, n_rows;
+    uint32_t* out;          // n_rows x 8 words
+    uint32_t cta_begin;
+};
 template <class F>
-__global__ void __launch_bounds__(128) k_hash_rows(const uint32_t* const* __restrict__ colptr, uint32_t ncols, uint32_t n_rows,
-                                                    uint32_t* __restrict__ out) {
-    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_rows) return;
+__global__ void __launch_bounds__(128) k_hash_rows(const HashJob* __restrict__ jobs, uint32_t n_jobs) {
+    uint32_t j = 0;
+    while (j + 1 < n_jobs && blockIdx.x >= jobs[j + 1].cta_begin) j++;
+    const HashJob job = jobs[j];
+    uint32_t r = (blockIdx.x - job.cta_begin) * blockDim.x + threadIdx.x;
+    if (r >= job.n_rows) return;
     uint32_t st[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) st[i] = 0;
-    for (uint32_t c0 = 0; c0 < ncols; c0 += 8) {
+    for (uint32_t c0 = 0; c0 < job.ncols; c0 += 8) {
 #pragma unroll
         for (int k = 0; k < 8; k++)
-            if (c0 + k < ncols) st[k] = __ldg(colptr[c0 + k] + r);
+            if (c0 + k < job.ncols) st[k] = __ldg(job.colptr[c0 + k] + r);
         poseidon2_permute<F>(st);
     }
-    uint4* o = reinterpret_cast<uint4*>(out + (size_t)r * 8);
+    uint4* o = reinterpret_cast<uint4*>(job.out + (size_t)r * 8);
     o[0] = make_uint4(st[0], st[1], st[2], st[3]);
     o[1] = make_uint4(st[4], st[5], st[6], st[7]);
 }
@@ -336,10 +349,11 @@ __global__ void __launch_bounds__(128) k_hash_rows_rowmajor(const uint32_t* __re
     o[0] = make_uint4(st[0], st[1], st[2], st[3]);
     o[1] = make_uint4(st[4], st[5], st[6], st[7]);
 }
-// next[i] = compress(prev[2i], prev[2i+1]); if inj_cols > 0 additionally next[i] = compress(next[i], hash(injected row i)).
+// next[i] = compress(prev[2i], prev[2i+1]); with inj != nullptr additionally next[i] = compress(next[i], inj[i]) where inj
+// holds the digests of the rows injected at this level.
 template <class F>
 __global__ void __launch_bounds__(128) k_compress(const uint32_t* __restrict__ prev, uint32_t* __restrict__ next, uint32_t n_next,
-                                                   const uint32_t* const* __restrict__ inj_colptr, uint32_t inj_cols) {
+                                                   const uint32_t* __restrict__ inj) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_next) return;
     uint32_t st[16];
@@ -353,119 +367,95 @@ __global__ void __launch_bounds__(128) k_compress(const uint32_t* __restrict__ p
         st[4 * q + 3] = v.w;
     }
     poseidon2_permute<F>(st);
-    if (inj_cols) {
-        uint32_t h[16];
-#pragma unroll
-        for (int k = 0; k < 16; k++) h[k] = 0;
-        for (uint32_t c0 = 0; c0 < inj_cols; c0 += 8) {
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-                if (c0 + k < inj_cols) h[k] = __ldg(inj_colptr[c0 + k] + i);
-            poseidon2_permute<F>(h);
-        }
-#pragma unroll
-        for (int k = 0; k < 8; k++) st[8 + k] = h[k];
+    if (inj) {
+        const uint4* h = reinterpret_cast<const uint4*>(inj + (size_t)i * 8);
+        uint4 h0 = h[0], h1 = h[1];
+        st[8] = h0.x, st[9] = h0.y, st[10] = h0.z, st[11] = h0.w;
+        st[12] = h1.x, st[13] = h1.y, st[14] = h1.z, st[15] = h1.w;
         poseidon2_permute<F>(st);
     }
     uint4* o = reinterpret_cast<uint4*>(next + (size_t)i * 8);
     o[0] = make_uint4(st[0], st[1], st[2], st[3]);
     o[1] = make_uint4(st[4], st[5], st[6], st[7]);
 }
-// ---- cooperative (16 lanes per permutation) Merkle kernels for the small levels -----------------------------------------
-// One half-warp = one node. hash of an injected / leaf row: lanes 0..7 absorb 8 columns per permutation.
-template <class F>
-__device__ __forceinline__ uint32_t coop_hash_cols(const uint32_t* const* __restrict__ colptr, uint32_t ncols, uint32_t row,
-                                                   uint32_t lane, const P2Lane& c) {
-    const uint32_t l16 = lane & 15u;
-    uint32_t x = 0;
-    for (uint32_t c0 = 0; c0 < ncols; c0 += 8) {
-        if (l16 < 8 && c0 + l16 < ncols) x = __ldg(colptr[c0 + l16] + row);
-        x = p2_coop_permute<F>(x, lane, c);
-    }
-    return x;
-}
-// compress(left, right) (+ optional injection) for node i, state distributed over the half-warp; returns lane value.
-template <class F>
-__device__ __forceinline__ uint32_t coop_node(const uint32_t* __restrict__ prev, uint32_t i, const uint32_t* const* inj,
-                                              uint32_t inj_cols, uint32_t lane, const P2Lane& c) {
-    const uint32_t l16 = lane & 15u;
-    uint32_t x = prev[(size_t)i * 16 + l16];  // left digest (8 words) then right digest (8 words)
-    x = p2_coop_permute<F>(x, lane, c);
-    if (inj_cols) {
-        uint32_t h = coop_hash_cols<F>(inj, inj_cols, i, lane, c);
-        uint32_t hs = __shfl_sync(0xffffffffu, h, (lane & ~15u) | (l16 & 7u));  // lanes 8..15 take h[0..8)
-        x = l16 < 8 ? x : hs;
-        x = p2_coop_permute<F>(x, lane, c);
-    }
-    return x;
-}
-template <class F>
-__global__ void __launch_bounds__(256) k_compress_coop(const uint32_t* __restrict__ prev, uint32_t* __restrict__ next,
-                                                        uint32_t n_next, const uint32_t* const* __restrict__ inj_colptr,
-                                                        uint32_t inj_cols, const Poseidon2Consts* __restrict__ gk) {
-    const uint32_t lane = threadIdx.x & 31u, l16 = lane & 15u;
-    const P2Lane c = p2_lane_consts<F>(gk, l16);
-    uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-    bool live = i < n_next;
-    uint32_t x = coop_node<F>(prev, live ? i : 0, inj_colptr, inj_cols, lane, c);
-    if (live && l16 < 8) next[(size_t)i * 8 + l16] = x;
-}
-// Leaf level of a row-major matrix of w words per row (FRI commit-phase matrices), one half-warp per row.
-template <class F>
-__global__ void __launch_bounds__(256) k_hash_rows_rowmajor_coop(const uint32_t* __restrict__ data, uint32_t w, uint32_t n_rows,
-                                                                  uint32_t* __restrict__ out, const Poseidon2Consts* __restrict__ gk) {
-    const uint32_t lane = threadIdx.x & 31u, l16 = lane & 15u;
-    const P2Lane c = p2_lane_consts<F>(gk, l16);
-    uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-    bool live = r < n_rows;
-    const uint32_t* row = data + (size_t)(live ? r : 0) * w;
-    uint32_t x = 0;
-    for (uint32_t c0 = 0; c0 < w; c0 += 8) {
-        if (l16 < 8 && c0 + l16 < w) x = row[c0 + l16];
-        x = p2_coop_permute<F>(x, lane, c);
-    }
-    if (live && l16 < 8) out[(size_t)r * 8 + l16] = x;
-}
-// Leaf level of column-major matrices, one half-warp per row (small heights only: loads are one word per column).
-template <class F>
-__global__ void __launch_bounds__(256) k_hash_rows_coop(const uint32_t* const* __restrict__ colptr, uint32_t ncols, uint32_t n_rows,
-                                                         uint32_t* __restrict__ out, const Poseidon2Consts* __restrict__ gk) {
-    const uint32_t lane = threadIdx.x & 31u, l16 = lane & 15u;
-    const P2Lane c = p2_lane_consts<F>(gk, l16);
-    uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-    bool live = r < n_rows;
-    uint32_t x = coop_hash_cols<F>(colptr, ncols, live ? r : 0, lane, c);
-    if (live && l16 < 8) out[(size_t)r * 8 + l16] = x;
-}
-// Tail of a Merkle tree in ONE launch: a single 1024-thread CTA (64 cooperative permutations at a time) walks the levels
-// with at most TAIL_NODES nodes, one barrier per level, instead of one latency-bound launch per level.
+// ---- cooperative (16 lanes per permutation) Merkle kernel for the small levels ---------------------------------------
+// Several consecutive Merkle levels in ONE launch. CTA b owns the subtree rooted at node b of the stage's last level:
+// with K = n_levels it produces 2^(K-1-j) nodes of level first_level + j (j < K), keeps them in shared memory for the
+// next level and writes every level to the tree in HBM (openings need all of them). One 16-lane group per node, so a
+// level costs one cooperative-permutation latency (plus the injected row's sponge) instead of one launch; the levels of a
+// tree with <= 2^13 nodes take ceil(levels/7) launches. Optionally the stage starts from the leaves (first_level == 0):
+// the CTA first hashes its 2^K leaf rows of one row-major matrix (leaf_rows, the ExtensionMmcs rows of the FRI commit phase,
+// recursion/src/pcs/mmcs.rs:434-441). Rows injected at a level arrive as digests (k_hash_rows).
 // Level l (2^(log_max_h - l) digests) lives at digest offset 2^(log_max_h+1) - 2^(log_max_h-l+1).
-struct TreeTail {
+constexpr uint32_t STAGE_MAX_LEVELS = 7;   // 2^(7-1) = 64 first-level nodes = the 64 lane groups of a 1024-thread CTA
+struct MerkleStage {
     uint32_t* digests;
     uint32_t log_max_h;
-    uint32_t first_level, last_level;
-    const uint32_t* const* inj_colptr[24];  // indexed by (level - first_level); nullptr = no injected matrices at that level
-    uint32_t inj_cols[24];
+    uint32_t first_level;   // first level produced by compression (>= 1); with leaves: levels 0 .. n_levels
+    uint32_t n_levels;      // K compression levels (may be 0 with leaves)
+    uint32_t with_leaves;   // hash the leaf level first
+    const uint32_t* leaf_rows;            // row-major leaf matrix
+    uint32_t leaf_w;                      // columns per leaf row
+    const uint32_t* inj[STAGE_MAX_LEVELS];  // by (level - first_level): digests of the rows injected there, or nullptr
 };
 template <class F>
-__global__ void __launch_bounds__(1024) k_tree_tail(TreeTail a, const Poseidon2Consts* __restrict__ gk) {
+__global__ void __launch_bounds__(1024) k_merkle_stage(MerkleStage a, const Poseidon2Consts* __restrict__ gk) {
+    __shared__ uint32_t buf[2][128 * 8];
     const uint32_t lane = threadIdx.x & 31u, l16 = lane & 15u;
     const P2Lane c = p2_lane_consts<F>(gk, l16);
-    const uint32_t per_pass = blockDim.x >> 4;
-    for (uint32_t l = a.first_level; l <= a.last_level; l++) {
-        uint32_t n_next = 1u << (a.log_max_h - l);
-        const uint32_t* prev = a.digests + (((size_t)2 << a.log_max_h) - ((size_t)2 << (a.log_max_h - (l - 1)))) * 8;
-        uint32_t* next = a.digests + (((size_t)2 << a.log_max_h) - ((size_t)2 << (a.log_max_h - l))) * 8;
-        const uint32_t* const* inj = a.inj_colptr[l - a.first_level];
-        uint32_t inj_cols = a.inj_cols[l - a.first_level];
-        for (uint32_t base = 0; base < n_next; base += per_pass) {
-            uint32_t i = base + (threadIdx.x >> 4);
-            bool live = i < n_next;
-            // whole warps with no live node skip (both half-warps dead); a warp with one live half runs both
-            uint32_t any = __ballot_sync(0xffffffffu, live);
-            if (any) {
-                uint32_t x = coop_node<F>(prev, live ? i : 0, inj, inj_cols, lane, c);
-                if (live && l16 < 8) next[(size_t)i * 8 + l16] = x;
+    const uint32_t group = threadIdx.x >> 4, n_groups = blockDim.x >> 4;
+    const uint32_t K = a.n_levels;
+    auto level_ptr = [&](uint32_t l) {
+        return a.digests + (((size_t)2 << a.log_max_h) - ((size_t)2 << (a.log_max_h - l))) * 8;
+    };
+    if (a.with_leaves) {
+        const uint32_t per_cta = 1u << K;
+        uint32_t* out = level_ptr(0);
+        for (uint32_t base = 0; base < per_cta; base += n_groups) {
+            const uint32_t loc = base + group;
+            const bool live = loc < per_cta;
+            if (__ballot_sync(0xffffffffu, live)) {
+                const uint32_t r = blockIdx.x * per_cta + (live ? loc : 0);
+                uint32_t x = 0;
+                const uint32_t* row = a.leaf_rows + (size_t)r * a.leaf_w;
+                for (uint32_t c0 = 0; c0 < a.leaf_w; c0 += 8) {
+                    if (l16 < 8 && c0 + l16 < a.leaf_w) x = row[c0 + l16];
+                    x = p2_coop_permute<F>(x, lane, c);
+                }
+                if (live && l16 < 8) {
+                    out[(size_t)r * 8 + l16] = x;
+                    buf[1][loc * 8 + l16] = x;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (uint32_t j = 0; j < K; j++) {
+        const uint32_t l = a.first_level + j;
+        const uint32_t per_cta = 1u << (K - 1 - j);
+        const uint32_t* prev = level_ptr(l - 1);
+        uint32_t* next = level_ptr(l);
+        const uint32_t* sprev = buf[(j + 1) & 1];
+        uint32_t* snext = buf[j & 1];
+        const bool from_smem = j > 0 || a.with_leaves;
+        const uint32_t* inj = a.inj[j];
+        for (uint32_t base = 0; base < per_cta; base += n_groups) {
+            const uint32_t loc = base + group;
+            const bool live = loc < per_cta;
+            // a warp holds two groups: it runs when either is live (the dead half computes node 0 again and drops it)
+            if (__ballot_sync(0xffffffffu, live)) {
+                const uint32_t ll = live ? loc : 0;
+                const uint32_t i = blockIdx.x * per_cta + ll;
+                uint32_t x = from_smem ? sprev[ll * 16 + l16] : prev[(size_t)i * 16 + l16];  // left digest || right digest
+                x = p2_coop_permute<F>(x, lane, c);
+                if (inj) {
+                    if (l16 >= 8) x = __ldg(inj + (size_t)i * 8 + (l16 - 8));  // lanes 8..15 take the injected digest
+                    x = p2_coop_permute<F>(x, lane, c);
+                }
+                if (live && l16 < 8) {
+                    next[(size_t)i * 8 + l16] = x;
+                    snext[loc * 8 + l16] = x;
+                }
             }
         }
         __syncthreads();

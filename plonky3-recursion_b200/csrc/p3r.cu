@@ -379,8 +379,7 @@ static int get_gtable(p3r_ctx* ctx, uint32_t log_n, GTable* out) {
 // scratch_coef: n*w words; scratch_tmp: N*w words (only touched when log_n > TILE_LOG).
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t TILE_LOG = 13;
-constexpr uint32_t TAIL_NODES = 128;       // Merkle levels with at most this many nodes are produced by one k_tree_tail launch
-constexpr uint32_t COOP_MAX_NODES = 1u << 15;  // levels up to this size use the 16-lanes-per-permutation kernels
+constexpr uint32_t STAGE_MAX_NODES = 1u << 13;  // Merkle levels up to this size go through the fused k_merkle_stage launches
 struct PassPlan {
     uint32_t s0, r, log_cw;
 };
@@ -553,6 +552,65 @@ static int coset_lde(p3r_ctx* ctx, const uint32_t* src, uint32_t* dst, uint32_t 
 // ------------------------------------------------------------------------------------------------
 // K5 host: MerkleTreeMmcs::commit over column-major device matrices (mixed heights).
 // ------------------------------------------------------------------------------------------------
+// Every compression level of one tree (and, for row-major leaves, the leaf level). Levels with more than STAGE_MAX_NODES
+// nodes are throughput-bound and use the one-thread-per-permutation kernel (one launch per level); the rest is latency-bound
+// and runs as fused k_merkle_stage launches of up to STAGE_MAX_LEVELS levels each. `inj_at(level)` = device digests of the
+// rows injected at that level (nullptr = none). `leaf_rows` != nullptr: level 0 is still to be hashed from that row-major
+// matrix of `leaf_w` words per row; otherwise level 0 is already in `digests`.
+template <class F, class InjAt>
+static int build_tree(p3r_ctx* ctx, const uint32_t* leaf_rows, uint32_t leaf_w, uint32_t lmax, uint32_t* digests, InjAt inj_at) {
+    const uint32_t cap = ctx->fri.cap_height;
+    const uint32_t last_level = lmax - cap;
+    const uint32_t rows = 1u << lmax;
+    auto level_off = [&](uint32_t l) { return (((size_t)2 << lmax) - ((size_t)2 << (lmax - l))) * 8; };
+    ctx->kstats.bytes[KC_COMPRESS] += 96ull * rows;
+    bool leaves_done = leaf_rows == nullptr;
+    if (!leaves_done && rows > STAGE_MAX_NODES) {
+        KT kt(ctx, KC_HASH, (uint64_t)rows * (4ull * leaf_w + 32));
+        k_hash_rows_rowmajor<F><<<(rows + 127) / 128, 128, 0, ctx->stream>>>(leaf_rows, leaf_w, rows, digests);
+        LAUNCH_CHECK_C(KC_HASH);
+        leaves_done = true;
+    }
+    KT kt_tree(ctx, KC_COMPRESS, 0);
+    uint32_t cur = 0;  // levels 0..cur are done (level 0 only if leaves_done)
+    while (cur < last_level || !leaves_done) {
+        const uint32_t l = cur + 1;
+        const uint32_t n_next = l <= lmax ? 1u << (lmax - l) : 0;
+        if (leaves_done && n_next > STAGE_MAX_NODES) {
+            const uint32_t* inj = inj_at(l);
+            if (inj) ctx->kstats.bytes[KC_COMPRESS] += 32ull * n_next;
+            k_compress<F><<<(n_next + 127) / 128, 128, 0, ctx->stream>>>(digests + level_off(l - 1), digests + level_off(l), n_next, inj);
+            LAUNCH_CHECK_C(KC_COMPRESS);
+            cur = l;
+            continue;
+        }
+        MerkleStage st{};
+        st.digests = digests;
+        st.log_max_h = lmax;
+        st.first_level = l;
+        st.n_levels = std::min(STAGE_MAX_LEVELS, last_level - cur);
+        st.with_leaves = leaves_done ? 0 : 1;
+        st.leaf_rows = leaf_rows;
+        st.leaf_w = leaf_w;
+        if (st.with_leaves) ctx->kstats.bytes[KC_HASH] += (uint64_t)rows * (4ull * leaf_w + 32);
+        for (uint32_t j = 0; j < st.n_levels; j++) {
+            st.inj[j] = inj_at(l + j);
+            if (st.inj[j]) ctx->kstats.bytes[KC_COMPRESS] += 32ull << (lmax - l - j);
+        }
+        const uint32_t grid = 1u << (lmax - (cur + st.n_levels));            // nodes of the stage's last level
+        const uint32_t widest = st.with_leaves ? (1u << st.n_levels) : (1u << (st.n_levels - 1));
+        const uint32_t threads = std::max(32u, std::min(widest * 16, 1024u));
+        k_merkle_stage<F><<<grid, threads, 0, ctx->stream>>>(st, ctx->d_p2);
+        LAUNCH_CHECK_C(KC_COMPRESS);
+        leaves_done = true;
+        cur += st.n_levels;
+    }
+    return P3R_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5 host: MerkleTreeMmcs::commit over column-major device matrices (mixed heights).
+// ------------------------------------------------------------------------------------------------
 template <class F>
 static int commit_tree(p3r_ctx* ctx, const std::vector<MatRef>& mats, Tree* t, uint32_t* digests) {
     t->mats = mats;
@@ -560,77 +618,54 @@ static int commit_tree(p3r_ctx* ctx, const std::vector<MatRef>& mats, Tree* t, u
     for (auto& m : mats) lmax = std::max(lmax, m.log_h);
     t->log_max_h = lmax;
     t->digests = digests;
-    const uint32_t cap = ctx->fri.cap_height;
-    if (lmax < cap) {
+    if (lmax < ctx->fri.cap_height) {
         set_err(ctx, "matrix shorter than the Merkle cap");
         return P3R_ERR_INVALID_ARG;
     }
-    auto cols_at = [&](uint32_t lh) {
-        std::vector<const uint32_t*> v;
+    // one k_hash_rows launch for the rows of every height: level 0 for the tallest, injected digests for the others
+    std::vector<HashJob> jobs;
+    std::vector<const uint32_t*> inj_digests(lmax + 1, nullptr);  // by level
+    uint64_t hash_bytes = 0;
+    for (uint32_t lh = lmax + 1; lh-- > 0;) {
+        std::vector<const uint32_t*> cols;
         for (auto& m : mats)
             if (m.log_h == lh)
-                for (uint32_t c = 0; c < m.w; c++) v.push_back(m.d + ((size_t)c << m.log_h));
-        return v;
-    };
-    auto top = cols_at(lmax);
-    const uint32_t* const* d_cols = upload_vec(ctx, top);
-    if (!d_cols) {
-        set_err(ctx, "staging exhausted");
-        return P3R_ERR_OOM;
+                for (uint32_t c = 0; c < m.w; c++) cols.push_back(m.d + ((size_t)c << m.log_h));
+        if (cols.empty()) continue;
+        if (lh < ctx->fri.cap_height) {
+            set_err(ctx, "matrix shorter than the Merkle cap");
+            return P3R_ERR_INVALID_ARG;
+        }
+        HashJob j{};
+        j.colptr = upload_vec(ctx, cols);
+        j.ncols = (uint32_t)cols.size();
+        j.n_rows = 1u << lh;
+        j.out = lh == lmax ? digests : arena_alloc<uint32_t>(ctx, (size_t)8 << lh);
+        if (!j.colptr || !j.out) {
+            set_err(ctx, "staging / arena exhausted");
+            return P3R_ERR_OOM;
+        }
+        if (lh != lmax) inj_digests[lmax - lh] = j.out;
+        hash_bytes += (uint64_t)j.n_rows * (4ull * j.ncols + 32);
+        jobs.push_back(j);
     }
-    uint32_t rows = 1u << lmax;
+    std::stable_sort(jobs.begin(), jobs.end(), [](const HashJob& a, const HashJob& b) { return a.ncols > b.ncols; });
+    uint32_t cta = 0;
+    for (auto& j : jobs) {
+        j.cta_begin = cta;
+        cta += (j.n_rows + 127) / 128;
+    }
     {
-        KT kt(ctx, KC_HASH, (uint64_t)rows * (4ull * top.size() + 32));
-        if (rows <= 4096)
-            k_hash_rows_coop<F><<<(rows * 16 + 255) / 256, 256, 0, ctx->stream>>>(d_cols, (uint32_t)top.size(), rows, digests, ctx->d_p2);
-        else
-            k_hash_rows<F><<<(rows + 127) / 128, 128, 0, ctx->stream>>>(d_cols, (uint32_t)top.size(), rows, digests);
+        const HashJob* d_jobs = upload_vec(ctx, jobs);
+        if (!d_jobs) {
+            set_err(ctx, "staging exhausted");
+            return P3R_ERR_OOM;
+        }
+        KT kt(ctx, KC_HASH, hash_bytes);
+        k_hash_rows<F><<<cta, 128, 0, ctx->stream>>>(d_jobs, (uint32_t)jobs.size());
         LAUNCH_CHECK_C(KC_HASH);
     }
-    KT kt_tree(ctx, KC_COMPRESS, 96ull * rows);
-    const uint32_t last_level = lmax - cap;
-    TreeTail tail{};
-    bool in_tail = false;
-    for (uint32_t l = 1; l <= last_level; l++) {
-        uint32_t n_next = 1u << (lmax - l);
-        auto inj = cols_at(lmax - l);
-        const uint32_t* const* d_inj = nullptr;
-        if (!inj.empty()) {
-            d_inj = upload_vec(ctx, inj);
-            if (!d_inj) {
-                set_err(ctx, "staging exhausted");
-                return P3R_ERR_OOM;
-            }
-        }
-        ctx->kstats.bytes[KC_COMPRESS] += 4ull * inj.size() * n_next;
-        if (n_next <= TAIL_NODES && last_level - l < 24) {
-            if (!in_tail) {
-                in_tail = true;
-                tail.digests = digests;
-                tail.log_max_h = lmax;
-                tail.first_level = l;
-                tail.last_level = last_level;
-            }
-            tail.inj_colptr[l - tail.first_level] = d_inj;
-            tail.inj_cols[l - tail.first_level] = (uint32_t)inj.size();
-            continue;
-        }
-        if (n_next <= COOP_MAX_NODES && inj.size() <= 16)
-            k_compress_coop<F><<<(n_next * 16 + 255) / 256, 256, 0, ctx->stream>>>(digests + t->level_off(l - 1) * 8,
-                                                                                   digests + t->level_off(l) * 8, n_next, d_inj,
-                                                                                   (uint32_t)inj.size(), ctx->d_p2);
-        else
-            k_compress<F><<<(n_next + 127) / 128, 128, 0, ctx->stream>>>(digests + t->level_off(l - 1) * 8,
-                                                                          digests + t->level_off(l) * 8, n_next, d_inj,
-                                                                          (uint32_t)inj.size());
-        LAUNCH_CHECK_C(KC_COMPRESS);
-    }
-    if (in_tail) {
-        uint32_t n_first = 1u << (lmax - tail.first_level);
-        k_tree_tail<F><<<1, std::max(32u, std::min(n_first * 16, 1024u)), 0, ctx->stream>>>(tail, ctx->d_p2);
-        LAUNCH_CHECK_C(KC_COMPRESS);
-    }
-    return P3R_OK;
+    return build_tree<F>(ctx, nullptr, 0, lmax, digests, [&](uint32_t level) { return inj_digests[level]; });
 }
 static size_t tree_digest_words(uint32_t log_max_h) { return ((size_t)2 << log_max_h) * 8; }
 static int read_cap(p3r_ctx* ctx, const Tree& t, uint32_t* cap_out) {
@@ -1389,48 +1424,8 @@ static int fri_commit_impl(p3r_session* s, uint32_t round, uint32_t* cap_out) {
     if (!dg) return P3R_ERR_OOM;
     fr.tree.log_max_h = log_rows;
     fr.tree.digests = dg;
-    uint32_t rows = 1u << log_rows, w = 4u << fr.log_arity;
-    {
-        KT kt(ctx, KC_HASH, (uint64_t)rows * (4ull * w + 32));
-        if (rows <= COOP_MAX_NODES)
-            k_hash_rows_rowmajor_coop<F><<<(rows * 16 + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(fr.vec), w,
-                                                                                           rows, dg, ctx->d_p2);
-        else
-            k_hash_rows_rowmajor<F><<<(rows + 127) / 128, 128, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(fr.vec), w, rows, dg);
-        LAUNCH_CHECK_C(KC_HASH);
-    }
-    KT kt_tree(ctx, KC_COMPRESS, 96ull * rows);
-    {
-        const uint32_t last_level = log_rows - ctx->fri.cap_height;
-        TreeTail tail{};
-        bool in_tail = false;
-        for (uint32_t l = 1; l <= last_level; l++) {
-            uint32_t n_next = 1u << (log_rows - l);
-            if (n_next <= TAIL_NODES && last_level - l < 24) {
-                if (!in_tail) {
-                    in_tail = true;
-                    tail.digests = dg;
-                    tail.log_max_h = log_rows;
-                    tail.first_level = l;
-                    tail.last_level = last_level;
-                }
-                continue;
-            }
-            if (n_next <= COOP_MAX_NODES)
-                k_compress_coop<F><<<(n_next * 16 + 255) / 256, 256, 0, ctx->stream>>>(dg + fr.tree.level_off(l - 1) * 8,
-                                                                                       dg + fr.tree.level_off(l) * 8, n_next, nullptr, 0,
-                                                                                       ctx->d_p2);
-            else
-                k_compress<F><<<(n_next + 127) / 128, 128, 0, ctx->stream>>>(dg + fr.tree.level_off(l - 1) * 8,
-                                                                              dg + fr.tree.level_off(l) * 8, n_next, nullptr, 0);
-            LAUNCH_CHECK_C(KC_COMPRESS);
-        }
-        if (in_tail) {
-            uint32_t n_first = 1u << (log_rows - tail.first_level);
-            k_tree_tail<F><<<1, std::max(32u, std::min(n_first * 16, 1024u)), 0, ctx->stream>>>(tail, ctx->d_p2);
-            LAUNCH_CHECK_C(KC_COMPRESS);
-        }
-    }
+    TRY(build_tree<F>(ctx, reinterpret_cast<const uint32_t*>(fr.vec), 4u << fr.log_arity, log_rows, dg,
+                      [](uint32_t) { return (const uint32_t*)nullptr; }));
     return read_cap(ctx, fr.tree, cap_out);
 }
 
@@ -1927,6 +1922,16 @@ int p3r_ctx_create(int device, const p3r_field_desc* field, const p3r_poseidon2_
     std::memset(ctx->p2.int_rc, 0, sizeof ctx->p2.int_rc);
     std::memcpy(ctx->p2.int_rc, p2->internal_rc, rp * 4);
     std::memcpy(ctx->p2.diag, p2->internal_diag, 16 * 4);
+    {
+        // structured diagonal (shift/add products) only when the caller's diagonal is the p3 one for this field
+        bool fast = true;
+        for (int i = 0; i < 16; i++) {
+            uint32_t want = ctx->field_id == 0 ? to_monty<KoalaBear>(diag_spec_canonical<KoalaBear>(i))
+                                               : to_monty<BabyBear>(diag_spec_canonical<BabyBear>(i));
+            fast = fast && ctx->p2.diag[i] == want;
+        }
+        ctx->p2.fast_diag = fast ? 1u : 0u;
+    }
     if (ctx->field_id == 0) {
         ctx->w_m = to_monty<KoalaBear>(field->w);
         ctx->gen_m = to_monty<KoalaBear>(field->generator);

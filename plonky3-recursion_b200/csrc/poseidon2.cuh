@@ -12,6 +12,8 @@ struct Poseidon2Consts {
     uint32_t ext_rc[8 * 16];   // initial 4 rounds then terminal 4 rounds (Montgomery)
     uint32_t int_rc[32];       // rounds_p entries used
     uint32_t diag[16];
+    uint32_t zero;               // always 0, opaque to the compiler: see fadd_alu
+    uint32_t fast_diag;          // diag equals the field's structured p3 diagonal (DiagSpec below): products become shifts/adds
 };
 
 #if defined(__CUDACC__)
@@ -30,26 +32,110 @@ struct FieldId<BabyBear> {
     static constexpr int value = 1;
 };
 
+// The internal-layer diagonals p3 uses for width 16 are +-small integers and +-2^-k, chosen so the products
+// need no general multiplication. Entry i: sign, and either an integer multiple m (k == 0) or the power 2^-k.
+//   KoalaBear: [-2, 1, 2, 1/2, 3, 4, -1/2, -3, -4, 1/2^8, 1/8, 1/2^24, -1/2^8, -1/8, -1/16, -1/2^24]
+//   BabyBear : [-2, 1, 2, 1/2, 3, 4, -1/2, -3, -4, 1/2^8, 1/4, 1/8, 1/2^27, -1/2^8, -1/16, -1/2^27]
+// The integer multiplier pipe (IMAD, "fmaheavy") bounds the permutation (ncu: 79 % busy, ALU 50 %), and a Montgomery product
+// costs 10 of its cycles, so these 16 products per partial round are the largest avoidable cost.
+struct DiagEntry {
+    int sign, m, k;
+};
+template <class F>
+struct DiagSpec;
+template <>
+struct DiagSpec<KoalaBear> {
+    static constexpr DiagEntry e[16] = {{-1, 2, 0}, {1, 1, 0},  {1, 2, 0},  {1, 1, 1},   {1, 3, 0},  {1, 4, 0},  {-1, 1, 1}, {-1, 3, 0},
+                                        {-1, 4, 0}, {1, 1, 8},  {1, 1, 3},  {1, 1, 24},  {-1, 1, 8}, {-1, 1, 3}, {-1, 1, 4}, {-1, 1, 24}};
+};
+template <>
+struct DiagSpec<BabyBear> {
+    static constexpr DiagEntry e[16] = {{-1, 2, 0}, {1, 1, 0},  {1, 2, 0},  {1, 1, 1},   {1, 3, 0},  {1, 4, 0},  {-1, 1, 1}, {-1, 3, 0},
+                                        {-1, 4, 0}, {1, 1, 8},  {1, 1, 2},  {1, 1, 3},   {1, 1, 27}, {-1, 1, 8}, {-1, 1, 4}, {-1, 1, 27}};
+};
+// Canonical value of entry i (host: checked against the caller's diagonal in p3r_ctx_create).
+template <class F>
+inline uint32_t diag_spec_canonical(int i) {
+    const DiagEntry d = DiagSpec<F>::e[i];
+    uint64_t v = (uint64_t)d.m % F::P;
+    for (int j = 0; j < d.k; j++) v = (v & 1) ? (v + F::P) >> 1 : v >> 1;
+    return d.sign > 0 ? (uint32_t)v : (uint32_t)((F::P - v) % F::P);
+}
+// x * 2^-K mod P for x in [0, P), 1 <= K <= two-adicity: with x = h*2^K + l and 2^-K = -(P-1)/2^K (mod P),
+// x * 2^-K = h - l*(P-1)/2^K, which lies in (-P, 2^(31-K)); one unsigned min brings it to [0, P). Montgomery form is
+// preserved (the factor is a plain field element).
+template <class F, int K>
+P3R_HD uint32_t fdiv2k(uint32_t x) {
+    if (K == 1) return (x >> 1) + (x & 1u) * ((F::P + 1) >> 1);
+    constexpr uint32_t C = (F::P - 1) >> K;
+    uint32_t d = (x >> K) - (x & ((1u << K) - 1)) * C;
+    uint32_t d2 = d + F::P;
+    return d2 < d ? d2 : d;
+}
+// sum + diag_I * x with the structured diagonal.
+template <class F, int I>
+P3R_HD uint32_t diag_apply(uint32_t sum, uint32_t x) {
+    constexpr DiagEntry d = DiagSpec<F>::e[I];
+    uint32_t y = x;
+    if (d.k > 0) y = fdiv2k<F, (d.k > 0 ? d.k : 1)>(x);
+    else if (d.m == 2) y = fadd<F>(x, x);
+    else if (d.m == 3) y = fadd<F>(fadd<F>(x, x), x);
+    else if (d.m == 4) {
+        y = fadd<F>(x, x);
+        y = fadd<F>(y, y);
+    }
+    return d.sign > 0 ? fadd<F>(sum, y) : fsub<F>(sum, y);
+}
+
+// Montgomery product without the final conditional subtraction: result in [0, 2P), valid as ONE operand of a later product.
+template <class F>
+P3R_HD uint32_t fmul_lazy(uint32_t a, uint32_t b) {
+    uint64_t t = (uint64_t)a * b;
+    uint32_t m = (uint32_t)t * (0u - F::MU);
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("{ .reg .u32 l2;\n\tmad.lo.cc.u32 l2, %1, %2, %3;\n\tmadc.hi.u32 %0, %1, %2, %4; }"
+        : "=r"(r)
+        : "r"(m), "r"(F::P), "r"((uint32_t)t), "r"((uint32_t)(t >> 32)));
+    return r;
+#else
+    return (uint32_t)(((uint64_t)m * F::P + t) >> 32);
+#endif
+}
+
 template <class F>
 P3R_HD uint32_t sbox(uint32_t x) {
+    if (F::SBOX == 3) return fmul<F>(fmul_lazy<F>(x, x), x);
     uint32_t x2 = fmul<F>(x, x);
-    if (F::SBOX == 3) return fmul<F>(x2, x);
-    uint32_t x3 = fmul<F>(x2, x);
+    uint32_t x3 = fmul_lazy<F>(x2, x);
     uint32_t x4 = fmul<F>(x2, x2);
     return fmul<F>(x3, x4);
 }
 
+// a + b mod P with the addition forced onto the ALU pipe: `z` is a run-time zero (Poseidon2Consts::zero), and a
+// three-input add can only be an IADD3. ptxas otherwise turns about half of the plain additions of the external layer into
+// IMAD.IADD on the integer-multiplier pipe, which the Montgomery products already saturate (ncu: fmaheavy 79 %, ALU 50 %).
 template <class F>
-P3R_HD void m4(uint32_t& x0, uint32_t& x1, uint32_t& x2, uint32_t& x3) {
-    uint32_t t01 = fadd<F>(x0, x1);
-    uint32_t t23 = fadd<F>(x2, x3);
-    uint32_t t0123 = fadd<F>(t01, t23);
-    uint32_t t01123 = fadd<F>(t0123, x1);
-    uint32_t t01233 = fadd<F>(t0123, x3);
-    uint32_t n3 = fadd<F>(t01233, fadd<F>(x0, x0));
-    uint32_t n1 = fadd<F>(t01123, fadd<F>(x2, x2));
-    uint32_t n0 = fadd<F>(t01123, t01);
-    uint32_t n2 = fadd<F>(t01233, t23);
+P3R_HD uint32_t fadd_alu(uint32_t a, uint32_t b, uint32_t z) {
+#if defined(P3R_NO_ALU_FORCE)
+    (void)z;
+    return fadd<F>(a, b);
+#else
+    uint32_t s = a + b + z, s2 = s - F::P;
+    return s2 < s ? s2 : s;
+#endif
+}
+template <class F>
+P3R_HD void m4(uint32_t& x0, uint32_t& x1, uint32_t& x2, uint32_t& x3, uint32_t z) {
+    uint32_t t01 = fadd_alu<F>(x0, x1, z);
+    uint32_t t23 = fadd_alu<F>(x2, x3, z);
+    uint32_t t0123 = fadd_alu<F>(t01, t23, z);
+    uint32_t t01123 = fadd_alu<F>(t0123, x1, z);
+    uint32_t t01233 = fadd_alu<F>(t0123, x3, z);
+    uint32_t n3 = fadd_alu<F>(t01233, fadd<F>(x0, x0), z);
+    uint32_t n1 = fadd_alu<F>(t01123, fadd<F>(x2, x2), z);
+    uint32_t n0 = fadd_alu<F>(t01123, t01, z);
+    uint32_t n2 = fadd_alu<F>(t01233, t23, z);
     x0 = n0;
     x1 = n1;
     x2 = n2;
@@ -57,14 +143,14 @@ P3R_HD void m4(uint32_t& x0, uint32_t& x1, uint32_t& x2, uint32_t& x3) {
 }
 
 template <class F>
-P3R_HD void external_linear(uint32_t* s) {
+P3R_HD void external_linear(uint32_t* s, uint32_t z = 0) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) m4<F>(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
+    for (int k = 0; k < 4; k++) m4<F>(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3], z);
     uint32_t sums[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) sums[j] = fadd<F>(fadd<F>(s[j], s[4 + j]), fadd<F>(s[8 + j], s[12 + j]));  // balanced
 #pragma unroll
-    for (int i = 0; i < 16; i++) s[i] = fadd<F>(s[i], sums[i & 3]);
+    for (int i = 0; i < 16; i++) s[i] = fadd_alu<F>(s[i], sums[i & 3], z);
 }
 
 // Internal (partial) round, arranged for instruction-level parallelism: the S-box chain on s[0], the balanced sum of
@@ -85,23 +171,51 @@ P3R_HD void internal_round(uint32_t* s, uint32_t rc, const uint32_t* diag) {
 #pragma unroll
     for (int i = 1; i < 16; i++) s[i] = fadd<F>(sum, prod[i]);
 }
+template <class F, int I>
+struct DiagLoop {
+    static P3R_HD void run(uint32_t* s, uint32_t sum) {
+        s[I] = diag_apply<F, I>(sum, s[I]);
+        DiagLoop<F, I + 1>::run(s, sum);
+    }
+};
+template <class F>
+struct DiagLoop<F, 16> {
+    static P3R_HD void run(uint32_t*, uint32_t) {}
+};
+// Same round with the structured diagonal: no general product outside the S-box.
+template <class F>
+P3R_HD void internal_round_fast(uint32_t* s, uint32_t rc) {
+    uint32_t a0 = fadd<F>(fadd<F>(s[1], s[2]), fadd<F>(s[3], s[4]));
+    uint32_t a1 = fadd<F>(fadd<F>(s[5], s[6]), fadd<F>(s[7], s[8]));
+    uint32_t a2 = fadd<F>(fadd<F>(s[9], s[10]), fadd<F>(s[11], s[12]));
+    uint32_t a3 = fadd<F>(fadd<F>(s[13], s[14]), s[15]);
+    uint32_t rest = fadd<F>(fadd<F>(a0, a1), fadd<F>(a2, a3));
+    s[0] = sbox<F>(fadd<F>(s[0], rc));
+    uint32_t sum = fadd<F>(rest, s[0]);
+    DiagLoop<F, 0>::run(s, sum);
+}
 
 template <class F>
 P3R_HD void poseidon2_permute_with(uint32_t* s, const Poseidon2Consts& k) {
-    external_linear<F>(s);
+    external_linear<F>(s, k.zero);
 #pragma unroll 1
     for (int r = 0; r < 4; r++) {
 #pragma unroll
         for (int i = 0; i < 16; i++) s[i] = sbox<F>(fadd<F>(s[i], k.ext_rc[16 * r + i]));
-        external_linear<F>(s);
+        external_linear<F>(s, k.zero);
     }
+    if (k.fast_diag) {
 #pragma unroll 1
-    for (int r = 0; r < F::ROUNDS_P; r++) internal_round<F>(s, k.int_rc[r], k.diag);
+        for (int r = 0; r < F::ROUNDS_P; r++) internal_round_fast<F>(s, k.int_rc[r]);
+    } else {
+#pragma unroll 1
+        for (int r = 0; r < F::ROUNDS_P; r++) internal_round<F>(s, k.int_rc[r], k.diag);
+    }
 #pragma unroll 1
     for (int r = 4; r < 8; r++) {
 #pragma unroll
         for (int i = 0; i < 16; i++) s[i] = sbox<F>(fadd<F>(s[i], k.ext_rc[16 * r + i]));
-        external_linear<F>(s);
+        external_linear<F>(s, k.zero);
     }
 }
 
@@ -113,6 +227,7 @@ P3R_HD void poseidon2_permute_with(uint32_t* s, const Poseidon2Consts& k) {
 struct P2Lane {
     uint32_t rc[8];
     uint32_t dg;
+    bool d0_neg2;   // diag[0] == -2 (true for both p3 parameter sets): lane 0's update is rest - s0, no product on the chain
 };
 template <class F>
 __device__ __forceinline__ P2Lane p2_lane_consts(const Poseidon2Consts* __restrict__ gk, uint32_t l16) {
@@ -120,7 +235,17 @@ __device__ __forceinline__ P2Lane p2_lane_consts(const Poseidon2Consts* __restri
 #pragma unroll
     for (int r = 0; r < 8; r++) c.rc[r] = __ldg(&gk->ext_rc[16 * r + l16]);
     c.dg = __ldg(&gk->diag[l16]);
+    c.d0_neg2 = __ldg(&gk->diag[0]) == fsub<F>(0u, fadd<F>(F::R, F::R));
     return c;
+}
+// Sum over the 4 lanes {l, l^m, l^2m, l^3m} in one shuffle round (3 independent shuffles + a depth-2 add tree): two rounds
+// reduce 16 lanes, against four dependent shuffle+add steps for the xor butterfly.
+template <class F>
+__device__ __forceinline__ uint32_t p2_sum4(uint32_t v, uint32_t m) {
+    uint32_t a = __shfl_xor_sync(0xffffffffu, v, m);
+    uint32_t b = __shfl_xor_sync(0xffffffffu, v, 2 * m);
+    uint32_t c = __shfl_xor_sync(0xffffffffu, v, 3 * m);
+    return fadd<F>(fadd<F>(v, a), fadd<F>(b, c));
 }
 template <class F>
 __device__ __forceinline__ uint32_t p2_coop_external(uint32_t x, uint32_t lane) {
@@ -130,9 +255,7 @@ __device__ __forceinline__ uint32_t p2_coop_external(uint32_t x, uint32_t lane) 
     uint32_t c = __shfl_sync(0xffffffffu, x, base | ((q + 3) & 3));
     uint32_t t = fadd<F>(x, a), u = fadd<F>(b, c);
     uint32_t o = fadd<F>(fadd<F>(t, t), fadd<F>(a, u));  // 2x + 3a + b + c
-    uint32_t y = fadd<F>(o, __shfl_xor_sync(0xffffffffu, o, 4));
-    y = fadd<F>(y, __shfl_xor_sync(0xffffffffu, y, 8));
-    return fadd<F>(o, y);
+    return fadd<F>(o, p2_sum4<F>(o, 4));                 // + column sum over the four M4 blocks
 }
 template <class F>
 __device__ __forceinline__ uint32_t p2_coop_permute(uint32_t x, uint32_t lane, const P2Lane& c) {
@@ -143,17 +266,14 @@ __device__ __forceinline__ uint32_t p2_coop_permute(uint32_t x, uint32_t lane, c
     for (int r = 0; r < 4; r++) x = p2_coop_external<F>(sbox<F>(fadd<F>(x, c.rc[r])), lane);
 #pragma unroll 1
     for (int r = 0; r < F::ROUNDS_P; r++) {
-        // sum of the 15 untouched lanes proceeds while lane 0's S-box chain runs
-        uint32_t rest = lane0 ? 0u : x;
-        rest = fadd<F>(rest, __shfl_xor_sync(0xffffffffu, rest, 1));
-        rest = fadd<F>(rest, __shfl_xor_sync(0xffffffffu, rest, 2));
-        rest = fadd<F>(rest, __shfl_xor_sync(0xffffffffu, rest, 4));
-        rest = fadd<F>(rest, __shfl_xor_sync(0xffffffffu, rest, 8));
-        uint32_t sb = sbox<F>(fadd<F>(x, k.int_rc[r]));
-        x = lane0 ? sb : x;
-        uint32_t s0 = __shfl_sync(0xffffffffu, x, lane & ~15u);
+        // Off the S-box chain: the diagonal products of the 15 untouched lanes and their sum (two shuffle rounds).
+        uint32_t prod = fmul<F>(c.dg, x);
+        uint32_t rest = p2_sum4<F>(p2_sum4<F>(lane0 ? 0u : x, 1), 4);
+        uint32_t sb = sbox<F>(fadd<F>(x, k.int_rc[r]));          // meaningful on lane 0
+        uint32_t s0 = __shfl_sync(0xffffffffu, sb, lane & ~15u);
         uint32_t sum = fadd<F>(rest, s0);
-        x = fadd<F>(sum, fmul<F>(c.dg, x));
+        uint32_t x0 = c.d0_neg2 ? fsub<F>(rest, s0) : fadd<F>(sum, fmul<F>(c.dg, s0));  // sum + diag[0]*s0
+        x = lane0 ? x0 : fadd<F>(sum, prod);
     }
 #pragma unroll
     for (int r = 4; r < 8; r++) x = p2_coop_external<F>(sbox<F>(fadd<F>(x, c.rc[r])), lane);
