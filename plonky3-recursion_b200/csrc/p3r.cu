@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "ntt_col.cuh"
 #include "spec.h"
 
 using namespace p3r;
@@ -94,6 +95,7 @@ struct p3r_ctx {
     cudaStream_t stream = nullptr;
     uint32_t* tws = nullptr;  // per-stage compact twiddle tables, 2^logT - 1 entries
     uint32_t* tw = nullptr;   // = tws + 2^(logT-1) - 1: half table of omega_T
+    bool use_col_ntt = true;  // whole-column LDE kernels for 2^5..2^15 rows (p3r_set_specialization bit 1 turns them off)
     uint32_t logT = 0;
     uint32_t r4 = 0, r8 = 0, r8_3 = 0;
     Poseidon2Consts* d_p2 = nullptr;  // global-memory copy of the Poseidon2 constants (per-lane reads of the cooperative kernels)
@@ -455,18 +457,192 @@ static int launch_pass_level(p3r_ctx* ctx, std::vector<NttPass>& passes) {
     LAUNCH_CHECK_C(KC_NTT);
     return P3R_OK;
 }
+// Whole-column path (ntt_col.cuh) for jobs with 2^5 <= n <= 2^15: one inverse and one forward launch per size class.
+static void col_plan(uint32_t log_n, uint32_t q[3]) {
+    static const uint8_t plans[11][3] = {{0, 0, 0}, {1, 0, 0}, {2, 0, 0}, {3, 0, 0}, {4, 0, 0}, {2, 3, 0},
+                                         {3, 3, 0}, {3, 4, 0}, {4, 4, 0}, {3, 3, 3}, {3, 3, 4}};
+    for (int i = 0; i < 3; i++) q[i] = plans[log_n - 5][i];
+}
+template <class F>
+static int coset_lde_cols(p3r_ctx* ctx, const std::vector<LdeJob>& jobs, uint32_t log_blowup) {
+    if (jobs.empty()) return P3R_OK;
+    static bool attr_set[2] = {false, false};
+    const int fid = FieldId<F>::value;
+    if (!attr_set[fid]) {
+        cudaFuncSetAttribute(k_ntt_col<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << COL_MAX_LOG);
+        cudaFuncSetAttribute(k_ntt_col<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << COL_MAX_LOG);
+        attr_set[fid] = true;
+    }
+    const uint32_t n_cosets = 1u << log_blowup;
+    // roots needed on the host: w_32 powers and w_N per job
+    const uint32_t w32 = fpow<F>(ctx->gen_m, ((uint64_t)F::P - 1) >> 5);
+    uint32_t st32[31], ist32[31];  // w_{2^(s+1)}^e and its inverse at (2^s - 1) + e, s < 5
+    for (uint32_t sgm = 0; sgm < 5; sgm++)
+        for (uint32_t e = 0; e < (1u << sgm); e++) {
+            uint32_t w = fpow<F>(w32, (uint64_t)e << (4 - sgm));
+            st32[(1u << sgm) - 1 + e] = w;
+            ist32[(1u << sgm) - 1 + e] = finv<F>(w);
+        }
+    std::vector<uint32_t> ctab;  // [inverse table (1 entry)] then per job, per coset
+    ctab.resize(COL_CTAB, 0);
+    for (int i = 0; i < 31; i++) ctab[i] = ist32[i];
+    std::vector<size_t> job_ctab(jobs.size());
+    for (size_t qi = 0; qi < jobs.size(); qi++) {
+        const LdeJob& j = jobs[qi];
+        const uint32_t logN = j.log_n + log_blowup;
+        const uint32_t wN = fpow<F>(ctx->gen_m, ((uint64_t)F::P - 1) >> logN);
+        job_ctab[qi] = ctab.size();
+        for (uint32_t cs = 0; cs < n_cosets; cs++) {
+            const uint32_t rj = bitrev32(cs, log_blowup);
+            const uint64_t e = ((uint64_t)rj + j.rot) & (((uint64_t)1 << logN) - 1);
+            uint32_t c = fpow<F>(wN, e);
+            if (j.use_g) c = fmul<F>(c, ctx->gen_m);
+            uint32_t C[20];
+            for (uint32_t sgm = 0; sgm < 20; sgm++) C[sgm] = F::R;
+            C[j.log_n - 1] = c;
+            for (uint32_t sgm = j.log_n - 1; sgm-- > 0;) C[sgm] = fmul<F>(C[sgm + 1], C[sgm + 1]);
+            size_t off = ctab.size();
+            ctab.resize(off + COL_CTAB);
+            for (uint32_t sgm = 0; sgm < 5; sgm++)
+                for (uint32_t ee = 0; ee < (1u << sgm); ee++)
+                    ctab[off + (1u << sgm) - 1 + ee] = fmul<F>(C[sgm], st32[(1u << sgm) - 1 + ee]);
+            for (uint32_t sgm = 0; sgm < 20; sgm++) ctab[off + 31 + sgm] = C[sgm];
+        }
+    }
+    const uint32_t* d_ctab = upload_vec(ctx, ctab);
+    if (!d_ctab) {
+        set_err(ctx, "staging exhausted");
+        return P3R_ERR_OOM;
+    }
+    ColJob base{};
+    base.tws = ctx->tws;
+    base.r4 = ctx->r4;
+    base.r8 = ctx->r8;
+    base.r8_3 = ctx->r8_3;
+    {
+        const uint32_t w16 = fmul<F>(w32, w32);
+        uint32_t p = F::R;
+        for (int e = 0; e < 8; e++) {
+            base.r16[e] = p;
+            p = fmul<F>(p, w16);
+        }
+    }
+    // one inverse and one forward launch for all jobs: every CTA works on up to 2^15 elements (2^(15 - log_n) columns),
+    // largest columns first. Columns of 2^16..2^19 rows: their 2^15-row sub-blocks go through the same launch as virtual
+    // columns, the stages >= 15 run in k_ntt_top (before the inverse launch / after the forward launch) through j.tmp.
+    std::vector<size_t> order(jobs.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return jobs[x].log_n > jobs[y].log_n; });
+    auto launch_top = [&](const LdeJob& j, size_t qi, bool fwd) -> int {
+        const uint32_t Q = j.log_n - COL_MAX_LOG;
+        const size_t n = (size_t)1 << j.log_n, N = n << log_blowup;
+        ColJob b = base;
+        b.ctab = d_ctab + job_ctab[qi];
+        dim3 grid((1u << COL_MAX_LOG) / 256, j.w, fwd ? n_cosets : 1);
+        if (fwd) {
+            b.src = j.tmp;
+            b.src_col_stride = n;
+            b.src_coset_stride = (uint64_t)j.w * n;
+            b.dst = j.dst;
+            b.dst_col_stride = N;
+            b.dst_coset_stride = n;
+        } else {
+            b.src = j.src;
+            b.src_col_stride = n;
+            b.src_coset_stride = 0;
+            b.dst = j.tmp;
+            b.dst_col_stride = n;
+            b.dst_coset_stride = 0;
+        }
+#define P3R_TOP(QQ)                                                                          \
+    if (fwd) k_ntt_top<F, QQ, true><<<grid, 256, 0, ctx->stream>>>(b);                      \
+    else k_ntt_top<F, QQ, false><<<grid, 256, 0, ctx->stream>>>(b)
+        if (Q == 1) { P3R_TOP(1); }
+        else if (Q == 2) { P3R_TOP(2); }
+        else if (Q == 3) { P3R_TOP(3); }
+        else { P3R_TOP(4); }
+#undef P3R_TOP
+        LAUNCH_CHECK_C(KC_NTT);
+        return P3R_OK;
+    };
+    for (int dir = 0; dir < 2; dir++) {
+        if (dir == 0)
+            for (size_t qi : order)
+                if (jobs[qi].log_n > COL_MAX_LOG) TRY(launch_top(jobs[qi], qi, false));
+        std::vector<ColJob> level;
+        uint32_t cta = 0;
+        for (size_t qi : order) {
+            const LdeJob& j = jobs[qi];
+            const size_t n = (size_t)1 << j.log_n, N = n << log_blowup;
+            const bool big = j.log_n > COL_MAX_LOG;
+            const uint32_t sub_log = big ? COL_MAX_LOG : j.log_n;   // rows handled inside one CTA column
+            const size_t sub_n = (size_t)1 << sub_log;
+            ColJob b = base;
+            b.log_n = sub_log;
+            b.n_cols = j.w << (j.log_n - sub_log);                   // virtual columns = sub-blocks of 2^15 rows
+            b.cols_per_cta = 1u << (COL_MAX_LOG - sub_log);
+            col_plan(sub_log, b.q);
+            b.n_inv = finv<F>(to_monty<F>(1u << j.log_n));
+            if (dir == 0) {
+                b.src = big ? j.tmp : j.src;
+                b.dst = j.coef;
+                b.src_col_stride = b.dst_col_stride = sub_n;         // == n for ordinary jobs; sub-blocks are contiguous
+                b.dst_coset_stride = 0;
+                b.n_cosets = 1;
+                b.ctab = d_ctab;
+            } else {
+                b.src = j.coef;
+                b.src_col_stride = sub_n;
+                b.n_cosets = n_cosets;
+                b.ctab = d_ctab + job_ctab[qi];
+                if (big) {
+                    b.dst = j.tmp;                                   // [coset][column][n], natural order
+                    b.dst_col_stride = sub_n;
+                    b.dst_coset_stride = (uint64_t)j.w * n;
+                    b.natural_out = 1;
+                } else {
+                    b.dst = j.dst;
+                    b.dst_col_stride = N;
+                    b.dst_coset_stride = n;
+                }
+            }
+            b.cta_begin = cta;
+            cta += ((b.n_cols + b.cols_per_cta - 1) / b.cols_per_cta) * b.n_cosets;
+            level.push_back(b);
+        }
+        const ColJob* d_jobs = upload_vec(ctx, level);
+        if (!d_jobs) {
+            set_err(ctx, "staging exhausted");
+            return P3R_ERR_OOM;
+        }
+        const size_t smem = (size_t)4 << COL_MAX_LOG;
+        if (dir == 0) k_ntt_col<F, false><<<cta, 512, smem, ctx->stream>>>(d_jobs, (uint32_t)level.size());
+        else k_ntt_col<F, true><<<cta, 512, smem, ctx->stream>>>(d_jobs, (uint32_t)level.size());
+        LAUNCH_CHECK_C(KC_NTT);
+        if (dir == 1)
+            for (size_t qi : order)
+                if (jobs[qi].log_n > COL_MAX_LOG) TRY(launch_top(jobs[qi], qi, true));
+    }
+    return P3R_OK;
+}
+
 // Batched coset LDE of several matrices (all tables of one commit round): the same pass level of every job shares a launch.
 template <class F>
-static int coset_lde_batch(p3r_ctx* ctx, const std::vector<LdeJob>& jobs, uint32_t log_blowup) {
-    if (jobs.empty()) return P3R_OK;
+static int coset_lde_batch(p3r_ctx* ctx, const std::vector<LdeJob>& all_jobs, uint32_t log_blowup) {
+    if (all_jobs.empty()) return P3R_OK;
     uint32_t max_logN = 0;
     uint64_t bytes = 0;
-    for (auto& j : jobs) {
+    std::vector<LdeJob> jobs, col_jobs;  // multi-pass tile kernel / whole-column kernel
+    for (auto& j : all_jobs) {
+        if (!j.w) continue;
         max_logN = std::max(max_logN, j.log_n + log_blowup);
         bytes += 4ull * (((size_t)1 << j.log_n) + ((size_t)1 << (j.log_n + log_blowup))) * j.w;
+        (ctx->use_col_ntt && j.log_n >= COL_MIN_LOG && j.log_n <= COL_TOP_MAX_LOG ? col_jobs : jobs).push_back(j);
     }
-    TRY(ensure_twiddles<F>(ctx, max_logN));
+    TRY(ensure_twiddles<F>(ctx, std::max(max_logN, 16u)));
     KT kt(ctx, KC_NTT, bytes);  // algorithmic bytes: read every trace once, write every LDE once
+    TRY(coset_lde_cols<F>(ctx, col_jobs, log_blowup));
+    if (jobs.empty()) return P3R_OK;
     std::vector<std::vector<PassPlan>> plans;
     std::vector<NttPass> base;
     size_t max_passes = 0;
@@ -2126,7 +2302,10 @@ int p3r_prove_resident(p3r_ctx* ctx, const p3r_prep* prep, const p3r_traces* tra
 }
 int p3r_set_specialization(p3r_ctx* ctx, int enable) {
     if (!ctx) return P3R_ERR_INVALID_ARG;
-    ctx->use_spec = enable != 0;
+    // bit 0: build-time specialised quotient kernels; bit 1 set = DISABLE the whole-column LDE kernels (tile kernel only),
+    // so enable = 1 / 0 keep their old meaning and the parity tests can cross-check both LDE paths.
+    ctx->use_spec = (enable & 1) != 0;
+    ctx->use_col_ntt = (enable & 2) == 0;
     return P3R_OK;
 }
 int p3r_timer_start(p3r_ctx* ctx) {

@@ -41,6 +41,25 @@ def test_coset_lde(pair, log_n, width, log_blowup):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("log_n,width,log_blowup", [(5, 2, 2), (6, 3, 1), (7, 1, 2), (9, 5, 2), (11, 7, 2), (12, 33, 2), (15, 3, 2),
+                                                    (17, 2, 2), (18, 3, 1), (19, 1, 1)])
+def test_coset_lde_column_kernels_match_tile_kernel(pair, log_n, width, log_blowup):
+    """The whole-column LDE kernels (k_ntt_col / k_ntt_top, every group plan 2^5..2^19) and the multi-pass tile kernel
+    (k_ntt_pass) are independent implementations of the same transform: bit-identical outputs; oracle-checked up to 2^17."""
+    ctx, orc = pair
+    rng = np.random.default_rng(300 + log_n)
+    m = ctx.field.rand(rng, (1 << log_n, width))
+    got = ctx.coset_lde(m, log_blowup)
+    ctx.set_specialization(1 | 2)  # bit 1: tile kernel only
+    try:
+        ref = ctx.coset_lde(m, log_blowup)
+    finally:
+        ctx.set_specialization(1)
+    assert np.array_equal(got, ref)
+    if log_n <= 17:
+        assert np.array_equal(got, orc.coset_lde(m, log_blowup))
+
+
 @pytest.mark.parametrize("shapes", [[(6, 5)], [(8, 9), (8, 16)], [(9, 3), (7, 20), (7, 1), (4, 11)], [(10, 8), (9, 8), (3, 8)]])
 def test_mmcs_commit_mixed_heights(pair, shapes):
     ctx, orc = pair
