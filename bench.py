@@ -29,6 +29,10 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
 import numpy as np  # noqa: E402
 
 FULL = dict(n_const=1500, n_public=43000, n_alu=60000, n_perms=12000, n_recompose=4000)
+# Thread instructions one Poseidon2 permutation costs in k_hash_rows / k_compress (ncu: smsp__inst_executed.sum * 32 /
+# permutations of a launch, profiles/r1_ncu_summary.md): the unit conversion of the INT32-pipe roofline below.
+INSTR_PER_PERM = {"koala-bear": 5300.0, "baby-bear": 6500.0}
+N_SMS, LANES_PER_SM = 148, 128
 METRIC = "prove_next_layer throughput (layer proofs/s; 1000/value = ms/layer at 1 GPU)"
 
 
@@ -56,6 +60,25 @@ class ClockSampler(threading.Thread):
         self.device, self.rows, self._stop_ev = device, [], threading.Event()
 
     def run(self):
+        # NVML in-process (a sample costs ~0.1 ms, so short timed regions still get many samples); nvidia-smi as fallback
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            bits = [(pynvml.nvmlClocksEventReasonHwSlowdown, 2), (pynvml.nvmlClocksEventReasonHwThermalSlowdown, 3),
+                    (pynvml.nvmlClocksEventReasonSwThermalSlowdown, 4), (pynvml.nvmlClocksEventReasonSwPowerCap, 5)]
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self._stop_ev.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                reasons = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                row = [str(sm), str(mx), "", "", "", ""]
+                for bit, pos in bits:
+                    row[pos] = "Active" if reasons & bit else "Not Active"
+                self.rows.append(row)
+                self._stop_ev.wait(0.005)
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self._stop_ev.is_set():
@@ -158,7 +181,8 @@ def run_ours(args):
         prover.prove_resident(tb_res, pd, copy=False)
     breakdown = {k: v["ms"] / 2 for k, v in ctx.kernel_stats().items()}
     dominant = max(breakdown, key=breakdown.get)
-    ctx.set_kernel_timing([dominant])  # live timing of the dominant kernel class inside the timed region
+    # live timing, inside the timed region, of the dominant kernel class and of the LDE (the HBM-roofline kernel)
+    ctx.set_kernel_timing(sorted({dominant, "ntt_lde"}))
     ctx.reset_kernel_stats()
 
     # ---- timed region A: device-resident inputs ----
@@ -169,7 +193,8 @@ def run_ours(args):
     t_res = timed_steps(lambda: prover.prove_resident(tb_res, pd, copy=False), args.steps)
     launches = ctx.launch_count() - l0
     barrier()
-    ks = ctx.kernel_stats()[dominant]
+    kstats = ctx.kernel_stats()
+    ks, ks_lde = kstats[dominant], kstats["ntt_lde"]
     ctx.set_kernel_timing([])
     proof_words = prover.last_proof_words
     # ---- timed region B: end to end through the C ABI with host buffers (H2D of traces + D2H of the proof inside) ----
@@ -189,12 +214,34 @@ def run_ours(args):
         ms_step = t_res / args.steps
         value = world * args.steps / (t_res / 1e3)
         e2e_value = world * args.steps / (t_e2e / 1e3)
-        achieved = (ks["bytes"] / 1e9) / (ks["ms"] / 1e3) if ks["ms"] > 0 else 0.0
-        traffic = None
+        traffic = {}
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get(dominant)
+                traffic = json.load(f)
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+
+        def hbm_roofline(name, st):
+            ach = (st["bytes"] / 1e9) / (st["ms"] / 1e3) if st["ms"] > 0 else 0.0
+            return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": traffic.get(name), "peak_source": peak_kind, "algorithmic_bytes_per_step": st["bytes"] / args.steps,
+                    "kernel_ms_per_step": st["ms"] / args.steps, "launches_per_step": st["launches"] / args.steps}
+
+        if dominant in ("hash_rows", "compress"):
+            # Poseidon2 is bound by the integer pipes (31-bit Montgomery arithmetic, no tensor cores): achieved = thread
+            # instructions per second of the class, peak = SMs x 128 lanes x SM clock sampled during the run.
+            perms_s = ks["perms"] / (ks["ms"] / 1e3) if ks["ms"] > 0 else 0.0
+            ach = perms_s * INSTR_PER_PERM[args.field] / 1e12
+            pk = N_SMS * LANES_PER_SM * sm_hz / 1e12
+            roofline = {"kernel": dominant, "bound": "int32_pipe", "achieved": ach, "peak": pk, "unit": "Tlane-instr/s",
+                        "frac": ach / pk, "traffic": traffic.get(dominant), "peak_source": "148 SMs x 128 lanes x sampled SM clock",
+                        "permutations_per_s": perms_s, "instr_per_permutation": INSTR_PER_PERM[args.field],
+                        "permutations_per_step": ks["perms"] / args.steps, "kernel_ms_per_step": ks["ms"] / args.steps,
+                        "launches_per_step": ks["launches"] / args.steps,
+                        "algorithmic_bytes_per_step": ks["bytes"] / args.steps,
+                        "hbm_frac": (ks["bytes"] / 1e9) / (ks["ms"] / 1e3) / peak if ks["ms"] > 0 else 0.0}
+        else:
+            roofline = hbm_roofline(dominant, ks)
         line = {
             "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "ms_per_layer": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -206,10 +253,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "proofs/s", "ms_per_layer": t_e2e / args.steps,
                     "h2d_bytes_per_step": tb_pin.h2d_bytes, "d2h_bytes_per_step": proof_words * 4},
             "gpu_launches": launches,
-            "roofline": {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
-                         "algorithmic_bytes_per_step": ks["bytes"] / args.steps, "kernel_ms_per_step": ks["ms"] / args.steps,
-                         "launches_per_step": ks["launches"] / args.steps},
+            "roofline": roofline,
+            "roofline_lde": hbm_roofline("ntt_lde", ks_lde),
             "kernel_breakdown_ms": {k: round(v, 4) for k, v in breakdown.items()},
             "clocks": clocks,
         }

@@ -311,6 +311,8 @@ int p3r_set_kernel_timing(p3r_ctx* ctx, uint32_t class_mask);
 int p3r_reset_kernel_stats(p3r_ctx* ctx);
 int p3r_kernel_stats(p3r_ctx* ctx, const char** names_out, double* ms_out, uint64_t* launches_out, uint64_t* bytes_out,
                      uint32_t cap, uint32_t* n_out);
+/* Poseidon2 permutations issued per class since the last reset (hash_rows / compress): the unit of the INT32-pipe roofline. */
+int p3r_kernel_perms(p3r_ctx* ctx, uint64_t* perms_out, uint32_t cap);
 /* Number of kernel launches issued by this ctx since creation (for bench.py's gpu_launches). */
 uint64_t p3r_launch_count(const p3r_ctx* ctx);
 

@@ -76,6 +76,7 @@ struct KernelStats {
     double ms[KC_COUNT] = {0};
     uint64_t launches[KC_COUNT] = {0};
     uint64_t bytes[KC_COUNT] = {0};  // algorithmic bytes (DESIGN.md "Kernels")
+    uint64_t perms[KC_COUNT] = {0};  // Poseidon2 permutations issued (hash_rows / compress classes)
 };
 
 struct p3r_ctx {
@@ -740,6 +741,8 @@ static int build_tree(p3r_ctx* ctx, const uint32_t* leaf_rows, uint32_t leaf_w, 
     const uint32_t rows = 1u << lmax;
     auto level_off = [&](uint32_t l) { return (((size_t)2 << lmax) - ((size_t)2 << (lmax - l))) * 8; };
     ctx->kstats.bytes[KC_COMPRESS] += 96ull * rows;
+    ctx->kstats.perms[KC_COMPRESS] += ((uint64_t)rows - ((uint64_t)1 << cap));   // one compression per internal node
+    if (leaf_rows) ctx->kstats.perms[rows > STAGE_MAX_NODES ? KC_HASH : KC_COMPRESS] += (uint64_t)rows * ((leaf_w + 7) / 8);
     bool leaves_done = leaf_rows == nullptr;
     if (!leaves_done && rows > STAGE_MAX_NODES) {
         KT kt(ctx, KC_HASH, (uint64_t)rows * (4ull * leaf_w + 32));
@@ -754,7 +757,7 @@ static int build_tree(p3r_ctx* ctx, const uint32_t* leaf_rows, uint32_t leaf_w, 
         const uint32_t n_next = l <= lmax ? 1u << (lmax - l) : 0;
         if (leaves_done && n_next > STAGE_MAX_NODES) {
             const uint32_t* inj = inj_at(l);
-            if (inj) ctx->kstats.bytes[KC_COMPRESS] += 32ull * n_next;
+            if (inj) ctx->kstats.bytes[KC_COMPRESS] += 32ull * n_next, ctx->kstats.perms[KC_COMPRESS] += n_next;
             k_compress<F><<<(n_next + 127) / 128, 128, 0, ctx->stream>>>(digests + level_off(l - 1), digests + level_off(l), n_next, inj);
             LAUNCH_CHECK_C(KC_COMPRESS);
             cur = l;
@@ -771,7 +774,7 @@ static int build_tree(p3r_ctx* ctx, const uint32_t* leaf_rows, uint32_t leaf_w, 
         if (st.with_leaves) ctx->kstats.bytes[KC_HASH] += (uint64_t)rows * (4ull * leaf_w + 32);
         for (uint32_t j = 0; j < st.n_levels; j++) {
             st.inj[j] = inj_at(l + j);
-            if (st.inj[j]) ctx->kstats.bytes[KC_COMPRESS] += 32ull << (lmax - l - j);
+            if (st.inj[j]) ctx->kstats.bytes[KC_COMPRESS] += 32ull << (lmax - l - j), ctx->kstats.perms[KC_COMPRESS] += 1ull << (lmax - l - j);
         }
         const uint32_t grid = 1u << (lmax - (cur + st.n_levels));            // nodes of the stage's last level
         const uint32_t widest = st.with_leaves ? (1u << st.n_levels) : (1u << (st.n_levels - 1));
@@ -823,6 +826,7 @@ static int commit_tree(p3r_ctx* ctx, const std::vector<MatRef>& mats, Tree* t, u
         }
         if (lh != lmax) inj_digests[lmax - lh] = j.out;
         hash_bytes += (uint64_t)j.n_rows * (4ull * j.ncols + 32);
+        ctx->kstats.perms[KC_HASH] += (uint64_t)j.n_rows * ((j.ncols + 7) / 8);
         jobs.push_back(j);
     }
     std::stable_sort(jobs.begin(), jobs.end(), [](const HashJob& a, const HashJob& b) { return a.ncols > b.ncols; });
@@ -2357,6 +2361,11 @@ int p3r_kernel_stats(p3r_ctx* ctx, const char** names_out, double* ms_out, uint6
         if (bytes_out) bytes_out[k] = ctx->kstats.bytes[k];
     }
     *n_out = KC_COUNT;
+    return P3R_OK;
+}
+int p3r_kernel_perms(p3r_ctx* ctx, uint64_t* perms_out, uint32_t cap) {
+    if (!ctx || !perms_out) return P3R_ERR_INVALID_ARG;
+    for (uint32_t k = 0; k < KC_COUNT && k < cap; k++) perms_out[k] = ctx->kstats.perms[k];
     return P3R_OK;
 }
 int p3r_coset_lde(p3r_ctx* ctx, const p3r_matrix_u32* in, uint32_t log_blowup, uint32_t* out) {

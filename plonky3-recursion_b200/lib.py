@@ -73,7 +73,7 @@ EXPORTS = ["p3r_abi_version", "p3r_build_info", "p3r_ctx_create", "p3r_ctx_destr
            "p3r_last_phase_times", "p3r_launch_count", "p3r_traces_upload", "p3r_traces_free", "p3r_prove_resident",
            "p3r_host_alloc", "p3r_host_free", "p3r_timer_start", "p3r_timer_stop", "p3r_set_kernel_timing",
            "p3r_reset_kernel_stats", "p3r_kernel_stats", "p3r_set_specialization", "p3r_prove_ex", "p3r_traces_upload_ex",
-           "p3r_traces_download"]
+           "p3r_traces_download", "p3r_kernel_perms"]
 
 KERNEL_CLASSES = ["ntt_lde", "hash_rows", "compress", "logup", "quotient", "open", "reduced_openings", "fri_fold", "transpose",
                   "misc"]
@@ -175,7 +175,10 @@ class Context:
         ms, la, by = (C.c_double * n)(), (C.c_uint64 * n)(), (C.c_uint64 * n)()
         cnt = C.c_uint32(0)
         self._check(self.lib.p3r_kernel_stats(self.h, None, ms, la, by, n, C.byref(cnt)))
-        return {KERNEL_CLASSES[k]: {"ms": float(ms[k]), "launches": int(la[k]), "bytes": int(by[k])} for k in range(n)}
+        pe = (C.c_uint64 * n)()
+        self._check(self.lib.p3r_kernel_perms(self.h, pe, n))
+        return {KERNEL_CLASSES[k]: {"ms": float(ms[k]), "launches": int(la[k]), "bytes": int(by[k]), "perms": int(pe[k])}
+                for k in range(n)}
 
     def pinned_empty(self, shape, dtype=np.uint32) -> np.ndarray:
         """numpy view of cudaHostAlloc'd memory (kept alive by the returned array's base object)."""
