@@ -794,24 +794,26 @@ __global__ void k_selectors(uint32_t* sel, uint32_t* inv_van, uint32_t log_n, ui
     sel[2 * NQ + s] = fsub<F>(x, ginv);
     if (i < (1u << log_qc)) inv_van[i] = finv<F>(z);
 }
+// out[k] = alpha^{n-1-k} for up to 8 tables in one launch (blockIdx.y = table): every thread raises alpha to its own power.
+struct PowDescJobs {
+    Ext4* out[8];
+    uint32_t n[8];
+};
 template <class F>
-__global__ void k_ext_powers_desc(Ext4* out, uint32_t n, Ext4 alpha, uint32_t wnr) {
-    // out[k] = alpha^{n-1-k}; n is small (number of constraints): one thread.
-    if (blockIdx.x || threadIdx.x) return;
-    Ext4 acc = ext_one<F>();
-    for (uint32_t k = n; k-- > 0;) {
-        out[k] = acc;
-        acc = emul<F>(acc, alpha, wnr);
-    }
+__global__ void __launch_bounds__(128) k_ext_powers_desc(PowDescJobs jobs, Ext4 alpha, uint32_t wnr) {
+    const uint32_t n = jobs.n[blockIdx.y];
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    jobs.out[blockIdx.y][k] = epow<F>(alpha, n - 1 - k, wnr);
 }
 template <class F>
 __global__ void k_ext_powers_asc(Ext4* out, uint32_t n, Ext4 alpha, uint32_t wnr) {
-    // out[k] = alpha^k, blocked so that n up to a few thousand stays cheap: thread t computes alpha^(t*64) then 64 steps.
+    // out[k] = alpha^k, blocked: thread t computes alpha^(t*8) then 8 steps.
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t lo = t * 64;
+    uint32_t lo = t * 8;
     if (lo >= n) return;
     Ext4 acc = epow<F>(alpha, lo, wnr);
-    for (uint32_t k = lo; k < min(lo + 64, n); k++) {
+    for (uint32_t k = lo; k < min(lo + 8, n); k++) {
         out[k] = acc;
         acc = emul<F>(acc, alpha, wnr);
     }
@@ -823,22 +825,35 @@ __global__ void k_ext_powers_asc(Ext4* out, uint32_t n, Ext4 alpha, uint32_t wnr
 // ------------------------------------------------------------------------------------------------
 struct WeightJob {
     Ext4 u;          // z / in_shift
+    Ext4 scale;      // (u^n - 1) / n (host-computed)
     uint32_t log_n;
     uint32_t offset; // into the weights buffer (Ext4 units)
 };
+// weights[i] = scale * w^i / (u - w^i). Each thread produces 4 weights (rows i, i + n/4, ...) and shares ONE extension
+// inversion between them (Montgomery's trick): the inversion's base-field Fermat power is most of the cost.
 template <class F>
 __global__ void __launch_bounds__(256) k_bary_weights(const WeightJob* __restrict__ jobs, Ext4* __restrict__ weights,
                                                        const uint32_t* tw, uint32_t logT, uint32_t wnr) {
-    WeightJob j = jobs[blockIdx.y];
-    uint32_t n = 1u << j.log_n;
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t wi = root_pow<F>(tw, logT, (uint64_t)i << (logT - j.log_n));
-    Ext4 un = j.u;
-    for (uint32_t k = 0; k < j.log_n; k++) un = emul<F>(un, un, wnr);
-    Ext4 num = emul_base<F>(esub_base<F>(un, F::R), fmul<F>(wi, finv<F>(to_monty<F>(n))));
-    Ext4 den = esub_base<F>(j.u, wi);
-    weights[j.offset + i] = emul<F>(num, einv<F>(den, wnr), wnr);
+    const WeightJob j = jobs[blockIdx.y];
+    const uint32_t n = 1u << j.log_n;
+    const uint32_t q = n >= 4 ? n / 4 : n, per = n >= 4 ? 4 : 1;
+    const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i0 >= q) return;
+    uint32_t wi[4];
+    Ext4 den[4], pre[4];
+    Ext4 acc = ext_one<F>();
+    for (uint32_t t = 0; t < per; t++) {
+        wi[t] = root_pow<F>(tw, logT, (uint64_t)(i0 + t * q) << (logT - j.log_n));
+        den[t] = esub_base<F>(j.u, wi[t]);
+        pre[t] = acc;
+        acc = emul<F>(acc, den[t], wnr);
+    }
+    Ext4 inv = einv<F>(acc, wnr);
+    for (uint32_t t = per; t-- > 0;) {
+        Ext4 di = emul<F>(inv, pre[t], wnr);  // 1 / den[t]
+        inv = emul<F>(inv, den[t], wnr);
+        weights[j.offset + i0 + t * q] = emul<F>(emul_base<F>(j.scale, wi[t]), di, wnr);
+    }
 }
 struct DotJob {
     const uint32_t* mat;   // column-major, height 2^log_n
@@ -848,51 +863,68 @@ struct DotJob {
 };
 constexpr uint32_t DOT_ROWS = 2048;  // rows per CTA
 constexpr uint32_t DOT_COLS = 8;     // columns per CTA
-// partial[job][chunk][col] ; grid = (max chunks, max col groups, jobs)
+struct DotTile {           // one CTA of k_bary_dot: rows [chunk*DOT_ROWS, ..) x columns [c0, c0 + DOT_COLS) of a job
+    uint32_t job, chunk, c0;
+};
+// partial[job][chunk][col]. Every thread walks its rows once, keeps the weight in registers and accumulates the DOT_COLS
+// columns in 64-bit sums of four Montgomery products (one reduction per four rows).
 template <class F>
-__global__ void __launch_bounds__(256) k_bary_dot(const DotJob* __restrict__ jobs, const Ext4* __restrict__ weights,
-                                                   Ext4* __restrict__ partial, uint32_t max_chunks, uint32_t max_width) {
-    DotJob j = jobs[blockIdx.z];
-    uint32_t n = 1u << j.log_n;
-    uint32_t r0 = blockIdx.x * DOT_ROWS;
-    uint32_t c0 = blockIdx.y * DOT_COLS;
-    if (r0 >= n || c0 >= j.width) return;
-    __shared__ Ext4 red[8];
+__global__ void __launch_bounds__(256) k_bary_dot(const DotJob* __restrict__ jobs, const DotTile* __restrict__ tiles,
+                                                   const Ext4* __restrict__ weights, Ext4* __restrict__ partial,
+                                                   uint32_t max_chunks, uint32_t max_width) {
+    const DotTile tl = tiles[blockIdx.x];
+    const DotJob j = jobs[tl.job];
+    const uint32_t n = 1u << j.log_n;
+    const uint32_t r0 = tl.chunk * DOT_ROWS, r1 = min(r0 + DOT_ROWS, n);
+    const uint32_t nc = min(DOT_COLS, j.width - tl.c0);
+    __shared__ Ext4 red[8][DOT_COLS];
     const Ext4* w = weights + j.w_offset;
-    for (uint32_t c = c0; c < min(c0 + DOT_COLS, j.width); c++) {
-        const uint32_t* col = j.mat + (size_t)c * n;
-        uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;  // 64-bit accumulators of Montgomery products
-        uint32_t cnt = 0;
-        Ext4 acc = ext_zero();
-        for (uint32_t r = r0 + threadIdx.x; r < min(r0 + DOT_ROWS, n); r += blockDim.x) {
-            uint32_t v = __ldg(col + r);
-            Ext4 wr = w[r];
-            a0 += (uint64_t)v * wr.c[0];
-            a1 += (uint64_t)v * wr.c[1];
-            a2 += (uint64_t)v * wr.c[2];
-            a3 += (uint64_t)v * wr.c[3];
-            if (++cnt == 4) {  // 4 products < 2^64
-                acc = eadd<F>(acc, Ext4{{fred64<F>(a0), fred64<F>(a1), fred64<F>(a2), fred64<F>(a3)}});
-                a0 = a1 = a2 = a3 = 0;
-                cnt = 0;
+    const uint32_t* col0 = j.mat + (size_t)tl.c0 * n;
+    Ext4 acc[DOT_COLS];
+    uint64_t a[DOT_COLS][4];
+#pragma unroll
+    for (int c = 0; c < (int)DOT_COLS; c++) {
+        acc[c] = ext_zero();
+        a[c][0] = a[c][1] = a[c][2] = a[c][3] = 0;
+    }
+    uint32_t cnt = 0;
+    for (uint32_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+        const Ext4 wr = w[r];
+#pragma unroll
+        for (int c = 0; c < (int)DOT_COLS; c++) {
+            if (c < (int)nc) {
+                const uint32_t v = __ldg(col0 + (size_t)c * n + r);
+                a[c][0] += (uint64_t)v * wr.c[0];
+                a[c][1] += (uint64_t)v * wr.c[1];
+                a[c][2] += (uint64_t)v * wr.c[2];
+                a[c][3] += (uint64_t)v * wr.c[3];
             }
         }
-        acc = eadd<F>(acc, Ext4{{fred64<F>(a0), fred64<F>(a1), fred64<F>(a2), fred64<F>(a3)}});
-        // block reduce
+        if (++cnt == 4) {  // 4 products < 2^64
+#pragma unroll
+            for (int c = 0; c < (int)DOT_COLS; c++) {
+                acc[c] = eadd<F>(acc[c], Ext4{{fred64<F>(a[c][0]), fred64<F>(a[c][1]), fred64<F>(a[c][2]), fred64<F>(a[c][3])}});
+                a[c][0] = a[c][1] = a[c][2] = a[c][3] = 0;
+            }
+            cnt = 0;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < (int)DOT_COLS; c++) {
+        acc[c] = eadd<F>(acc[c], Ext4{{fred64<F>(a[c][0]), fred64<F>(a[c][1]), fred64<F>(a[c][2]), fred64<F>(a[c][3])}});
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            uint32_t v = acc.c[k];
+            uint32_t v = acc[c].c[k];
             for (int off = 16; off > 0; off >>= 1) v = fadd<F>(v, __shfl_down_sync(0xffffffffu, v, off));
-            acc.c[k] = v;
+            acc[c].c[k] = v;
         }
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            Ext4 t = red[0];
-            for (uint32_t q = 1; q < blockDim.x / 32; q++) t = eadd<F>(t, red[q]);
-            partial[((size_t)blockIdx.z * max_chunks + blockIdx.x) * max_width + c] = t;
-        }
-        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][c] = acc[c];
+    }
+    __syncthreads();
+    if (threadIdx.x < nc) {
+        Ext4 t = red[0][threadIdx.x];
+        for (uint32_t q = 1; q < blockDim.x / 32; q++) t = eadd<F>(t, red[q][threadIdx.x]);
+        partial[((size_t)tl.job * max_chunks + tl.chunk) * max_width + tl.c0 + threadIdx.x] = t;
     }
 }
 template <class F>
@@ -921,17 +953,24 @@ struct RoMat {
     uint32_t alpha_off[2];   // exponent offset alpha^{off}
 };
 template <class F>
-__global__ void k_ro_prepare(const RoMat* __restrict__ mats, uint32_t n_mats, const Ext4* __restrict__ opened,
-                             const Ext4* __restrict__ apow, Ext4* __restrict__ coef /* [mat][2]: alpha^off * P */, uint32_t wnr) {
-    // one warp-free thread per (matrix, point): widths are a few hundred at most
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) k_ro_prepare(const RoMat* __restrict__ mats, uint32_t n_mats, const Ext4* __restrict__ opened,
+                                                     const Ext4* __restrict__ apow, Ext4* __restrict__ coef /* [mat][2]: alpha^off * P */,
+                                                     uint32_t wnr) {
+    // one warp per (matrix, point): lanes stride over the columns, then a shuffle reduction
+    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
     if (t >= n_mats * 2) return;
-    RoMat m = mats[t >> 1];
-    uint32_t j = t & 1;
+    const RoMat m = mats[t >> 1];
+    const uint32_t j = t & 1;
     if (j >= m.n_points) return;
     Ext4 acc = ext_zero();
-    for (uint32_t k = 0; k < m.width; k++) acc = eadd<F>(acc, emul<F>(apow[k], opened[m.opened_off[j] + k], wnr));
-    coef[t] = emul<F>(acc, apow[m.alpha_off[j]], wnr);
+    for (uint32_t k = lane; k < m.width; k += 32) acc = eadd<F>(acc, emul<F>(apow[k], opened[m.opened_off[j] + k], wnr));
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        uint32_t v = acc.c[c];
+        for (int off = 16; off > 0; off >>= 1) v = fadd<F>(v, __shfl_down_sync(0xffffffffu, v, off));
+        acc.c[c] = v;
+    }
+    if (lane == 0) coef[t] = emul<F>(acc, apow[m.alpha_off[j]], wnr);
 }
 struct RoArgs {
     const RoMat* mats;
@@ -945,25 +984,49 @@ struct RoArgs {
     uint32_t logT;
     Ext4* ro;               // 2^log_h entries (overwritten)
     uint32_t wnr;
+    uint32_t max_width;     // widest matrix of this height (alpha powers staged in shared memory)
+    uint32_t cta_begin;     // multi-height launch: first CTA of this height
 };
+// All heights in one launch (flat grid, jobs sorted by decreasing height). Per row: R_m = sum_k alpha^k * lde_m[k][s]
+// accumulated as 64-bit sums of four Montgomery products (alpha powers from shared memory, four independent loads in flight),
+// and one extension inversion shared by 1/(zeta - x) and 1/(zeta*g - x).
 template <class F>
-__global__ void __launch_bounds__(128) k_reduced_openings(RoArgs a) {
-    uint32_t N = 1u << a.log_h;
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) k_reduced_openings(const RoArgs* __restrict__ jobs, uint32_t n_jobs) {
+    extern __shared__ Ext4 sap[];
+    uint32_t jb = 0;
+    while (jb + 1 < n_jobs && blockIdx.x >= jobs[jb + 1].cta_begin) jb++;
+    const RoArgs& a = jobs[jb];
+    for (uint32_t k = threadIdx.x; k < a.max_width; k += blockDim.x) sap[k] = a.apow[k];
+    __syncthreads();
+    const uint32_t N = 1u << a.log_h;
+    const uint32_t s = (blockIdx.x - a.cta_begin) * blockDim.x + threadIdx.x;
     if (s >= N) return;
+    const uint32_t wnr = a.wnr;
     uint32_t x = fmul<F>(a.gen, root_pow<F>(a.tw, a.logT, (uint64_t)bitrev32(s, a.log_h) << (a.logT - a.log_h)));
-    Ext4 inv0 = einv<F>(esub_base<F>(a.z[0], x), a.wnr);
-    Ext4 inv1 = einv<F>(esub_base<F>(a.z[1], x), a.wnr);
+    const Ext4 d0 = esub_base<F>(a.z[0], x), d1 = esub_base<F>(a.z[1], x);
+    const Ext4 inv01 = einv<F>(emul<F>(d0, d1, wnr), wnr);
+    const Ext4 inv0 = emul<F>(inv01, d1, wnr), inv1 = emul<F>(inv01, d0, wnr);
     Ext4 acc = ext_zero();
     for (uint32_t mi = 0; mi < a.n_mats; mi++) {
-        RoMat m = a.mats[mi];
+        const RoMat m = a.mats[mi];
         Ext4 R = ext_zero();
         const uint32_t* p = m.lde + s;
-        for (uint32_t k = 0; k < m.width; k++) R = eadd<F>(R, emul_base<F>(a.apow[k], __ldg(p + (size_t)k * N)));
+        uint32_t k = 0;
+        for (; k + 4 <= m.width; k += 4) {
+            const uint32_t v0 = __ldg(p + (size_t)k * N), v1 = __ldg(p + (size_t)(k + 1) * N), v2 = __ldg(p + (size_t)(k + 2) * N),
+                           v3 = __ldg(p + (size_t)(k + 3) * N);
+            const Ext4 a0 = sap[k], a1 = sap[k + 1], a2 = sap[k + 2], a3 = sap[k + 3];
+            Ext4 t;
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                t.c[c] = fred64<F>((uint64_t)v0 * a0.c[c] + (uint64_t)v1 * a1.c[c] + (uint64_t)v2 * a2.c[c] + (uint64_t)v3 * a3.c[c]);
+            R = eadd<F>(R, t);
+        }
+        for (; k < m.width; k++) R = eadd<F>(R, emul_base<F>(sap[k], __ldg(p + (size_t)k * N)));
         for (uint32_t j = 0; j < m.n_points; j++) {
             // alpha^off * (P - R) = coef - alpha^off * R
-            Ext4 t = esub<F>(a.coef[2 * mi + j], emul<F>(a.apow[m.alpha_off[j]], R, a.wnr));
-            acc = eadd<F>(acc, emul<F>(t, j ? inv1 : inv0, a.wnr));
+            Ext4 t = esub<F>(a.coef[2 * mi + j], emul<F>(a.apow[m.alpha_off[j]], R, wnr));
+            acc = eadd<F>(acc, emul<F>(t, j ? inv1 : inv0, wnr));
         }
     }
     a.ro[s] = acc;

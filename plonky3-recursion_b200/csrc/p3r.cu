@@ -1272,16 +1272,30 @@ static int commit_quotient_impl(p3r_session* s, const uint32_t alpha[4], uint32_
     std::vector<MatRef> mats;
     std::vector<LdeJob> jobs;
     uint32_t lmax = 0;
+    // alpha^{N-1-k} for every table, eight tables per launch
+    std::vector<Ext4*> alpha_pows(pp->inst.size());
+    for (size_t i0 = 0; i0 < pp->inst.size(); i0 += 8) {
+        PowDescJobs pj{};
+        uint32_t max_n = 1, cnt = 0;
+        for (size_t i = i0; i < std::min(pp->inst.size(), i0 + 8); i++, cnt++) {
+            const uint32_t nc = pp->inst[i].n_constraints;
+            alpha_pows[i] = arena_alloc<Ext4>(ctx, std::max<uint32_t>(nc, 1));
+            if (!alpha_pows[i]) return P3R_ERR_OOM;
+            pj.out[cnt] = alpha_pows[i];
+            pj.n[cnt] = nc;
+            max_n = std::max(max_n, nc);
+        }
+        k_ext_powers_desc<F><<<dim3((max_n + 127) / 128, cnt), 128, 0, ctx->stream>>>(pj, al, wnr);
+        LAUNCH_CHECK();
+    }
     for (size_t i = 0; i < pp->inst.size(); i++) {
         const InstDev& d = pp->inst[i];
         size_t n = (size_t)1 << d.log_h;
         uint32_t qc = 1u << d.log_qc;
         s->chunks[i] = arena_alloc<uint32_t>(ctx, n * 4 * qc);
         s->chunk_lde[i] = arena_alloc<uint32_t>(ctx, (n << lb) * 4 * qc);
-        Ext4* ap = arena_alloc<Ext4>(ctx, std::max<uint32_t>(d.n_constraints, 1));
-        if (!s->chunks[i] || !s->chunk_lde[i] || !ap) return P3R_ERR_OOM;
-        k_ext_powers_desc<F><<<1, 32, 0, ctx->stream>>>(ap, d.n_constraints, al, wnr);
-        LAUNCH_CHECK();
+        Ext4* ap = alpha_pows[i];
+        if (!s->chunks[i] || !s->chunk_lde[i]) return P3R_ERR_OOM;
         QuotientArgs qa{};
         qa.insns = d.cons;
         qa.n_insns = d.n_cons_insns;
@@ -1359,11 +1373,17 @@ static int open_impl(p3r_session* s, const uint32_t zeta_w[4], uint32_t* opened_
         // g_n = w_n ; zeta*g
         uint32_t gn = fpow<F>(ctx->gen_m, ((uint64_t)F::P - 1) >> d.log_h);
         Ext4 znext = emul_base<F>(zeta, gn);
+        const uint32_t n_inv_m = finv<F>(to_monty<F>(n));
+        auto wjob = [&](const Ext4& u, uint32_t off) {  // scale = (u^n - 1) / n
+            Ext4 un = u;
+            for (uint32_t k = 0; k < d.log_h; k++) un = emul<F>(un, un, wnr);
+            return WeightJob{u, emul_base<F>(esub_base<F>(un, F::R), n_inv_m), d.log_h, off};
+        };
         uint32_t wz = w_off;
-        wjobs.push_back({zeta, d.log_h, wz});
+        wjobs.push_back(wjob(zeta, wz));
         w_off += n;
         uint32_t wzn = w_off;
-        wjobs.push_back({znext, d.log_h, wzn});
+        wjobs.push_back(wjob(znext, wzn));
         w_off += n;
         auto add = [&](const uint32_t* mat, uint32_t width, uint32_t woff) {
             djobs.push_back({mat, d.log_h, width, woff, o_off});
@@ -1399,7 +1419,7 @@ static int open_impl(p3r_session* s, const uint32_t zeta_w[4], uint32_t* opened_
             uint32_t shift = fmul<F>(ctx->gen_m, fpow<F>(wq, c));
             Ext4 u = emul_base<F>(zeta, finv<F>(shift));
             uint32_t wc = w_off;
-            wjobs.push_back({u, d.log_h, wc});
+            wjobs.push_back(wjob(u, wc));
             w_off += n;
             p3r_session::OpenRef q{(uint32_t)i, 1, c, {0, 0}, 1, 4};
             q.off[0] = add(s->chunks[i] + (size_t)c * 4 * n, 4, wc);
@@ -1412,18 +1432,25 @@ static int open_impl(p3r_session* s, const uint32_t zeta_w[4], uint32_t* opened_
     s->d_opened = arena_alloc<Ext4>(ctx, o_off);
     uint32_t max_chunks = ((1u << max_n_log) + DOT_ROWS - 1) / DOT_ROWS;
     Ext4* partial = arena_alloc<Ext4>(ctx, djobs.size() * (size_t)max_chunks * max_w);
+    std::vector<DotTile> tiles;
+    for (uint32_t ji = 0; ji < djobs.size(); ji++) {
+        const uint32_t chunks = ((1u << djobs[ji].log_n) + DOT_ROWS - 1) / DOT_ROWS;
+        for (uint32_t c0 = 0; c0 < djobs[ji].width; c0 += DOT_COLS)
+            for (uint32_t ch = 0; ch < chunks; ch++) tiles.push_back({ji, ch, c0});
+    }
     WeightJob* d_wj = upload_vec(ctx, wjobs);
     DotJob* d_dj = upload_vec(ctx, djobs);
-    if (!d_w || !s->d_opened || !partial || !d_wj || !d_dj) return P3R_ERR_OOM;
+    DotTile* d_tiles = upload_vec(ctx, tiles);
+    if (!d_w || !s->d_opened || !partial || !d_wj || !d_dj || !d_tiles) return P3R_ERR_OOM;
     KT kt_open(ctx, KC_OPEN);
     {
-        dim3 grid(((1u << max_n_log) + 255) / 256, (unsigned)wjobs.size());
+        const uint32_t per_job = std::max(1u, (1u << max_n_log) / 4);  // four weights per thread
+        dim3 grid((per_job + 255) / 256, (unsigned)wjobs.size());
         k_bary_weights<F><<<grid, 256, 0, ctx->stream>>>(d_wj, d_w, ctx->tw, ctx->logT, wnr);
         LAUNCH_CHECK();
     }
     {
-        dim3 grid(max_chunks, (max_w + DOT_COLS - 1) / DOT_COLS, (unsigned)djobs.size());
-        k_bary_dot<F><<<grid, 256, 0, ctx->stream>>>(d_dj, d_w, partial, max_chunks, max_w);
+        k_bary_dot<F><<<(unsigned)tiles.size(), 256, 0, ctx->stream>>>(d_dj, d_tiles, d_w, partial, max_chunks, max_w);
         LAUNCH_CHECK();
         dim3 g2((max_w + 127) / 128, (unsigned)djobs.size());
         k_bary_reduce<F><<<g2, 128, 0, ctx->stream>>>(d_dj, partial, s->d_opened, max_chunks, max_w);
@@ -1523,27 +1550,37 @@ static int fri_begin_impl(p3r_session* s, const uint32_t alpha_w[4], uint32_t* n
     }
     Ext4* apow = arena_alloc<Ext4>(ctx, max_exp);
     if (!apow) return P3R_ERR_OOM;
-    k_ext_powers_asc<F><<<(max_exp / 64 + 128) / 128, 128, 0, ctx->stream>>>(apow, max_exp, alpha, wnr);
+    k_ext_powers_asc<F><<<((max_exp + 7) / 8 + 127) / 128, 128, 0, ctx->stream>>>(apow, max_exp, alpha, wnr);  // 8 powers per thread
     LAUNCH_CHECK();
     s->heights.clear();
     s->ro.clear();
+    // all heights: one k_ro_prepare launch over every (matrix, point), one k_reduced_openings launch over every row
+    std::vector<RoMat> all_mats;
+    for (auto& kv : groups) all_mats.insert(all_mats.end(), kv.second.mats.begin(), kv.second.mats.end());
+    RoMat* d_all = upload_vec(ctx, all_mats);
+    Ext4* coef_all = arena_alloc<Ext4>(ctx, all_mats.size() * 2);
+    if (!d_all || !coef_all) return P3R_ERR_OOM;
+    {
+        const uint32_t nm = (uint32_t)all_mats.size();
+        k_ro_prepare<F><<<(nm * 2 * 32 + 127) / 128, 128, 0, ctx->stream>>>(d_all, nm, s->d_opened, apow, coef_all, wnr);
+        LAUNCH_CHECK();
+    }
+    std::vector<RoArgs> ro_jobs;
+    uint32_t cta = 0, widest = 1;
+    uint64_t ro_bytes = 0;
+    size_t mat_off = 0;
     for (auto& kv : groups) {
         uint32_t lh = kv.first;
         HGroup& g = kv.second;
         s->heights.push_back(lh);
-        RoMat* d_m = upload_vec(ctx, g.mats);
-        Ext4* coef = arena_alloc<Ext4>(ctx, g.mats.size() * 2);
         Ext4* ro = arena_alloc<Ext4>(ctx, (size_t)1 << lh);
-        if (!d_m || !coef || !ro) return P3R_ERR_OOM;
-        uint32_t nm = (uint32_t)g.mats.size();
-        k_ro_prepare<F><<<(nm * 2 + 63) / 64, 64, 0, ctx->stream>>>(d_m, nm, s->d_opened, apow, coef, wnr);
-        LAUNCH_CHECK();
+        if (!ro) return P3R_ERR_OOM;
         RoArgs ra{};
-        ra.mats = d_m;
-        ra.n_mats = nm;
+        ra.mats = d_all + mat_off;
+        ra.n_mats = (uint32_t)g.mats.size();
         ra.log_h = lh;
         ra.apow = apow;
-        ra.coef = coef;
+        ra.coef = coef_all + 2 * mat_off;
         ra.z[0] = s->zeta;
         ra.z[1] = emul_base<F>(s->zeta, fpow<F>(ctx->gen_m, ((uint64_t)F::P - 1) >> g.log_n));
         ra.gen = ctx->gen_m;
@@ -1551,15 +1588,25 @@ static int fri_begin_impl(p3r_session* s, const uint32_t alpha_w[4], uint32_t* n
         ra.logT = ctx->logT;
         ra.ro = ro;
         ra.wnr = wnr;
-        uint32_t N = 1u << lh;
-        {
-            uint64_t wsum = 0;
-            for (auto& m : g.mats) wsum += m.width;
-            KT kt(ctx, KC_REDUCE, (uint64_t)N * (4 * wsum + 16));
-            k_reduced_openings<F><<<(N + 127) / 128, 128, 0, ctx->stream>>>(ra);
-            LAUNCH_CHECK_C(KC_REDUCE);
+        uint64_t wsum = 0;
+        for (auto& m : g.mats) {
+            wsum += m.width;
+            ra.max_width = std::max(ra.max_width, m.width);
         }
+        widest = std::max(widest, ra.max_width);
+        ra.cta_begin = cta;
+        cta += ((1u << lh) + 127) / 128;
+        ro_bytes += ((uint64_t)1 << lh) * (4 * wsum + 16);
+        mat_off += g.mats.size();
+        ro_jobs.push_back(ra);
         s->ro[lh] = ro;
+    }
+    {
+        const RoArgs* d_jobs = upload_vec(ctx, ro_jobs);
+        if (!d_jobs) return P3R_ERR_OOM;
+        KT kt(ctx, KC_REDUCE, ro_bytes);
+        k_reduced_openings<F><<<cta, 128, (size_t)widest * sizeof(Ext4), ctx->stream>>>(d_jobs, (uint32_t)ro_jobs.size());
+        LAUNCH_CHECK_C(KC_REDUCE);
     }
     bool ok = false;
     std::vector<uint32_t> sched = arity_schedule(ctx->fri, s->heights, &ok);
