@@ -96,6 +96,7 @@ struct p3r_ctx {
     cudaStream_t stream = nullptr;
     uint32_t* tws = nullptr;  // per-stage compact twiddle tables, 2^logT - 1 entries
     uint32_t* tw = nullptr;   // = tws + 2^(logT-1) - 1: half table of omega_T
+    void (*host_permute)(uint32_t*, const Poseidon2Consts&) = nullptr;  // transcript permutation (AVX2 or scalar), set at creation
     bool use_col_ntt = true;  // whole-column LDE kernels for 2^5..2^15 rows (p3r_set_specialization bit 1 turns them off)
     uint32_t logT = 0;
     uint32_t r4 = 0, r8 = 0, r8_3 = 0;
@@ -277,15 +278,48 @@ struct p3r_session {
 // ------------------------------------------------------------------------------------------------
 // Host DuplexChallenger — product code, Montgomery arithmetic, shares nothing with oracle/.
 // ------------------------------------------------------------------------------------------------
+// host_p2_avx2.cpp (the only translation unit built with -mavx2)
+namespace p3r {
+void host_permute_avx2_koalabear(uint32_t* st, const Poseidon2Consts& k);
+void host_permute_avx2_babybear(uint32_t* st, const Poseidon2Consts& k);
+}  // namespace p3r
+template <class F>
+static void host_permute_scalar(uint32_t* st, const Poseidon2Consts& k) {
+    poseidon2_permute_with<F>(st, k);
+}
+typedef void (*HostPermuteFn)(uint32_t*, const Poseidon2Consts&);
+// AVX2 permutation when the CPU has it and it reproduces the scalar twin on a probe state; the scalar twin otherwise.
+template <class F>
+static HostPermuteFn pick_host_permute(const Poseidon2Consts& k) {
+    HostPermuteFn scalar = host_permute_scalar<F>;
+#if defined(__x86_64__)
+    if (__builtin_cpu_supports("avx2")) {
+        HostPermuteFn fast = FieldId<F>::value == 0 ? host_permute_avx2_koalabear : host_permute_avx2_babybear;
+        uint32_t a[16], b[16];
+        for (int i = 0; i < 16; i++) a[i] = b[i] = (uint32_t)((i + 1) * 0x9E3779B1u) % F::P;
+        for (int it = 0; it < 3; it++) {
+            fast(a, k);
+            scalar(b, k);
+        }
+        if (std::memcmp(a, b, sizeof a) == 0) return fast;
+    }
+#endif
+    return scalar;
+}
+
 template <class F>
 struct HostChallenger {
     const Poseidon2Consts* k;
+    HostPermuteFn permute;
     uint32_t st[16];
     uint32_t in[8], out[8];
     int n_in = 0, n_out = 0;
     double host_ms = 0;  // wall time spent in host permutations
     uint32_t n_perms = 0;
-    explicit HostChallenger(const Poseidon2Consts* k_) : k(k_) { std::memset(st, 0, sizeof st); }
+    explicit HostChallenger(const Poseidon2Consts* k_, HostPermuteFn fn = nullptr)
+        : k(k_), permute(fn ? fn : host_permute_scalar<F>) {
+        std::memset(st, 0, sizeof st);
+    }
     void duplex() {
         auto t0 = std::chrono::steady_clock::now();
         for (int i = 0; i < n_in; i++) st[i] = in[i];
@@ -294,7 +328,7 @@ struct HostChallenger {
             st[8] = fadd<F>(st[8], to_monty<F>((uint32_t)n_in));
         }
         n_in = 0;
-        poseidon2_permute_with<F>(st, *k);
+        permute(st, *k);
         for (int i = 0; i < 8; i++) out[i] = st[i];
         n_out = 8;
         n_perms++;
@@ -1845,7 +1879,7 @@ static int prove_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* 
     const size_t capw = (size_t)8 << ctx->fri.cap_height;
     std::vector<uint32_t> blob;
     auto put = [&](const uint32_t* p, size_t n) { blob.insert(blob.end(), p, p + n); };
-    HostChallenger<F> ch(&ctx->p2);
+    HostChallenger<F> ch(&ctx->p2, ctx->host_permute);
 
     std::vector<uint32_t> main_cap(capw), perm_cap(capw), quot_cap(capw);
     TRY(commit_main_impl<F>(s, main_cap.data()));
@@ -2159,6 +2193,7 @@ int p3r_ctx_create(int device, const p3r_field_desc* field, const p3r_poseidon2_
         }
         ctx->p2.fast_diag = fast ? 1u : 0u;
     }
+    ctx->host_permute = ctx->field_id == 0 ? pick_host_permute<KoalaBear>(ctx->p2) : pick_host_permute<BabyBear>(ctx->p2);
     if (ctx->field_id == 0) {
         ctx->w_m = to_monty<KoalaBear>(field->w);
         ctx->gen_m = to_monty<KoalaBear>(field->generator);
