@@ -43,7 +43,7 @@ def monty_insns(F, prog):
 
 def emit_kernel(name: str, fname: str, ins: np.ndarray, nb: int, ne: int) -> str:
     o = []
-    o.append(f"__global__ void __launch_bounds__(128) {name}(QuotientArgs a) {{")
+    o.append(f"__global__ void __launch_bounds__(128, 4) {name}(QuotientArgs a) {{")
     o.append(f"    using F = {fname};")
     o.append("    const uint32_t lq = a.log_n + a.log_qc, NQ = 1u << lq, n = 1u << a.log_n;")
     o.append("    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;")
