@@ -590,6 +590,10 @@ struct LogupArgs {
     uint32_t* perm;         // column-major flattened, (n_lookups+1)*4 columns of height n
     Ext4* rowsum;           // n entries
     uint32_t wnr;
+    uint32_t cta_begin;     // multi-table launch (k_logup_rows): first CTA of this table
+    Ext4* chunk_sum;        // scan scratch: one partial per SCAN_CHUNK rows
+    Ext4* terminal;         // out: total of the table
+    uint32_t scan_cta_begin;  // first CTA of this table in the two scan launches
 };
 struct OutSink {
     uint32_t* outs;
@@ -597,10 +601,14 @@ struct OutSink {
     __device__ __forceinline__ void assert_e(uint32_t, const Ext4&) {}
     __device__ __forceinline__ void out_b(uint32_t i, uint32_t v) { outs[i] = v; }
 };
+// All tables with lookups in one launch (flat grid, largest tables first).
 template <class F>
-__global__ void __launch_bounds__(128) k_logup_rows(LogupArgs a) {
+__global__ void __launch_bounds__(128) k_logup_rows(const LogupArgs* __restrict__ tables, uint32_t n_tables) {
+    uint32_t jb = 0;
+    while (jb + 1 < n_tables && blockIdx.x >= tables[jb + 1].cta_begin) jb++;
+    const LogupArgs a = tables[jb];
     uint32_t n = 1u << a.log_n;
-    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t r = (blockIdx.x - a.cta_begin) * blockDim.x + threadIdx.x;
     if (r >= n) return;
     uint32_t outs[MAX_LK_OUTS];
     RowSrc rs;
@@ -679,23 +687,33 @@ __device__ __forceinline__ Ext4 block_sum_256(Ext4 v, Ext4* red) {
     return t;
 }
 template <class F>
-__global__ void __launch_bounds__(256) k_logup_chunk_sums(const Ext4* __restrict__ rowsum, uint32_t n, Ext4* __restrict__ chunk_sum) {
+__global__ void __launch_bounds__(256) k_logup_chunk_sums(const LogupArgs* __restrict__ tables, uint32_t n_tables) {
     __shared__ Ext4 red[8];
-    uint32_t r = blockIdx.x * SCAN_CHUNK + threadIdx.x;
+    uint32_t jb = 0;
+    while (jb + 1 < n_tables && blockIdx.x >= tables[jb + 1].scan_cta_begin) jb++;
+    const Ext4* rowsum = tables[jb].rowsum;
+    const uint32_t n = 1u << tables[jb].log_n, chunk = blockIdx.x - tables[jb].scan_cta_begin;
+    uint32_t r = chunk * SCAN_CHUNK + threadIdx.x;
     Ext4 v = r < n ? rowsum[r] : ext_zero();
     Ext4 t = block_sum_256<F>(v, red);
-    if (threadIdx.x == 0) chunk_sum[blockIdx.x] = t;
+    if (threadIdx.x == 0) tables[jb].chunk_sum[chunk] = t;
 }
 template <class F>
-__global__ void __launch_bounds__(256) k_logup_scan_apply(const Ext4* __restrict__ rowsum, const Ext4* __restrict__ chunk_sum,
-                                                           uint32_t n, uint32_t* __restrict__ perm, Ext4* __restrict__ terminal) {
+__global__ void __launch_bounds__(256) k_logup_scan_apply(const LogupArgs* __restrict__ tables, uint32_t n_tables) {
     __shared__ Ext4 red[8];
     __shared__ Ext4 buf[SCAN_CHUNK];
+    uint32_t jb = 0;
+    while (jb + 1 < n_tables && blockIdx.x >= tables[jb + 1].scan_cta_begin) jb++;
+    const Ext4* rowsum = tables[jb].rowsum;
+    const Ext4* chunk_sum = tables[jb].chunk_sum;
+    uint32_t* perm = tables[jb].perm;
+    Ext4* terminal = tables[jb].terminal;
+    const uint32_t n = 1u << tables[jb].log_n, chunk = blockIdx.x - tables[jb].scan_cta_begin;
     // prefix over earlier chunks
     Ext4 pre = ext_zero();
-    for (uint32_t c = threadIdx.x; c < blockIdx.x; c += blockDim.x) pre = eadd<F>(pre, chunk_sum[c]);
+    for (uint32_t c = threadIdx.x; c < chunk; c += blockDim.x) pre = eadd<F>(pre, chunk_sum[c]);
     pre = block_sum_256<F>(pre, red);
-    uint32_t r = blockIdx.x * SCAN_CHUNK + threadIdx.x;
+    uint32_t r = chunk * SCAN_CHUNK + threadIdx.x;
     Ext4 own = r < n ? rowsum[r] : ext_zero();
     buf[threadIdx.x] = own;
     __syncthreads();
@@ -861,7 +879,7 @@ struct DotJob {
     uint32_t w_offset;     // weights
     uint32_t out_offset;   // into opened values buffer (Ext4 units), width entries
 };
-constexpr uint32_t DOT_ROWS = 2048;  // rows per CTA
+constexpr uint32_t DOT_ROWS = 8192;  // rows per CTA
 constexpr uint32_t DOT_COLS = 8;     // columns per CTA
 struct DotTile {           // one CTA of k_bary_dot: rows [chunk*DOT_ROWS, ..) x columns [c0, c0 + DOT_COLS) of a job
     uint32_t job, chunk, c0;

@@ -1230,6 +1230,8 @@ static int commit_perm_impl(p3r_session* s, const uint32_t alpha[4], const uint3
     if (!s->d_chal || !d_bp || !s->d_terminals) return P3R_ERR_OOM;
     std::vector<MatRef> mats;
     std::vector<LdeJob> jobs;
+    std::vector<LogupArgs> logup_tables;
+    uint64_t logup_bytes = 0;
     uint32_t lmax = 0;
     for (size_t i = 0; i < n_inst; i++) {
         const InstDev& d = pp->inst[i];
@@ -1255,24 +1257,39 @@ static int commit_perm_impl(p3r_session* s, const uint32_t alpha[4], const uint3
         la.perm = s->perm[i];
         la.rowsum = rowsum;
         la.wnr = wnr;
-        {
-            KT kt(ctx, KC_LOGUP, (uint64_t)n * 4 * (d.main_w + d.prep_w + pw));
-            k_logup_rows<F><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(la);
-            LAUNCH_CHECK_C(KC_LOGUP);
-            uint32_t n_chunks = (uint32_t)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
-            Ext4* chunk_sum = arena_alloc<Ext4>(ctx, n_chunks);
-            if (!chunk_sum) return P3R_ERR_OOM;
-            k_logup_chunk_sums<F><<<n_chunks, 256, 0, ctx->stream>>>(rowsum, (uint32_t)n, chunk_sum);
-            LAUNCH_CHECK_C(KC_LOGUP);
-            k_logup_scan_apply<F><<<n_chunks, 256, 0, ctx->stream>>>(rowsum, chunk_sum, (uint32_t)n, s->perm[i], s->d_terminals + i);
-            LAUNCH_CHECK_C(KC_LOGUP);
-        }
+        la.chunk_sum = arena_alloc<Ext4>(ctx, (n + SCAN_CHUNK - 1) / SCAN_CHUNK);
+        la.terminal = s->d_terminals + i;
+        if (!la.chunk_sum) return P3R_ERR_OOM;
+        logup_tables.push_back(la);
+        logup_bytes += (uint64_t)n * 4 * (d.main_w + d.prep_w + pw);
         uint32_t* coef = arena_alloc<uint32_t>(ctx, n * pw);
         uint32_t* tmp = d.log_h > TILE_LOG ? arena_alloc<uint32_t>(ctx, (n << lb) * pw) : nullptr;
         if (!coef || (d.log_h > TILE_LOG && !tmp)) return P3R_ERR_OOM;
         jobs.push_back({s->perm[i], s->perm_lde[i], d.log_h, pw, true, 0, coef, tmp});
         mats.push_back({s->perm_lde[i], d.log_h + lb, pw});
         lmax = std::max(lmax, d.log_h + lb);
+    }
+    {
+        // every table in one launch each: rows (largest first), chunk sums, scan
+        std::stable_sort(logup_tables.begin(), logup_tables.end(), [](const LogupArgs& x, const LogupArgs& y) { return x.log_n > y.log_n; });
+        uint32_t cta = 0, scan_cta = 0;
+        for (auto& la : logup_tables) {
+            const uint32_t n = 1u << la.log_n;
+            la.cta_begin = cta;
+            la.scan_cta_begin = scan_cta;
+            cta += (n + 127) / 128;
+            scan_cta += (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+        }
+        const LogupArgs* d_tabs = upload_vec(ctx, logup_tables);
+        if (!d_tabs) return P3R_ERR_OOM;
+        KT kt(ctx, KC_LOGUP, logup_bytes);
+        const uint32_t nt = (uint32_t)logup_tables.size();
+        k_logup_rows<F><<<cta, 128, 0, ctx->stream>>>(d_tabs, nt);
+        LAUNCH_CHECK_C(KC_LOGUP);
+        k_logup_chunk_sums<F><<<scan_cta, 256, 0, ctx->stream>>>(d_tabs, nt);
+        LAUNCH_CHECK_C(KC_LOGUP);
+        k_logup_scan_apply<F><<<scan_cta, 256, 0, ctx->stream>>>(d_tabs, nt);
+        LAUNCH_CHECK_C(KC_LOGUP);
     }
     TRY(coset_lde_batch<F>(ctx, jobs, lb));
     uint32_t* dg = arena_alloc<uint32_t>(ctx, tree_digest_words(lmax));
@@ -1352,7 +1369,7 @@ static int commit_quotient_impl(p3r_session* s, const uint32_t alpha[4], uint32_
         {
             KT kt(ctx, KC_QUOTIENT, (uint64_t)NQ * (8ull * (d.main_w + d.prep_w + d.aux_w() * 4) + 16));
             if (d.spec && ctx->use_spec)
-                p3r_spec_launch(d.spec, qa, (NQ + 127) / 128, 128, ctx->stream);
+                p3r_spec_launch(d.spec, qa, (NQ + 31) / 32, 128, ctx->stream);  // 32 rows x 4 constraint groups per CTA
             else
                 k_quotient<F><<<(NQ + 127) / 128, 128, 0, ctx->stream>>>(qa);
             LAUNCH_CHECK_C(KC_QUOTIENT);
