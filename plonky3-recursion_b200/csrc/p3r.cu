@@ -1369,7 +1369,7 @@ static int commit_quotient_impl(p3r_session* s, const uint32_t alpha[4], uint32_
         {
             KT kt(ctx, KC_QUOTIENT, (uint64_t)NQ * (8ull * (d.main_w + d.prep_w + d.aux_w() * 4) + 16));
             if (d.spec && ctx->use_spec)
-                p3r_spec_launch(d.spec, qa, (NQ + 31) / 32, 128, ctx->stream);  // 32 rows x 4 constraint groups per CTA
+                p3r_spec_launch(d.spec, qa, (NQ + 31) / 32, p3r_spec_threads(), ctx->stream);  // 32 rows x 4 constraint groups per CTA
             else
                 k_quotient<F><<<(NQ + 127) / 128, 128, 0, ctx->stream>>>(qa);
             LAUNCH_CHECK_C(KC_QUOTIENT);

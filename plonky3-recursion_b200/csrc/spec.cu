@@ -6,6 +6,7 @@ const SpecEntry* p3r_spec_registry(size_t* n) {
     *n = sizeof(SPEC_QUOTIENT) / sizeof(SPEC_QUOTIENT[0]);
     return SPEC_QUOTIENT;
 }
+unsigned p3r_spec_threads() { return SPEC_THREADS; }
 void p3r_spec_launch(SpecQuotientKernel fn, const QuotientArgs& a, unsigned grid, unsigned block, cudaStream_t stream) {
     fn<<<grid, block, 0, stream>>>(a);
 }

@@ -10,5 +10,6 @@ struct SpecEntry {
     SpecQuotientKernel fn;
 };
 const SpecEntry* p3r_spec_registry(size_t* n);
+unsigned p3r_spec_threads();   // threads per CTA of the generated kernels (32 rows x constraint groups)
 void p3r_spec_launch(SpecQuotientKernel fn, const QuotientArgs& a, unsigned grid, unsigned block, cudaStream_t stream);
 }  // namespace p3r

@@ -42,7 +42,7 @@ def monty_insns(F, prog):
     return ins
 
 
-N_GROUPS = 4   # warps per CTA; each evaluates one group of constraints for the CTA's 32 rows
+N_GROUPS = 8   # warps per CTA; each evaluates one group of constraints for the CTA's 32 rows
 COST = {}
 
 
