@@ -21,7 +21,7 @@
 
 namespace p3r {
 
-constexpr uint32_t COL_MIN_LOG = 5, COL_MAX_LOG = 15, COL_TOP_MAX_LOG = 19;  // up to 2^19 rows with k_ntt_top
+constexpr uint32_t COL_MIN_LOG = 5, COL_MAX_LOG = 15, COL_TOP_MAX_LOG = 27;  // taller columns: k_ntt_top passes above stage 15
 
 struct ColJob {
     const uint32_t* src;
@@ -35,12 +35,12 @@ struct ColJob {
     uint32_t cta_begin;                       // first flat CTA of this job; CTA order: (coset, column group)
     uint32_t n_inv;                           // inverse: 1/n (Montgomery)
     uint32_t q[3];                            // plan: stages of the groups after the radix-32 one, bottom-up (0 = none)
-    const uint32_t* ctab;                     // per coset COL_CTAB words: 31 first-group twiddles, then C_s for s < 20
+    const uint32_t* ctab;                     // per coset COL_CTAB words: 31 first-group twiddles, then C_s for s < 28
     const uint32_t* tws;                      // per-stage compact twiddle tables (w_{2^(s+1)}^e at (2^s - 1) + e)
     uint32_t r4, r8, r8_3;                    // w_4, w_8, w_8^3
     uint32_t r16[8];                          // w_16^e, e < 8
 };
-constexpr uint32_t COL_CTAB = 31 + 20;
+constexpr uint32_t COL_CTAB = 31 + 28;
 
 __device__ __forceinline__ uint32_t col_sigma(uint32_t x) { return x ^ (((x >> 5) & 7u) << 2); }
 
@@ -281,24 +281,28 @@ __global__ void __launch_bounds__(512) k_ntt_col(const ColJob* __restrict__ jobs
     }
 }
 
-// Stages 15 .. 15 + Q - 1 of a column of 2^(15 + Q) rows, straight from and to HBM (one task = 2^Q elements 2^15 apart,
-// consecutive lanes on consecutive rows). Forward: after k_ntt_col ran stages 0..14 on the 2^Q sub-blocks (natural order),
-// stores bit-reversed rows into the coset block. Inverse: runs first, natural in -> natural out, k_ntt_col follows.
+// Stages j .. j + Q - 1 (j >= 15) of columns of 2^log_n rows, straight from and to HBM: one task = 2^Q elements 2^j apart,
+// consecutive lanes on consecutive rows. Columns taller than 2^15 rows run k_ntt_col on their 2^15-row sub-blocks and one or
+// more of these passes for the stages above. Forward: passes ascend, in place in natural order; the pass that ends at
+// log_n stores bit-reversed rows into the coset block. Inverse: passes descend from the top (natural in -> natural out),
+// k_ntt_col follows.
 template <class F, int Q, bool FWD>
-__global__ void __launch_bounds__(256) k_ntt_top(ColJob a) {
-    const uint32_t j = COL_MAX_LOG;
-    const uint32_t lo = blockIdx.x * blockDim.x + threadIdx.x, col = blockIdx.y, coset = blockIdx.z;
+__global__ void __launch_bounds__(256) k_ntt_top(ColJob a, uint32_t j, uint32_t bitrev_out) {
+    const uint32_t tau = blockIdx.x * blockDim.x + threadIdx.x, col = blockIdx.y, coset = blockIdx.z;
+    const uint32_t lo = tau & ((1u << j) - 1), hi = tau >> j;
+    const size_t base = ((size_t)hi << (j + Q)) | lo;
     const uint32_t* tab = a.tws + ((1u << (j + Q - 1)) - 1);
     uint32_t W;
     if (FWD) W = fmul<F>(__ldg(tab + lo), __ldg(a.ctab + (size_t)coset * COL_CTAB + 31 + (j + Q - 1)));
     else W = lo ? fneg<F>(__ldg(tab + ((1u << (j + Q - 1)) - lo))) : F::R;
-    const uint32_t* src = a.src + (size_t)coset * a.src_coset_stride + (size_t)col * a.src_col_stride + lo;
+    const uint32_t* src = a.src + (size_t)coset * a.src_coset_stride + (size_t)col * a.src_col_stride + base;
     uint32_t v[1 << Q];
 #pragma unroll
-    for (int k = 0; k < (1 << Q); k++) v[k] = __ldg(src + ((size_t)k << j));
+    for (int k = 0; k < (1 << Q); k++) v[k] = src[(size_t)k << j];
     col_group<F, Q, FWD>(v, W, a);
     uint32_t* dst = a.dst + (size_t)col * a.dst_col_stride + (size_t)coset * a.dst_coset_stride;
-    if (FWD) {
+    if (FWD && bitrev_out) {
+        // j + Q == log_n, hi == 0: natural index (k << j) | lo -> bit-reversed row (rev_j(lo) << Q) | rev_Q(k)
         uint32_t* o = dst + ((size_t)(__brev(lo) >> (32 - j)) << Q);
         if (Q >= 2) {
 #pragma unroll
@@ -315,7 +319,7 @@ __global__ void __launch_bounds__(256) k_ntt_top(ColJob a) {
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < (1 << Q); k++) dst[lo + ((size_t)k << j)] = v[k];
+        for (int k = 0; k < (1 << Q); k++) dst[base + ((size_t)k << j)] = v[k];
     }
 }
 

@@ -532,8 +532,8 @@ static int coset_lde_cols(p3r_ctx* ctx, const std::vector<LdeJob>& jobs, uint32_
             const uint64_t e = ((uint64_t)rj + j.rot) & (((uint64_t)1 << logN) - 1);
             uint32_t c = fpow<F>(wN, e);
             if (j.use_g) c = fmul<F>(c, ctx->gen_m);
-            uint32_t C[20];
-            for (uint32_t sgm = 0; sgm < 20; sgm++) C[sgm] = F::R;
+            uint32_t C[28];
+            for (uint32_t sgm = 0; sgm < 28; sgm++) C[sgm] = F::R;
             C[j.log_n - 1] = c;
             for (uint32_t sgm = j.log_n - 1; sgm-- > 0;) C[sgm] = fmul<F>(C[sgm + 1], C[sgm + 1]);
             size_t off = ctab.size();
@@ -541,7 +541,7 @@ static int coset_lde_cols(p3r_ctx* ctx, const std::vector<LdeJob>& jobs, uint32_
             for (uint32_t sgm = 0; sgm < 5; sgm++)
                 for (uint32_t ee = 0; ee < (1u << sgm); ee++)
                     ctab[off + (1u << sgm) - 1 + ee] = fmul<F>(C[sgm], st32[(1u << sgm) - 1 + ee]);
-            for (uint32_t sgm = 0; sgm < 20; sgm++) ctab[off + 31 + sgm] = C[sgm];
+            for (uint32_t sgm = 0; sgm < 28; sgm++) ctab[off + 31 + sgm] = C[sgm];
         }
     }
     const uint32_t* d_ctab = upload_vec(ctx, ctab);
@@ -569,35 +569,44 @@ static int coset_lde_cols(p3r_ctx* ctx, const std::vector<LdeJob>& jobs, uint32_
     for (size_t i = 0; i < order.size(); i++) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return jobs[x].log_n > jobs[y].log_n; });
     auto launch_top = [&](const LdeJob& j, size_t qi, bool fwd) -> int {
-        const uint32_t Q = j.log_n - COL_MAX_LOG;
+        const uint32_t T = j.log_n - COL_MAX_LOG;                 // stages above the shared-memory kernel
+        const uint32_t n_pass = (T + 3) / 4;
+        std::vector<uint32_t> qs(n_pass, T / n_pass);
+        for (uint32_t i = 0; i < T % n_pass; i++) qs[i]++;
         const size_t n = (size_t)1 << j.log_n, N = n << log_blowup;
-        ColJob b = base;
-        b.ctab = d_ctab + job_ctab[qi];
-        dim3 grid((1u << COL_MAX_LOG) / 256, j.w, fwd ? n_cosets : 1);
-        if (fwd) {
-            b.src = j.tmp;
+        // forward: ascending from stage 15; inverse: descending from the top
+        uint32_t jj = fwd ? COL_MAX_LOG : j.log_n;
+        for (uint32_t pi = 0; pi < n_pass; pi++) {
+            const uint32_t Q = qs[pi];
+            if (!fwd) jj -= Q;
+            const bool last_fwd = fwd && pi + 1 == n_pass, first_inv = !fwd && pi == 0;
+            ColJob b = base;
+            b.log_n = j.log_n;
+            b.ctab = d_ctab + job_ctab[qi];
+            b.src = first_inv ? j.src : j.tmp;
             b.src_col_stride = n;
-            b.src_coset_stride = (uint64_t)j.w * n;
-            b.dst = j.dst;
-            b.dst_col_stride = N;
-            b.dst_coset_stride = n;
-        } else {
-            b.src = j.src;
-            b.src_col_stride = n;
-            b.src_coset_stride = 0;
-            b.dst = j.tmp;
-            b.dst_col_stride = n;
-            b.dst_coset_stride = 0;
-        }
-#define P3R_TOP(QQ)                                                                          \
-    if (fwd) k_ntt_top<F, QQ, true><<<grid, 256, 0, ctx->stream>>>(b);                      \
-    else k_ntt_top<F, QQ, false><<<grid, 256, 0, ctx->stream>>>(b)
-        if (Q == 1) { P3R_TOP(1); }
-        else if (Q == 2) { P3R_TOP(2); }
-        else if (Q == 3) { P3R_TOP(3); }
-        else { P3R_TOP(4); }
+            b.src_coset_stride = fwd ? (uint64_t)j.w * n : 0;
+            if (last_fwd) {
+                b.dst = j.dst;
+                b.dst_col_stride = N;
+                b.dst_coset_stride = n;
+            } else {
+                b.dst = j.tmp;
+                b.dst_col_stride = n;
+                b.dst_coset_stride = fwd ? (uint64_t)j.w * n : 0;
+            }
+            dim3 grid((unsigned)((n >> Q) / 256), j.w, fwd ? n_cosets : 1);
+#define P3R_TOP(QQ)                                                                                   \
+    if (fwd) k_ntt_top<F, QQ, true><<<grid, 256, 0, ctx->stream>>>(b, jj, last_fwd ? 1u : 0u);       \
+    else k_ntt_top<F, QQ, false><<<grid, 256, 0, ctx->stream>>>(b, jj, 0u)
+            if (Q == 1) { P3R_TOP(1); }
+            else if (Q == 2) { P3R_TOP(2); }
+            else if (Q == 3) { P3R_TOP(3); }
+            else { P3R_TOP(4); }
 #undef P3R_TOP
-        LAUNCH_CHECK_C(KC_NTT);
+            LAUNCH_CHECK_C(KC_NTT);
+            if (fwd) jj += Q;
+        }
         return P3R_OK;
     };
     for (int dir = 0; dir < 2; dir++) {

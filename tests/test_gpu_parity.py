@@ -42,9 +42,9 @@ def test_coset_lde(pair, log_n, width, log_blowup):
 
 
 @pytest.mark.parametrize("log_n,width,log_blowup", [(5, 2, 2), (6, 3, 1), (7, 1, 2), (9, 5, 2), (11, 7, 2), (12, 33, 2), (15, 3, 2),
-                                                    (17, 2, 2), (18, 3, 1), (19, 1, 1)])
+                                                    (17, 2, 2), (18, 3, 1), (19, 1, 1), (20, 2, 1), (21, 1, 1), (22, 1, 1)])
 def test_coset_lde_column_kernels_match_tile_kernel(pair, log_n, width, log_blowup):
-    """The whole-column LDE kernels (k_ntt_col / k_ntt_top, every group plan 2^5..2^19) and the multi-pass tile kernel
+    """The whole-column LDE kernels (k_ntt_col / k_ntt_top, every group plan 2^5..2^15, one and two passes above stage 15) and the multi-pass tile kernel
     (k_ntt_pass) are independent implementations of the same transform: bit-identical outputs; oracle-checked up to 2^17."""
     ctx, orc = pair
     rng = np.random.default_rng(300 + log_n)
