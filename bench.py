@@ -108,6 +108,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 for its workers; the CPU arm is meant to use every host core
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from common import make_oracle
     lib = importlib.import_module("plonky3-recursion_b200.lib")
     sample = 1.0 / 16
