@@ -388,6 +388,7 @@ __global__ void __launch_bounds__(128) k_compress(const uint32_t* __restrict__ p
 // recursion/src/pcs/mmcs.rs:434-441). Rows injected at a level arrive as digests (k_hash_rows).
 // Level l (2^(log_max_h - l) digests) lives at digest offset 2^(log_max_h+1) - 2^(log_max_h-l+1).
 constexpr uint32_t STAGE_MAX_LEVELS = 7;   // 2^(7-1) = 64 first-level nodes = the 64 lane groups of a 1024-thread CTA
+constexpr uint32_t STAGE_DEFAULT_LEVELS = 5;   // measured best of 4..7 on the layer workload (more CTAs, no issue contention at the widest level)
 struct MerkleStage {
     uint32_t* digests;
     uint32_t log_max_h;

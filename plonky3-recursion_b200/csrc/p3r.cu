@@ -810,7 +810,14 @@ static int build_tree(p3r_ctx* ctx, const uint32_t* leaf_rows, uint32_t leaf_w, 
         st.digests = digests;
         st.log_max_h = lmax;
         st.first_level = l;
-        st.n_levels = std::min(STAGE_MAX_LEVELS, last_level - cur);
+        // levels per launch: tunable (env P3R_STAGE_LEVELS, default below). Fewer levels per CTA = more CTAs, less issue
+        // contention at the widest level, at the price of one more launch per tree.
+        static const uint32_t stage_levels = [] {
+            const char* e = getenv("P3R_STAGE_LEVELS");
+            uint32_t v = e ? (uint32_t)atoi(e) : STAGE_DEFAULT_LEVELS;
+            return std::max(1u, std::min(v, STAGE_MAX_LEVELS));
+        }();
+        st.n_levels = std::min(stage_levels, last_level - cur);
         st.with_leaves = leaves_done ? 0 : 1;
         st.leaf_rows = leaf_rows;
         st.leaf_w = leaf_w;
