@@ -1058,11 +1058,13 @@ __global__ void __launch_bounds__(128) k_reduced_openings(const RoArgs* __restri
 // ------------------------------------------------------------------------------------------------
 template <class F>
 __global__ void __launch_bounds__(128) k_fri_fold(const Ext4* __restrict__ in, Ext4* __restrict__ out, uint32_t log_len,
-                                                   uint32_t log_arity, Ext4 beta, const Ext4* __restrict__ roll, uint32_t inv2,
-                                                   const uint32_t* tw, uint32_t logT, uint32_t wnr) {
+                                                   uint32_t log_arity, Ext4 beta, const Ext4* __restrict__ beta_dev,
+                                                   const Ext4* __restrict__ roll, uint32_t inv2, const uint32_t* tw, uint32_t logT,
+                                                   uint32_t wnr) {
     uint32_t out_len = 1u << (log_len - log_arity);
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= out_len) return;
+    if (beta_dev) beta = *beta_dev;   // challenge sampled on the device (k_fri_round_transcript)
     Ext4 v[16];
     uint32_t arity = 1u << log_arity;
     for (uint32_t j = 0; j < arity; j++) v[j] = in[(size_t)i * arity + j];
@@ -1101,6 +1103,62 @@ __global__ void k_final_poly(const Ext4* __restrict__ folded, Ext4* __restrict__
         acc = eadd<F>(acc, emul_base<F>(v, root_pow<F>(tw, logT, e << (logT - log_fpl))));
     }
     coeffs[k] = emul_base<F>(acc, finv<F>(to_monty<F>(n)));
+}
+
+// DuplexChallenger on the device for the FRI commit rounds of the one-shot prover (same semantics as the
+// host HostChallenger: overwrite mode, zero-fill, length tag in state[8], samples popped from the back). One warp: lanes
+// 0..15 hold the sponge state for the cooperative permutation. Per round it observes the round's cap and samples beta, so the
+// host does not have to synchronise between rounds; the host replays the same operations afterwards on its own challenger.
+struct DevChallenger {
+    uint32_t st[16];
+    uint32_t in[8], out[8];
+    uint32_t n_in, n_out;
+};
+template <class F>
+__global__ void __launch_bounds__(32) k_fri_round_transcript(DevChallenger* __restrict__ ch, const uint32_t* __restrict__ cap,
+                                                             uint32_t n_cap_words, Ext4* __restrict__ beta_out,
+                                                             const Poseidon2Consts* __restrict__ gk) {
+    __shared__ DevChallenger s;
+    const uint32_t lane = threadIdx.x, l16 = lane & 15u;
+    const P2Lane c = p2_lane_consts<F>(gk, l16);
+    for (uint32_t i = lane; i < sizeof(DevChallenger) / 4; i += 32) reinterpret_cast<uint32_t*>(&s)[i] = reinterpret_cast<const uint32_t*>(ch)[i];
+    __syncwarp();
+    auto duplex = [&]() {
+        // every lane runs the permutation; lanes 0..15 carry the state
+        uint32_t x = s.st[l16];
+        const uint32_t n_in = s.n_in;
+        if (l16 < n_in) x = s.in[l16];
+        else if (n_in > 0 && l16 < 8) x = 0;
+        if (n_in > 0 && l16 == 8) x = fadd<F>(x, to_monty<F>(n_in));
+        x = p2_coop_permute<F>(x, lane, c);
+        __syncwarp();
+        if (lane < 16) s.st[lane] = x;
+        if (lane < 8) s.out[lane] = x;
+        if (lane == 0) {
+            s.n_in = 0;
+            s.n_out = 8;
+        }
+        __syncwarp();
+    };
+    for (uint32_t w = 0; w < n_cap_words; w++) {   // observe
+        if (lane == 0) {
+            s.n_out = 0;
+            s.in[s.n_in] = cap[w];
+            s.n_in = s.n_in + 1;
+        }
+        __syncwarp();
+        if (s.n_in == 8) duplex();
+    }
+    Ext4 beta;
+    for (int k = 0; k < 4; k++) {                  // sample_ext
+        if (s.n_in > 0 || s.n_out == 0) duplex();
+        beta.c[k] = s.out[s.n_out - 1];
+        __syncwarp();
+        if (lane == 0) s.n_out = s.n_out - 1;
+        __syncwarp();
+    }
+    if (lane == 0) *beta_out = beta;
+    for (uint32_t i = lane; i < sizeof(DevChallenger) / 4; i += 32) reinterpret_cast<uint32_t*>(ch)[i] = reinterpret_cast<const uint32_t*>(&s)[i];
 }
 
 // ------------------------------------------------------------------------------------------------

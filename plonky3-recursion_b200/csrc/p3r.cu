@@ -97,6 +97,7 @@ struct p3r_ctx {
     uint32_t* tws = nullptr;  // per-stage compact twiddle tables, 2^logT - 1 entries
     uint32_t* tw = nullptr;   // = tws + 2^(logT-1) - 1: half table of omega_T
     void (*host_permute)(uint32_t*, const Poseidon2Consts&) = nullptr;  // transcript permutation (AVX2 or scalar), set at creation
+    bool dev_fri_transcript = true;  // FRI commit rounds without host round trips (p3r_set_specialization bit 2 turns it off)
     bool use_col_ntt = true;  // whole-column LDE kernels for 2^5..2^15 rows (p3r_set_specialization bit 1 turns them off)
     uint32_t logT = 0;
     uint32_t r4 = 0, r8 = 0, r8_3 = 0;
@@ -1702,7 +1703,7 @@ static int fri_begin_impl(p3r_session* s, const uint32_t alpha_w[4], uint32_t* n
 }
 
 template <class F>
-static int fri_commit_impl(p3r_session* s, uint32_t round, uint32_t* cap_out) {
+static int fri_commit_impl(p3r_session* s, uint32_t round, uint32_t* cap_out, bool read_back = true) {
     p3r_ctx* ctx = s->ctx;
     if (s->phase != PH_FRI || round >= s->rounds.size()) {
         set_err(ctx, "fri_commit: wrong phase/round");
@@ -1720,19 +1721,19 @@ static int fri_commit_impl(p3r_session* s, uint32_t round, uint32_t* cap_out) {
     fr.tree.digests = dg;
     TRY(build_tree<F>(ctx, reinterpret_cast<const uint32_t*>(fr.vec), 4u << fr.log_arity, log_rows, dg,
                       [](uint32_t) { return (const uint32_t*)nullptr; }));
-    return read_cap(ctx, fr.tree, cap_out);
+    return read_back ? read_cap(ctx, fr.tree, cap_out) : P3R_OK;
 }
 
 template <class F>
-static int fri_fold_impl(p3r_session* s, uint32_t round, const uint32_t beta_w[4]) {
+static int fri_fold_impl(p3r_session* s, uint32_t round, const uint32_t beta_w[4], const Ext4* beta_dev = nullptr) {
     p3r_ctx* ctx = s->ctx;
     if (s->phase != PH_FRI || round >= s->rounds.size()) {
         set_err(ctx, "fri_fold: wrong phase/round");
         return P3R_ERR_STATE;
     }
     FriRound& fr = s->rounds[round];
-    Ext4 beta;
-    std::memcpy(beta.c, beta_w, 16);
+    Ext4 beta{};
+    if (beta_w) std::memcpy(beta.c, beta_w, 16);
     uint32_t out_log = fr.log_len - fr.log_arity;
     Ext4* out = (round + 1 < s->rounds.size()) ? s->rounds[round + 1].vec : s->final_vec;
     const Ext4* roll = nullptr;
@@ -1740,8 +1741,8 @@ static int fri_fold_impl(p3r_session* s, uint32_t round, const uint32_t beta_w[4
     if (it != s->ro.end() && out_log != s->log_max) roll = it->second;
     uint32_t n_out = 1u << out_log;
     KT kt(ctx, KC_FOLD);
-    k_fri_fold<F><<<(n_out + 127) / 128, 128, 0, ctx->stream>>>(fr.vec, out, fr.log_len, fr.log_arity, beta, roll, ctx->inv2_m,
-                                                                ctx->tw, ctx->logT, ctx->w_m);
+    k_fri_fold<F><<<(n_out + 127) / 128, 128, 0, ctx->stream>>>(fr.vec, out, fr.log_len, fr.log_arity, beta, beta_dev, roll,
+                                                                ctx->inv2_m, ctx->tw, ctx->logT, ctx->w_m);
     ctx->kstats.bytes[KC_FOLD] += 16ull * (((size_t)1 << fr.log_len) + n_out);
     LAUNCH_CHECK_C(KC_FOLD);
     return P3R_OK;
@@ -2003,13 +2004,53 @@ static int prove_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* 
     TRY(fri_begin_impl<F>(s, alpha_fri, &n_rounds, log_arities));
     pt.mark("fri_reduce");
     std::vector<uint32_t> fri_caps(n_rounds * capw), commit_pow(n_rounds);
-    for (uint32_t r = 0; r < n_rounds; r++) {
-        TRY(fri_commit_impl<F>(s, r, fri_caps.data() + r * capw));
-        ch.observe_words(fri_caps.data() + r * capw, capw);
-        TRY(challenger_grind<F>(ctx, ch, ctx->fri.commit_pow_bits, &commit_pow[r]));
-        uint32_t beta[4];
-        ch.sample_ext(beta);
-        TRY(fri_fold_impl<F>(s, r, beta));
+    if (ctx->fri.commit_pow_bits == 0 && ctx->dev_fri_transcript && n_rounds > 0) {
+        // No commit-phase PoW: the rounds' caps are observed and the betas sampled by a one-warp kernel, so all rounds are
+        // enqueued without a host round trip; afterwards the host challenger replays the same operations on the caps.
+        DevChallenger hc{};
+        std::memcpy(hc.st, ch.st, sizeof hc.st);
+        std::memcpy(hc.in, ch.in, sizeof hc.in);
+        std::memcpy(hc.out, ch.out, sizeof hc.out);
+        hc.n_in = (uint32_t)ch.n_in;
+        hc.n_out = (uint32_t)ch.n_out;
+        DevChallenger* d_ch = reinterpret_cast<DevChallenger*>(upload_small(ctx, &hc, sizeof hc));
+        Ext4* d_beta = arena_alloc<Ext4>(ctx, n_rounds);
+        if (!d_ch || !d_beta) return P3R_ERR_OOM;
+        for (uint32_t r = 0; r < n_rounds; r++) {
+            TRY(fri_commit_impl<F>(s, r, nullptr, false));
+            const Tree& t = s->rounds[r].tree;
+            k_fri_round_transcript<F><<<1, 32, 0, ctx->stream>>>(d_ch, t.digests + t.level_off(t.log_max_h - ctx->fri.cap_height) * 8,
+                                                                 (uint32_t)capw, d_beta + r, ctx->d_p2);
+            LAUNCH_CHECK();
+            TRY(fri_fold_impl<F>(s, r, nullptr, d_beta + r));
+        }
+        for (uint32_t r = 0; r < n_rounds; r++) {
+            const Tree& t = s->rounds[r].tree;
+            CUDA_TRY(cudaMemcpyAsync(fri_caps.data() + r * capw, t.digests + t.level_off(t.log_max_h - ctx->fri.cap_height) * 8,
+                                     capw * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        std::vector<Ext4> dev_betas(n_rounds);
+        CUDA_TRY(cudaMemcpyAsync(dev_betas.data(), d_beta, n_rounds * sizeof(Ext4), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        for (uint32_t r = 0; r < n_rounds; r++) {
+            ch.observe_words(fri_caps.data() + r * capw, capw);
+            commit_pow[r] = 0;
+            uint32_t beta[4];
+            ch.sample_ext(beta);
+            if (std::memcmp(beta, dev_betas[r].c, 16) != 0) {
+                set_err(ctx, "device FRI transcript diverged from the host challenger");
+                return P3R_ERR_CUDA;
+            }
+        }
+    } else {
+        for (uint32_t r = 0; r < n_rounds; r++) {
+            TRY(fri_commit_impl<F>(s, r, fri_caps.data() + r * capw));
+            ch.observe_words(fri_caps.data() + r * capw, capw);
+            TRY(challenger_grind<F>(ctx, ch, ctx->fri.commit_pow_bits, &commit_pow[r]));
+            uint32_t beta[4];
+            ch.sample_ext(beta);
+            TRY(fri_fold_impl<F>(s, r, beta));
+        }
     }
     std::vector<uint32_t> final_poly((size_t)4 << ctx->fri.log_final_poly_len);
     TRY(fri_final_poly_impl<F>(s, final_poly.data()));
@@ -2425,6 +2466,7 @@ int p3r_set_specialization(p3r_ctx* ctx, int enable) {
     // so enable = 1 / 0 keep their old meaning and the parity tests can cross-check both LDE paths.
     ctx->use_spec = (enable & 1) != 0;
     ctx->use_col_ntt = (enable & 2) == 0;
+    ctx->dev_fri_transcript = (enable & 4) == 0;
     return P3R_OK;
 }
 int p3r_timer_start(p3r_ctx* ctx) {
