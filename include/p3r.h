@@ -293,9 +293,14 @@ int p3r_bench_commit(p3r_ctx* ctx, uint32_t log_height, uint32_t width, uint32_t
 /* Per-session device timings (CUDA events on the session stream) of the last one-shot p3r_prove:
  * names_out receives a pointer to a static NUL-separated list; ms_out up to cap entries. */
 int p3r_last_phase_times(p3r_ctx* ctx, const char** names_out, float* ms_out, uint32_t cap, uint32_t* n_out);
-/* Quotient kernels: the library carries build-time specialised (straight-line) kernels for the constraint programs of the
- * recursion layer's ALU and Poseidon2 tables (scripts/gen_specialized.py); a program whose hash matches uses them, any
- * other program is interpreted. enable = 0 forces the interpreter (used by the parity tests to compare both paths). */
+/* Alternative code paths, for parity tests that compare two independent implementations of the same step. `enable` is a
+ * bit set (default 1):
+ *   bit 0  set   : build-time specialised (straight-line, constraint-group) quotient kernels for the constraint programs of
+ *                  the recursion layer's ALU / Poseidon2 / Const / Public / Recompose tables (scripts/gen_specialized.py) when
+ *                  the program hash matches; clear: always the bytecode interpreter.
+ *   bit 1  set   : DISABLE the whole-column LDE kernels (k_ntt_col / k_ntt_top): every LDE goes through the multi-pass tile
+ *                  kernel k_ntt_pass.
+ *   bit 2  set   : DISABLE the device-side transcript of the FRI commit rounds in p3r_prove* (one host round trip per round). */
 int p3r_set_specialization(p3r_ctx* ctx, int enable);
 
 /* CUDA-event stopwatch on the ctx stream (the stream every kernel of this ctx is launched on): start synchronises the

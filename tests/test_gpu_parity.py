@@ -337,6 +337,25 @@ def test_specialized_and_interpreted_quotient_agree(pair):
     pd.close()
 
 
+def test_device_and_host_fri_transcripts_agree(pair):
+    """p3r_prove samples the FRI commit-phase betas on the device (k_fri_round_transcript) and replays them on the host
+    challenger; with bit 2 of p3r_set_specialization the host samples them round by round. Same proof either way, equal to the
+    oracle's; every code-path switch combined (interpreter + tile-kernel LDE + host transcript) also gives the same bytes."""
+    wl = importlib.import_module("plonky3-recursion_b200.workload")
+    ctx, orc = pair
+    L = wl.synthetic_layer(ctx.field, 33, n_const=12, n_public=50, n_alu=150, n_perms=40, n_recompose=6, min_height=32)
+    pd = lib.ProverData.from_airs_and_degrees(ctx, L.insts, L.preps)
+    prover = lib.BatchStarkProver(ctx)
+    want = orc.prove(L.insts, L.preps, L.traces, L.pubs)
+    try:
+        for flags in (1, 1 | 4, 0 | 2 | 4, 1 | 2):
+            ctx.set_specialization(flags)
+            assert np.array_equal(prover.prove_all_tables(L.traces, pd, L.pubs), want), flags
+    finally:
+        ctx.set_specialization(1)
+    pd.close()
+
+
 def test_gpu_poseidon2_table_fill_matches_reference_builder(pair):
     """K3: the device-generated Poseidon2 table equals the host restatement of generate_trace_rows bit for bit (padding rows,
     Merkle index accumulator, S-box registers for BabyBear), and proofs from ops == proofs from the uploaded matrix."""
