@@ -280,7 +280,8 @@ def run_ours(args):
         def hbm_roofline(name, st):
             ach = (st["bytes"] / 1e9) / (st["ms"] / 1e3) if st["ms"] > 0 else 0.0
             return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": traffic.get(name), "peak_source": peak_kind, "algorithmic_bytes_per_step": st["bytes"] / args.steps,
+                    "traffic": traffic.get(name), "traffic_scope": traffic.get(name + "_scope"), "peak_source": peak_kind,
+                    "algorithmic_bytes_per_step": st["bytes"] / args.steps,
                     "kernel_ms_per_step": st["ms"] / args.steps, "launches_per_step": st["launches"] / args.steps}
 
         if dominant in ("hash_rows", "compress"):
@@ -290,7 +291,8 @@ def run_ours(args):
             ach = perms_s * INSTR_PER_PERM[args.field] / 1e12
             pk = N_SMS * LANES_PER_SM * sm_hz / 1e12
             roofline = {"kernel": dominant, "bound": "int32_pipe", "achieved": ach, "peak": pk, "unit": "Tlane-instr/s",
-                        "frac": ach / pk, "traffic": traffic.get(dominant), "peak_source": "148 SMs x 128 lanes x sampled SM clock",
+                        "frac": ach / pk, "traffic": traffic.get(dominant), "traffic_scope": traffic.get(dominant + "_scope"),
+                        "peak_source": "148 SMs x 128 lanes x sampled SM clock",
                         "permutations_per_s": perms_s, "instr_per_permutation": INSTR_PER_PERM[args.field],
                         "permutations_per_step": ks["perms"] / args.steps, "kernel_ms_per_step": ks["ms"] / args.steps,
                         "launches_per_step": ks["launches"] / args.steps,
@@ -349,7 +351,7 @@ def main():
     ap.add_argument("--field", default="koala-bear", choices=["koala-bear", "baby-bear"])
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=2, help="concurrent proofs per GPU in the throughput regions")
+    ap.add_argument("--inflight", type=int, default=3, help="concurrent proofs per GPU in the throughput regions")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 20:
