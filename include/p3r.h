@@ -290,6 +290,10 @@ int p3r_poseidon2_permute(p3r_ctx* ctx, uint32_t* states, uint32_t n);
 int p3r_bench_commit(p3r_ctx* ctx, uint32_t log_height, uint32_t width, uint32_t iters, uint64_t seed,
                      float* times_ms_out);
 
+/* Device-resident benchmark of one FRI commit round on a synthetic extension-field vector of 2^log_len elements: fold by
+ * 2^log_arity (k_fri_fold) and Merkle-commit the folded vector as rows of 2^log_arity elements. times_ms_out: [fold, commit]. */
+int p3r_bench_fri_round(p3r_ctx* ctx, uint32_t log_len, uint32_t log_arity, uint32_t iters, uint64_t seed, float* times_ms_out);
+
 /* Per-session device timings (CUDA events on the session stream) of the last one-shot p3r_prove:
  * names_out receives a pointer to a static NUL-separated list; ms_out up to cap entries. */
 int p3r_last_phase_times(p3r_ctx* ctx, const char** names_out, float* ms_out, uint32_t cap, uint32_t* n_out);

@@ -2540,6 +2540,59 @@ int p3r_poseidon2_permute(p3r_ctx* ctx, uint32_t* states, uint32_t n) {
     cudaSetDevice(ctx->device);
     return DISPATCH(ctx, permute_host_impl<F>(ctx, states, n));
 }
+}  // extern "C" (template below)
+// Device-resident benchmark of one FRI commit round on a synthetic EF vector of 2^log_len elements: fold by 2^log_arity,
+// then Merkle-commit the folded vector's arity-wide rows.
+template <class F>
+static int bench_fri_round_impl(p3r_ctx* ctx, uint32_t log_len, uint32_t log_arity, uint32_t iters, uint64_t seed, float* ms_out) {
+    ctx->arena.reset();
+    ctx->pin_used = 0;
+    if (log_arity < 1 || log_arity > 4 || log_len < 2 * log_arity + ctx->fri.cap_height) return P3R_ERR_INVALID_ARG;
+    TRY(ensure_twiddles<F>(ctx, log_len));
+    const size_t L = (size_t)1 << log_len;
+    const uint32_t out_log = log_len - log_arity, rows_log = out_log - log_arity;
+    Ext4* in = arena_alloc<Ext4>(ctx, L);
+    Ext4* out = arena_alloc<Ext4>(ctx, L >> log_arity);
+    uint32_t* dg = arena_alloc<uint32_t>(ctx, tree_digest_words(rows_log));
+    if (!in || !out || !dg) return P3R_ERR_OOM;
+    k_fill_random<F><<<(unsigned)((L * 4 + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<uint32_t*>(in), L * 4, seed);
+    LAUNCH_CHECK();
+    Ext4 beta{{to_monty<F>(3), to_monty<F>(5), to_monty<F>(7), to_monty<F>(11)}};
+    cudaEvent_t e0, e1, e2;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventCreate(&e2);
+    float t_fold = 0, t_tree = 0;
+    for (uint32_t it = 0; it <= iters; it++) {   // iteration 0 = warm-up
+        size_t pin_mark = ctx->pin_used;
+        cudaEventRecord(e0, ctx->stream);
+        k_fri_fold<F><<<(unsigned)(((L >> log_arity) + 127) / 128), 128, 0, ctx->stream>>>(in, out, log_len, log_arity, beta, nullptr,
+                                                                                          nullptr, ctx->inv2_m, ctx->tw, ctx->logT, ctx->w_m);
+        LAUNCH_CHECK();
+        cudaEventRecord(e1, ctx->stream);
+        TRY(build_tree<F>(ctx, reinterpret_cast<const uint32_t*>(out), 4u << log_arity, rows_log, dg,
+                          [](uint32_t) { return (const uint32_t*)nullptr; }));
+        cudaEventRecord(e2, ctx->stream);
+        CUDA_TRY(cudaEventSynchronize(e2));
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, e0, e1);
+        cudaEventElapsedTime(&b, e1, e2);
+        if (it) t_fold += a, t_tree += b;
+        ctx->pin_used = pin_mark;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    ms_out[0] = t_fold / iters;
+    ms_out[1] = t_tree / iters;
+    return P3R_OK;
+}
+extern "C" {
+int p3r_bench_fri_round(p3r_ctx* ctx, uint32_t log_len, uint32_t log_arity, uint32_t iters, uint64_t seed, float* times_ms_out) {
+    if (!ctx || !times_ms_out || !iters) return P3R_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    return DISPATCH(ctx, bench_fri_round_impl<F>(ctx, log_len, log_arity, iters, seed, times_ms_out));
+}
 int p3r_bench_commit(p3r_ctx* ctx, uint32_t log_height, uint32_t width, uint32_t iters, uint64_t seed, float* times_ms_out) {
     if (!ctx || !times_ms_out || !iters) return P3R_ERR_INVALID_ARG;
     cudaSetDevice(ctx->device);

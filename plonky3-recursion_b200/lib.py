@@ -73,7 +73,7 @@ EXPORTS = ["p3r_abi_version", "p3r_build_info", "p3r_ctx_create", "p3r_ctx_destr
            "p3r_last_phase_times", "p3r_launch_count", "p3r_traces_upload", "p3r_traces_free", "p3r_prove_resident",
            "p3r_host_alloc", "p3r_host_free", "p3r_timer_start", "p3r_timer_stop", "p3r_set_kernel_timing",
            "p3r_reset_kernel_stats", "p3r_kernel_stats", "p3r_set_specialization", "p3r_prove_ex", "p3r_traces_upload_ex",
-           "p3r_traces_download", "p3r_kernel_perms"]
+           "p3r_traces_download", "p3r_kernel_perms", "p3r_bench_fri_round"]
 
 KERNEL_CLASSES = ["ntt_lde", "hash_rows", "compress", "logup", "quotient", "open", "reduced_openings", "fri_fold", "transpose",
                   "misc"]
@@ -149,6 +149,11 @@ class Context:
         t = (C.c_float * 3)()
         self._check(self.lib.p3r_bench_commit(self.h, log_height, width, iters, C.c_uint64(seed), t))
         return {"lde_ms": t[0], "merkle_ms": t[1]}
+
+    def bench_fri_round(self, log_len: int, log_arity: int, iters: int = 5, seed: int = 0xB200):
+        t = (C.c_float * 2)()
+        self._check(self.lib.p3r_bench_fri_round(self.h, log_len, log_arity, iters, C.c_uint64(seed), t))
+        return {"fold_ms": t[0], "commit_ms": t[1]}
 
     def set_specialization(self, enable: bool):
         self._check(self.lib.p3r_set_specialization(self.h, int(enable)))

@@ -28,4 +28,16 @@ for log_blowup in (1, 2, 3):
                           "lde_algorithmic_GBps": round(gbs, 1), "lde_hbm_frac": round(gbs / peak, 4),
                           "merkle_ms": round(r["merkle_ms"], 3), "merkle_perms_per_ns": round(perms / (r["merkle_ms"] * 1e6), 3)}),
               flush=True)
+    if log_blowup == 2:
+        # FRI commit rounds: fold 2^(k + log_blowup) extension elements by arity 2/4/8 and commit the folded rows
+        for log_n in (18, 20) if quick else (18, 20, 22):
+            for log_arity in (1, 2, 3):
+                log_len = log_n + log_blowup
+                r = ctx.bench_fri_round(log_len, log_arity, iters=3)
+                L = 1 << log_len
+                fold_bytes = 16.0 * (L + (L >> log_arity))
+                print(json.dumps({"field": field, "fri_log_len": log_len, "arity": 1 << log_arity, "fold_ms": round(r["fold_ms"], 4),
+                                  "fold_GBps": round(fold_bytes / 1e9 / (r["fold_ms"] / 1e3), 1),
+                                  "fold_hbm_frac": round(fold_bytes / 1e9 / (r["fold_ms"] / 1e3) / peak, 4),
+                                  "commit_ms": round(r["commit_ms"], 3)}), flush=True)
     ctx.close()
