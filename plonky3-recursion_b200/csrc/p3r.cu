@@ -117,7 +117,6 @@ struct p3r_ctx {
 static void set_err(p3r_ctx* ctx, const std::string& s) {
     if (ctx) ctx->err = s;
 }
-static void set_err(const p3r_ctx* ctx, const std::string& s) { set_err(const_cast<p3r_ctx*>(ctx), s); }
 
 #define LAUNCH_CHECK_C(cls)                                              \
     do {                                                                 \
@@ -428,7 +427,6 @@ static std::vector<PassPlan> plan_passes(uint32_t log_n) {
         return p;
     }
     // contiguous first chunk, then strided chunks of <= 8 stages (tile rows <= 256, >= 32 consecutive elements per row)
-    uint32_t rest = log_n;
     uint32_t n_strided = (log_n - TILE_LOG + 7) / 8;
     uint32_t strided_total = log_n - std::min(log_n, TILE_LOG);
     // balance: last chunk at least 5 stages so bit-reversed stores form >=128-byte runs
@@ -453,7 +451,6 @@ static std::vector<PassPlan> plan_passes(uint32_t log_n) {
         p.push_back({s0, r, log_cw});
         s0 += r;
     }
-    (void)rest;
     return p;
 }
 struct LdeJob {
