@@ -299,9 +299,9 @@ int p3r_bench_fri_round(p3r_ctx* ctx, uint32_t log_len, uint32_t log_arity, uint
 int p3r_last_phase_times(p3r_ctx* ctx, const char** names_out, float* ms_out, uint32_t cap, uint32_t* n_out);
 /* Alternative code paths, for parity tests that compare two independent implementations of the same step. `enable` is a
  * bit set (default 1):
- *   bit 0  set   : build-time specialised (straight-line, constraint-group) quotient kernels for the constraint programs of
- *                  the recursion layer's ALU / Poseidon2 / Const / Public / Recompose tables (scripts/gen_specialized.py) when
- *                  the program hash matches; clear: always the bytecode interpreter.
+ *   bit 0  set   : build-time specialised (straight-line) quotient kernels (constraint groups) and LogUp-trace kernels (lookup
+ *                  groups) for the programs of the recursion layer's ALU / Poseidon2 / Const / Public / Recompose tables
+ *                  (scripts/gen_specialized.py) when the program hash matches; clear: always the bytecode interpreter.
  *   bit 1  set   : DISABLE the whole-column LDE kernels (k_ntt_col / k_ntt_top): every LDE goes through the multi-pass tile
  *                  kernel k_ntt_pass.
  *   bit 2  set   : DISABLE the device-side transcript of the FRI commit rounds in p3r_prove* (one host round trip per round). */

@@ -219,6 +219,7 @@ struct InstDev {
     uint32_t* sel = nullptr;
     uint32_t* inv_van = nullptr;
     SpecQuotientKernel spec = nullptr;  // build-time specialised quotient kernel whose program hash matches, if any
+    SpecLogupKernel spec_logup = nullptr;  // same for the LogUp trace rows
     uint32_t aux_w() const { return lookups.empty() ? 0 : (uint32_t)lookups.size() + 1; }
 };
 struct p3r_prep {
@@ -1036,6 +1037,26 @@ static int prep_commit_impl(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_de
         s.inter.assign(d.interactions, d.interactions + d.n_interactions);
         s.d_lookups = (p3r_lookup*)up(d.lookups, (size_t)d.n_lookups * sizeof(p3r_lookup));
         s.d_inter = (p3r_interaction*)up(d.interactions, (size_t)d.n_interactions * sizeof(p3r_interaction));
+        if (d.n_lookups && d.lookup_inputs.n_insns) {
+            // FNV-1a over the lookup-input program and the lookup / interaction structure (scripts/gen_specialized.py logup_hash)
+            uint64_t h = 0xCBF29CE484222325ull;
+            auto mix = [&](uint32_t w) {
+                for (int k = 0; k < 4; k++) {
+                    h ^= (w >> (8 * k)) & 0xFFu;
+                    h *= 0x100000001B3ull;
+                }
+            };
+            const uint32_t* iw = reinterpret_cast<const uint32_t*>(d.lookup_inputs.insns);
+            for (size_t k = 0; k < (size_t)d.lookup_inputs.n_insns * 4; k++) mix(iw[k]);
+            for (uint32_t k = 0; k < d.n_lookups; k++) mix(d.lookups[k].first_interaction), mix(d.lookups[k].n_interactions);
+            for (uint32_t k = 0; k < d.n_interactions; k++)
+                mix(d.interactions[k].mult_out), mix(d.interactions[k].elem_out_first), mix(d.interactions[k].n_elems);
+            size_t n_spec = 0;
+            const SpecLogupEntry* reg = p3r_spec_logup_registry(&n_spec);
+            for (size_t q = 0; q < n_spec; q++)
+                if (reg[q].hash == h && reg[q].field_id == ctx->field_id && reg[q].n_insns == d.lookup_inputs.n_insns)
+                    s.spec_logup = reg[q].fn;
+        }
         if (!s.cons || !s.cons_econst || !s.lk || !s.d_lookups || !s.d_inter) {
             set_err(ctx, "device allocation failed");
             return fail(P3R_ERR_OOM);
@@ -1245,6 +1266,7 @@ static int commit_perm_impl(p3r_session* s, const uint32_t alpha[4], const uint3
     std::vector<MatRef> mats;
     std::vector<LdeJob> jobs;
     std::vector<LogupArgs> logup_tables;
+    std::vector<SpecLogupKernel> logup_spec;   // generated kernel per table, or nullptr (interpreter)
     uint64_t logup_bytes = 0;
     uint32_t lmax = 0;
     for (size_t i = 0; i < n_inst; i++) {
@@ -1275,6 +1297,7 @@ static int commit_perm_impl(p3r_session* s, const uint32_t alpha[4], const uint3
         la.terminal = s->d_terminals + i;
         if (!la.chunk_sum) return P3R_ERR_OOM;
         logup_tables.push_back(la);
+        logup_spec.push_back(ctx->use_spec ? d.spec_logup : nullptr);
         logup_bytes += (uint64_t)n * 4 * (d.main_w + d.prep_w + pw);
         uint32_t* coef = arena_alloc<uint32_t>(ctx, n * pw);
         uint32_t* tmp = d.log_h > TILE_LOG ? arena_alloc<uint32_t>(ctx, (n << lb) * pw) : nullptr;
@@ -1284,22 +1307,42 @@ static int commit_perm_impl(p3r_session* s, const uint32_t alpha[4], const uint3
         lmax = std::max(lmax, d.log_h + lb);
     }
     {
-        // every table in one launch each: rows (largest first), chunk sums, scan
-        std::stable_sort(logup_tables.begin(), logup_tables.end(), [](const LogupArgs& x, const LogupArgs& y) { return x.log_n > y.log_n; });
+        // rows: tables with a generated kernel get their own launch (32 rows x lookup groups per CTA), the others share one
+        // interpreter launch; chunk sums and scan: one launch each for all tables
+        std::vector<size_t> order(logup_tables.size());
+        for (size_t i = 0; i < order.size(); i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return logup_tables[x].log_n > logup_tables[y].log_n; });
+        std::vector<LogupArgs> sorted_tabs, generic;
+        std::vector<SpecLogupKernel> sorted_spec;
         uint32_t cta = 0, scan_cta = 0;
-        for (auto& la : logup_tables) {
+        for (size_t i : order) {
+            LogupArgs la = logup_tables[i];
             const uint32_t n = 1u << la.log_n;
-            la.cta_begin = cta;
             la.scan_cta_begin = scan_cta;
-            cta += (n + 127) / 128;
             scan_cta += (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+            if (!logup_spec[i]) {
+                la.cta_begin = cta;
+                cta += (n + 127) / 128;
+                generic.push_back(la);
+            }
+            sorted_tabs.push_back(la);
+            sorted_spec.push_back(logup_spec[i]);
         }
-        const LogupArgs* d_tabs = upload_vec(ctx, logup_tables);
+        const LogupArgs* d_tabs = upload_vec(ctx, sorted_tabs);
         if (!d_tabs) return P3R_ERR_OOM;
         KT kt(ctx, KC_LOGUP, logup_bytes);
-        const uint32_t nt = (uint32_t)logup_tables.size();
-        k_logup_rows<F><<<cta, 128, 0, ctx->stream>>>(d_tabs, nt);
-        LAUNCH_CHECK_C(KC_LOGUP);
+        const uint32_t nt = (uint32_t)sorted_tabs.size();
+        for (size_t i = 0; i < sorted_tabs.size(); i++)
+            if (sorted_spec[i]) {
+                p3r_spec_logup_launch(sorted_spec[i], sorted_tabs[i], ((1u << sorted_tabs[i].log_n) + 31) / 32, ctx->stream);
+                LAUNCH_CHECK_C(KC_LOGUP);
+            }
+        if (!generic.empty()) {
+            const LogupArgs* d_gen = upload_vec(ctx, generic);
+            if (!d_gen) return P3R_ERR_OOM;
+            k_logup_rows<F><<<cta, 128, 0, ctx->stream>>>(d_gen, (uint32_t)generic.size());
+            LAUNCH_CHECK_C(KC_LOGUP);
+        }
         k_logup_chunk_sums<F><<<scan_cta, 256, 0, ctx->stream>>>(d_tabs, nt);
         LAUNCH_CHECK_C(KC_LOGUP);
         k_logup_scan_apply<F><<<scan_cta, 256, 0, ctx->stream>>>(d_tabs, nt);

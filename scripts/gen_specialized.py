@@ -106,6 +106,8 @@ def to_ssa(ins):
             src = ("val", B(x))
         elif op == sym.OP_ASSERT_E:
             src = ("val", E(x))
+        elif op == sym.OP_OUT_B:
+            src = ("val", B(x))
         else:
             raise ValueError(op)
         vid = len(nodes)
@@ -153,8 +155,13 @@ def split_groups(nodes, n_groups):
     return [sorted(closure(g, set())) for g in groups]
 
 
-def emit_node(o, nodes, v, row):
+def emit_node(o, nodes, v, row, sel=None):
     op, d, src = nodes[v]
+    if op == sym.OP_OUT_B:
+        return
+    if op == sym.OP_B_SEL and sel is not None:
+        o.append(f"        const uint32_t b{v} = {sel[src[1]]};")
+        return
     bn = lambda k: f"b{k}"
     en = lambda k: f"e{k}"
     if op == sym.OP_B_MAIN:
@@ -250,8 +257,126 @@ def emit_kernel(name: str, fname: str, ins: np.ndarray, nb: int, ne: int) -> str
     return "\n".join(o)
 
 
+LOGUP_GROUPS = 4   # warps per CTA of the generated LogUp kernels; each handles a contiguous group of lookups for 32 rows
+
+
+def logup_hash(ins, lookups, interactions) -> int:
+    """FNV-1a over the lookup-input program and the lookup / interaction structure (the library recomputes it at prep time)."""
+    words = list(ins.reshape(-1).tolist())
+    for _, first, n in lookups:
+        words += [first, n]
+    for mult_out, elem_first, n_elems in interactions:
+        words += [mult_out, elem_first, n_elems]
+    return fnv1a(np.array(words, dtype=np.uint64))
+
+
+def emit_logup_kernel(name: str, fname: str, ins: np.ndarray, lookups, interactions) -> str:
+    """LogUp permutation-trace rows (k_logup_rows) as straight-line code. A CTA = 32 trace rows x LOGUP_GROUPS warps; warp g
+    evaluates the tuple elements its lookups need (dead-code-eliminated program), the denominators
+    prefix + sum_k beta^k * field_k, ONE extension inversion per lookup (its interactions share it), the fraction column, and
+    a partial row sum; the partial sums meet in shared memory."""
+    nodes = to_ssa(ins)
+    out_node = {}
+    for v, (op, d, src) in enumerate(nodes):
+        if op == sym.OP_OUT_B:
+            out_node[d] = src[1]
+    n_lk = len(lookups)
+    G = min(LOGUP_GROUPS, max(1, n_lk))
+    # contiguous groups of lookups, balanced by interaction count
+    total = sum(n for _, _, n in lookups)
+    groups, cur, acc = [], [], 0
+    for c, (_, first, n) in enumerate(lookups):
+        cur.append(c)
+        acc += n
+        if acc >= total * (len(groups) + 1) / G and len(groups) < G - 1:
+            groups.append(cur)
+            cur = []
+    groups.append(cur)
+    while len(groups) < G:
+        groups.append([])
+
+    def closure(roots):
+        seen, stack = set(), list(roots)
+        while stack:
+            v = stack.pop()
+            if v in seen:
+                continue
+            seen.add(v)
+            src = nodes[v][2]
+            if src[0] == "val":
+                stack.extend(src[1:])
+        return sorted(seen)
+
+    o = []
+    o.append(f"__global__ void __launch_bounds__({32 * LOGUP_GROUPS}, 4) {name}(LogupArgs a) {{")
+    o.append(f"    using F = {fname};")
+    o.append("    const uint32_t n = 1u << a.log_n;")
+    o.append("    const uint32_t g = threadIdx.x >> 5, lane = threadIdx.x & 31u;")
+    o.append("    const uint32_t r_raw = blockIdx.x * 32 + lane;")
+    o.append("    const uint32_t r0 = r_raw < n ? r_raw : n - 1, r1 = (r0 + 1) & (n - 1);")
+    o.append("    const bool live = r_raw < n;")
+    o.append("    const size_t cs = n;")
+    o.append("    const uint32_t wnr = a.wnr;")
+    o.append("    Ext4 tot = ext_zero();")
+    o.append("    Ext4 bp[8];")
+    o.append("    for (int k = 0; k < 8; k++) bp[k] = a.beta_pows[k];")
+    row = ["r0", "r1"]
+    sel = ["(r0 == 0 ? F::R : 0u)", "(r0 == n - 1 ? F::R : 0u)", "(r0 != n - 1 ? F::R : 0u)"]
+    o.append("    switch (g) {")
+    for gi, lks in enumerate(groups):
+        o.append(f"    case {gi}: {{")
+        roots = []
+        for c in lks:
+            _, first, nint = lookups[c]
+            for j in range(first, first + nint):
+                mult_out, elem_first, n_elems = interactions[j]
+                roots.append(out_node[mult_out])
+                roots += [out_node[elem_first + k] for k in range(n_elems)]
+        for v in closure(roots):
+            emit_node(o, nodes, v, row, sel)
+        for c in lks:
+            _, first, nint = lookups[c]
+            o.append(f"        {{   // lookup {c}")
+            o.append(f"            const Ext4 prefix = a.chal[{2 * c}];")
+            for q, j in enumerate(range(first, first + nint)):
+                mult_out, elem_first, n_elems = interactions[j]
+                o.append(f"            Ext4 den{q} = prefix;")
+                for k in range(n_elems):
+                    o.append(f"            den{q} = eadd<F>(den{q}, emul_base<F>(bp[{k}], b{out_node[elem_first + k]}));")
+            # shared inversion: prefix products
+            o.append("            Ext4 acc = den0;")
+            for q in range(1, nint):
+                o.append(f"            const Ext4 pre{q} = acc;")
+                o.append(f"            acc = emul<F>(acc, den{q}, wnr);")
+            o.append("            Ext4 inv = einv<F>(acc, wnr);")
+            o.append("            Ext4 frac = ext_zero();")
+            for q in range(nint - 1, 0, -1):
+                mult_out = interactions[first + q][0]
+                o.append(f"            frac = eadd<F>(frac, emul_base<F>(emul<F>(inv, pre{q}, wnr), b{out_node[mult_out]}));")
+                o.append(f"            inv = emul<F>(inv, den{q}, wnr);")
+            o.append(f"            frac = eadd<F>(frac, emul_base<F>(inv, b{out_node[interactions[first][0]]}));")
+            o.append("            if (live) {")
+            o.append(f"                for (int k = 0; k < 4; k++) a.perm[(size_t)({4 * (c + 1)} + k) * n + r0] = frac.c[k];")
+            o.append("            }")
+            o.append("            tot = eadd<F>(tot, frac);")
+            o.append("        }")
+        o.append("    } break;")
+    o.append("    default: break;")
+    o.append("    }")
+    o.append(f"    __shared__ Ext4 part[{LOGUP_GROUPS}][32];")
+    o.append("    part[g][lane] = tot;")
+    o.append("    __syncthreads();")
+    o.append("    if (g == 0 && live) {")
+    o.append(f"        for (int k = 1; k < {LOGUP_GROUPS}; k++) tot = eadd<F>(tot, part[k][lane]);")
+    o.append("        a.rowsum[r0] = tot;")
+    o.append("    }")
+    o.append("}")
+    print(name, "lookups per group:", [len(x) for x in groups], "of", n_lk)
+    return "\n".join(o)
+
+
 def main(out_path):
-    kernels, registry = [], []
+    kernels, registry, lk_registry = [], [], []
     for fname, cname in (("koala-bear", "KoalaBear"), ("baby-bear", "BabyBear")):
         F = fm.get_field(fname)
         prm = p2mod.Poseidon2Params(F.field_id)
@@ -270,12 +395,21 @@ def main(out_path):
             kname = f"k_quotient_spec_{tag}_{cname}"
             kernels.append(emit_kernel(kname, cname, ins, inst.constraints.n_base_slots, inst.constraints.n_ext_slots))
             registry.append((h, F.field_id, kname, ins.shape[0]))
+            if inst.lookup_inputs is not None and inst.lookups:
+                lins = monty_insns(F, inst.lookup_inputs)
+                lh = logup_hash(lins, inst.lookups, inst.interactions)
+                lname = f"k_logup_spec_{tag}_{cname}"
+                kernels.append(emit_logup_kernel(lname, cname, lins, inst.lookups, inst.interactions))
+                lk_registry.append((lh, F.field_id, lname, lins.shape[0]))
     with open(out_path, "w") as f:
         f.write("// GENERATED by scripts/gen_specialized.py — do not edit. Straight-line quotient kernels for fixed constraint programs.\n")
         f.write("#pragma once\n#include \"spec.h\"\nnamespace p3r {\n\n")
         f.write("\n\n".join(kernels))
         f.write("\n\nconstexpr unsigned SPEC_ROWS_PER_CTA = 32, SPEC_THREADS = %d;\nstatic const SpecEntry SPEC_QUOTIENT[] = {\n" % (32 * N_GROUPS))
         for h, fid, kname, n in registry:
+            f.write(f"    {{0x{h:016x}ull, {fid}, {n}u, {kname}}},\n")
+        f.write("};\n\nconstexpr unsigned SPEC_LOGUP_THREADS = %d;\nstatic const SpecLogupEntry SPEC_LOGUP[] = {\n" % (32 * LOGUP_GROUPS))
+        for h, fid, kname, n in lk_registry:
             f.write(f"    {{0x{h:016x}ull, {fid}, {n}u, {kname}}},\n")
         f.write("};\n\n}  // namespace p3r\n")
     print("wrote", out_path, [(hex(h), fid, k, n) for h, fid, k, n in registry])
