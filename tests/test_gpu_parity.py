@@ -68,6 +68,34 @@ def test_mmcs_commit_mixed_heights(pair, shapes):
     assert np.array_equal(ctx.mmcs_commit(mats), orc.mmcs_commit(mats))
 
 
+@pytest.mark.parametrize("shapes", [[(15, 3), (14, 9), (13, 1), (9, 20), (5, 2)], [(16, 1), (15, 17), (12, 8), (11, 8)],
+                                    [(14, 2), (14, 7), (8, 40)]])
+def test_mmcs_commit_tall_trees_cross_every_kernel_boundary(pair, shapes):
+    """Trees tall enough to use all three Merkle kernels (one-thread-per-node levels above 2^13 nodes, fused k_merkle_stage
+    launches below, several stage launches per tree) with rows injected at levels handled by each of them."""
+    ctx, orc = pair
+    rng = np.random.default_rng(77)
+    mats = [ctx.field.rand(rng, (1 << lh, w)) for lh, w in shapes]
+    assert np.array_equal(ctx.mmcs_commit(mats), orc.mmcs_commit(mats))
+
+
+@pytest.mark.parametrize("sizes", [dict(n_const=1, n_public=1, n_alu=1, n_perms=1, n_recompose=1),
+                                   dict(n_const=9, n_public=30, n_alu=77, n_perms=0, n_recompose=0),
+                                   dict(n_const=40, n_public=3, n_alu=5, n_perms=33, n_recompose=0)])
+def test_edge_layers_bit_identical(pair, sizes):
+    """Degenerate layers: tables that are almost entirely padding rows (one real operation each), layers without the
+    non-primitive tables, and a layer whose widest table is not the tallest."""
+    wl = importlib.import_module("plonky3-recursion_b200.workload")
+    ctx, orc = pair
+    L = wl.synthetic_layer(ctx.field, 5, min_height=16, **sizes)
+    pd = lib.ProverData.from_airs_and_degrees(ctx, L.insts, L.preps)
+    proof = lib.BatchStarkProver(ctx).prove_all_tables(L.traces, pd, L.pubs)
+    want = orc.prove(L.insts, L.preps, L.traces, L.pubs)
+    assert proof.size == want.size and np.array_equal(proof, want)
+    orc.verify(L.insts, pd.preprocessed_commitment, L.pubs, proof)
+    pd.close()
+
+
 def test_grind_smallest_witness(pair):
     ctx, orc = pair
     rng = np.random.default_rng(11)
