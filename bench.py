@@ -31,7 +31,7 @@ import numpy as np  # noqa: E402
 FULL = dict(n_const=1500, n_public=43000, n_alu=60000, n_perms=12000, n_recompose=4000)
 # Thread instructions one Poseidon2 permutation costs in k_hash_rows / k_compress (ncu: smsp__inst_executed.sum * 32 /
 # permutations of a launch, profiles/r1_ncu_summary.md): the unit conversion of the INT32-pipe roofline below.
-INSTR_PER_PERM = {"koala-bear": 5300.0, "baby-bear": 6500.0}
+INSTR_PER_PERM = {"koala-bear": 5370.0, "baby-bear": 5600.0}   # ncu (koala) / SASS count (baby)
 N_SMS, LANES_PER_SM = 148, 128
 METRIC = "prove_next_layer throughput (layer proofs/s, whole job; ms_per_layer = latency of one proof alone)"
 
