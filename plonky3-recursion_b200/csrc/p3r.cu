@@ -94,6 +94,11 @@ struct p3r_ctx {
     Poseidon2Consts p2{};
     uint32_t w_m = 0, gen_m = 0, inv2_m = 0;  // Montgomery
     cudaStream_t stream = nullptr;
+    // Side streams for independent kernels of one phase (the per-table quotient / LogUp kernels are latency-bound and touch
+    // disjoint data): fork_streams() makes them wait for everything queued on `stream`, join_streams() the reverse.
+    static constexpr int N_AUX = 4;
+    cudaStream_t aux[N_AUX] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t aux_ev[N_AUX + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     uint32_t* tws = nullptr;  // per-stage compact twiddle tables, 2^logT - 1 entries
     uint32_t* tw = nullptr;   // = tws + 2^(logT-1) - 1: half table of omega_T
     void (*host_permute)(uint32_t*, const Poseidon2Consts&) = nullptr;  // transcript permutation (AVX2 or scalar), set at creation
@@ -188,6 +193,25 @@ template <class T>
 static T* upload_vec(p3r_ctx* ctx, const std::vector<T>& v) {
     if (v.empty()) return reinterpret_cast<T*>(ctx->dstage);
     return reinterpret_cast<T*>(upload_small(ctx, v.data(), v.size() * sizeof(T)));
+}
+
+static int fork_streams(p3r_ctx* ctx) {
+    for (int i = 0; i < p3r_ctx::N_AUX; i++)
+        if (!ctx->aux[i]) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&ctx->aux_ev[i], cudaEventDisableTiming));
+        }
+    if (!ctx->aux_ev[p3r_ctx::N_AUX]) CUDA_TRY(cudaEventCreateWithFlags(&ctx->aux_ev[p3r_ctx::N_AUX], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(ctx->aux_ev[p3r_ctx::N_AUX], ctx->stream));
+    for (int i = 0; i < p3r_ctx::N_AUX; i++) CUDA_TRY(cudaStreamWaitEvent(ctx->aux[i], ctx->aux_ev[p3r_ctx::N_AUX], 0));
+    return P3R_OK;
+}
+static int join_streams(p3r_ctx* ctx) {
+    for (int i = 0; i < p3r_ctx::N_AUX; i++) {
+        CUDA_TRY(cudaEventRecord(ctx->aux_ev[i], ctx->aux[i]));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->aux_ev[i], 0));
+    }
+    return P3R_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1330,19 +1354,22 @@ static int commit_perm_impl(p3r_session* s, const uint32_t alpha[4], const uint3
         }
         const LogupArgs* d_tabs = upload_vec(ctx, sorted_tabs);
         if (!d_tabs) return P3R_ERR_OOM;
+        const LogupArgs* d_gen = generic.empty() ? nullptr : upload_vec(ctx, generic);
+        if (!generic.empty() && !d_gen) return P3R_ERR_OOM;
         KT kt(ctx, KC_LOGUP, logup_bytes);
         const uint32_t nt = (uint32_t)sorted_tabs.size();
+        TRY(fork_streams(ctx));   // independent per-table kernels on side streams
         for (size_t i = 0; i < sorted_tabs.size(); i++)
             if (sorted_spec[i]) {
-                p3r_spec_logup_launch(sorted_spec[i], sorted_tabs[i], ((1u << sorted_tabs[i].log_n) + 31) / 32, ctx->stream);
+                p3r_spec_logup_launch(sorted_spec[i], sorted_tabs[i], ((1u << sorted_tabs[i].log_n) + 31) / 32,
+                                      ctx->aux[i % p3r_ctx::N_AUX]);
                 LAUNCH_CHECK_C(KC_LOGUP);
             }
-        if (!generic.empty()) {
-            const LogupArgs* d_gen = upload_vec(ctx, generic);
-            if (!d_gen) return P3R_ERR_OOM;
-            k_logup_rows<F><<<cta, 128, 0, ctx->stream>>>(d_gen, (uint32_t)generic.size());
+        if (d_gen) {
+            k_logup_rows<F><<<cta, 128, 0, ctx->aux[p3r_ctx::N_AUX - 1]>>>(d_gen, (uint32_t)generic.size());
             LAUNCH_CHECK_C(KC_LOGUP);
         }
+        TRY(join_streams(ctx));
         k_logup_chunk_sums<F><<<scan_cta, 256, 0, ctx->stream>>>(d_tabs, nt);
         LAUNCH_CHECK_C(KC_LOGUP);
         k_logup_scan_apply<F><<<scan_cta, 256, 0, ctx->stream>>>(d_tabs, nt);
@@ -1396,6 +1423,9 @@ static int commit_quotient_impl(p3r_session* s, const uint32_t alpha[4], uint32_
         k_ext_powers_desc<F><<<dim3((max_n + 127) / 128, cnt), 128, 0, ctx->stream>>>(pj, al, wnr);
         LAUNCH_CHECK();
     }
+    {
+    KT kt_quot(ctx, KC_QUOTIENT, 0);
+    TRY(fork_streams(ctx));
     for (size_t i = 0; i < pp->inst.size(); i++) {
         const InstDev& d = pp->inst[i];
         size_t n = (size_t)1 << d.log_h;
@@ -1424,11 +1454,13 @@ static int commit_quotient_impl(p3r_session* s, const uint32_t alpha[4], uint32_
         qa.wnr = wnr;
         uint32_t NQ = (uint32_t)(n << d.log_qc);
         {
-            KT kt(ctx, KC_QUOTIENT, (uint64_t)NQ * (8ull * (d.main_w + d.prep_w + d.aux_w() * 4) + 16));
+            // the tables' quotient kernels are independent and latency-bound: one side stream each (round robin)
+            cudaStream_t qs = ctx->aux[i % p3r_ctx::N_AUX];
+            ctx->kstats.bytes[KC_QUOTIENT] += (uint64_t)NQ * (8ull * (d.main_w + d.prep_w + d.aux_w() * 4) + 16);
             if (d.spec && ctx->use_spec)
-                p3r_spec_launch(d.spec, qa, (NQ + 31) / 32, p3r_spec_threads(), ctx->stream);  // 32 rows x 4 constraint groups per CTA
+                p3r_spec_launch(d.spec, qa, (NQ + 31) / 32, p3r_spec_threads(), qs);  // 32 rows x constraint groups per CTA
             else
-                k_quotient<F><<<(NQ + 127) / 128, 128, 0, ctx->stream>>>(qa);
+                k_quotient<F><<<(NQ + 127) / 128, 128, 0, qs>>>(qa);
             LAUNCH_CHECK_C(KC_QUOTIENT);
         }
         // chunk c lives on the coset GENERATOR * w_NQ^c * H_n: LDE without the GENERATOR factor, rotated by -c*(N/NQ)
@@ -1444,6 +1476,8 @@ static int commit_quotient_impl(p3r_session* s, const uint32_t alpha[4], uint32_
             mats.push_back({dst, logN, 4});
         }
         lmax = std::max(lmax, logN);
+    }
+    TRY(join_streams(ctx));
     }
     TRY(coset_lde_batch<F>(ctx, jobs, lb));
     uint32_t* dg = arena_alloc<uint32_t>(ctx, tree_digest_words(lmax));
@@ -2347,6 +2381,11 @@ void p3r_ctx_destroy(p3r_ctx* ctx) {
     if (ctx->d_p2) cudaFree(ctx->d_p2);
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->dstage) cudaFree(ctx->dstage);
+    for (int i = 0; i < p3r_ctx::N_AUX; i++) {
+        if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
+        if (ctx->aux_ev[i]) cudaEventDestroy(ctx->aux_ev[i]);
+    }
+    if (ctx->aux_ev[p3r_ctx::N_AUX]) cudaEventDestroy(ctx->aux_ev[p3r_ctx::N_AUX]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
