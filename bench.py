@@ -152,9 +152,9 @@ def run_ours(args):
     pd = lib.ProverData.from_airs_and_degrees(ctx, L.insts, L.preps)
     prover = lib.BatchStarkProver(ctx, pinned_output=True)
     tb_res = lib.TraceBatch(ctx, L.traces, L.pubs).upload(pd)       # device-resident inputs -> `value`
-    # pinned host inputs -> `e2e`: row-major table matrices as the reference's trace builders leave them; the Poseidon2 table
-    # goes in as its operation list and is generated on the device (p3r_prove_ex)
-    tb_pin = lib.TraceBatch(ctx, L.traces, L.pubs, pinned=True, p2_ops=L.p2_ops)
+    # pinned host inputs -> `e2e`: row-major matrices for Const / Public / Recompose as the reference's trace builders leave
+    # them; the Poseidon2 and ALU tables go in as operation lists and are expanded on the device (p3r_prove_ops)
+    tb_pin = lib.TraceBatch(ctx, L.traces, L.pubs, pinned=True, p2_ops=L.p2_ops, alu_ops=L.alu_ops)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
 
     def barrier():
@@ -209,7 +209,7 @@ def run_ours(args):
         c2 = lib.Context(args.field, lib.DEFAULT_FRI, device=local)
         pd2 = lib.ProverData.from_airs_and_degrees(c2, L.insts, L.preps)
         lanes.append((c2, pd2, lib.BatchStarkProver(c2, pinned_output=True), lib.TraceBatch(c2, L.traces, L.pubs).upload(pd2),
-                      lib.TraceBatch(c2, L.traces, L.pubs, pinned=True, p2_ops=L.p2_ops)))
+                      lib.TraceBatch(c2, L.traces, L.pubs, pinned=True, p2_ops=L.p2_ops, alu_ops=L.alu_ops)))
 
     def batch_steps(e2e, steps):
         """`steps` batches of len(lanes) concurrent proofs. Per batch: L2 flush (untimed), a start event on every stream, the

@@ -184,6 +184,25 @@ typedef struct {
     const uint32_t* mmcs_index_sum;    /* n_ops Montgomery words (value where the accumulator restarts) */
 } p3r_poseidon2_ops;
 
+/* Operation list of the ALU table: the schedule (static per circuit shape: AluAir::compute_schedule,
+ * circuit-prover/src/air/alu_air.rs:349-463) and the operand values the runner produced. The library scatters them into
+ * the main trace on the device (replaces AluAir::trace_to_matrix, alu_air.rs:497-608), including the packed-Horner
+ * intermediates, (a_t, c_t) operands and b^2 of lane 0. Only D = 4 with horner k_max = 4 (the recursion-layer packing). */
+typedef struct {
+    uint32_t lanes, d, k_max;
+    uint32_t n_slots;              /* schedule slots in use (slot = row * lanes + lane); the rest of the table is padding */
+    const uint32_t* slot_kind;     /* per slot: 0 = separator / empty, 1 = one operation, k >= 2 = packed Horner of k operations */
+    const uint32_t* slot_first;    /* per slot: index of its (first) operation */
+    uint32_t n_ops;
+    const uint32_t* values;        /* n_ops * 4 * d Montgomery words: a, b, c, out */
+} p3r_alu_ops;
+
+/* Where the main trace of one instance comes from: the matrix passed alongside (both pointers NULL) or an operation list. */
+typedef struct {
+    const p3r_poseidon2_ops* poseidon2;
+    const p3r_alu_ops* alu;
+} p3r_table_ops;
+
 /* ---------------------------------------------------------------------------------------------- */
 
 /* Library/ABI version and a description of the build (arch, fields). */
@@ -263,6 +282,12 @@ int p3r_prove_ex(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* trace
                  const uint32_t* const* public_values, uint32_t* proof_out, size_t cap_words, size_t* n_words);
 int p3r_traces_upload_ex(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces,
                          const p3r_poseidon2_ops* const* p2_ops, p3r_traces** out);
+/* General form: table_ops (n_instances entries, or NULL) says per instance whether the trace is the matrix or an operation
+ * list expanded on the device (Poseidon2 and ALU tables). */
+int p3r_prove_ops(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, const p3r_table_ops* table_ops,
+                  const uint32_t* const* public_values, uint32_t* proof_out, size_t cap_words, size_t* n_words);
+int p3r_traces_upload_ops(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, const p3r_table_ops* table_ops,
+                          p3r_traces** out);
 /* Debug/parity helper: download the (row-major) main trace of instance `inst` from device-resident traces. */
 int p3r_traces_download(p3r_ctx* ctx, const p3r_prep* prep, const p3r_traces* traces, uint32_t inst, uint32_t* out);
 

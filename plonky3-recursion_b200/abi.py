@@ -47,6 +47,15 @@ class Poseidon2OpsC(C.Structure):
     _fields_ = [("n_ops", u32), ("input_values", u32p), ("mmcs_bit", C.POINTER(C.c_uint8)), ("mmcs_index_sum", u32p)]
 
 
+class AluOpsC(C.Structure):
+    _fields_ = [("lanes", u32), ("d", u32), ("k_max", u32), ("n_slots", u32), ("slot_kind", u32p), ("slot_first", u32p),
+                ("n_ops", u32), ("values", u32p)]
+
+
+class TableOpsC(C.Structure):
+    _fields_ = [("poseidon2", C.POINTER(Poseidon2OpsC)), ("alu", C.POINTER(AluOpsC))]
+
+
 class InteractionC(C.Structure):
     _fields_ = [("mult_out", u32), ("elem_out_first", u32), ("n_elems", u32)]
 
@@ -154,6 +163,31 @@ class Marshal:
             st = Poseidon2OpsC(ops.n, as_u32p(iv), bit.ctypes.data_as(C.POINTER(C.c_uint8)), as_u32p(sm))
             self.keep(st)
             arr[i] = C.pointer(st)
+        return self.keep(arr)
+
+    def table_ops(self, p2_by_instance: dict, alu_by_instance: dict, n_inst: int, alloc=None):
+        """{instance: Poseidon2Ops}, {instance: airs.alu.AluTableOps} -> array of n_inst p3r_table_ops (both NULL = matrix).
+        alloc(shape, dtype) -> array places the operand arrays (pinned host memory for the e2e path); default numpy."""
+        def put(a, dtype=np.uint32):
+            a = np.ascontiguousarray(a, dtype=dtype)
+            if alloc is None:
+                return self.keep(a)
+            buf = alloc(a.shape, dtype)
+            buf[...] = a
+            return self.keep(buf)
+
+        arr = (TableOpsC * n_inst)()
+        for i, ops in (p2_by_instance or {}).items():
+            iv = put(self.field.to_monty(ops.input_values.reshape(-1)))
+            bit = put(ops.mmcs_bit, np.uint8)
+            sm = put(self.field.to_monty(ops.mmcs_index_sum))
+            st = self.keep(Poseidon2OpsC(ops.n, as_u32p(iv), bit.ctypes.data_as(C.POINTER(C.c_uint8)), as_u32p(sm)))
+            arr[i].poseidon2 = C.pointer(st)
+        for i, t in (alu_by_instance or {}).items():
+            kind, first = put(t.slot_kind), put(t.slot_first)
+            vals = put(self.field.to_monty(t.values.reshape(-1)))
+            st = self.keep(AluOpsC(t.lanes, t.d, t.k_max, kind.size, as_u32p(kind), as_u32p(first), t.values.shape[0], as_u32p(vals)))
+            arr[i].alu = C.pointer(st)
         return self.keep(arr)
 
     def public_values(self, pubs) -> C.Array:

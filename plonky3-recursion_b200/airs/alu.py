@@ -239,6 +239,28 @@ def _pad_height(rows: int, min_height: int) -> int:
     return max(min_height, 1 << max(rows - 1, 0).bit_length(), 1)
 
 
+class AluTableOps:
+    """What the device table fill needs (p3r_alu_ops): the schedule slots (static per circuit shape) and the operand values."""
+
+    def __init__(self, ops: AluOps, d: int, lanes: int, k_max: int):
+        sched = compute_schedule(ops.prep13, lanes, k_max)
+        entries = sched if sched is not None else [("op", i) for i in range(ops.values.shape[0])]
+        kind = np.zeros(len(entries), dtype=np.uint32)
+        first = np.zeros(len(entries), dtype=np.uint32)
+        for pos, ent in enumerate(entries):
+            if ent[0] == "op":
+                kind[pos], first[pos] = 1, ent[1]
+            elif ent[0] == "packed":
+                kind[pos], first[pos] = ent[2], ent[1]
+        self.d, self.lanes, self.k_max = d, lanes, k_max
+        self.slot_kind, self.slot_first = kind, first
+        self.values = np.ascontiguousarray(ops.values, dtype=np.uint32)   # (n_ops, 4, d) canonical
+
+    @property
+    def h2d_bytes(self):
+        return int(self.slot_kind.nbytes + self.slot_first.nbytes + self.values.nbytes)
+
+
 def build_tables(ops: AluOps, field, d: int, lanes: int, k_max: int, min_height: int):
     """Returns (main matrix, preprocessed matrix), canonical uint32, padded with zero rows."""
     p = field.p

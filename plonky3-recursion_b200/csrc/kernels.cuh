@@ -1288,6 +1288,85 @@ __global__ void __launch_bounds__(128) k_poseidon2_table_fill(P2FillArgs a) {
     out[(size_t)(col++) * H] = acc;
 }
 
+// ------------------------------------------------------------------------------------------------
+// ALU table fill (AluAir::trace_to_matrix, /root/reference circuit-prover/src/air/alu_air.rs:497-608; layout :22-58,
+// columns air/alu_columns.rs:8-46). One thread per table row. Slot (row, lane) holds nothing, one operation [a, b, c, out], or
+// (lane 0 only) a packed Horner run of k operations: a, b, c of the first, out of the last, plus the intermediate
+// accumulators, the (a_t, c_t) operands of steps 1..k-1 and b^2. The reference's sequential `prev_lane0_out` carry is the
+// out value of the previous row's lane-0 slot, so rows are independent. The matrix is zeroed before the launch.
+// ------------------------------------------------------------------------------------------------
+struct AluFillArgs {
+    const uint32_t* kind;
+    const uint32_t* first;
+    const uint32_t* values;   // n_ops x 4 x 4 Montgomery words
+    uint32_t n_slots, lanes, k_max, log_h, wnr;
+    uint32_t* out;            // column-major main trace, height H
+};
+template <class F>
+__global__ void __launch_bounds__(128) k_alu_table_fill(AluFillArgs a) {
+    constexpr uint32_t D = 4;
+    const uint32_t H = 1u << a.log_h;
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= H) return;
+    uint32_t* out = a.out + row;
+    auto put = [&](uint32_t col, uint32_t v) { out[(size_t)col * H] = v; };
+    auto val = [&](uint32_t op, uint32_t which) {
+        const uint32_t* p = a.values + ((size_t)op * 4 + which) * D;
+        return Ext4{{p[0], p[1], p[2], p[3]}};
+    };
+    for (uint32_t lane = 0; lane < a.lanes; lane++) {
+        const uint32_t slot = row * a.lanes + lane;
+        if (slot >= a.n_slots) break;
+        const uint32_t k = a.kind[slot];
+        if (k == 0) continue;
+        const uint32_t first = a.first[slot], last = first + k - 1, m = lane * 4 * D;
+#pragma unroll
+        for (uint32_t w = 0; w < 3; w++) {
+            const Ext4 v = val(first, w);
+#pragma unroll
+            for (uint32_t c = 0; c < D; c++) put(m + w * D + c, v.c[c]);
+        }
+        const Ext4 o = val(last, 3);
+#pragma unroll
+        for (uint32_t c = 0; c < D; c++) put(m + 3 * D + c, o.c[c]);
+        if (k >= 2 && lane == 0) {
+            const uint32_t extra = a.lanes * 4 * D, num_int = (a.k_max - 1) / 2;
+            const uint32_t ac_base = extra + num_int * D, bsq_base = ac_base + 2 * (a.k_max - 1) * D;
+            // accumulator entering this row = out of the previous row's lane-0 slot (0 after a separator / at row 0)
+            Ext4 acc = ext_zero();
+            if (row > 0) {
+                const uint32_t ps = (row - 1) * a.lanes, pk = a.kind[ps];
+                if (pk) acc = val(a.first[ps] + pk - 1, 3);
+            }
+            const Ext4 b = val(first, 1);
+            uint32_t step = 0;
+            for (uint32_t si = 0; si < num_int; si++) {
+                const uint32_t i0 = first + step, i1 = i0 + 1;
+                // acc <- acc*b + c - a  (HornerAcc), twice when the second operation belongs to the run
+                acc = esub<F>(eadd<F>(emul<F>(acc, b, a.wnr), val(i0, 2)), val(i0, 0));
+                step++;
+                if (i1 < first + k) {
+                    acc = esub<F>(eadd<F>(emul<F>(acc, b, a.wnr), val(i1, 2)), val(i1, 0));
+                    step++;
+                }
+#pragma unroll
+                for (uint32_t c = 0; c < D; c++) put(extra + si * D + c, acc.c[c]);
+            }
+            for (uint32_t t = 1; t < k; t++) {
+                const Ext4 at = val(first + t, 0), ct = val(first + t, 2);
+#pragma unroll
+                for (uint32_t c = 0; c < D; c++) {
+                    put(ac_base + 2 * (t - 1) * D + c, at.c[c]);
+                    put(ac_base + (2 * (t - 1) + 1) * D + c, ct.c[c]);
+                }
+            }
+            const Ext4 bb = emul<F>(b, b, a.wnr);
+#pragma unroll
+            for (uint32_t c = 0; c < D; c++) put(bsq_base + c, bb.c[c]);
+        }
+    }
+}
+
 // Synthetic data for the isolated commit benchmark: splitmix64(seed + index) reduced mod P.
 template <class F>
 __global__ void k_fill_random(uint32_t* out, size_t n, uint64_t seed) {

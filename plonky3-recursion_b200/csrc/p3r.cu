@@ -978,6 +978,53 @@ static int fill_poseidon2_table(p3r_ctx* ctx, const InstDev& d, const p3r_poseid
     return P3R_OK;
 }
 
+// Host: generate the ALU table of instance `d` on the device from its schedule + operand values.
+template <class F>
+static int fill_alu_table(p3r_ctx* ctx, const InstDev& d, const p3r_alu_ops& ops, uint32_t* d_colmajor) {
+    const uint32_t H = 1u << d.log_h;
+    const uint32_t num_int = ops.k_max ? (ops.k_max - 1) / 2 : 0;
+    if (ops.d != 4 || ops.k_max != 4 || ops.lanes == 0 ||
+        d.main_w != ops.lanes * 16 + (num_int + 2 * (ops.k_max - 1) + 1) * 4 || (uint64_t)ops.n_slots > (uint64_t)H * ops.lanes ||
+        (ops.n_slots && (!ops.slot_kind || !ops.slot_first)) || (ops.n_ops && !ops.values)) {
+        set_err(ctx, "alu ops given for an instance that is not a D=4, k=4 ALU table of this shape");
+        return P3R_ERR_INVALID_ARG;
+    }
+    for (uint32_t i = 0; i < ops.n_slots; i++) {   // every referenced operation must exist (the kernel does not re-check)
+        const uint32_t k = ops.slot_kind[i];
+        if (k > ops.k_max || (k && (uint64_t)ops.slot_first[i] + k > ops.n_ops) || (k >= 2 && i % ops.lanes != 0)) {
+            set_err(ctx, "alu ops: malformed schedule slot " + std::to_string(i));
+            return P3R_ERR_INVALID_ARG;
+        }
+    }
+    const size_t ns = std::max<size_t>(ops.n_slots, 4), nv = std::max<size_t>((size_t)ops.n_ops * 16, 4);
+    uint32_t* d_kind = arena_alloc<uint32_t>(ctx, ns);
+    uint32_t* d_first = arena_alloc<uint32_t>(ctx, ns);
+    uint32_t* d_val = arena_alloc<uint32_t>(ctx, nv);
+    if (!d_kind || !d_first || !d_val) return P3R_ERR_OOM;
+    CUDA_TRY(cudaMemcpyAsync(d_kind, ops.slot_kind, (size_t)ops.n_slots * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_first, ops.slot_first, (size_t)ops.n_slots * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_val, ops.values, (size_t)ops.n_ops * 64, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(d_colmajor, 0, (size_t)H * d.main_w * 4, ctx->stream));
+    AluFillArgs a{};
+    a.kind = d_kind;
+    a.first = d_first;
+    a.values = d_val;
+    a.n_slots = ops.n_slots;
+    a.lanes = ops.lanes;
+    a.k_max = ops.k_max;
+    a.log_h = d.log_h;
+    a.wnr = ctx->w_m;
+    a.out = d_colmajor;
+    KT kt(ctx, KC_MISC, (uint64_t)H * d.main_w * 4);
+    k_alu_table_fill<F><<<(H + 127) / 128, 128, 0, ctx->stream>>>(a);
+    LAUNCH_CHECK_C(KC_MISC);
+    return P3R_OK;
+}
+template <class F>
+static int fill_from_ops(p3r_ctx* ctx, const InstDev& d, const p3r_table_ops& t, uint32_t* d_colmajor) {
+    return t.poseidon2 ? fill_poseidon2_table<F>(ctx, d, *t.poseidon2, d_colmajor) : fill_alu_table<F>(ctx, d, *t.alu, d_colmajor);
+}
+
 static bool is_pow2(uint32_t x) { return x && !(x & (x - 1)); }
 static uint32_t ilog2(uint32_t x) {
     uint32_t l = 0;
@@ -1152,7 +1199,7 @@ static int prep_commit_impl(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_de
 template <class F>
 static int prove_begin_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces,
                             const uint32_t* const* public_values, p3r_session** out, const p3r_traces* resident = nullptr,
-                            const p3r_poseidon2_ops* const* p2_ops = nullptr) {
+                            const p3r_table_ops* tops = nullptr) {
     ctx->arena.reset();
     ctx->pin_used = 0;
     auto* s = new p3r_session();
@@ -1170,7 +1217,7 @@ static int prove_begin_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix
     size_t max_rm = 0;
     for (size_t i = 0; i < n_inst; i++) {
         const InstDev& d = prep->inst[i];
-        const bool from_ops = p2_ops && p2_ops[i];
+        const bool from_ops = tops && (tops[i].poseidon2 || tops[i].alu);
         if (!resident && !from_ops && (traces[i].height != (1u << d.log_h) || traces[i].width != d.main_w || !traces[i].data)) {
             set_err(ctx, "trace shape mismatch for instance " + std::to_string(i));
             delete s;
@@ -1196,8 +1243,8 @@ static int prove_begin_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix
             return P3R_ERR_OOM;
         }
         if (!resident) {
-            int rc = (p2_ops && p2_ops[i]) ? fill_poseidon2_table<F>(ctx, d, *p2_ops[i], s->trace[i])
-                                           : upload_matrix(ctx, traces[i], rm, s->trace[i]);
+            int rc = (tops && (tops[i].poseidon2 || tops[i].alu)) ? fill_from_ops<F>(ctx, d, tops[i], s->trace[i])
+                                                                  : upload_matrix(ctx, traces[i], rm, s->trace[i]);
             if (rc) {
                 delete s;
                 return rc;
@@ -1975,9 +2022,9 @@ static int challenger_grind(p3r_ctx* ctx, HostChallenger<F>& ch, uint32_t bits, 
 template <class F>
 static int prove_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, const uint32_t* const* public_values,
                       uint32_t* proof_out, size_t cap_words, size_t* n_words, const p3r_traces* resident = nullptr,
-                      const p3r_poseidon2_ops* const* p2_ops = nullptr) {
+                      const p3r_table_ops* tops = nullptr) {
     p3r_session* s = nullptr;
-    TRY(prove_begin_impl<F>(ctx, prep, traces, public_values, &s, resident, p2_ops));
+    TRY(prove_begin_impl<F>(ctx, prep, traces, public_values, &s, resident, tops));
     struct Guard {
         p3r_session* s;
         ~Guard() { delete s; }
@@ -2466,13 +2513,13 @@ int p3r_prove(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, 
 }  // extern "C" (template below)
 template <class F>
 static int traces_upload_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces,
-                              const p3r_poseidon2_ops* const* p2_ops, p3r_traces** out) {
+                              const p3r_table_ops* tops, p3r_traces** out) {
     auto* t = new p3r_traces();
     t->ctx = ctx;
     ctx->arena.reset();
     for (size_t i = 0; i < prep->inst.size(); i++) {
         const InstDev& d = prep->inst[i];
-        const bool from_ops = p2_ops && p2_ops[i];
+        const bool from_ops = tops && (tops[i].poseidon2 || tops[i].alu);
         if (!from_ops && (traces[i].height != (1u << d.log_h) || traces[i].width != d.main_w || !traces[i].data)) {
             set_err(ctx, "traces_upload: shape mismatch");
             p3r_traces_free(t);
@@ -2486,7 +2533,7 @@ static int traces_upload_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matr
             return P3R_ERR_OOM;
         }
         t->d.push_back(dm);
-        int rc = from_ops ? fill_poseidon2_table<F>(ctx, d, *p2_ops[i], dm) : upload_matrix(ctx, traces[i], rm, dm);
+        int rc = from_ops ? fill_from_ops<F>(ctx, d, tops[i], dm) : upload_matrix(ctx, traces[i], rm, dm);
         if (rc) {
             p3r_traces_free(t);
             return rc;
@@ -2497,11 +2544,23 @@ static int traces_upload_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matr
     return P3R_OK;
 }
 extern "C" {
+static std::vector<p3r_table_ops> tops_from_p2(const p3r_prep* prep, const p3r_poseidon2_ops* const* p2_ops) {
+    std::vector<p3r_table_ops> v(prep->inst.size(), p3r_table_ops{nullptr, nullptr});
+    if (p2_ops)
+        for (size_t i = 0; i < v.size(); i++) v[i].poseidon2 = p2_ops[i];
+    return v;
+}
+int p3r_traces_upload_ops(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, const p3r_table_ops* table_ops,
+                          p3r_traces** out) {
+    if (!ctx || !prep || !traces || !out) return P3R_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    return DISPATCH(ctx, traces_upload_impl<F>(ctx, prep, traces, table_ops, out));
+}
 int p3r_traces_upload_ex(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, const p3r_poseidon2_ops* const* p2_ops,
                          p3r_traces** out) {
     if (!ctx || !prep || !traces || !out) return P3R_ERR_INVALID_ARG;
-    cudaSetDevice(ctx->device);
-    return DISPATCH(ctx, traces_upload_impl<F>(ctx, prep, traces, p2_ops, out));
+    std::vector<p3r_table_ops> tops = tops_from_p2(prep, p2_ops);
+    return p3r_traces_upload_ops(ctx, prep, traces, tops.data(), out);
 }
 int p3r_traces_upload(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, p3r_traces** out) {
     return p3r_traces_upload_ex(ctx, prep, traces, nullptr, out);
@@ -2525,7 +2584,14 @@ int p3r_prove_ex(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* trace
                  const uint32_t* const* public_values, uint32_t* proof_out, size_t cap_words, size_t* n_words) {
     if (!ctx || !prep || !traces || !n_words) return P3R_ERR_INVALID_ARG;
     cudaSetDevice(ctx->device);
-    return DISPATCH(ctx, prove_impl<F>(ctx, prep, traces, public_values, proof_out, cap_words, n_words, nullptr, p2_ops));
+    std::vector<p3r_table_ops> tops = tops_from_p2(prep, p2_ops);
+    return DISPATCH(ctx, prove_impl<F>(ctx, prep, traces, public_values, proof_out, cap_words, n_words, nullptr, tops.data()));
+}
+int p3r_prove_ops(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, const p3r_table_ops* table_ops,
+                  const uint32_t* const* public_values, uint32_t* proof_out, size_t cap_words, size_t* n_words) {
+    if (!ctx || !prep || !traces || !n_words) return P3R_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    return DISPATCH(ctx, prove_impl<F>(ctx, prep, traces, public_values, proof_out, cap_words, n_words, nullptr, table_ops));
 }
 void p3r_traces_free(p3r_traces* t) {
     if (!t) return;

@@ -73,7 +73,8 @@ EXPORTS = ["p3r_abi_version", "p3r_build_info", "p3r_ctx_create", "p3r_ctx_destr
            "p3r_last_phase_times", "p3r_launch_count", "p3r_traces_upload", "p3r_traces_free", "p3r_prove_resident",
            "p3r_host_alloc", "p3r_host_free", "p3r_timer_start", "p3r_timer_stop", "p3r_set_kernel_timing",
            "p3r_reset_kernel_stats", "p3r_kernel_stats", "p3r_set_specialization", "p3r_prove_ex", "p3r_traces_upload_ex",
-           "p3r_traces_download", "p3r_kernel_perms", "p3r_bench_fri_round"]
+           "p3r_traces_download", "p3r_kernel_perms", "p3r_bench_fri_round", "p3r_prove_ops",
+           "p3r_traces_upload_ops"]
 
 KERNEL_CLASSES = ["ntt_lde", "hash_rows", "compress", "logup", "quotient", "open", "reduced_openings", "fri_fold", "transpose",
                   "misc"]
@@ -242,13 +243,15 @@ class TraceBatch:
     """Traces marshalled once (Montgomery, row-major) so repeated proofs do not pay the numpy conversion.
     pinned=True places the Montgomery matrices in cudaHostAlloc'd memory (the e2e path of bench.py)."""
 
-    def __init__(self, ctx: Context, traces, pubs, pinned: bool = False, p2_ops: dict | None = None):
-        """p2_ops: {instance index: Poseidon2Ops}; those instances' traces are generated on the device (K3) and their
-        entry in `traces` may be None."""
+    def __init__(self, ctx: Context, traces, pubs, pinned: bool = False, p2_ops: dict | None = None,
+                 alu_ops: dict | None = None):
+        """p2_ops: {instance index: Poseidon2Ops}, alu_ops: {instance index: airs.alu.AluTableOps}; those instances' traces
+        are generated on the device from the operation lists and their entry in `traces` may be None."""
         self.ctx = ctx
         self.m = abi.Marshal(ctx.field)
-        self.p2 = self.m.poseidon2_ops(p2_ops, len(traces)) if p2_ops else None
-        skip = set(p2_ops or {})
+        self.tops = (self.m.table_ops(p2_ops, alu_ops, len(traces), ctx.pinned_empty if pinned else None)
+                     if (p2_ops or alu_ops) else None)
+        skip = set(p2_ops or {}) | set(alu_ops or {})
         traces = [None if k in skip else t for k, t in enumerate(traces)]
         if pinned:
             arr = (abi.MatrixU32 * len(traces))()
@@ -268,12 +271,14 @@ class TraceBatch:
         self.h2d_bytes = int(sum(int(t.size) * 4 for t in traces if t is not None))
         if p2_ops:
             self.h2d_bytes += int(sum(o.n * (64 + 4 + 1) for o in p2_ops.values()))
+        if alu_ops:
+            self.h2d_bytes += int(sum(o.h2d_bytes for o in alu_ops.values()))
         self.resident = None
 
     def upload(self, prover_data):
         """Make the traces device-resident (p3r_traces_upload)."""
         h = C.c_void_p()
-        self.ctx._check(self.ctx.lib.p3r_traces_upload_ex(self.ctx.h, prover_data.h, self.tm, self.p2, C.byref(h)))
+        self.ctx._check(self.ctx.lib.p3r_traces_upload_ops(self.ctx.h, prover_data.h, self.tm, self.tops, C.byref(h)))
         self.resident = h
         return self
 
@@ -315,12 +320,12 @@ class BatchStarkProver:
             pubs = public_values if public_values is not None else [None] * len(traces)
             traces = TraceBatch(ctx, traces, pubs)
         n = C.c_size_t(0)
-        rc = ctx.lib.p3r_prove_ex(ctx.h, prover_data.h, traces.tm, traces.p2, traces.pv, abi.as_u32p(self._buf),
-                                  C.c_size_t(self._buf.size), C.byref(n))
+        rc = ctx.lib.p3r_prove_ops(ctx.h, prover_data.h, traces.tm, traces.tops, traces.pv, abi.as_u32p(self._buf),
+                                   C.c_size_t(self._buf.size), C.byref(n))
         if rc == 6 and n.value > self._buf.size:  # P3R_ERR_BUFFER: grow once
             self._buf = np.zeros(n.value, dtype=np.uint32)
-            rc = ctx.lib.p3r_prove_ex(ctx.h, prover_data.h, traces.tm, traces.p2, traces.pv, abi.as_u32p(self._buf),
-                                      C.c_size_t(self._buf.size), C.byref(n))
+            rc = ctx.lib.p3r_prove_ops(ctx.h, prover_data.h, traces.tm, traces.tops, traces.pv, abi.as_u32p(self._buf),
+                                       C.c_size_t(self._buf.size), C.byref(n))
         ctx._check(rc)
         self.last_proof_words = n.value
         return self._buf[: n.value].copy()

@@ -242,9 +242,10 @@ class NpoTables:
 
 
 class LayerWorkload:
-    def __init__(self, insts, preps, traces, pubs, shapes, p2_ops=None):
+    def __init__(self, insts, preps, traces, pubs, shapes, p2_ops=None, alu_ops=None):
         self.insts, self.preps, self.traces, self.pubs, self.shapes = insts, preps, traces, pubs, shapes
         self.p2_ops = p2_ops or {}   # {instance index: Poseidon2Ops} for the GPU table-fill path
+        self.alu_ops = alu_ops or {}  # {instance index: airs.alu.AluTableOps}
 
     @property
     def h2d_bytes(self):
@@ -299,4 +300,5 @@ def synthetic_layer(F: Field, seed: int, n_const: int, n_public: int, n_alu: int
         traces += et
         pubs += epub
     shapes = [(s.name, t.shape[0], t.shape[1], 0 if pm is None else pm.shape[1]) for s, t, pm in zip(insts, traces, prep_mats)]
-    return LayerWorkload(insts, prep_mats, traces, pubs, shapes, p2_ops)
+    alu_ops = {2: alu.AluTableOps(ops, D, alu_lanes, horner_k)} if (D == 4 and horner_k == 4) else {}
+    return LayerWorkload(insts, prep_mats, traces, pubs, shapes, p2_ops, alu_ops)

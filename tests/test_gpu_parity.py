@@ -365,6 +365,31 @@ def test_specialized_and_interpreted_quotient_agree(pair):
     pd.close()
 
 
+def test_gpu_alu_table_fill_matches_reference_builder(pair):
+    """The device-generated ALU table (schedule slots + operand values -> 80 columns incl. packed-Horner intermediates,
+    (a_t, c_t) operands and b^2) equals the host restatement of AluAir::trace_to_matrix bit for bit; proofs from operation
+    lists (ALU + Poseidon2 both generated on the device) equal proofs from uploaded matrices and the oracle's."""
+    wl = importlib.import_module("plonky3-recursion_b200.workload")
+    ctx, orc = pair
+    for seed, n_alu in ((51, 300), (52, 1), (53, 97)):
+        L = wl.synthetic_layer(ctx.field, seed, n_const=10, n_public=40, n_alu=n_alu, n_perms=20, n_recompose=5, min_height=32)
+        (idx, _), = L.alu_ops.items()
+        assert (L.alu_ops[idx].slot_kind >= 2).any() or n_alu == 1
+        pd = lib.ProverData.from_airs_and_degrees(ctx, L.insts, L.preps)
+        tb = lib.TraceBatch(ctx, L.traces, L.pubs, p2_ops=L.p2_ops, alu_ops=L.alu_ops).upload(pd)
+        got = tb.download(pd, idx)
+        assert got.shape == L.traces[idx].shape and np.array_equal(got, L.traces[idx])
+        prover = lib.BatchStarkProver(ctx)
+        from_ops = prover.prove_all_tables(lib.TraceBatch(ctx, L.traces, L.pubs, p2_ops=L.p2_ops, alu_ops=L.alu_ops), pd)
+        pinned_ops = prover.prove_all_tables(lib.TraceBatch(ctx, L.traces, L.pubs, pinned=True, p2_ops=L.p2_ops, alu_ops=L.alu_ops), pd)
+        assert np.array_equal(from_ops, prover.prove_all_tables(L.traces, pd, L.pubs))
+        assert np.array_equal(from_ops, pinned_ops)
+        assert np.array_equal(from_ops, prover.prove_resident(tb, pd))
+        assert np.array_equal(from_ops, orc.prove(L.insts, L.preps, L.traces, L.pubs))
+        tb.close()
+        pd.close()
+
+
 def test_device_and_host_fri_transcripts_agree(pair):
     """p3r_prove samples the FRI commit-phase betas on the device (k_fri_round_transcript) and replays them on the host
     challenger; with bit 2 of p3r_set_specialization the host samples them round by round. Same proof either way, equal to the
