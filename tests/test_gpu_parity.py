@@ -96,6 +96,18 @@ def test_edge_layers_bit_identical(pair, sizes):
     pd.close()
 
 
+def test_isolated_benchmark_entry_points_run(pair):
+    """p3r_bench_commit / p3r_bench_fri_round (the isolated sweep of BASELINE.json configs[4]) run and report positive device
+    times; argument errors are rejected instead of crashing."""
+    ctx, _ = pair
+    r = ctx.bench_commit(10, 9, iters=1)
+    assert r["lde_ms"] > 0 and r["merkle_ms"] > 0
+    f = ctx.bench_fri_round(12, 2, iters=1)
+    assert f["fold_ms"] > 0 and f["commit_ms"] > 0
+    with pytest.raises(lib.P3RError):
+        ctx.bench_fri_round(12, 7, iters=1)   # arity 2^7 is not supported
+
+
 def test_grind_smallest_witness(pair):
     ctx, orc = pair
     rng = np.random.default_rng(11)
