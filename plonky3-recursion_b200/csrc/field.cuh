@@ -70,19 +70,25 @@ P3R_HD uint32_t fmul(uint32_t a, uint32_t b) {
     uint32_t r2 = r - F::P;
     return r2 < r ? r2 : r;               // min(r, r - P) as unsigned: r - P wraps above r exactly when r < P
 }
-// Reduce a 64-bit accumulator of Montgomery products (value < 2^64) to a Montgomery residue of acc / 2^32.
+// Reduce a 64-bit accumulator of at most FOUR Montgomery products (t <= 4(P-1)^2, so its high word is < 2P) to the
+// Montgomery residue of t / 2^32: one unsigned min brings the high word below P, then the same positive-form reduction as
+// fmul (IMAD, IMAD.HI with the 64-bit addend, VIADDMNMX) — 5 instructions instead of ~12 for a generic 64-bit reduction.
 template <class F>
 P3R_HD uint32_t fred64(uint64_t t) {
-    uint32_t m = (uint32_t)t * F::MU;
-    uint32_t u = (uint32_t)(((uint64_t)m * F::P) >> 32);
-    uint32_t hi = (uint32_t)(t >> 32);
-    // hi may be >= P here (t up to 2^64): bring into range first
-    uint32_t r = hi - u;
-    if (hi < u) r += F::P;  // r in (-P, 2^32): after wrap fix r in [0, 2^32 - ?]
-    // r < 2^32 - may still exceed P up to 2 times (hi < 2^32 ~ 2.02 P)
-    if (r >= F::P) r -= F::P;
-    if (r >= F::P) r -= F::P;
-    return r;
+    uint32_t lo = (uint32_t)t, hi = (uint32_t)(t >> 32);
+    uint32_t h2 = hi - F::P;
+    hi = h2 < hi ? h2 : hi;  // hi < 2P  ->  [0, P): t' = hi * 2^32 + lo < P * 2^32, t' = t (mod P)
+    uint32_t m = lo * (0u - F::MU);
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("{ .reg .u32 l2;\n\tmad.lo.cc.u32 l2, %1, %2, %3;\n\tmadc.hi.u32 %0, %1, %2, %4; }"
+        : "=r"(r)
+        : "r"(m), "r"(F::P), "r"(lo), "r"(hi));
+#else
+    uint32_t r = (uint32_t)(((uint64_t)m * F::P + (((uint64_t)hi << 32) | lo)) >> 32);
+#endif
+    uint32_t r2 = r - F::P;
+    return r2 < r ? r2 : r;
 }
 template <class F>
 P3R_HD uint32_t to_monty(uint32_t canonical) {

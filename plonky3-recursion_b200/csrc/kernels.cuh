@@ -881,14 +881,14 @@ struct DotJob {
     uint32_t out_offset;   // into opened values buffer (Ext4 units), width entries
 };
 constexpr uint32_t DOT_ROWS = 8192;  // rows per CTA
-constexpr uint32_t DOT_COLS = 8;     // columns per CTA
+constexpr uint32_t DOT_COLS = 4;     // columns per CTA (8 needs 158 registers: one CTA per SM)
 struct DotTile {           // one CTA of k_bary_dot: rows [chunk*DOT_ROWS, ..) x columns [c0, c0 + DOT_COLS) of a job
     uint32_t job, chunk, c0;
 };
 // partial[job][chunk][col]. Every thread walks its rows once, keeps the weight in registers and accumulates the DOT_COLS
 // columns in 64-bit sums of four Montgomery products (one reduction per four rows).
 template <class F>
-__global__ void __launch_bounds__(256) k_bary_dot(const DotJob* __restrict__ jobs, const DotTile* __restrict__ tiles,
+__global__ void __launch_bounds__(256, 3) k_bary_dot(const DotJob* __restrict__ jobs, const DotTile* __restrict__ tiles,
                                                    const Ext4* __restrict__ weights, Ext4* __restrict__ partial,
                                                    uint32_t max_chunks, uint32_t max_width) {
     const DotTile tl = tiles[blockIdx.x];
@@ -907,17 +907,20 @@ __global__ void __launch_bounds__(256) k_bary_dot(const DotJob* __restrict__ job
         a[c][0] = a[c][1] = a[c][2] = a[c][3] = 0;
     }
     uint32_t cnt = 0;
+    // columns past the job's width are clamped to its last column (computed, never stored): no predicated accumulates
+    const uint32_t* colp[DOT_COLS];
+#pragma unroll
+    for (int c = 0; c < (int)DOT_COLS; c++) colp[c] = col0 + (size_t)min((uint32_t)c, nc - 1) * n;
+    const uint4* w4 = reinterpret_cast<const uint4*>(w);   // weights are 16-byte aligned (arena)
     for (uint32_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
-        const Ext4 wr = w[r];
+        const uint4 wr = __ldg(w4 + r);
 #pragma unroll
         for (int c = 0; c < (int)DOT_COLS; c++) {
-            if (c < (int)nc) {
-                const uint32_t v = __ldg(col0 + (size_t)c * n + r);
-                a[c][0] += (uint64_t)v * wr.c[0];
-                a[c][1] += (uint64_t)v * wr.c[1];
-                a[c][2] += (uint64_t)v * wr.c[2];
-                a[c][3] += (uint64_t)v * wr.c[3];
-            }
+            const uint32_t v = __ldg(colp[c] + r);
+            a[c][0] += (uint64_t)v * wr.x;
+            a[c][1] += (uint64_t)v * wr.y;
+            a[c][2] += (uint64_t)v * wr.z;
+            a[c][3] += (uint64_t)v * wr.w;
         }
         if (++cnt == 4) {  // 4 products < 2^64
 #pragma unroll
@@ -1011,11 +1014,14 @@ struct RoArgs {
 // and one extension inversion shared by 1/(zeta - x) and 1/(zeta*g - x).
 template <class F>
 __global__ void __launch_bounds__(128) k_reduced_openings(const RoArgs* __restrict__ jobs, uint32_t n_jobs) {
-    extern __shared__ Ext4 sap[];
+    extern __shared__ __align__(16) uint4 sap[];   // alpha^k, one 16-byte load each
     uint32_t jb = 0;
     while (jb + 1 < n_jobs && blockIdx.x >= jobs[jb + 1].cta_begin) jb++;
     const RoArgs& a = jobs[jb];
-    for (uint32_t k = threadIdx.x; k < a.max_width; k += blockDim.x) sap[k] = a.apow[k];
+    for (uint32_t k = threadIdx.x; k < a.max_width; k += blockDim.x) {
+        const Ext4 ap = a.apow[k];
+        sap[k] = make_uint4(ap.c[0], ap.c[1], ap.c[2], ap.c[3]);
+    }
     __syncthreads();
     const uint32_t N = 1u << a.log_h;
     const uint32_t s = (blockIdx.x - a.cta_begin) * blockDim.x + threadIdx.x;
@@ -1030,18 +1036,22 @@ __global__ void __launch_bounds__(128) k_reduced_openings(const RoArgs* __restri
         const RoMat m = a.mats[mi];
         Ext4 R = ext_zero();
         const uint32_t* p = m.lde + s;
+        const uint32_t* q = p;   // running column pointer (one 64-bit add per column instead of a shift + add + scale)
         uint32_t k = 0;
-        for (; k + 4 <= m.width; k += 4) {
-            const uint32_t v0 = __ldg(p + (size_t)k * N), v1 = __ldg(p + (size_t)(k + 1) * N), v2 = __ldg(p + (size_t)(k + 2) * N),
-                           v3 = __ldg(p + (size_t)(k + 3) * N);
-            const Ext4 a0 = sap[k], a1 = sap[k + 1], a2 = sap[k + 2], a3 = sap[k + 3];
+        for (; k + 4 <= m.width; k += 4, q += 4 * (size_t)N) {
+            const uint32_t v0 = __ldg(q), v1 = __ldg(q + N), v2 = __ldg(q + 2 * (size_t)N), v3 = __ldg(q + 3 * (size_t)N);
+            const uint4 a0 = sap[k], a1 = sap[k + 1], a2 = sap[k + 2], a3 = sap[k + 3];
             Ext4 t;
-#pragma unroll
-            for (int c = 0; c < 4; c++)
-                t.c[c] = fred64<F>((uint64_t)v0 * a0.c[c] + (uint64_t)v1 * a1.c[c] + (uint64_t)v2 * a2.c[c] + (uint64_t)v3 * a3.c[c]);
+            t.c[0] = fred64<F>((uint64_t)v0 * a0.x + (uint64_t)v1 * a1.x + (uint64_t)v2 * a2.x + (uint64_t)v3 * a3.x);
+            t.c[1] = fred64<F>((uint64_t)v0 * a0.y + (uint64_t)v1 * a1.y + (uint64_t)v2 * a2.y + (uint64_t)v3 * a3.y);
+            t.c[2] = fred64<F>((uint64_t)v0 * a0.z + (uint64_t)v1 * a1.z + (uint64_t)v2 * a2.z + (uint64_t)v3 * a3.z);
+            t.c[3] = fred64<F>((uint64_t)v0 * a0.w + (uint64_t)v1 * a1.w + (uint64_t)v2 * a2.w + (uint64_t)v3 * a3.w);
             R = eadd<F>(R, t);
         }
-        for (; k < m.width; k++) R = eadd<F>(R, emul_base<F>(sap[k], __ldg(p + (size_t)k * N)));
+        for (; k < m.width; k++) {
+            const uint4 ak = sap[k];
+            R = eadd<F>(R, emul_base<F>(Ext4{{ak.x, ak.y, ak.z, ak.w}}, __ldg(p + (size_t)k * N)));
+        }
         for (uint32_t j = 0; j < m.n_points; j++) {
             // alpha^off * (P - R) = coef - alpha^off * R
             Ext4 t = esub<F>(a.coef[2 * mi + j], emul<F>(a.apow[m.alpha_off[j]], R, wnr));
