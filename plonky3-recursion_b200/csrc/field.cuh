@@ -150,22 +150,17 @@ template <class F>
 P3R_HD Ext4 esub_base(const Ext4& a, uint32_t b) {
     return Ext4{{fsub<F>(a.c[0], b), a.c[1], a.c[2], a.c[3]}};
 }
-// Schoolbook product with delayed reduction: each output coefficient accumulates <= 4 products (< 2^62 each, sum < 2^64),
-// the x^4 = W wrap-around terms are reduced once and multiplied by W.
+// Schoolbook product with delayed reduction. The wrap-around operands are multiplied by W first (b_i*W for i = 1..3), so
+// every output coefficient is ONE sum of four products (< 4P^2 < 2^64) and one fred64: 16 wide products, 3 products by W and
+// 4 reductions (the form with separately reduced wrap-around sums needs 7 reductions and 3 more products).
 template <class F>
 P3R_HD Ext4 emul(const Ext4& a, const Ext4& b, uint32_t w) {
-    uint64_t lo0 = (uint64_t)a.c[0] * b.c[0];
-    uint64_t lo1 = (uint64_t)a.c[0] * b.c[1] + (uint64_t)a.c[1] * b.c[0];
-    uint64_t lo2 = (uint64_t)a.c[0] * b.c[2] + (uint64_t)a.c[1] * b.c[1] + (uint64_t)a.c[2] * b.c[0];
-    uint64_t lo3 = (uint64_t)a.c[0] * b.c[3] + (uint64_t)a.c[1] * b.c[2] + (uint64_t)a.c[2] * b.c[1] + (uint64_t)a.c[3] * b.c[0];
-    uint64_t hi0 = (uint64_t)a.c[1] * b.c[3] + (uint64_t)a.c[2] * b.c[2] + (uint64_t)a.c[3] * b.c[1];
-    uint64_t hi1 = (uint64_t)a.c[2] * b.c[3] + (uint64_t)a.c[3] * b.c[2];
-    uint64_t hi2 = (uint64_t)a.c[3] * b.c[3];
+    const uint32_t bw1 = fmul<F>(b.c[1], w), bw2 = fmul<F>(b.c[2], w), bw3 = fmul<F>(b.c[3], w);
     Ext4 r;
-    r.c[0] = fadd<F>(fred64<F>(lo0), fmul<F>(fred64<F>(hi0), w));
-    r.c[1] = fadd<F>(fred64<F>(lo1), fmul<F>(fred64<F>(hi1), w));
-    r.c[2] = fadd<F>(fred64<F>(lo2), fmul<F>(fred64<F>(hi2), w));
-    r.c[3] = fred64<F>(lo3);
+    r.c[0] = fred64<F>((uint64_t)a.c[0] * b.c[0] + (uint64_t)a.c[1] * bw3 + (uint64_t)a.c[2] * bw2 + (uint64_t)a.c[3] * bw1);
+    r.c[1] = fred64<F>((uint64_t)a.c[0] * b.c[1] + (uint64_t)a.c[1] * b.c[0] + (uint64_t)a.c[2] * bw3 + (uint64_t)a.c[3] * bw2);
+    r.c[2] = fred64<F>((uint64_t)a.c[0] * b.c[2] + (uint64_t)a.c[1] * b.c[1] + (uint64_t)a.c[2] * b.c[0] + (uint64_t)a.c[3] * bw3);
+    r.c[3] = fred64<F>((uint64_t)a.c[0] * b.c[3] + (uint64_t)a.c[1] * b.c[2] + (uint64_t)a.c[2] * b.c[1] + (uint64_t)a.c[3] * b.c[0]);
     return r;
 }
 // Inverse via the tower F -> F(y = x^2) -> F(x): a*(A - Bx) = A^2 - y*B^2 =: n0 + n1*y, 1/(n0+n1 y) = (n0 - n1 y)/(n0^2 - W n1^2).
