@@ -61,8 +61,11 @@ static __global__ void k_transpose_out(const uint32_t* __restrict__ in, uint32_t
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4: batched coset LDE = radix-2 NTT passes over shared-memory tiles, butterflies done in REGISTERS in groups of up to
-// three stages (radix-8): one shared-memory round trip and one barrier per group instead of per stage.
+// K4 (second implementation): multi-pass tile kernel for the batched coset LDE. The product path uses the whole-column
+// kernels of ntt_col.cuh for every column of 2^5 rows or more; this kernel serves columns shorter than 32 rows and is the
+// independent implementation the parity tests compare against (p3r_set_specialization bit 1).
+// Radix-2 NTT passes over shared-memory tiles, butterflies done in REGISTERS in groups of up to three stages (radix-8):
+// one shared-memory round trip and one barrier per group instead of per stage.
 // A pass executes butterfly stages [s0, s0+r) of a size-2^log_n transform on every column (grid.y) and, for forward passes,
 // every output coset (grid.z). Stage s pairs i and i + 2^s with twiddle omega_{2^{s+1}}^{i mod 2^s}.
 //   inverse  : decimation-in-frequency, stages descending, natural in -> bit-reversed out, inverse twiddles (no 1/n here);
