@@ -195,3 +195,73 @@ def test_specialized_kernels_are_current():
                      air_mod.build_instance("p2", p2air.make_eval(prm), F.p, 8, *p2air.widths(prm), 0, buses)):
             ins = g.monty_insns(F, inst.constraints)
             assert (f"{g.fnv1a(ins):016x}", str(F.field_id), str(ins.shape[0])) in have, (fname, inst.name)
+
+
+def test_specialized_logup_kernels_are_current():
+    """Same for the generated LogUp-trace kernels: hash over the lookup-input program and the lookup / interaction structure."""
+    import importlib.util
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_specialized", os.path.join(root, "scripts", "gen_specialized.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    text = open(os.path.join(root, "plonky3-recursion_b200", "csrc", "specialized_gen.cuh")).read()
+    have = set(re.findall(r"\{0x([0-9a-f]{16})ull, (\d), (\d+)u, k_logup_spec", text))
+    F = field_mod.get_field("koala-bear")
+    L = wl.synthetic_layer(F, 3, n_const=10, n_public=20, n_alu=60, n_perms=12, n_recompose=4, min_height=16)
+    for inst in L.insts:   # the layer's own instances must hit the registry, bus ids and all
+        ins = g.monty_insns(F, inst.lookup_inputs)
+        key = (f"{g.logup_hash(ins, inst.lookups, inst.interactions):016x}", str(F.field_id), str(ins.shape[0]))
+        assert key in have, inst.name
+
+
+@pytest.mark.parametrize("field", ["koala-bear", "baby-bear"])
+def test_alu_schedule_slots_reproduce_the_table(field):
+    """AluTableOps (what p3r_alu_ops carries: schedule slots + operand values) determines the ALU main trace: a numpy
+    restatement of k_alu_table_fill — rows independent, lane-0 accumulator = out of the previous row's lane-0 slot — rebuilds
+    the matrix of AluAir::trace_to_matrix (alu.build_tables) exactly."""
+    F = field_mod.get_field(field)
+    L = wl.synthetic_layer(F, 9, n_const=10, n_public=30, n_alu=250, n_perms=10, n_recompose=4, min_height=16)
+    (idx, t), = L.alu_ops.items()
+    want = L.traces[idx]
+    d, lanes, k_max = t.d, t.lanes, t.k_max
+    assert (d, k_max) == (4, 4) and (t.slot_kind >= 2).any()
+    assert not ((t.slot_kind >= 2) & (np.arange(t.slot_kind.size) % lanes != 0)).any()   # packed runs sit in lane 0
+    H = want.shape[0]
+    got = np.zeros_like(want)
+    extra, num_int = lanes * 4 * d, (k_max - 1) // 2
+    ac_base = extra + num_int * d
+    bsq = ac_base + 2 * (k_max - 1) * d
+    mul = lambda x, y: F.ext_mul([int(v) for v in x], [int(v) for v in y])
+    add = lambda x, y: [(int(u) + int(v)) % F.p for u, v in zip(x, y)]
+    sub = lambda x, y: [(int(u) - int(v)) % F.p for u, v in zip(x, y)]
+    for row in range(H):
+        for lane in range(lanes):
+            s = row * lanes + lane
+            if s >= t.slot_kind.size or t.slot_kind[s] == 0:
+                continue
+            k, first = int(t.slot_kind[s]), int(t.slot_first[s])
+            m = lane * 4 * d
+            got[row, m:m + 3 * d] = t.values[first, :3].reshape(-1)
+            got[row, m + 3 * d:m + 4 * d] = t.values[first + k - 1, 3]
+            if k >= 2 and lane == 0:
+                acc = [0] * d
+                if row > 0 and t.slot_kind[(row - 1) * lanes]:
+                    ps = (row - 1) * lanes
+                    acc = list(t.values[int(t.slot_first[ps]) + int(t.slot_kind[ps]) - 1, 3])
+                b = t.values[first, 1]
+                step = 0
+                for si in range(num_int):
+                    i0 = first + step
+                    acc = sub(add(mul(acc, b), t.values[i0, 2]), t.values[i0, 0])
+                    step += 1
+                    if i0 + 1 < first + k:
+                        acc = sub(add(mul(acc, b), t.values[i0 + 1, 2]), t.values[i0 + 1, 0])
+                        step += 1
+                    got[row, extra + si * d:extra + (si + 1) * d] = acc
+                for tt in range(1, k):
+                    got[row, ac_base + 2 * (tt - 1) * d:ac_base + (2 * (tt - 1) + 1) * d] = t.values[first + tt, 0]
+                    got[row, ac_base + (2 * (tt - 1) + 1) * d:ac_base + 2 * tt * d] = t.values[first + tt, 2]
+                got[row, bsq:bsq + d] = mul(b, b)
+    assert np.array_equal(got, want)
