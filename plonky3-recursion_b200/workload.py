@@ -142,7 +142,8 @@ class NpoTables:
     """Poseidon2 + Recompose operation lists of a synthetic layer (NPO registration order [Poseidon2, Recompose],
     recursion/src/backend/fri.rs:693-721). Operations read Const/Public witnesses and create new ones that the ALU reads."""
 
-    def __init__(self, F: Field, rng, W: Witnesses, sources, new_public, n_perms: int, n_recompose: int):
+    def __init__(self, F: Field, rng, W: Witnesses, sources, new_public, n_perms: int, n_recompose: int,
+                 recompose_coeff: bool = False):
         self.F, self.params = F, Poseidon2Params(F.field_id)
         p = F.p
         rows = []  # dicts, one per permutation row
@@ -207,6 +208,18 @@ class NpoTables:
         # Recompose: EF witnesses packed from base coefficients (creator side only)
         self.recompose_ids = [W.new(_rand_ext(F, rng)) for _ in range(n_recompose)]
         self.created = created + self.recompose_ids
+        # `recompose/coeff` (recompose_air.rs:175-197): every coefficient v_i is itself a witness (v_i, 0, 0, 0). Even
+        # operations create theirs (hint outputs: multiplicity = number of reads); odd operations point at witnesses a
+        # Public row creates, so their coefficient multiplicity is 0 (batch_stark_prover/recompose.rs:341-352).
+        self.recompose_coeff = recompose_coeff
+        self.coeff_ids, self.coeff_hint = [], []
+        if recompose_coeff:
+            for k, rid in enumerate(self.recompose_ids):
+                hint = k % 2 == 0
+                ids = [(W.new if hint else new_public)([c, 0, 0, 0]) for c in W.values[rid]]
+                self.coeff_ids.append(ids)
+                self.coeff_hint.append(hint)
+                self.created.extend(ids)
 
     def finish(self, W: Witnesses, buses, min_height: int, recompose_lanes: int = 1):
         F, params = self.F, self.params
@@ -233,9 +246,18 @@ class NpoTables:
             m = np.array([W.reads[i] for i in self.recompose_ids], dtype=np.uint32)
             idx = np.array(self.recompose_ids, dtype=np.uint32) * D
             tr = witness_send.trace_to_matrix(v, D, recompose_lanes, min_height)
-            pr = witness_send.preprocessed_matrix(m, idx, recompose_lanes, min_height, idx_first=True)
-            insts.append(air.build_instance("recompose", witness_send.make_eval(D, recompose_lanes, idx_first=True), F.p, lh(tr),
-                                            D * recompose_lanes, 2 * recompose_lanes, 0, buses))
+            cidx = cmult = None
+            if self.recompose_coeff:
+                cidx = np.array(self.coeff_ids, dtype=np.uint32) * D
+                cmult = np.array([[W.reads[c] if h else 0 for c in ids] for ids, h in zip(self.coeff_ids, self.coeff_hint)],
+                                 dtype=np.uint32)
+            pr = witness_send.preprocessed_matrix(m, idx, recompose_lanes, min_height, idx_first=True,
+                                                  coeff_idxs=cidx, coeff_mults=cmult)
+            plw = witness_send.prep_lane_width(D, self.recompose_coeff)
+            insts.append(air.build_instance("recompose/coeff" if self.recompose_coeff else "recompose",
+                                            witness_send.make_eval(D, recompose_lanes, idx_first=True,
+                                                                   coeff_lookups=self.recompose_coeff),
+                                            F.p, lh(tr), D * recompose_lanes, plw * recompose_lanes, 0, buses))
             preps.append(pr)
             traces.append(tr)
         return insts, preps, traces, [None] * len(insts)
@@ -254,7 +276,7 @@ class LayerWorkload:
 
 def synthetic_layer(F: Field, seed: int, n_const: int, n_public: int, n_alu: int, n_perms: int = 0, n_recompose: int = 0,
                     alu_lanes: int = 3, horner_k: int = 4, public_lanes: int = 1, recompose_lanes: int = 1,
-                    min_height: int = 256) -> LayerWorkload:
+                    min_height: int = 256, recompose_coeff: bool = False) -> LayerWorkload:
     """Tables in the reference's instance order [Const, Public, ALU, Poseidon2, Recompose]
     (circuit-prover/src/batch_stark_prover.rs:1493-1519; NPO order recursion/src/backend/fri.rs:693-721)."""
     rng = np.random.default_rng(seed)
@@ -268,7 +290,8 @@ def synthetic_layer(F: Field, seed: int, n_const: int, n_public: int, n_alu: int
         public_ids.append(wid)
         return wid
 
-    npo = NpoTables(F, rng, W, const_ids + public_ids, new_public, n_perms, n_recompose) if (n_perms or n_recompose) else None
+    npo = (NpoTables(F, rng, W, const_ids + public_ids, new_public, n_perms, n_recompose, recompose_coeff)
+           if (n_perms or n_recompose) else None)
     sources = const_ids + public_ids + (npo.created if npo else [])
     vals, preps13, pool = gen_alu_ops(F, rng, W, sources, n_alu)
     ops = finalize_alu(F, W, vals, preps13)

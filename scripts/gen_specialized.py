@@ -388,6 +388,8 @@ def main(out_path):
             # Const / Public (1 lane) and Recompose: no local constraints, only the LogUp ones
             ("send_d4_l1", air.build_instance("send", ws.make_eval(4, 1), F.p, 8, 4, 2, 0, buses)),
             ("recompose_d4_l1", air.build_instance("recompose", ws.make_eval(4, 1, idx_first=True), F.p, 8, 4, 2, 0, buses)),
+            ("recompose_coeff_d4_l1", air.build_instance("recompose/coeff", ws.make_eval(4, 1, idx_first=True, coeff_lookups=True),
+                                                         F.p, 8, 4, ws.prep_lane_width(4, True), 0, buses)),
         ]
         for tag, inst in specs:
             ins = monty_insns(F, inst.constraints)

@@ -209,11 +209,32 @@ def test_specialized_logup_kernels_are_current():
     text = open(os.path.join(root, "plonky3-recursion_b200", "csrc", "specialized_gen.cuh")).read()
     have = set(re.findall(r"\{0x([0-9a-f]{16})ull, (\d), (\d+)u, k_logup_spec", text))
     F = field_mod.get_field("koala-bear")
-    L = wl.synthetic_layer(F, 3, n_const=10, n_public=20, n_alu=60, n_perms=12, n_recompose=4, min_height=16)
-    for inst in L.insts:   # the layer's own instances must hit the registry, bus ids and all
-        ins = g.monty_insns(F, inst.lookup_inputs)
-        key = (f"{g.logup_hash(ins, inst.lookups, inst.interactions):016x}", str(F.field_id), str(ins.shape[0]))
-        assert key in have, inst.name
+    for coeff in (False, True):
+        L = wl.synthetic_layer(F, 3, n_const=10, n_public=20, n_alu=60, n_perms=12, n_recompose=4, min_height=16,
+                               recompose_coeff=coeff)
+        for inst in L.insts:   # the layer's own instances must hit the registry, bus ids and all
+            ins = g.monty_insns(F, inst.lookup_inputs)
+            key = (f"{g.logup_hash(ins, inst.lookups, inst.interactions):016x}", str(F.field_id), str(ins.shape[0]))
+            assert key in have, inst.name
+
+
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_recompose_coeff_table_shape(lanes):
+    """`recompose/coeff` (circuit-prover/src/air/recompose_air.rs:60-70,150-197): D main columns and 2 + 2D preprocessed
+    columns per lane; 1 + D interactions per lane, one per lookup at this degree (no local constraints -> one quotient
+    chunk -> budget 2), so 1 + lanes*(1 + D) permutation columns; coefficient tuples are (idx, v_i, 0, .., 0)."""
+    F = field_mod.get_field("koala-bear")
+    L = wl.synthetic_layer(F, 5, n_const=8, n_public=12, n_alu=80, n_perms=0, n_recompose=9, min_height=16,
+                           recompose_coeff=True, recompose_lanes=lanes)
+    inst, prep, trace = L.insts[-1], L.preps[-1], L.traces[-1]
+    assert inst.name == "recompose/coeff"
+    assert (inst.main_width, inst.prep_width) == (4 * lanes, 10 * lanes) == (trace.shape[1], prep.shape[1])
+    assert inst.log_quotient_chunks == 0 and inst.aux_width == 1 + 5 * lanes and not inst.uses_next_row
+    assert [n for _, _, n in inst.interactions] == [5] * (5 * lanes)
+    # hint-output operations (even) carry read counts, the others multiplicity 0; padding rows are all zero
+    flat = prep.reshape(-1, 10)
+    assert (flat[1:9:2, 3::2] == 0).all() and (flat[9:] == 0).all()
+    assert flat[0:9:2, 3::2].sum() > 0
 
 
 @pytest.mark.parametrize("field", ["koala-bear", "baby-bear"])

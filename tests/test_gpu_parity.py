@@ -377,6 +377,27 @@ def test_specialized_and_interpreted_quotient_agree(pair):
     pd.close()
 
 
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_recompose_with_coefficient_lookups_bit_identical(pair, lanes):
+    """`recompose/coeff` table (recompose_air.rs:175-197; 1 + D lookups per lane): one lane runs the generated quotient /
+    LogUp kernels, two lanes the bytecode interpreter; both equal the oracle, with and without specialisation."""
+    wl = importlib.import_module("plonky3-recursion_b200.workload")
+    ctx, orc = pair
+    L = wl.synthetic_layer(ctx.field, 41, n_const=12, n_public=50, n_alu=300, n_perms=40, n_recompose=37, min_height=32,
+                           recompose_coeff=True, recompose_lanes=lanes)
+    assert L.insts[-1].name == "recompose/coeff" and L.insts[-1].aux_width == 1 + 5 * lanes
+    pd = lib.ProverData.from_airs_and_degrees(ctx, L.insts, L.preps)
+    prover = lib.BatchStarkProver(ctx)
+    want = orc.prove(L.insts, L.preps, L.traces, L.pubs)
+    a = prover.prove_all_tables(L.traces, pd, L.pubs)
+    ctx.set_specialization(False)
+    b = prover.prove_all_tables(L.traces, pd, L.pubs)
+    ctx.set_specialization(True)
+    assert np.array_equal(a, want) and np.array_equal(b, want)
+    orc.verify(L.insts, pd.preprocessed_commitment, L.pubs, a)
+    pd.close()
+
+
 def test_gpu_alu_table_fill_matches_reference_builder(pair):
     """The device-generated ALU table (schedule slots + operand values -> 80 columns incl. packed-Horner intermediates,
     (a_t, c_t) operands and b^2) equals the host restatement of AluAir::trace_to_matrix bit for bit; proofs from operation
@@ -441,3 +462,38 @@ def test_gpu_poseidon2_table_fill_matches_reference_builder(pair):
         assert np.array_equal(from_ops, orc.prove(L.insts, L.preps, L.traces, L.pubs))
         tb.close()
         pd.close()
+
+
+def test_full_size_layer_is_accepted_by_the_oracle_verifier():
+    """BASELINE.json's headline configuration (the KoalaBear steady-state layer `bench.py` times: ALU 2^15 x 80, Poseidon2
+    2^14 x 166, Public 2^16 x 4, production FRI parameters) is too large for the oracle *prover* inside a test, so parity at
+    this size rests on size-independent properties: the oracle VERIFIER accepts the GPU proof; proving is deterministic;
+    matrices, pinned matrices, device-resident traces and operation lists (tables generated on the device) give the same
+    bytes; the specialised and interpreted paths agree; a flipped word anywhere is rejected."""
+    wl = importlib.import_module("plonky3-recursion_b200.workload")
+    ctx = lib.Context("koala-bear", lib.DEFAULT_FRI)
+    orc = make_oracle("koala-bear", lib.DEFAULT_FRI)
+    L = wl.synthetic_layer(ctx.field, 1, n_const=1500, n_public=43000, n_alu=60000, n_perms=12000, n_recompose=4000,
+                           min_height=256)
+    assert [s[1] for s in L.shapes] == [2048, 65536, 32768, 16384, 4096]
+    pd = lib.ProverData.from_airs_and_degrees(ctx, L.insts, L.preps)
+    prover = lib.BatchStarkProver(ctx)
+    proof = prover.prove_all_tables(L.traces, pd, L.pubs)
+    orc.verify(L.insts, pd.preprocessed_commitment, L.pubs, proof)
+    assert np.array_equal(proof, prover.prove_all_tables(L.traces, pd, L.pubs))
+    tb = lib.TraceBatch(ctx, L.traces, L.pubs).upload(pd)
+    assert np.array_equal(proof, prover.prove_resident(tb, pd))
+    tb.close()
+    ops = lib.TraceBatch(ctx, L.traces, L.pubs, pinned=True, p2_ops=L.p2_ops, alu_ops=L.alu_ops)
+    assert np.array_equal(proof, prover.prove_all_tables(ops, pd))
+    ctx.set_specialization(False)
+    assert np.array_equal(proof, prover.prove_all_tables(L.traces, pd, L.pubs))
+    ctx.set_specialization(True)
+    rng = np.random.default_rng(0)
+    for pos in [3, 20, proof.size // 3, proof.size // 2, proof.size - 9] + [int(x) for x in rng.integers(0, proof.size, 6)]:
+        bad = proof.copy()
+        bad[pos] = (int(bad[pos]) + 1) % ctx.field.p
+        with pytest.raises(RuntimeError):
+            orc.verify(L.insts, pd.preprocessed_commitment, L.pubs, bad)
+    pd.close()
+    ctx.close()

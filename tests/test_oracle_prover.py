@@ -97,6 +97,23 @@ def test_fri_parameter_variants(fri):
     assert proof[1] == n_inst and proof[4] == cap_words
 
 
+@pytest.mark.parametrize("field,lanes", [("koala-bear", 1), ("baby-bear", 2)])
+def test_recompose_with_coefficient_lookups(field, lanes):
+    """Layer whose Recompose table is the `recompose/coeff` variant (recompose_air.rs:175-197): the bus balances only if
+    every coefficient receive (idx, v_i, 0, 0, 0) is matched, so a wrong coefficient multiplicity must be rejected."""
+    orc = make_oracle(field)
+    L = wl.synthetic_layer(orc.field, 8, n_const=10, n_public=20, n_alu=150, n_perms=20, n_recompose=7, min_height=32,
+                           recompose_coeff=True, recompose_lanes=lanes)
+    proof = orc.prove(L.insts, L.preps, L.traces, L.pubs)
+    orc.verify(L.insts, orc.prep_commit(L.insts, L.preps), L.pubs, proof)
+    preps = [None if m is None else m.copy() for m in L.preps]
+    row = np.nonzero(preps[-1][:, 3])[0][0]
+    preps[-1][row, 3] += 1          # coeff_0_mult of a hint-output operation
+    bad = orc.prove(L.insts, preps, L.traces, L.pubs)
+    with pytest.raises(RuntimeError):
+        orc.verify(L.insts, orc.prep_commit(L.insts, preps), L.pubs, bad)
+
+
 def test_layer_with_public_values_and_mixed_heights():
     """Fibonacci (public values, no lookups) next to the 5 recursion tables: instances with and without lookups /
     preprocessed columns / next-row openings in one batch."""
