@@ -258,7 +258,8 @@ struct p3r_prep {
 
 struct p3r_traces {  // device-resident column-major copies of one layer's traces
     p3r_ctx* ctx = nullptr;
-    std::vector<uint32_t*> d;
+    std::vector<uint32_t*> d;   // per instance, pointers into `slab`
+    void* slab = nullptr;       // one allocation for all instances
 };
 
 enum Phase { PH_BEGIN = 0, PH_MAIN, PH_PERM, PH_QUOT, PH_OPEN, PH_FRI };
@@ -1045,14 +1046,36 @@ static int prep_commit_impl(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_de
         delete pp;
         return rc;
     };
+    // Device memory owned by the prep: sub-allocated from a few large slabs (cudaMalloc goes through the kernel-mode driver
+    // and costs milliseconds when anything else holds its lock; ~80 separate allocations dominated this call).
+    char* slab = nullptr;
+    size_t slab_left = 0;
     auto dmalloc = [&](size_t bytes) -> void* {
-        void* p = nullptr;
-        if (cudaMalloc(&p, std::max<size_t>(bytes, 16)) != cudaSuccess) return nullptr;
-        pp->owned.push_back(p);
-        return p;
+        bytes = (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255;
+        if (bytes > slab_left) {
+            size_t sz = std::max<size_t>(bytes, (size_t)32 << 20);
+            void* p = nullptr;
+            if (cudaMalloc(&p, sz) != cudaSuccess) return nullptr;
+            pp->owned.push_back(p);
+            slab = static_cast<char*>(p);
+            slab_left = sz;
+        }
+        void* r = slab;
+        slab += bytes;
+        slab_left -= bytes;
+        return r;
     };
     ctx->arena.reset();
     ctx->pin_used = 0;
+    const bool trace_prep = getenv("P3R_TRACE_PREP") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace_prep) return;
+        cudaStreamSynchronize(ctx->stream);
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[p3r prep] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     const uint32_t lb = ctx->fri.log_blowup;
     uint32_t max_logN = 0;
     for (uint32_t i = 0; i < n_inst; i++) max_logN = std::max(max_logN, descs[i].log_height + lb);
@@ -1060,6 +1083,7 @@ static int prep_commit_impl(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_de
         int rc = ensure_twiddles<F>(ctx, max_logN);
         if (rc) return fail(rc);
     }
+    lap("twiddles");
     for (uint32_t i = 0; i < n_inst; i++) {
         const p3r_instance_desc& d = descs[i];
         InstDev s;
@@ -1132,6 +1156,7 @@ static int prep_commit_impl(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_de
             set_err(ctx, "device allocation failed");
             return fail(P3R_ERR_OOM);
         }
+        lap("programs");
         for (auto& it : s.inter) pp->max_msg_w = std::max(pp->max_msg_w, it.n_elems);
         for (auto& l : s.lookups) pp->n_buses = std::max(pp->n_buses, l.bus + 1);
         if (pp->max_msg_w > 8) {
@@ -1147,6 +1172,7 @@ static int prep_commit_impl(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_de
         k_selectors<F><<<(NQ + 255) / 256, 256, 0, ctx->stream>>>(s.sel, s.inv_van, s.log_h, s.log_qc, ctx->gen_m, ctx->tw,
                                                                   ctx->logT);
         ctx->launches++;
+        lap("selectors");
         if (s.prep_w) {
             if (!prep || !prep[i].data || prep[i].height != (1u << s.log_h) || prep[i].width != s.prep_w) {
                 set_err(ctx, "preprocessed matrix shape mismatch");
@@ -1160,10 +1186,13 @@ static int prep_commit_impl(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_de
             uint32_t* coef = arena_alloc<uint32_t>(ctx, n * s.prep_w);
             uint32_t* tmp = s.log_h > TILE_LOG ? arena_alloc<uint32_t>(ctx, (n << lb) * s.prep_w) : nullptr;
             if (!s.prep_trace || !s.prep_lde || !rm || !coef || (s.log_h > TILE_LOG && !tmp)) return fail(P3R_ERR_OOM);
+            lap("alloc");
             int rc = upload_matrix(ctx, prep[i], rm, s.prep_trace);
             if (rc) return fail(rc);
+            lap("upload");
             rc = coset_lde<F>(ctx, s.prep_trace, s.prep_lde, s.log_h, s.prep_w, lb, true, 0, coef, tmp);
             if (rc) return fail(rc);
+            lap("lde");
         }
         pp->inst.push_back(std::move(s));
     }
@@ -1183,6 +1212,7 @@ static int prep_commit_impl(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_de
         rc = read_cap(ctx, pp->prep_tree, pp->prep_cap.data());
         if (rc) return fail(rc);
         if (cap_out) std::memcpy(cap_out, pp->prep_cap.data(), pp->prep_cap.size() * 4);
+        lap("tree");
     }
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
         set_err(ctx, "prep: stream sync failed");
@@ -2517,6 +2547,13 @@ static int traces_upload_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matr
     auto* t = new p3r_traces();
     t->ctx = ctx;
     ctx->arena.reset();
+    size_t total = 0;
+    for (const InstDev& d : prep->inst) total += ((((size_t)1 << d.log_h) * d.main_w * 4) + 255) & ~(size_t)255;
+    if (cudaMalloc(&t->slab, std::max<size_t>(total, 256)) != cudaSuccess) {
+        delete t;
+        return P3R_ERR_OOM;
+    }
+    char* next = static_cast<char*>(t->slab);
     for (size_t i = 0; i < prep->inst.size(); i++) {
         const InstDev& d = prep->inst[i];
         const bool from_ops = tops && (tops[i].poseidon2 || tops[i].alu);
@@ -2526,9 +2563,10 @@ static int traces_upload_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matr
             return P3R_ERR_INVALID_ARG;
         }
         size_t words = ((size_t)1 << d.log_h) * d.main_w;
-        uint32_t* dm = nullptr;
+        uint32_t* dm = reinterpret_cast<uint32_t*>(next);
+        next += (words * 4 + 255) & ~(size_t)255;
         uint32_t* rm = from_ops ? reinterpret_cast<uint32_t*>(ctx->dstage) : arena_alloc<uint32_t>(ctx, words);
-        if (!rm || cudaMalloc(&dm, words * 4) != cudaSuccess) {
+        if (!rm) {
             p3r_traces_free(t);
             return P3R_ERR_OOM;
         }
@@ -2596,7 +2634,7 @@ int p3r_prove_ops(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* trac
 void p3r_traces_free(p3r_traces* t) {
     if (!t) return;
     cudaStreamSynchronize(t->ctx->stream);
-    for (auto* p : t->d) cudaFree(p);
+    cudaFree(t->slab);
     delete t;
 }
 int p3r_prove_resident(p3r_ctx* ctx, const p3r_prep* prep, const p3r_traces* traces, const uint32_t* const* public_values,

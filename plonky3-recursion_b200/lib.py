@@ -7,6 +7,7 @@ Host-side mirror of the reference interface for this path:
 """
 from __future__ import annotations
 
+import time
 import ctypes as C
 import os
 import subprocess
@@ -224,8 +225,11 @@ class ProverData:
         cap = np.zeros(ctx.cap_words, dtype=np.uint32)
         has_prep = C.c_uint32(0)
         h = C.c_void_p()
+        t0 = time.perf_counter()
         ctx._check(ctx.lib.p3r_prep_commit(ctx.h, len(insts), descs, pm, C.byref(h), abi.as_u32p(cap), C.byref(has_prep)))
-        return cls(ctx, insts, prep_mats, h, cap, bool(has_prep.value))
+        pd = cls(ctx, insts, prep_mats, h, cap, bool(has_prep.value))
+        pd.commit_ms = (time.perf_counter() - t0) * 1e3   # the C-ABI call alone (returns after the tree root is on the host)
+        return pd
 
     def close(self):
         if getattr(self, "h", None) and self.ctx.h:

@@ -325,3 +325,61 @@ def synthetic_layer(F: Field, seed: int, n_const: int, n_public: int, n_alu: int
     shapes = [(s.name, t.shape[0], t.shape[1], 0 if pm is None else pm.shape[1]) for s, t, pm in zip(insts, traces, prep_mats)]
     alu_ops = {2: alu.AluTableOps(ops, D, alu_lanes, horner_k)} if (D == 4 and horner_k == 4) else {}
     return LayerWorkload(insts, prep_mats, traces, pubs, shapes, p2_ops, alu_ops)
+
+
+def base_layer_fibonacci(F: Field, n: int = 1000, min_height: int = 256) -> LayerWorkload:
+    """The base circuit of `recursive_fibonacci` (recursion/examples/recursive_fibonacci.rs:315-327), extension degree 1,
+    `TablePacking::new(1, 1)`: one public input `expected_result`, constants 0 and 1, n - 1 ADD operations, and
+    `connect(b, expected_result)` — the last ADD's output IS the public witness, so that row reads it (`out_is_creator`
+    false -> multiplicity -1, circuit-prover/src/common.rs:268-275) instead of creating it. Tables [Const, Public, ALU];
+    for n = 1000: ALU 1024 x 7 with 20 preprocessed columns, Const / Public 256 x 1 (air/shape_golden.rs:33-52)."""
+    p, d = F.p, 1
+    values, reads = [0, 0, 1], [0, 0, 0]      # w0 = expected_result (value filled below), w1 = F(0), w2 = F(1)
+    a_id, b_id = 1, 2
+    vals, prep13 = [], []
+    for step in range(2, n + 1):
+        out = (values[a_id] + values[b_id]) % p
+        last = step == n
+        out_id = 0 if last else len(values)
+        if last:
+            values[0] = out
+        else:
+            values.append(out)
+            reads.append(0)
+        reads[a_id] += 1
+        reads[b_id] += 1
+        if last:
+            reads[0] += 1
+        pr = [0] * 13
+        pr[alu.MULT_A] = pr[alu.MULT_B] = p - 1
+        pr[alu.SEL_ADD], pr[alu.A_READER] = 1, 1
+        pr[alu.A_IDX], pr[alu.B_IDX], pr[alu.OUT_IDX] = a_id * d, b_id * d, out_id * d
+        pr[alu.MULT_OUT] = p - 1 if last else -1
+        vals.append([[values[a_id]], [values[b_id]], [0], [out]])
+        prep13.append(pr)
+        a_id, b_id = b_id, out_id
+    arr = np.zeros((len(prep13), 13), dtype=np.uint32)
+    for i, pr in enumerate(prep13):
+        if pr[alu.MULT_OUT] == -1:
+            pr[alu.MULT_OUT] = reads[pr[alu.OUT_IDX] // d] % p
+        arr[i] = pr
+    ops = alu.AluOps(np.array(vals, dtype=np.uint32).reshape(-1, 4, d), arr)
+
+    def send_table(ids):
+        v = np.array([[values[i]] for i in ids], dtype=np.uint32)
+        m = np.array([reads[i] for i in ids], dtype=np.uint32)
+        idx = np.array(ids, dtype=np.uint32) * d
+        return witness_send.trace_to_matrix(v, d, 1, min_height), witness_send.preprocessed_matrix(m, idx, 1, min_height)
+
+    buses = air.BusRegistry()
+    tc, pc = send_table([1, 2])
+    tp, pp = send_table([0])
+    ta, pa = alu.build_tables(ops, F, d, 1, 2, min_height)
+    lh = lambda m: int(m.shape[0]).bit_length() - 1
+    aw, apw = alu.widths(d, 1, 2)
+    insts = [air.build_instance("const", witness_send.make_eval(d, 1), p, lh(tc), d, 2, 0, buses),
+             air.build_instance("public", witness_send.make_eval(d, 1), p, lh(tp), d, 2, 0, buses),
+             air.build_instance("alu", alu.make_eval(d, 1, 2, None), p, lh(ta), aw, apw, 0, buses)]
+    traces, preps = [tc, tp, ta], [pc, pp, pa]
+    shapes = [(s.name, t.shape[0], t.shape[1], pm.shape[1]) for s, t, pm in zip(insts, traces, preps)]
+    return LayerWorkload(insts, preps, traces, [None, None, None], shapes)

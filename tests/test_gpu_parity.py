@@ -398,6 +398,21 @@ def test_recompose_with_coefficient_lookups_bit_identical(pair, lanes):
     pd.close()
 
 
+@pytest.mark.parametrize("n", [1000, 40])
+def test_base_layer_fibonacci_circuit_bit_identical(pair, n):
+    """BASELINE configs[0]: the extension-degree-1 base circuit of recursive_fibonacci (ALU 1024 x 7, Const / Public 256 x 1,
+    WitnessChecks tuples of width 2) — interpreter path for every table, equal to the oracle bit for bit."""
+    wl = importlib.import_module("plonky3-recursion_b200.workload")
+    ctx, orc = pair
+    L = wl.base_layer_fibonacci(ctx.field, n, min_height=256 if n == 1000 else 16)
+    pd = lib.ProverData.from_airs_and_degrees(ctx, L.insts, L.preps)
+    proof = lib.BatchStarkProver(ctx).prove_all_tables(L.traces, pd, L.pubs)
+    assert np.array_equal(pd.preprocessed_commitment, orc.prep_commit(L.insts, L.preps))
+    assert np.array_equal(proof, orc.prove(L.insts, L.preps, L.traces, L.pubs))
+    orc.verify(L.insts, pd.preprocessed_commitment, L.pubs, proof)
+    pd.close()
+
+
 def test_gpu_alu_table_fill_matches_reference_builder(pair):
     """The device-generated ALU table (schedule slots + operand values -> 80 columns incl. packed-Horner intermediates,
     (a_t, c_t) operands and b^2) equals the host restatement of AluAir::trace_to_matrix bit for bit; proofs from operation

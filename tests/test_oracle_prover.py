@@ -114,6 +114,28 @@ def test_recompose_with_coefficient_lookups(field, lanes):
         orc.verify(L.insts, orc.prep_commit(L.insts, preps), L.pubs, bad)
 
 
+@pytest.mark.parametrize("field", ["koala-bear", "baby-bear"])
+def test_base_layer_fibonacci_circuit(field):
+    """BASELINE configs[0]'s base circuit (recursive_fibonacci --n 1000, extension degree 1, TablePacking::new(1, 1)):
+    shapes of air/shape_golden.rs (ALU 1024 x 7 / 20, Const and Public 256 x 1), F(1000) as the public witness that the last
+    ADD reads back (`connect`), proof accepted; a wrong expected_result unbalances the bus and is rejected."""
+    orc = make_oracle(field)
+    F = orc.field
+    L = wl.base_layer_fibonacci(F, 1000)
+    assert L.shapes == [("const", 256, 1, 2), ("public", 256, 1, 2), ("alu", 1024, 7, 20)]
+    a, b = 0, 1
+    for _ in range(2, 1001):
+        a, b = b, (a + b) % F.p
+    assert int(L.traces[1][0, 0]) == b and int(L.traces[2][998, 3]) == b and not L.traces[2][999:].any()
+    cap = orc.prep_commit(L.insts, L.preps)
+    proof = orc.prove(L.insts, L.preps, L.traces, L.pubs)
+    orc.verify(L.insts, cap, L.pubs, proof)
+    traces = [t.copy() for t in L.traces]
+    traces[1][0, 0] = (b + 1) % F.p
+    with pytest.raises(RuntimeError):
+        orc.verify(L.insts, cap, L.pubs, orc.prove(L.insts, L.preps, traces, L.pubs))
+
+
 def test_layer_with_public_values_and_mixed_heights():
     """Fibonacci (public values, no lookups) next to the 5 recursion tables: instances with and without lookups /
     preprocessed columns / next-row openings in one batch."""
