@@ -144,6 +144,8 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # NCCL's version banner goes to stdout, where only the JSON line belongs
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     lib = importlib.import_module("plonky3-recursion_b200.lib")
@@ -356,7 +358,7 @@ def main():
     ap.add_argument("--field", default="koala-bear", choices=["koala-bear", "baby-bear"])
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=3, help="concurrent proofs per GPU in the throughput regions")
+    ap.add_argument("--inflight", type=int, default=4, help="concurrent proofs per GPU in the throughput regions")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 20:
