@@ -256,6 +256,12 @@ def run_ours(args):
             t.join()
         return total, sum(ln[0].launch_count() for ln in lanes) - l0
 
+    # Host wait mode of the prover threads (p3r_set_wait_mode). Measured on B200 with the process confined to 2 cores and four
+    # proofs in flight: spin 325, yield 324, block 309 proofs/s (16 cores: 396 / - / 381) — the host-side limit is the launch work
+    # itself, not the waiting, so the default stays the driver's spin wait.
+    cores = len(os.sched_getaffinity(0))
+    wait_mode = args.wait or "spin"
+    ctx.set_wait_mode(wait_mode)
     batch_steps(False, max(args.warmup, 3))
     barrier()
     t_batch, launches_batch = batch_steps(False, args.steps)
@@ -315,7 +321,7 @@ def run_ours(args):
                                    f"one proof per GPU per step", "shapes": L.shapes, "fri": lib.DEFAULT_FRI, "scale": args.scale,
                        "l2": "flushed between timed steps (256 MiB fill)",
                        "parallelism": f"independent proofs x{world} GPUs, {args.inflight} proofs in flight per GPU and step",
-                       "proofs_per_step": world * args.inflight,
+                       "proofs_per_step": world * args.inflight, "host_wait": wait_mode, "host_cores": cores,
                        "single_proof_latency_ms": ms_layer, "single_proof_proofs_per_s": world * args.steps / (t_res / 1e3),
                        "proof_words": proof_words, "prep_commit_ms": prep_commit_ms},
             "e2e": {"value": e2e_value, "unit": "proofs/s", "ms_per_step": t_e2e / args.steps,
@@ -358,6 +364,8 @@ def main():
     ap.add_argument("--field", default="koala-bear", choices=["koala-bear", "baby-bear"])
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--wait", choices=["spin", "yield", "block"], default=None,
+                    help="host wait mode in the throughput regions (default spin)")
     ap.add_argument("--inflight", type=int, default=4, help="concurrent proofs per GPU in the throughput regions")
     args = ap.parse_args()
     if args.impl == "reference":

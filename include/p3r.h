@@ -332,6 +332,12 @@ int p3r_last_phase_times(p3r_ctx* ctx, const char** names_out, float* ms_out, ui
  *   bit 2  set   : DISABLE the device-side transcript of the FRI commit rounds in p3r_prove* (one host round trip per round). */
 int p3r_set_specialization(p3r_ctx* ctx, int enable);
 
+/* How host threads wait for the GPU (process-wide): 0 = spin (cudaStreamSynchronize; lowest latency, default), 1 = poll +
+ * sched_yield, 2 = block on an event (the thread sleeps; use when proofs in flight x ranks exceed the host cores — an
+ * aggregation service on a box with few cores per GPU). Also settable with the environment variable
+ * P3R_WAIT=spin|yield|block. No reference counterpart (rayon owns the reference's threads). */
+void p3r_set_wait_mode(int mode);
+
 /* CUDA-event stopwatch on the ctx stream (the stream every kernel of this ctx is launched on): start synchronises the
  * stream and records; stop records, synchronises and returns the elapsed device milliseconds. */
 int p3r_timer_start(p3r_ctx* ctx);

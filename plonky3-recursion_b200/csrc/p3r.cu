@@ -3,6 +3,8 @@
 // BatchStarkProver::prove, /root/reference circuit-prover/src/batch_stark_prover.rs:1275-1642 -> p3_batch_stark::prove_batch).
 // No CPU fallback: every compute entry point runs CUDA kernels from kernels.cuh or fails.
 #include <algorithm>
+#include <sched.h>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -35,6 +37,40 @@ struct Slab {
     char* base = nullptr;
     size_t size = 0, used = 0;
 };
+// Host wait for a stream. Mode 0 (default): cudaStreamSynchronize (the driver spins: lowest latency, one core per waiting
+// thread). Mode 1: poll cudaStreamQuery + sched_yield. Mode 2: block on a cudaEventBlockingSync event — the thread sleeps until
+// the interrupt, which matters when host threads outnumber cores (8 ranks x 4 proofs in flight on 16 cores): spinning or
+// polling waiters then starve the threads that have kernels to launch. Process-wide; set with P3R_WAIT=spin|yield|block or
+// p3r_set_wait_mode().
+static std::atomic<int> g_wait_mode{-1};
+static inline int wait_mode() {
+    int m = g_wait_mode.load(std::memory_order_relaxed);
+    if (m >= 0) return m;
+    const char* e = getenv("P3R_WAIT");
+    m = !e ? 0 : (!strcmp(e, "block") ? 2 : (!strcmp(e, "yield") ? 1 : 0));
+    g_wait_mode.store(m, std::memory_order_relaxed);
+    return m;
+}
+static inline cudaError_t stream_wait(cudaStream_t s) {
+    const int m = wait_mode();
+    if (m == 0) return cudaStreamSynchronize(s);
+    if (m == 1) {
+        for (;;) {
+            cudaError_t e = cudaStreamQuery(s);
+            if (e != cudaErrorNotReady) return e;
+            sched_yield();
+        }
+    }
+    thread_local cudaEvent_t ev = nullptr;   // one device per process (one rank per GPU), so one event per host thread
+    if (!ev) {
+        cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = cudaEventRecord(ev, s);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ev);
+}
+
 struct Arena {  // bump allocator over cudaMalloc'd slabs; reset() keeps the slabs for the next session
     std::vector<Slab> slabs;
     size_t cur = 0;
@@ -164,7 +200,7 @@ struct KT {
 };
 static void kstats_collect(p3r_ctx* ctx) {
     if (ctx->ev_pending.empty()) return;
-    cudaStreamSynchronize(ctx->stream);
+    stream_wait(ctx->stream);
     for (auto& pr : ctx->ev_pending) {
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev_pool[pr.second], ctx->ev_pool[pr.second + 1]);
@@ -395,7 +431,7 @@ static int ensure_twiddles(p3r_ctx* ctx, uint32_t logT) {
         set_err(ctx, "domain exceeds the field's two-adicity");
         return P3R_ERR_INVALID_ARG;
     }
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(stream_wait(ctx->stream));
     if (ctx->tws) cudaFree(ctx->tws);
     ctx->tws = ctx->tw = nullptr;
     size_t count = ((size_t)1 << logT) - 1;
@@ -927,7 +963,7 @@ static int read_cap(p3r_ctx* ctx, const Tree& t, uint32_t* cap_out) {
     uint32_t l = t.log_max_h - cap;
     CUDA_TRY(cudaMemcpyAsync(cap_out, t.digests + t.level_off(l) * 8, ((size_t)8 << cap) * 4, cudaMemcpyDeviceToHost,
                              ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(stream_wait(ctx->stream));
     return P3R_OK;
 }
 
@@ -1071,7 +1107,7 @@ static int prep_commit_impl(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_de
     auto t_prev = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) {
         if (!trace_prep) return;
-        cudaStreamSynchronize(ctx->stream);
+        stream_wait(ctx->stream);
         auto now = std::chrono::steady_clock::now();
         fprintf(stderr, "[p3r prep] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
         t_prev = now;
@@ -1214,7 +1250,7 @@ static int prep_commit_impl(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_de
         if (cap_out) std::memcpy(cap_out, pp->prep_cap.data(), pp->prep_cap.size() * 4);
         lap("tree");
     }
-    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    if (stream_wait(ctx->stream) != cudaSuccess) {
         set_err(ctx, "prep: stream sync failed");
         return fail(P3R_ERR_CUDA);
     }
@@ -1678,7 +1714,7 @@ static int open_impl(p3r_session* s, const uint32_t zeta_w[4], uint32_t* opened_
     // download; re-order into the per-instance ABI layout
     std::vector<Ext4> host(o_off);
     CUDA_TRY(cudaMemcpyAsync(host.data(), s->d_opened, (size_t)o_off * 16, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(stream_wait(ctx->stream));
     std::vector<uint32_t> outw;
     outw.reserve((size_t)o_off * 4);
     auto push = [&](uint32_t off, uint32_t width) {
@@ -1912,7 +1948,7 @@ static int fri_final_poly_impl(p3r_session* s, uint32_t* coeffs_out) {
     k_final_poly<F><<<(n + 63) / 64, 64, 0, ctx->stream>>>(s->final_vec, d_c, lf, ctx->tw, ctx->logT);
     LAUNCH_CHECK();
     CUDA_TRY(cudaMemcpyAsync(coeffs_out, d_c, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(stream_wait(ctx->stream));
     return P3R_OK;
 }
 
@@ -1964,7 +2000,7 @@ static int fri_query_impl(p3r_session* s, const uint32_t* indices, uint32_t nq, 
     k_query_gather<<<grid, 256, 0, ctx->stream>>>(d_segs, (uint32_t)segs.size(), d_idx, off, d_out);
     LAUNCH_CHECK();
     CUDA_TRY(cudaMemcpyAsync(out, d_out, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(stream_wait(ctx->stream));
     return P3R_OK;
 }
 
@@ -1996,7 +2032,7 @@ static int grind_impl(p3r_ctx* ctx, const uint32_t state[16], const uint32_t* pe
         LAUNCH_CHECK();
         uint32_t best;
         CUDA_TRY(cudaMemcpyAsync(&best, d + 24, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(stream_wait(ctx->stream));
         if (best != 0xffffffffu) {
             *witness_out = to_monty<F>(best);
             return P3R_OK;
@@ -2182,7 +2218,7 @@ static int prove_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* 
         }
         std::vector<Ext4> dev_betas(n_rounds);
         CUDA_TRY(cudaMemcpyAsync(dev_betas.data(), d_beta, n_rounds * sizeof(Ext4), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(stream_wait(ctx->stream));
         for (uint32_t r = 0; r < n_rounds; r++) {
             ch.observe_words(fri_caps.data() + r * capw, capw);
             commit_pow[r] = 0;
@@ -2275,7 +2311,7 @@ static int coset_lde_host_impl(p3r_ctx* ctx, const p3r_matrix_u32* in, uint32_t 
     k_transpose_out<<<grid, block, 0, ctx->stream>>>(lde, rm, (uint32_t)N, (uint32_t)w);
     LAUNCH_CHECK();
     CUDA_TRY(cudaMemcpyAsync(out, rm, N * w * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(stream_wait(ctx->stream));
     return P3R_OK;
 }
 template <class F>
@@ -2312,7 +2348,7 @@ static int permute_host_impl(p3r_ctx* ctx, uint32_t* states, uint32_t n) {
     k_permute_states<F><<<(n + 127) / 128, 128, 0, ctx->stream>>>(d, n);
     LAUNCH_CHECK();
     CUDA_TRY(cudaMemcpyAsync(states, d, (size_t)n * 64, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(stream_wait(ctx->stream));
     return P3R_OK;
 }
 template <class F>
@@ -2447,7 +2483,7 @@ int p3r_ctx_create(int device, const p3r_field_desc* field, const p3r_poseidon2_
 void p3r_ctx_destroy(p3r_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    stream_wait(ctx->stream);
     ctx->arena.destroy();
     for (auto& kv : ctx->gtables) {
         cudaFree(kv.second.lo);
@@ -2474,10 +2510,11 @@ int p3r_prep_commit(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_desc* desc
     cudaSetDevice(ctx->device);
     return DISPATCH(ctx, prep_commit_impl<F>(ctx, n_inst, descs, prep, out, cap_out, has_prep_out));
 }
+void p3r_set_wait_mode(int mode) { g_wait_mode.store(mode < 0 || mode > 2 ? 0 : mode, std::memory_order_relaxed); }
 void p3r_prep_free(p3r_prep* prep) {
     if (!prep) return;
     cudaSetDevice(prep->ctx->device);
-    cudaStreamSynchronize(prep->ctx->stream);
+    stream_wait(prep->ctx->stream);
     for (void* p : prep->owned) cudaFree(p);
     delete prep;
 }
@@ -2525,7 +2562,7 @@ int p3r_fri_query(p3r_session* s, const uint32_t* indices, uint32_t n, uint32_t*
 }
 void p3r_session_free(p3r_session* s) {
     if (!s) return;
-    cudaStreamSynchronize(s->ctx->stream);
+    stream_wait(s->ctx->stream);
     delete s;
 }
 int p3r_grind(p3r_ctx* ctx, const uint32_t state[16], const uint32_t* pending, uint32_t n_pending, uint32_t bits,
@@ -2577,7 +2614,7 @@ static int traces_upload_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matr
             return rc;
         }
     }
-    cudaStreamSynchronize(ctx->stream);
+    stream_wait(ctx->stream);
     *out = t;
     return P3R_OK;
 }
@@ -2615,7 +2652,7 @@ int p3r_traces_download(p3r_ctx* ctx, const p3r_prep* prep, const p3r_traces* tr
     k_transpose_out<<<grid, block, 0, ctx->stream>>>(traces->d[inst], rm, H, d.main_w);
     LAUNCH_CHECK();
     CUDA_TRY(cudaMemcpyAsync(out, rm, (size_t)H * d.main_w * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(stream_wait(ctx->stream));
     return P3R_OK;
 }
 int p3r_prove_ex(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, const p3r_poseidon2_ops* const* p2_ops,
@@ -2633,7 +2670,7 @@ int p3r_prove_ops(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* trac
 }
 void p3r_traces_free(p3r_traces* t) {
     if (!t) return;
-    cudaStreamSynchronize(t->ctx->stream);
+    stream_wait(t->ctx->stream);
     cudaFree(t->slab);
     delete t;
 }
@@ -2659,7 +2696,7 @@ int p3r_timer_start(p3r_ctx* ctx) {
         cudaEventCreate(&ctx->timer_ev[0]);
         cudaEventCreate(&ctx->timer_ev[1]);
     }
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(stream_wait(ctx->stream));
     CUDA_TRY(cudaEventRecord(ctx->timer_ev[0], ctx->stream));
     return P3R_OK;
 }

@@ -60,6 +60,8 @@ def load():
         lib.p3r_host_alloc.argtypes = [C.c_size_t]
         lib.p3r_host_free.restype = None
         lib.p3r_host_free.argtypes = [C.c_void_p]
+        lib.p3r_set_wait_mode.restype = None
+        lib.p3r_set_wait_mode.argtypes = [C.c_int]
         for name in ("p3r_ctx_destroy", "p3r_prep_free", "p3r_session_free", "p3r_traces_free"):
             getattr(lib, name).restype = None
             getattr(lib, name).argtypes = [C.c_void_p]
@@ -75,7 +77,7 @@ EXPORTS = ["p3r_abi_version", "p3r_build_info", "p3r_ctx_create", "p3r_ctx_destr
            "p3r_host_alloc", "p3r_host_free", "p3r_timer_start", "p3r_timer_stop", "p3r_set_kernel_timing",
            "p3r_reset_kernel_stats", "p3r_kernel_stats", "p3r_set_specialization", "p3r_prove_ex", "p3r_traces_upload_ex",
            "p3r_traces_download", "p3r_kernel_perms", "p3r_bench_fri_round", "p3r_prove_ops",
-           "p3r_traces_upload_ops"]
+           "p3r_traces_upload_ops", "p3r_set_wait_mode"]
 
 KERNEL_CLASSES = ["ntt_lde", "hash_rows", "compress", "logup", "quotient", "open", "reduced_openings", "fri_fold", "transpose",
                   "misc"]
@@ -156,6 +158,10 @@ class Context:
         t = (C.c_float * 2)()
         self._check(self.lib.p3r_bench_fri_round(self.h, log_len, log_arity, iters, C.c_uint64(seed), t))
         return {"fold_ms": t[0], "commit_ms": t[1]}
+
+    def set_wait_mode(self, mode: str):
+        """'spin' | 'yield' | 'block' (process-wide, p3r_set_wait_mode)."""
+        self.lib.p3r_set_wait_mode({"spin": 0, "yield": 1, "block": 2}[mode])
 
     def set_specialization(self, enable: bool):
         self._check(self.lib.p3r_set_specialization(self.h, int(enable)))
