@@ -256,11 +256,9 @@ def run_ours(args):
             t.join()
         return total, sum(ln[0].launch_count() for ln in lanes) - l0
 
-    # Host wait mode of the prover threads (p3r_set_wait_mode). Measured on B200 with the process confined to 2 cores and four
-    # proofs in flight: spin 325, yield 324, block 309 proofs/s (16 cores: 396 / - / 381) — the host-side limit is the launch work
-    # itself, not the waiting, so the default stays the driver's spin wait.
+    # Host wait mode of the prover threads in the throughput regions (p3r_set_wait_mode; the library default is yield).
     cores = len(os.sched_getaffinity(0))
-    wait_mode = args.wait or "spin"
+    wait_mode = args.wait or os.environ.get("P3R_WAIT", "yield")
     ctx.set_wait_mode(wait_mode)
     batch_steps(False, max(args.warmup, 3))
     barrier()
@@ -365,7 +363,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--wait", choices=["spin", "yield", "block"], default=None,
-                    help="host wait mode in the throughput regions (default spin)")
+                    help="host wait mode in the throughput regions (default: the library default, yield)")
     ap.add_argument("--inflight", type=int, default=4, help="concurrent proofs per GPU in the throughput regions")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -332,9 +332,10 @@ int p3r_last_phase_times(p3r_ctx* ctx, const char** names_out, float* ms_out, ui
  *   bit 2  set   : DISABLE the device-side transcript of the FRI commit rounds in p3r_prove* (one host round trip per round). */
 int p3r_set_specialization(p3r_ctx* ctx, int enable);
 
-/* How host threads wait for the GPU (process-wide): 0 = spin (cudaStreamSynchronize; lowest latency, default), 1 = poll +
- * sched_yield, 2 = block on an event (the thread sleeps; use when proofs in flight x ranks exceed the host cores — an
- * aggregation service on a box with few cores per GPU). Also settable with the environment variable
+/* How host threads wait for the GPU (process-wide): 1 = poll + sched_yield with device->host results staged through pinned
+ * memory (default: a waiting thread yields its core to a thread that has kernels to launch; best throughput with several
+ * proofs in flight per GPU and few host cores per GPU), 0 = spin inside the driver (cudaStreamSynchronize, direct copies),
+ * 2 = block on an event (the thread sleeps; least CPU, highest latency). Also settable with the environment variable
  * P3R_WAIT=spin|yield|block. No reference counterpart (rayon owns the reference's threads). */
 void p3r_set_wait_mode(int mode);
 

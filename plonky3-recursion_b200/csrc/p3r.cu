@@ -37,17 +37,19 @@ struct Slab {
     char* base = nullptr;
     size_t size = 0, used = 0;
 };
-// Host wait for a stream. Mode 0 (default): cudaStreamSynchronize (the driver spins: lowest latency, one core per waiting
-// thread). Mode 1: poll cudaStreamQuery + sched_yield. Mode 2: block on a cudaEventBlockingSync event — the thread sleeps until
-// the interrupt, which matters when host threads outnumber cores (8 ranks x 4 proofs in flight on 16 cores): spinning or
-// polling waiters then starve the threads that have kernels to launch. Process-wide; set with P3R_WAIT=spin|yield|block or
+// Host wait for a stream. Mode 1 (default): poll cudaStreamQuery + sched_yield, with every device->host result staged through
+// pinned memory (d2h_async / ctx_wait) so that no call blocks inside the driver: a waiting thread gives its core to a thread
+// that has kernels to launch. Mode 0: cudaStreamSynchronize and direct copies (the driver spins; with a pageable destination
+// the spin happens inside cudaMemcpyAsync). Mode 2: block on a cudaEventBlockingSync event (the thread sleeps; 0.8 ms of CPU
+// per proof instead of 3.9, but each wake-up costs latency). Measured on one B200, four proofs in flight: yield 412 proofs/s
+// (406 with the process confined to 2 cores), spin 379-397 (314), block 350 (351). Process-wide; P3R_WAIT=spin|yield|block or
 // p3r_set_wait_mode().
 static std::atomic<int> g_wait_mode{-1};
 static inline int wait_mode() {
     int m = g_wait_mode.load(std::memory_order_relaxed);
     if (m >= 0) return m;
     const char* e = getenv("P3R_WAIT");
-    m = !e ? 0 : (!strcmp(e, "block") ? 2 : (!strcmp(e, "yield") ? 1 : 0));
+    m = !e ? 1 : (!strcmp(e, "block") ? 2 : (!strcmp(e, "spin") ? 0 : 1));
     g_wait_mode.store(m, std::memory_order_relaxed);
     return m;
 }
@@ -148,6 +150,15 @@ struct p3r_ctx {
     // pinned staging for small uploads/downloads
     char* pin = nullptr;
     size_t pin_size = 0, pin_used = 0;
+    // D2H staging for the yield / block wait modes (d2h_async, ctx_wait)
+    char* pin_out = nullptr;
+    size_t pin_out_size = 0, pin_out_used = 0;
+    struct PendingCopy {
+        void* dst;
+        const void* src;
+        size_t bytes;
+    };
+    std::vector<PendingCopy> pending;
     char* dstage = nullptr;  // device mirror for small uploads
     size_t dstage_size = 0;
     std::string err;
@@ -198,9 +209,10 @@ struct KT {
         if (on) cudaEventRecord(ctx->ev_pool[ctx->ev_pending.back().second + 1], ctx->stream);
     }
 };
+static cudaError_t ctx_wait(p3r_ctx* ctx);
 static void kstats_collect(p3r_ctx* ctx) {
     if (ctx->ev_pending.empty()) return;
-    stream_wait(ctx->stream);
+    ctx_wait(ctx);
     for (auto& pr : ctx->ev_pending) {
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev_pool[pr.second], ctx->ev_pool[pr.second + 1]);
@@ -213,6 +225,26 @@ static void kstats_collect(p3r_ctx* ctx) {
 template <class T>
 static T* arena_alloc(p3r_ctx* ctx, size_t count) {
     return reinterpret_cast<T*>(ctx->arena.alloc(count * sizeof(T)));
+}
+// Device -> host copy of a result the host reads after the next ctx_wait(). With the driver's spin wait (mode 0) it is a plain
+// cudaMemcpyAsync: for a pageable destination the driver itself spins until the data has arrived. In the yield / block modes
+// the copy lands in pinned staging (truly asynchronous) and ctx_wait() moves it to `dst` after the stream has drained, so the
+// thread really sleeps while the GPU works.
+static cudaError_t d2h_async(p3r_ctx* ctx, void* dst, const void* dsrc, size_t bytes) {
+    const size_t b = (bytes + 63) & ~(size_t)63;
+    if (wait_mode() == 0 || !ctx->pin_out || ctx->pin_out_used + b > ctx->pin_out_size)
+        return cudaMemcpyAsync(dst, dsrc, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    char* h = ctx->pin_out + ctx->pin_out_used;
+    ctx->pin_out_used += b;
+    ctx->pending.push_back({dst, h, bytes});
+    return cudaMemcpyAsync(h, dsrc, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+}
+static cudaError_t ctx_wait(p3r_ctx* ctx) {
+    cudaError_t e = stream_wait(ctx->stream);
+    for (auto& c : ctx->pending) std::memcpy(c.dst, c.src, c.bytes);
+    ctx->pending.clear();
+    ctx->pin_out_used = 0;
+    return e;
 }
 // Copy a small host blob to the device through the pinned staging area (valid until the next session begins).
 static void* upload_small(p3r_ctx* ctx, const void* src, size_t bytes) {
@@ -431,7 +463,7 @@ static int ensure_twiddles(p3r_ctx* ctx, uint32_t logT) {
         set_err(ctx, "domain exceeds the field's two-adicity");
         return P3R_ERR_INVALID_ARG;
     }
-    CUDA_TRY(stream_wait(ctx->stream));
+    CUDA_TRY(ctx_wait(ctx));
     if (ctx->tws) cudaFree(ctx->tws);
     ctx->tws = ctx->tw = nullptr;
     size_t count = ((size_t)1 << logT) - 1;
@@ -961,9 +993,8 @@ static size_t tree_digest_words(uint32_t log_max_h) { return ((size_t)2 << log_m
 static int read_cap(p3r_ctx* ctx, const Tree& t, uint32_t* cap_out) {
     uint32_t cap = ctx->fri.cap_height;
     uint32_t l = t.log_max_h - cap;
-    CUDA_TRY(cudaMemcpyAsync(cap_out, t.digests + t.level_off(l) * 8, ((size_t)8 << cap) * 4, cudaMemcpyDeviceToHost,
-                             ctx->stream));
-    CUDA_TRY(stream_wait(ctx->stream));
+    CUDA_TRY(d2h_async(ctx, cap_out, t.digests + t.level_off(l) * 8, ((size_t)8 << cap) * 4));
+    CUDA_TRY(ctx_wait(ctx));
     return P3R_OK;
 }
 
@@ -1107,7 +1138,7 @@ static int prep_commit_impl(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_de
     auto t_prev = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) {
         if (!trace_prep) return;
-        stream_wait(ctx->stream);
+        ctx_wait(ctx);
         auto now = std::chrono::steady_clock::now();
         fprintf(stderr, "[p3r prep] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
         t_prev = now;
@@ -1250,7 +1281,7 @@ static int prep_commit_impl(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_de
         if (cap_out) std::memcpy(cap_out, pp->prep_cap.data(), pp->prep_cap.size() * 4);
         lap("tree");
     }
-    if (stream_wait(ctx->stream) != cudaSuccess) {
+    if (ctx_wait(ctx) != cudaSuccess) {
         set_err(ctx, "prep: stream sync failed");
         return fail(P3R_ERR_CUDA);
     }
@@ -1494,7 +1525,7 @@ static int commit_perm_impl(p3r_session* s, const uint32_t alpha[4], const uint3
     TRY(commit_tree<F>(ctx, mats, &s->perm_tree, dg));
     // terminals of instances with lookups, in order
     std::vector<Ext4> term(n_inst);
-    CUDA_TRY(cudaMemcpyAsync(term.data(), s->d_terminals, n_inst * sizeof(Ext4), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(d2h_async(ctx, term.data(), s->d_terminals, n_inst * sizeof(Ext4)));
     TRY(read_cap(ctx, s->perm_tree, cap_out));
     size_t k = 0;
     for (size_t i = 0; i < n_inst; i++)
@@ -1713,8 +1744,8 @@ static int open_impl(p3r_session* s, const uint32_t zeta_w[4], uint32_t* opened_
     }
     // download; re-order into the per-instance ABI layout
     std::vector<Ext4> host(o_off);
-    CUDA_TRY(cudaMemcpyAsync(host.data(), s->d_opened, (size_t)o_off * 16, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(stream_wait(ctx->stream));
+    CUDA_TRY(d2h_async(ctx, host.data(), s->d_opened, (size_t)o_off * 16));
+    CUDA_TRY(ctx_wait(ctx));
     std::vector<uint32_t> outw;
     outw.reserve((size_t)o_off * 4);
     auto push = [&](uint32_t off, uint32_t width) {
@@ -1947,8 +1978,8 @@ static int fri_final_poly_impl(p3r_session* s, uint32_t* coeffs_out) {
     if (!d_c) return P3R_ERR_OOM;
     k_final_poly<F><<<(n + 63) / 64, 64, 0, ctx->stream>>>(s->final_vec, d_c, lf, ctx->tw, ctx->logT);
     LAUNCH_CHECK();
-    CUDA_TRY(cudaMemcpyAsync(coeffs_out, d_c, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(stream_wait(ctx->stream));
+    CUDA_TRY(d2h_async(ctx, coeffs_out, d_c, (size_t)n * 16));
+    CUDA_TRY(ctx_wait(ctx));
     return P3R_OK;
 }
 
@@ -1999,8 +2030,8 @@ static int fri_query_impl(p3r_session* s, const uint32_t* indices, uint32_t nq, 
     dim3 grid(nq, 8);
     k_query_gather<<<grid, 256, 0, ctx->stream>>>(d_segs, (uint32_t)segs.size(), d_idx, off, d_out);
     LAUNCH_CHECK();
-    CUDA_TRY(cudaMemcpyAsync(out, d_out, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(stream_wait(ctx->stream));
+    CUDA_TRY(d2h_async(ctx, out, d_out, total * 4));
+    CUDA_TRY(ctx_wait(ctx));
     return P3R_OK;
 }
 
@@ -2031,8 +2062,8 @@ static int grind_impl(p3r_ctx* ctx, const uint32_t state[16], const uint32_t* pe
         k_grind<F><<<(batch + 127) / 128, 128, 0, ctx->stream>>>(d, d + 16, n_pending, bits, (uint32_t)base, batch, d + 24);
         LAUNCH_CHECK();
         uint32_t best;
-        CUDA_TRY(cudaMemcpyAsync(&best, d + 24, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(stream_wait(ctx->stream));
+        CUDA_TRY(d2h_async(ctx, &best, d + 24, 4));
+        CUDA_TRY(ctx_wait(ctx));
         if (best != 0xffffffffu) {
             *witness_out = to_monty<F>(best);
             return P3R_OK;
@@ -2213,12 +2244,12 @@ static int prove_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* 
         }
         for (uint32_t r = 0; r < n_rounds; r++) {
             const Tree& t = s->rounds[r].tree;
-            CUDA_TRY(cudaMemcpyAsync(fri_caps.data() + r * capw, t.digests + t.level_off(t.log_max_h - ctx->fri.cap_height) * 8,
-                                     capw * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(d2h_async(ctx, fri_caps.data() + r * capw, t.digests + t.level_off(t.log_max_h - ctx->fri.cap_height) * 8,
+                                     capw * 4));
         }
         std::vector<Ext4> dev_betas(n_rounds);
-        CUDA_TRY(cudaMemcpyAsync(dev_betas.data(), d_beta, n_rounds * sizeof(Ext4), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(stream_wait(ctx->stream));
+        CUDA_TRY(d2h_async(ctx, dev_betas.data(), d_beta, n_rounds * sizeof(Ext4)));
+        CUDA_TRY(ctx_wait(ctx));
         for (uint32_t r = 0; r < n_rounds; r++) {
             ch.observe_words(fri_caps.data() + r * capw, capw);
             commit_pow[r] = 0;
@@ -2310,8 +2341,8 @@ static int coset_lde_host_impl(p3r_ctx* ctx, const p3r_matrix_u32* in, uint32_t 
     dim3 grid((unsigned)((N + 31) / 32), (unsigned)((w + 31) / 32)), block(32, 8);
     k_transpose_out<<<grid, block, 0, ctx->stream>>>(lde, rm, (uint32_t)N, (uint32_t)w);
     LAUNCH_CHECK();
-    CUDA_TRY(cudaMemcpyAsync(out, rm, N * w * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(stream_wait(ctx->stream));
+    CUDA_TRY(d2h_async(ctx, out, rm, N * w * 4));
+    CUDA_TRY(ctx_wait(ctx));
     return P3R_OK;
 }
 template <class F>
@@ -2347,8 +2378,8 @@ static int permute_host_impl(p3r_ctx* ctx, uint32_t* states, uint32_t n) {
     CUDA_TRY(cudaMemcpyAsync(d, states, (size_t)n * 64, cudaMemcpyHostToDevice, ctx->stream));
     k_permute_states<F><<<(n + 127) / 128, 128, 0, ctx->stream>>>(d, n);
     LAUNCH_CHECK();
-    CUDA_TRY(cudaMemcpyAsync(states, d, (size_t)n * 64, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(stream_wait(ctx->stream));
+    CUDA_TRY(d2h_async(ctx, states, d, (size_t)n * 64));
+    CUDA_TRY(ctx_wait(ctx));
     return P3R_OK;
 }
 template <class F>
@@ -2467,6 +2498,8 @@ int p3r_ctx_create(int device, const p3r_field_desc* field, const p3r_poseidon2_
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ctx->pin_size = ctx->dstage_size = (size_t)8 << 20;
     ok = ok && cudaHostAlloc((void**)&ctx->pin, ctx->pin_size, cudaHostAllocDefault) == cudaSuccess;
+    ctx->pin_out_size = (size_t)4 << 20;
+    ok = ok && cudaHostAlloc((void**)&ctx->pin_out, ctx->pin_out_size, cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&ctx->dstage, ctx->dstage_size) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&ctx->d_p2, sizeof(Poseidon2Consts)) == cudaSuccess;
     ok = ok && cudaMemcpy(ctx->d_p2, &ctx->p2, sizeof(Poseidon2Consts), cudaMemcpyHostToDevice) == cudaSuccess;
@@ -2483,7 +2516,7 @@ int p3r_ctx_create(int device, const p3r_field_desc* field, const p3r_poseidon2_
 void p3r_ctx_destroy(p3r_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    stream_wait(ctx->stream);
+    ctx_wait(ctx);
     ctx->arena.destroy();
     for (auto& kv : ctx->gtables) {
         cudaFree(kv.second.lo);
@@ -2493,6 +2526,7 @@ void p3r_ctx_destroy(p3r_ctx* ctx) {
     if (ctx->tws) cudaFree(ctx->tws);
     if (ctx->d_p2) cudaFree(ctx->d_p2);
     if (ctx->pin) cudaFreeHost(ctx->pin);
+    if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
     if (ctx->dstage) cudaFree(ctx->dstage);
     for (int i = 0; i < p3r_ctx::N_AUX; i++) {
         if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
@@ -2510,11 +2544,11 @@ int p3r_prep_commit(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_desc* desc
     cudaSetDevice(ctx->device);
     return DISPATCH(ctx, prep_commit_impl<F>(ctx, n_inst, descs, prep, out, cap_out, has_prep_out));
 }
-void p3r_set_wait_mode(int mode) { g_wait_mode.store(mode < 0 || mode > 2 ? 0 : mode, std::memory_order_relaxed); }
+void p3r_set_wait_mode(int mode) { g_wait_mode.store(mode < 0 || mode > 2 ? 1 : mode, std::memory_order_relaxed); }
 void p3r_prep_free(p3r_prep* prep) {
     if (!prep) return;
     cudaSetDevice(prep->ctx->device);
-    stream_wait(prep->ctx->stream);
+    ctx_wait(prep->ctx);
     for (void* p : prep->owned) cudaFree(p);
     delete prep;
 }
@@ -2562,7 +2596,7 @@ int p3r_fri_query(p3r_session* s, const uint32_t* indices, uint32_t n, uint32_t*
 }
 void p3r_session_free(p3r_session* s) {
     if (!s) return;
-    stream_wait(s->ctx->stream);
+    ctx_wait(s->ctx);
     delete s;
 }
 int p3r_grind(p3r_ctx* ctx, const uint32_t state[16], const uint32_t* pending, uint32_t n_pending, uint32_t bits,
@@ -2614,7 +2648,7 @@ static int traces_upload_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matr
             return rc;
         }
     }
-    stream_wait(ctx->stream);
+    ctx_wait(ctx);
     *out = t;
     return P3R_OK;
 }
@@ -2651,8 +2685,8 @@ int p3r_traces_download(p3r_ctx* ctx, const p3r_prep* prep, const p3r_traces* tr
     dim3 grid((H + 31) / 32, (d.main_w + 31) / 32), block(32, 8);
     k_transpose_out<<<grid, block, 0, ctx->stream>>>(traces->d[inst], rm, H, d.main_w);
     LAUNCH_CHECK();
-    CUDA_TRY(cudaMemcpyAsync(out, rm, (size_t)H * d.main_w * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(stream_wait(ctx->stream));
+    CUDA_TRY(d2h_async(ctx, out, rm, (size_t)H * d.main_w * 4));
+    CUDA_TRY(ctx_wait(ctx));
     return P3R_OK;
 }
 int p3r_prove_ex(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, const p3r_poseidon2_ops* const* p2_ops,
@@ -2670,7 +2704,7 @@ int p3r_prove_ops(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* trac
 }
 void p3r_traces_free(p3r_traces* t) {
     if (!t) return;
-    stream_wait(t->ctx->stream);
+    ctx_wait(t->ctx);
     cudaFree(t->slab);
     delete t;
 }
@@ -2696,7 +2730,7 @@ int p3r_timer_start(p3r_ctx* ctx) {
         cudaEventCreate(&ctx->timer_ev[0]);
         cudaEventCreate(&ctx->timer_ev[1]);
     }
-    CUDA_TRY(stream_wait(ctx->stream));
+    CUDA_TRY(ctx_wait(ctx));
     CUDA_TRY(cudaEventRecord(ctx->timer_ev[0], ctx->stream));
     return P3R_OK;
 }
