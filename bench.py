@@ -33,6 +33,7 @@ FULL = dict(n_const=1500, n_public=43000, n_alu=60000, n_perms=12000, n_recompos
 # permutations of a launch, profiles/r1_ncu_summary.md): the unit conversion of the INT32-pipe roofline below.
 INSTR_PER_PERM = {"koala-bear": 5370.0, "baby-bear": 5600.0}   # ncu (koala) / SASS count (baby)
 N_SMS, LANES_PER_SM = 148, 128
+OUT = sys.stdout
 METRIC = "prove_next_layer throughput (layer proofs/s, whole job; ms_per_layer = latency of one proof alone)"
 
 
@@ -133,7 +134,7 @@ def run_reference(args):
                                    "value = (1/16)/seconds, i.e. extrapolated linearly in rows to the full layer"},
         "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=OUT, flush=True)
 
 
 def run_ours(args):
@@ -144,7 +145,6 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / warnings: stdout carries only the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     lib = importlib.import_module("plonky3-recursion_b200.lib")
@@ -343,7 +343,7 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": sample / dt, "unit": "proofs/s", "cores": os.cpu_count() or 1, "kind": "port",
                                     "sample": f"1/8-scale layer (rows/8 per table) proved {reps}x by oracle/liboracle.so (OpenMP), "
                                               f"{dt:.2f} s each; value extrapolated linearly in rows to the full layer"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=OUT, flush=True)
     for c_, p_, _, tr_, _ in lanes:
         tr_.close()
         p_.close()
@@ -365,6 +365,12 @@ def main():
                     help="host wait mode in the throughput regions (default: the library default, yield)")
     ap.add_argument("--inflight", type=int, default=4, help="concurrent proofs per GPU in the throughput regions")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: keep the real stdout aside and point fd 1 at stderr, so that anything a library
+    # prints there (NCCL's version banner, for one) cannot precede it.
+    global OUT
+    sys.stdout.flush()
+    OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         if args.steps == 20:
             args.steps = 3
