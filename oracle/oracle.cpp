@@ -20,7 +20,9 @@
 
 #include <algorithm>
 #include <cassert>
+#include <chrono>
 #include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <functional>
@@ -46,11 +48,23 @@ uint32_t TWO_ADICITY = 0;
 struct Fp {
     uint32_t v;
 };
-inline Fp mk(uint64_t x) { return Fp{(uint32_t)(x % P)}; }
-inline Fp operator+(Fp a, Fp b) { return mk((uint64_t)a.v + b.v); }
-inline Fp operator-(Fp a, Fp b) { return mk((uint64_t)a.v + P - b.v); }
+// x mod P. P is a run-time value (the field comes in through the C boundary); for the two moduli the reference is configured
+// with, the remainder is taken by a compile-time constant so the compiler can use multiply-and-shift instead of a 64-bit
+// division. Same canonical result either way.
+inline uint32_t reduce(uint64_t x) {
+    if (P == 0x7f000001u) return (uint32_t)(x % 0x7f000001ull);
+    if (P == 0x78000001u) return (uint32_t)(x % 0x78000001ull);
+    return (uint32_t)(x % P);
+}
+inline Fp mk(uint64_t x) { return Fp{reduce(x)}; }
+// every Fp holds a canonical residue (< P < 2^31): sums and differences need one conditional correction, no division
+inline Fp operator+(Fp a, Fp b) {
+    uint32_t s = a.v + b.v;
+    return Fp{s >= P ? s - P : s};
+}
+inline Fp operator-(Fp a, Fp b) { return Fp{a.v >= b.v ? a.v - b.v : a.v + P - b.v}; }
 inline Fp operator*(Fp a, Fp b) { return mk((uint64_t)a.v * b.v); }
-inline Fp operator-(Fp a) { return mk((uint64_t)P - a.v); }
+inline Fp operator-(Fp a) { return Fp{a.v ? P - a.v : 0u}; }
 inline bool operator==(Fp a, Fp b) { return a.v == b.v; }
 inline bool operator!=(Fp a, Fp b) { return a.v != b.v; }
 Fp fpow(Fp a, uint64_t e) {
@@ -586,8 +600,8 @@ void run_program(const Program& p, const RowCtx<BT>& rc, std::vector<Ext>* cons,
                 break;
             case P3R_OP_B_SEL: B[in.dst] = rc.sel[in.a]; break;
             case P3R_OP_B_CONST:
-                if constexpr (std::is_same<BT, Fp>::value) B[in.dst] = Fp{in.a};
-                else B[in.dst] = lift(Fp{in.a});
+                if constexpr (std::is_same<BT, Fp>::value) B[in.dst] = mk(in.a);
+                else B[in.dst] = lift(mk(in.a));
                 break;
             case P3R_OP_B_ADD: B[in.dst] = B[in.a] + B[in.b]; break;
             case P3R_OP_B_SUB: B[in.dst] = B[in.a] - B[in.b]; break;
@@ -975,6 +989,15 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
         if (s.log_qc > lb) throw std::runtime_error("oracle: quotient degree exceeds blowup");
     }
     Challenger ch;
+    // ORACLE_TRACE=1: wall-clock laps per phase on stderr (where a CPU run of this restatement spends its time)
+    const bool trace = getenv("ORACLE_TRACE") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[oracle] %-22s %9.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
 
     // -- preprocessed (ProverData::from_airs_and_degrees) --
     std::vector<Mat> prep_lde(n_inst);
@@ -987,6 +1010,7 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
     MerkleTree prep_tree;
     if (cm.has_prep) prep_tree = mmcs_commit(prep_ptrs);
 
+    lap("preprocessed");
     // -- main commit --
     std::vector<Mat> main_lde(n_inst);
     std::vector<const Mat*> main_ptrs;
@@ -999,6 +1023,7 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
     if (cm.has_prep) prep_cap = prep_tree.cap();
     transcript_head(ch, cm, main_tree.cap(), pubs, cm.has_prep ? &prep_cap : nullptr);
 
+    lap("main commit");
     // -- permutation --
     std::vector<std::vector<Ext>> chal(n_inst);
     std::vector<Mat> perm(n_inst), perm_lde(n_inst);
@@ -1023,6 +1048,7 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
     }
     Ext alpha = ch.sample_ext();
 
+    lap("permutation");
     // -- quotient --
     std::vector<std::vector<Mat>> qchunk_lde(n_inst);
     std::vector<std::vector<Mat>> qchunk(n_inst);
@@ -1101,6 +1127,7 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
     ch.observe_cap(quot_tree.cap());
     Ext zeta = ch.sample_ext();
 
+    lap("quotient");
     // -- openings: evaluate the committed polynomials at zeta / zeta*g by Horner on their coefficients --
     auto eval_cols = [&](const Mat& m, Fp in_shift, const Ext& z) {
         std::vector<Ext> out(m.w);
@@ -1133,6 +1160,7 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
     observe_openings(ch, rounds);
     Ext alpha_fri = ch.sample_ext();
 
+    lap("openings");
     // -- reduced openings per height --
     std::vector<const MerkleTree*> trees = {&main_tree, &quot_tree};
     if (cm.has_prep) trees.push_back(&prep_tree);
@@ -1173,6 +1201,7 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
     std::vector<uint32_t> sched = arity_schedule(in_heights);
     uint32_t log_max = in_heights[0];
 
+    lap("reduced openings");
     // -- FRI commit phase --
     std::vector<Ext> folded = ro[log_max];
     std::vector<Mat> fri_mats(sched.size());
@@ -1215,6 +1244,7 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
     for (auto k : sched) ch.observe(mk(k));
     Fp query_pow = ch.grind(FRI.query_pow_bits);
 
+    lap("fri commit + queries");
     // -- proof blob --
     Writer w;
     size_t cap_n = (size_t)1 << CAP_HEIGHT;
