@@ -1063,6 +1063,7 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
             o.h = NQ;
             o.w = m.w;
             o.d.resize(NQ * m.w);
+#pragma omp parallel for schedule(dynamic)
             for (size_t c = 0; c < m.w; c++) {
                 std::vector<Fp> col(m.h);
                 for (size_t r = 0; r < m.h; r++) col[r] = m.at(r, c);
@@ -1131,6 +1132,7 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
     // -- openings: evaluate the committed polynomials at zeta / zeta*g by Horner on their coefficients --
     auto eval_cols = [&](const Mat& m, Fp in_shift, const Ext& z) {
         std::vector<Ext> out(m.w);
+#pragma omp parallel for schedule(dynamic)
         for (size_t c = 0; c < m.w; c++) {
             std::vector<Fp> col(m.h);
             for (size_t r = 0; r < m.h; r++) col[r] = m.at(r, c);
