@@ -310,6 +310,15 @@ int p3r_coset_lde(p3r_ctx* ctx, const p3r_matrix_u32* in, uint32_t log_blowup, u
 int p3r_mmcs_commit(p3r_ctx* ctx, uint32_t n_mats, const p3r_matrix_u32* mats, uint32_t* cap_out);
 /* Poseidon2 permutation of n states of 16 words (in place). */
 int p3r_poseidon2_permute(p3r_ctx* ctx, uint32_t* states, uint32_t n);
+
+/* Host-only Poseidon2 (no CUDA call, usable without a GPU): the permutation the prover's host transcript uses (AVX2 when the
+ * CPU has it, checked against the scalar twin at creation), for host code that must hash exactly like the prover — the
+ * circuit runner's Poseidon2 rows (circuit/src/ops/poseidon_perm/executor.rs) when a GPU batch is not worth a round trip, and
+ * the synthetic-workload generator. `states`: n x 16 Montgomery words, permuted in place. Not a proving fallback. */
+typedef struct p3r_host_hasher p3r_host_hasher;
+int p3r_host_hasher_create(const p3r_field_desc* field, const p3r_poseidon2_consts* p2, p3r_host_hasher** out);
+int p3r_host_hasher_permute(const p3r_host_hasher* h, uint32_t* states, size_t n);
+void p3r_host_hasher_free(p3r_host_hasher* h);
 /* Device-resident benchmark of the commit path (LDE + Merkle) on a synthetic matrix:
  * returns CUDA-event milliseconds per phase, averaged over `iters`. times_ms_out: [lde, leaves, tree]. */
 int p3r_bench_commit(p3r_ctx* ctx, uint32_t log_height, uint32_t width, uint32_t iters, uint64_t seed,

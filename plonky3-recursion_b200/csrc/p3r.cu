@@ -2870,3 +2870,45 @@ int p3r_last_phase_times(p3r_ctx* ctx, const char** names_out, float* ms_out, ui
 uint64_t p3r_launch_count(const p3r_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 }  // extern "C"
+
+// ---- host-only Poseidon2 (no CUDA call): the transcript's permutation behind a handle, for host code that needs the same
+// hash the prover uses — the circuit runner's Poseidon2 rows (SURVEY.md §8f item 4 when no GPU batch is worth it) and the
+// synthetic-workload generator. States are Montgomery words, like p3r_poseidon2_permute.
+struct p3r_host_hasher {
+    int field_id = 0;
+    Poseidon2Consts k{};
+    HostPermuteFn fn = nullptr;
+};
+extern "C" {
+int p3r_host_hasher_create(const p3r_field_desc* field, const p3r_poseidon2_consts* p2, p3r_host_hasher** out) {
+    if (!field || !p2 || !out || !p2->external_rc || !p2->internal_rc || !p2->internal_diag) return P3R_ERR_INVALID_ARG;
+    uint32_t want_p = field->field_id == P3R_FIELD_KOALABEAR ? KoalaBear::P : BabyBear::P;
+    if (field->field_id > 1 || field->p != want_p) return P3R_ERR_UNSUPPORTED;
+    uint32_t rp = field->field_id == P3R_FIELD_KOALABEAR ? KoalaBear::ROUNDS_P : BabyBear::ROUNDS_P;
+    uint32_t sb = field->field_id == P3R_FIELD_KOALABEAR ? KoalaBear::SBOX : BabyBear::SBOX;
+    if (p2->width != 16 || p2->rounds_f != 8 || p2->rounds_p != rp || p2->sbox_degree != sb) return P3R_ERR_UNSUPPORTED;
+    auto* h = new p3r_host_hasher();
+    h->field_id = (int)field->field_id;
+    std::memcpy(h->k.ext_rc, p2->external_rc, 8 * 16 * 4);
+    std::memset(h->k.int_rc, 0, sizeof h->k.int_rc);
+    std::memcpy(h->k.int_rc, p2->internal_rc, rp * 4);
+    std::memcpy(h->k.diag, p2->internal_diag, 16 * 4);
+    h->k.zero = 0;
+    bool fast = true;
+    for (int i = 0; i < 16; i++) {
+        uint32_t want = h->field_id == 0 ? to_monty<KoalaBear>(diag_spec_canonical<KoalaBear>(i))
+                                         : to_monty<BabyBear>(diag_spec_canonical<BabyBear>(i));
+        fast = fast && h->k.diag[i] == want;
+    }
+    h->k.fast_diag = fast ? 1u : 0u;
+    h->fn = h->field_id == 0 ? pick_host_permute<KoalaBear>(h->k) : pick_host_permute<BabyBear>(h->k);
+    *out = h;
+    return P3R_OK;
+}
+int p3r_host_hasher_permute(const p3r_host_hasher* h, uint32_t* states, size_t n) {
+    if (!h || (!states && n)) return P3R_ERR_INVALID_ARG;
+    for (size_t i = 0; i < n; i++) h->fn(states + 16 * i, h->k);
+    return P3R_OK;
+}
+void p3r_host_hasher_free(p3r_host_hasher* h) { delete h; }
+}  // extern "C"

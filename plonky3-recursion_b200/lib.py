@@ -60,6 +60,9 @@ def load():
         lib.p3r_host_alloc.argtypes = [C.c_size_t]
         lib.p3r_host_free.restype = None
         lib.p3r_host_free.argtypes = [C.c_void_p]
+        lib.p3r_host_hasher_permute.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        lib.p3r_host_hasher_free.restype = None
+        lib.p3r_host_hasher_free.argtypes = [C.c_void_p]
         lib.p3r_set_wait_mode.restype = None
         lib.p3r_set_wait_mode.argtypes = [C.c_int]
         for name in ("p3r_ctx_destroy", "p3r_prep_free", "p3r_session_free", "p3r_traces_free"):
@@ -77,10 +80,44 @@ EXPORTS = ["p3r_abi_version", "p3r_build_info", "p3r_ctx_create", "p3r_ctx_destr
            "p3r_host_alloc", "p3r_host_free", "p3r_timer_start", "p3r_timer_stop", "p3r_set_kernel_timing",
            "p3r_reset_kernel_stats", "p3r_kernel_stats", "p3r_set_specialization", "p3r_prove_ex", "p3r_traces_upload_ex",
            "p3r_traces_download", "p3r_kernel_perms", "p3r_bench_fri_round", "p3r_prove_ops",
-           "p3r_traces_upload_ops", "p3r_set_wait_mode"]
+           "p3r_traces_upload_ops", "p3r_set_wait_mode", "p3r_host_hasher_create", "p3r_host_hasher_permute",
+           "p3r_host_hasher_free"]
 
 KERNEL_CLASSES = ["ntt_lde", "hash_rows", "compress", "logup", "quotient", "open", "reduced_openings", "fri_fold", "transpose",
                   "misc"]
+
+
+class HostHasher:
+    """p3r_host_hasher: the prover's host-side Poseidon2 permutation (no GPU needed). Canonical states in, canonical out."""
+
+    def __init__(self, field="koala-bear", poseidon2: Poseidon2Params | None = None):
+        self.lib = load()
+        self.field = get_field(field) if isinstance(field, str) else field
+        self._m = abi.Marshal(self.field)
+        fd, pc = self._m.field_desc(), self._m.poseidon2(poseidon2 or Poseidon2Params(self.field.field_id))
+        h = C.c_void_p()
+        rc = self.lib.p3r_host_hasher_create(C.byref(fd), C.byref(pc), C.byref(h))
+        if rc != 0:
+            raise P3RError(rc, "p3r_host_hasher_create failed")
+        self.h = h
+
+    def permute(self, states_canonical) -> np.ndarray:
+        s = np.ascontiguousarray(self.field.to_monty(np.asarray(states_canonical, dtype=np.uint32)).reshape(-1, 16))
+        rc = self.lib.p3r_host_hasher_permute(self.h, abi.as_u32p(s), s.shape[0])
+        if rc != 0:
+            raise P3RError(rc, "p3r_host_hasher_permute failed")
+        return self.field.from_monty(s)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.p3r_host_hasher_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Context:

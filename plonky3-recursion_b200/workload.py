@@ -152,7 +152,18 @@ class NpoTables:
         def pick():
             return sources[int(rng.integers(0, len(sources)))]
 
+        # One dependent permutation per table row: the library's host hasher (p3r_host_hasher, 20 us per call) when it is
+        # built, the numpy restatement (1 ms per call, same values) otherwise — this is input generation, not the prover.
+        hasher = None
+        try:
+            from . import lib as _lib
+            hasher = _lib.HostHasher(F, self.params)
+        except Exception:
+            hasher = None
+
         def perm(state):
+            if hasher is not None:
+                return [int(x) for x in hasher.permute(np.array(state, dtype=np.uint32))[0]]
             return [int(x) for x in self.params.permute(np.array(state, dtype=np.uint64).reshape(1, 16))[0]]
 
         def row(**kw):

@@ -52,3 +52,25 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"oracle_py|liboracle|orc_[a-z_]+\(", text):
                     offenders.append(os.path.join(dirpath, f))
     assert not offenders, offenders
+
+
+@pytest.mark.parametrize("field", ["koala-bear", "baby-bear"])
+def test_host_hasher_matches_the_oracle_and_the_numpy_restatement(field):
+    """p3r_host_hasher (the prover's host-side transcript permutation; host code only, so it runs without a GPU) against two
+    independent restatements: the oracle's Poseidon2 and poseidon2_params.permute."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from common import make_oracle
+    p2mod = importlib.import_module("plonky3-recursion_b200.poseidon2_params")
+    orc = make_oracle(field)
+    F = orc.field
+    rng = np.random.default_rng(11)
+    st = np.concatenate([F.rand(rng, (64, 16)), np.zeros((1, 16), dtype=np.uint32), np.full((1, 16), F.p - 1, dtype=np.uint32)])
+    hh = lib.HostHasher(field)
+    got = hh.permute(st)
+    assert np.array_equal(got, np.asarray(orc.poseidon2_permute(st), dtype=np.uint32))
+    assert np.array_equal(got, np.asarray(p2mod.Poseidon2Params(F.field_id).permute(st.astype(np.uint64)), dtype=np.uint32))
+    one = hh.permute(st[3])
+    assert one.shape == (1, 16) and np.array_equal(one[0], got[3])
+    hh.close()
