@@ -38,6 +38,13 @@ __global__ void __launch_bounds__(256) k_pipe(uint32_t* out, uint32_t seed) {
                 uint32_t r2 = r - 0x7f000001u;
                 a[i] = r2 < r ? r2 : r;
             }
+            if (OP == 9) {  // Shoup product by a fixed multiplier w with w' = floor(w * 2^32 / P): a*w - hi(a*w')*P in [0, 2P)
+                const uint32_t P = 0x7f000001u;
+                uint32_t q = __umulhi(a[i], c);   // c plays w'
+                uint32_t r = a[i] * b - q * P;    // b plays w
+                uint32_t r2 = r - P;
+                a[i] = r2 < r ? r2 : r;
+            }
         }
     }
     uint32_t s = 0;
@@ -125,6 +132,7 @@ int main() {
     run<5>("LOP3", 1, d);
     run<6>("SHF", 1, d);
     run<7>("IMAD+IADD3 1:1 (pairs)", 2, d);
+    run<9>("Shoup product (fixed w)", 1, d);
     run<8>("Montgomery fmul", 1, d);
     lat<0>("SHFL.BFLY", d);
     lat<8>("SHFL.IDX", d);
