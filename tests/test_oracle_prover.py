@@ -146,3 +146,20 @@ def test_layer_with_public_values_and_mixed_heights():
     insts, preps, traces, pubs = L.insts + fi, L.preps + fp, L.traces + ft, L.pubs + fpub
     proof = orc.prove(insts, preps, traces, pubs)
     orc.verify(insts, orc.prep_commit(insts, preps), pubs, proof)
+
+
+@pytest.mark.parametrize("public_lanes,alu_lanes,horner_k", [(1, 1, 2), (2, 2, 4), (2, 4, 3), (4, 3, 2)])
+def test_table_packing_variants(public_lanes, alu_lanes, horner_k):
+    """`TablePacking::new(public_lanes, alu_lanes)` with different packed-Horner depths (alu_air.rs:22-58): widths follow
+    `widths()`, every AIR holds on its trace, the bus balances and the proof verifies."""
+    orc = make_oracle("koala-bear")
+    L = wl.synthetic_layer(orc.field, 13, n_const=10, n_public=33, n_alu=260, n_perms=20, n_recompose=5, min_height=16,
+                           public_lanes=public_lanes, alu_lanes=alu_lanes, horner_k=horner_k)
+    alu_mod = importlib.import_module("plonky3-recursion_b200.airs.alu")
+    assert (L.insts[2].main_width, L.insts[2].prep_width) == alu_mod.widths(4, alu_lanes, horner_k)
+    assert (L.insts[1].main_width, L.insts[1].prep_width) == (4 * public_lanes, 2 * public_lanes)
+    assert len(L.insts[2].interactions) == 4 * alu_lanes + 2 * (horner_k - 1)
+    for s, pm, tr in zip(L.insts, L.preps, L.traces):
+        assert orc.check_constraints(s, pm, tr, None) is None, s.name
+    proof = orc.prove(L.insts, L.preps, L.traces, L.pubs)
+    orc.verify(L.insts, orc.prep_commit(L.insts, L.preps), L.pubs, proof)
