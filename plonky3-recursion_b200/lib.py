@@ -33,7 +33,8 @@ class P3RError(RuntimeError):
 
 def build(force: bool = False) -> str:
     """Compile csrc/ for sm_100a into libp3r_b200.so (in-tree)."""
-    srcs = [os.path.join(_HERE, "csrc", f) for f in ("p3r.cu", "spec.cu", "spec.h", "kernels.cuh", "field.cuh", "poseidon2.cuh", "specialized_gen.cuh")]
+    csrc = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(csrc, f) for f in sorted(os.listdir(csrc)) if f.endswith((".cu", ".cuh", ".h", ".cpp")) or f == "Makefile"]
     srcs.append(os.path.join(_HERE, "..", "include", "p3r.h"))
     stale = not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in srcs)
     if force or stale:
