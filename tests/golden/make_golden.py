@@ -28,7 +28,11 @@ wl = importlib.import_module("plonky3-recursion_b200.workload")
 
 PERM_INPUTS = [[0] * 16, list(range(16)), [(i * 0x9E3779B1) % 0x78000001 for i in range(1, 17)]]
 LAYERS = [dict(seed=7, n_const=20, n_public=30, n_alu=200, n_perms=50, n_recompose=10, min_height=32),
-          dict(seed=11, n_const=5, n_public=70, n_alu=90, n_perms=17, n_recompose=3, min_height=16)]
+          dict(seed=11, n_const=5, n_public=70, n_alu=90, n_perms=17, n_recompose=3, min_height=16),
+          # `recompose/coeff` table, two lanes (recompose_air.rs:175-197)
+          dict(seed=41, n_const=12, n_public=50, n_alu=300, n_perms=40, n_recompose=37, min_height=32, recompose_coeff=True,
+               recompose_lanes=2)]
+BASE_FIB = [dict(n=1000, min_height=256), dict(n=40, min_height=16)]   # recursive_fibonacci's base circuit, extension degree 1
 
 
 def sha(a: np.ndarray) -> str:
@@ -56,6 +60,14 @@ def vectors(field: str) -> dict:
         orc.verify(L.insts, orc.prep_commit(L.insts, L.preps), L.pubs, proof)
         out["layers"].append({"cfg": cfg, "shapes": [list(s) for s in L.shapes], "words": int(proof.size), "sha256": sha(proof),
                               "prep_cap": orc.prep_commit(L.insts, L.preps).tolist(), "head": proof[:40].tolist()})
+    out["base_fibonacci"] = []
+    for cfg in BASE_FIB:
+        L = wl.base_layer_fibonacci(F, cfg["n"], min_height=cfg["min_height"])
+        proof = orc.prove(L.insts, L.preps, L.traces, L.pubs)
+        orc.verify(L.insts, orc.prep_commit(L.insts, L.preps), L.pubs, proof)
+        out["base_fibonacci"].append({"cfg": cfg, "shapes": [list(s) for s in L.shapes], "words": int(proof.size),
+                                      "sha256": sha(proof), "prep_cap": orc.prep_commit(L.insts, L.preps).tolist(),
+                                      "expected_result": int(L.traces[1][0, 0])})
     return out
 
 
