@@ -7,8 +7,9 @@
 A step = one `prove_all_tables` over one synthetic steady-state recursion layer (tables Const/Public/ALU/Poseidon2/Recompose
 at the reference's layer shapes; DEFAULT_FRI = the examples' parameters: log_blowup 2, max_log_arity 2,
 log_final_poly_len 5, 54 queries, 15-bit query PoW). Multi-GPU: the path shards over independent proofs (leaves / subtrees
-of the 2-to-1 aggregation tree), one proof stream per GPU, no data-path collective (weak scaling).
-Prints ONE JSON line on rank 0.
+of the 2-to-1 aggregation tree), no data-path collective (weak scaling). `ms_per_layer` is one proof alone on the GPU; `value`
+and `e2e` are measured with `--inflight` (default 4) proofs in flight per GPU, one context + stream + host thread each.
+Prints ONE JSON line on rank 0 (fd 1 is pointed at stderr for everything else).
 """
 from __future__ import annotations
 
