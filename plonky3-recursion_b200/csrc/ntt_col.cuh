@@ -18,8 +18,38 @@
 #include <cuda_runtime.h>
 
 #include "field.cuh"
+#if defined(P3R_NTT_ALU_ADDS)
+#include "poseidon2.cuh"   // c_p2[..].zero: a run-time zero in constant memory
+#endif
 
 namespace p3r {
+
+// Butterfly addition / subtraction. ptxas balances integer additions between the ALU pipe (IADD3) and the multiplier pipe
+// (IMAD.IADD) as if IMAD.WIDE / IMAD.HI cost one slot; they cost two, so in these loops the multiplier pipe is the crowded one
+// (scripts/sass_pipe_model.py: radix-32 loop 1213 multiplier-pipe cycles against 584 ALU). With P3R_NTT_ALU_ADDS the additions
+// take a third, run-time-zero operand, which only an IADD3 can encode: 1213 -> 967 / 584 -> 818 cycles in that loop, same
+// instruction count and registers (static model; to be measured on the GPU before it becomes the default).
+#if defined(P3R_NTT_ALU_ADDS)
+template <class F>
+__device__ __forceinline__ uint32_t ntt_add(uint32_t a, uint32_t b) {
+    uint32_t s = a + b + c_p2[FieldId<F>::value].zero, s2 = s - F::P;
+    return s2 < s ? s2 : s;
+}
+template <class F>
+__device__ __forceinline__ uint32_t ntt_sub(uint32_t a, uint32_t b) {
+    uint32_t d = a - b + c_p2[FieldId<F>::value].zero, d2 = d + F::P;
+    return d2 < d ? d2 : d;
+}
+#else
+template <class F>
+__device__ __forceinline__ uint32_t ntt_add(uint32_t a, uint32_t b) {
+    return fadd<F>(a, b);
+}
+template <class F>
+__device__ __forceinline__ uint32_t ntt_sub(uint32_t a, uint32_t b) {
+    return fsub<F>(a, b);
+}
+#endif
 
 constexpr uint32_t COL_MIN_LOG = 5, COL_MAX_LOG = 15, COL_TOP_MAX_LOG = 27;  // taller columns: k_ntt_top passes above stage 15
 
@@ -88,11 +118,11 @@ __device__ __forceinline__ void col_group(uint32_t (&v)[1 << Q], uint32_t W, con
             const uint32_t x = v[k], y = v[k1];
             if (FWD) {
                 const uint32_t ty = fmul<F>(y, t);
-                v[k] = fadd<F>(x, ty);
-                v[k1] = fsub<F>(x, ty);
+                v[k] = ntt_add<F>(x, ty);
+                v[k1] = ntt_sub<F>(x, ty);
             } else {
-                v[k] = fadd<F>(x, y);
-                v[k1] = fmul<F>(fsub<F>(x, y), t);
+                v[k] = ntt_add<F>(x, y);
+                v[k1] = fmul<F>(ntt_sub<F>(x, y), t);
             }
         }
     }
@@ -180,12 +210,12 @@ __device__ __forceinline__ void col_radix32(uint32_t* sm, uint32_t n_elems, cons
                 const uint32_t x = v[c], y = v[c + m];
                 if (FWD) {
                     const uint32_t ty = fmul<F>(y, tw);
-                    v[c] = fadd<F>(x, ty);
-                    v[c + m] = fsub<F>(x, ty);
+                    v[c] = ntt_add<F>(x, ty);
+                    v[c + m] = ntt_sub<F>(x, ty);
                 } else {
-                    v[c] = fadd<F>(x, y);
+                    v[c] = ntt_add<F>(x, y);
                     // the inverse twiddle of e == 0 is 1: no product
-                    v[c + m] = (c & (m - 1)) ? fmul<F>(fsub<F>(x, y), tw) : fsub<F>(x, y);
+                    v[c + m] = (c & (m - 1)) ? fmul<F>(ntt_sub<F>(x, y), tw) : ntt_sub<F>(x, y);
                 }
             }
         }
