@@ -512,3 +512,19 @@ def test_full_size_layer_is_accepted_by_the_oracle_verifier():
             orc.verify(L.insts, pd.preprocessed_commitment, L.pubs, bad)
     pd.close()
     ctx.close()
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: first run is the round-end suite; the "
+                                        "oracle side of the same systems is covered by test_table_packing_variants on CPU")
+@pytest.mark.parametrize("public_lanes,alu_lanes,horner_k", [(2, 2, 4), (2, 4, 3), (4, 3, 2)])
+def test_table_packing_variants_bit_identical(pair, public_lanes, alu_lanes, horner_k):
+    """Other `TablePacking` shapes (public lanes, ALU lanes, packed-Horner depth): interpreter kernels for every table."""
+    wl = importlib.import_module("plonky3-recursion_b200.workload")
+    ctx, orc = pair
+    L = wl.synthetic_layer(ctx.field, 13, n_const=10, n_public=33, n_alu=260, n_perms=20, n_recompose=5, min_height=16,
+                           public_lanes=public_lanes, alu_lanes=alu_lanes, horner_k=horner_k)
+    pd = lib.ProverData.from_airs_and_degrees(ctx, L.insts, L.preps)
+    proof = lib.BatchStarkProver(ctx).prove_all_tables(L.traces, pd, L.pubs)
+    assert np.array_equal(proof, orc.prove(L.insts, L.preps, L.traces, L.pubs))
+    orc.verify(L.insts, pd.preprocessed_commitment, L.pubs, proof)
+    pd.close()
