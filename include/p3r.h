@@ -296,6 +296,12 @@ int p3r_traces_download(p3r_ctx* ctx, const p3r_prep* prep, const p3r_traces* tr
  * bench.py uses it for the device-resident `value` next to the host-buffer `e2e` number. */
 int p3r_traces_upload(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* traces, p3r_traces** out);
 void p3r_traces_free(p3r_traces* t);
+/* Overwrite rows [row0, row0 + n_rows) of the device-resident main trace of instance `inst` with `rows` (row-major,
+ * n_rows x main_width Montgomery words, host memory). This is how the per-proof part of an otherwise cached witness reaches the
+ * device: in the aggregation tree (recursion/examples/recursive_aggregation.rs:676-704) a node's Public table carries values
+ * taken from its two child proofs while the rest of its traces keep their shape. Synchronous (returns after the copy). */
+int p3r_traces_write_rows(p3r_ctx* ctx, const p3r_prep* prep, p3r_traces* traces, uint32_t inst, uint32_t row0,
+                          uint32_t n_rows, const uint32_t* rows);
 int p3r_prove_resident(p3r_ctx* ctx, const p3r_prep* prep, const p3r_traces* traces, const uint32_t* const* public_values,
                        uint32_t* proof_out, size_t cap_words, size_t* n_words);
 /* Pinned host memory for trace/proof buffers (cudaHostAlloc); plain malloc'd buffers also work, just slower to copy. */

@@ -190,9 +190,15 @@ class Marshal:
             arr[i].alu = C.pointer(st)
         return self.keep(arr)
 
-    def public_values(self, pubs) -> C.Array:
+    def public_values(self, pubs, insts=None) -> C.Array:
+        """pubs[k]: canonical public values of instance k (None / empty when it has none). With `insts` the lengths are
+        checked against n_public here; the library checks for NULL again (P3R_ERR_INVALID_ARG)."""
         arr = (u32p * len(pubs))()
         for k, pv in enumerate(pubs):
+            if insts is not None:
+                have = 0 if pv is None else len(pv)
+                if have != insts[k].n_public:
+                    raise ValueError(f"instance {k}: {have} public values given, the AIR declares {insts[k].n_public}")
             if pv is None or len(pv) == 0:
                 arr[k] = None
             else:

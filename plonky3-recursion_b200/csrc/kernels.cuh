@@ -60,6 +60,15 @@ static __global__ void k_transpose_out(const uint32_t* __restrict__ in, uint32_t
     }
 }
 
+// rows [row0, row0 + n_rows) of a column-major device matrix (height h, width w) <- row-major `rows` (p3r_traces_write_rows).
+static __global__ void k_scatter_rows(const uint32_t* __restrict__ rows, uint32_t* __restrict__ out, uint32_t h, uint32_t w,
+                                      uint32_t row0, uint32_t n_rows) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows * w) return;
+    const uint32_t r = i / w, c = i % w;
+    out[(size_t)c * h + row0 + r] = rows[i];
+}
+
 // ------------------------------------------------------------------------------------------------
 // K4 (second implementation): multi-pass tile kernel for the batched coset LDE. The product path uses the whole-column
 // kernels of ntt_col.cuh for every column of 2^5 rows or more; this kernel serves columns shorter than 32 rows and is the

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -159,6 +160,7 @@ struct p3r_ctx {
         size_t bytes;
     };
     std::vector<PendingCopy> pending;
+    uint32_t *grind_pin = nullptr, *grind_dev = nullptr;  // private 128-byte staging of p3r_grind
     char* dstage = nullptr;  // device mirror for small uploads
     size_t dstage_size = 0;
     std::string err;
@@ -1314,6 +1316,11 @@ static int prove_begin_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix
     size_t max_rm = 0;
     for (size_t i = 0; i < n_inst; i++) {
         const InstDev& d = prep->inst[i];
+        if (d.n_pub && (!public_values || !public_values[i])) {
+            set_err(ctx, "public values missing for instance " + std::to_string(i) + " (n_public = " + std::to_string(d.n_pub) + ")");
+            delete s;
+            return P3R_ERR_INVALID_ARG;
+        }
         const bool from_ops = tops && (tops[i].poseidon2 || tops[i].alu);
         if (!resident && !from_ops && (traces[i].height != (1u << d.log_h) || traces[i].width != d.main_w || !traces[i].data)) {
             set_err(ctx, "trace shape mismatch for instance " + std::to_string(i));
@@ -1349,6 +1356,11 @@ static int prove_begin_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix
         }
         if (d.n_pub) {
             s->d_pub[i] = (uint32_t*)upload_small(ctx, public_values[i], (size_t)d.n_pub * 4);
+            if (!s->d_pub[i]) {
+                set_err(ctx, "staging exhausted (public values)");
+                delete s;
+                return P3R_ERR_OOM;
+            }
         } else {
             s->d_pub[i] = reinterpret_cast<uint32_t*>(ctx->dstage);
         }
@@ -2051,12 +2063,15 @@ static int grind_impl(p3r_ctx* ctx, const uint32_t state[16], const uint32_t* pe
     std::memset(host + 16, 0, 32);
     if (n_pending) std::memcpy(host + 16, pending, (size_t)n_pending * 4);
     host[24] = 0xffffffffu;
-    uint32_t* d = (uint32_t*)upload_small(ctx, host, sizeof host);
-    if (!d) {  // staging may be exhausted outside a session: fall back to a private buffer
-        ctx->pin_used = 0;
-        d = (uint32_t*)upload_small(ctx, host, sizeof host);
-        if (!d) return P3R_ERR_OOM;
+    // dedicated staging (never the session's ring: earlier async copies / descriptors of the session may still be in use)
+    if (!ctx->grind_pin) {
+        CUDA_TRY(cudaHostAlloc((void**)&ctx->grind_pin, 128, cudaHostAllocDefault));
+        CUDA_TRY(cudaMalloc((void**)&ctx->grind_dev, 128));
     }
+    CUDA_TRY(ctx_wait(ctx));   // a previous grind's upload must have been consumed before its pinned source is rewritten
+    std::memcpy(ctx->grind_pin, host, sizeof host);
+    uint32_t* d = ctx->grind_dev;
+    CUDA_TRY(cudaMemcpyAsync(d, ctx->grind_pin, sizeof host, cudaMemcpyHostToDevice, ctx->stream));
     uint32_t batch = std::max(1u << 16, 4u << bits);
     for (uint64_t base = 0; base < F::P; base += batch) {
         k_grind<F><<<(batch + 127) / 128, 128, 0, ctx->stream>>>(d, d + 16, n_pending, bits, (uint32_t)base, batch, d + 24);
@@ -2443,6 +2458,41 @@ static int bench_commit_impl(p3r_ctx* ctx, uint32_t log_height, uint32_t width, 
 
 static thread_local std::string g_noctx_err;
 
+// The one-thread-per-permutation kernels read the Poseidon2 constants from `__constant__ c_p2[field]`, which is one copy per
+// device. Live contexts of one (device, field) therefore have to agree on the constants: the registry loads the symbol for the
+// first context, lets later contexts with the SAME constants share it (no copy while kernels may be in flight) and refuses a
+// context whose constants differ (P3R_ERR_UNSUPPORTED) instead of silently changing the hashes of the others.
+struct P2Slot {
+    int refs = 0;
+    Poseidon2Consts k{};
+};
+static std::mutex g_p2_mu;
+static std::map<std::pair<int, int>, P2Slot> g_p2_slots;
+static int p2_registry_acquire(int device, int field_id, const Poseidon2Consts& k) {
+    std::lock_guard<std::mutex> lock(g_p2_mu);
+    P2Slot& slot = g_p2_slots[{device, field_id}];
+    if (slot.refs > 0) {
+        if (std::memcmp(&slot.k, &k, sizeof k) != 0) {
+            g_noctx_err = "ctx_create: a live context on this device uses different Poseidon2 constants for this field";
+            return P3R_ERR_UNSUPPORTED;
+        }
+        slot.refs++;
+        return P3R_OK;
+    }
+    if (cudaMemcpyToSymbol(c_p2, &k, sizeof(Poseidon2Consts), (size_t)field_id * sizeof(Poseidon2Consts)) != cudaSuccess) {
+        g_noctx_err = std::string("ctx_create: ") + cudaGetErrorString(cudaGetLastError());
+        return P3R_ERR_CUDA;
+    }
+    slot.k = k;
+    slot.refs = 1;
+    return P3R_OK;
+}
+static void p2_registry_release(int device, int field_id) {
+    std::lock_guard<std::mutex> lock(g_p2_mu);
+    auto it = g_p2_slots.find({device, field_id});
+    if (it != g_p2_slots.end() && it->second.refs > 0) it->second.refs--;
+}
+
 extern "C" {
 
 uint32_t p3r_abi_version(void) { return 1; }
@@ -2450,7 +2500,7 @@ const char* p3r_build_info(void) { return "libp3r_b200 sm_100a; fields: koala-be
 
 int p3r_ctx_create(int device, const p3r_field_desc* field, const p3r_poseidon2_consts* p2, const p3r_fri_params* fri,
                    p3r_ctx** out) {
-    if (!field || !p2 || !fri || !out) return P3R_ERR_INVALID_ARG;
+    if (!field || !p2 || !fri || !out || !p2->external_rc || !p2->internal_rc || !p2->internal_diag) return P3R_ERR_INVALID_ARG;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) {
         g_noctx_err = "no usable CUDA device (this library has no CPU fallback)";
@@ -2503,12 +2553,16 @@ int p3r_ctx_create(int device, const p3r_field_desc* field, const p3r_poseidon2_
     ok = ok && cudaMalloc((void**)&ctx->dstage, ctx->dstage_size) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&ctx->d_p2, sizeof(Poseidon2Consts)) == cudaSuccess;
     ok = ok && cudaMemcpy(ctx->d_p2, &ctx->p2, sizeof(Poseidon2Consts), cudaMemcpyHostToDevice) == cudaSuccess;
-    ok = ok && cudaMemcpyToSymbol(c_p2, &ctx->p2, sizeof(Poseidon2Consts), (size_t)ctx->field_id * sizeof(Poseidon2Consts)) ==
-                   cudaSuccess;
-    if (!ok) {
-        g_noctx_err = std::string("ctx_create: ") + cudaGetErrorString(cudaGetLastError());
+    if (!ok) g_noctx_err = std::string("ctx_create: ") + cudaGetErrorString(cudaGetLastError());
+    int reg_rc = ok ? p2_registry_acquire(device, ctx->field_id, ctx->p2) : P3R_ERR_CUDA;
+    if (reg_rc != P3R_OK) {
+        if (ctx->stream) cudaStreamDestroy(ctx->stream);
+        if (ctx->pin) cudaFreeHost(ctx->pin);
+        if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
+        if (ctx->dstage) cudaFree(ctx->dstage);
+        if (ctx->d_p2) cudaFree(ctx->d_p2);
         delete ctx;
-        return P3R_ERR_CUDA;
+        return reg_rc;
     }
     *out = ctx;
     return P3R_OK;
@@ -2528,12 +2582,15 @@ void p3r_ctx_destroy(p3r_ctx* ctx) {
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
     if (ctx->dstage) cudaFree(ctx->dstage);
+    if (ctx->grind_pin) cudaFreeHost(ctx->grind_pin);
+    if (ctx->grind_dev) cudaFree(ctx->grind_dev);
     for (int i = 0; i < p3r_ctx::N_AUX; i++) {
         if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
         if (ctx->aux_ev[i]) cudaEventDestroy(ctx->aux_ev[i]);
     }
     if (ctx->aux_ev[p3r_ctx::N_AUX]) cudaEventDestroy(ctx->aux_ev[p3r_ctx::N_AUX]);
     cudaStreamDestroy(ctx->stream);
+    p2_registry_release(ctx->device, ctx->field_id);
     delete ctx;
 }
 const char* p3r_last_error(const p3r_ctx* ctx) { return ctx ? ctx->err.c_str() : g_noctx_err.c_str(); }
@@ -2701,6 +2758,28 @@ int p3r_prove_ops(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* trac
     if (!ctx || !prep || !traces || !n_words) return P3R_ERR_INVALID_ARG;
     cudaSetDevice(ctx->device);
     return DISPATCH(ctx, prove_impl<F>(ctx, prep, traces, public_values, proof_out, cap_words, n_words, nullptr, table_ops));
+}
+int p3r_traces_write_rows(p3r_ctx* ctx, const p3r_prep* prep, p3r_traces* traces, uint32_t inst, uint32_t row0, uint32_t n_rows,
+                          const uint32_t* rows) {
+    if (!ctx || !prep || !traces || !rows || inst >= prep->inst.size() || traces->d.size() != prep->inst.size())
+        return P3R_ERR_INVALID_ARG;
+    const InstDev& d = prep->inst[inst];
+    const uint32_t H = 1u << d.log_h;
+    if (n_rows == 0) return P3R_OK;
+    if (row0 >= H || n_rows > H - row0 || (size_t)n_rows * d.main_w * 4 > ((size_t)1 << 20)) {
+        set_err(ctx, "traces_write_rows: rows outside the table (or more than 1 MiB at once)");
+        return P3R_ERR_INVALID_ARG;
+    }
+    cudaSetDevice(ctx->device);
+    CUDA_TRY(ctx_wait(ctx));   // staging is about to be reused from its start
+    ctx->pin_used = 0;
+    const uint32_t* d_rows = (const uint32_t*)upload_small(ctx, rows, (size_t)n_rows * d.main_w * 4);
+    if (!d_rows) return P3R_ERR_OOM;
+    const uint32_t words = n_rows * d.main_w;
+    k_scatter_rows<<<(words + 255) / 256, 256, 0, ctx->stream>>>(d_rows, traces->d[inst], H, d.main_w, row0, n_rows);
+    LAUNCH_CHECK_C(KC_TRANSPOSE);
+    CUDA_TRY(ctx_wait(ctx));   // the next session resets the staging ring
+    return P3R_OK;
 }
 void p3r_traces_free(p3r_traces* t) {
     if (!t) return;

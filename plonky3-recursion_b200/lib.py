@@ -19,7 +19,8 @@ from .field import get_field
 from .poseidon2_params import Poseidon2Params
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libp3r_b200.so")
+# P3R_LIB selects another BUILD of the same library (A/B timing of compile-time variants, scripts/ab_time.py); never the oracle.
+_LIB_PATH = os.environ.get("P3R_LIB") or os.path.join(_HERE, "libp3r_b200.so")
 
 DEFAULT_FRI = dict(log_blowup=2, log_final_poly_len=5, max_log_arity=2, num_queries=54, commit_pow_bits=0,
                    query_pow_bits=15, cap_height=0)  # /root/reference recursion/examples/recursive_fibonacci.rs:71-132
@@ -82,7 +83,7 @@ EXPORTS = ["p3r_abi_version", "p3r_build_info", "p3r_ctx_create", "p3r_ctx_destr
            "p3r_reset_kernel_stats", "p3r_kernel_stats", "p3r_set_specialization", "p3r_prove_ex", "p3r_traces_upload_ex",
            "p3r_traces_download", "p3r_kernel_perms", "p3r_bench_fri_round", "p3r_prove_ops",
            "p3r_traces_upload_ops", "p3r_set_wait_mode", "p3r_host_hasher_create", "p3r_host_hasher_permute",
-           "p3r_host_hasher_free"]
+           "p3r_host_hasher_free", "p3r_traces_write_rows"]
 
 KERNEL_CLASSES = ["ntt_lde", "hash_rows", "compress", "logup", "quotient", "open", "reduced_openings", "fri_fold", "transpose",
                   "misc"]
@@ -140,8 +141,11 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.p3r_ctx_destroy(self.h)
+            self.lib.p3r_ctx_destroy(self.h)   # drains the stream first: nothing reads the pinned blocks afterwards
             self.h = None
+            for ptr in getattr(self, "_pinned", []):
+                self.lib.p3r_host_free(ptr)
+            self._pinned = []
 
     def __del__(self):
         try:
@@ -232,7 +236,8 @@ class Context:
                 for k in range(n)}
 
     def pinned_empty(self, shape, dtype=np.uint32) -> np.ndarray:
-        """numpy view of cudaHostAlloc'd memory (kept alive by the returned array's base object)."""
+        """numpy view of cudaHostAlloc'd memory owned by this context: freed in close(), so the array must not be used after
+        the context is closed (TraceBatch / BatchStarkProver hold it and are bound to the context anyway)."""
         nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
         ptr = self.lib.p3r_host_alloc(C.c_size_t(max(nbytes, 16)))
         if not ptr:
@@ -248,8 +253,12 @@ class Context:
         ms = (C.c_float * 32)()
         n = C.c_uint32(0)
         self._check(self.lib.p3r_last_phase_times(self.h, C.byref(names), ms, 32, C.byref(n)))
-        raw = C.string_at(names, 1024).split(b"\0")
-        return {raw[i].decode(): float(ms[i]) for i in range(n.value)}
+        out, addr = {}, C.cast(names, C.c_void_p).value
+        for i in range(min(n.value, 32)):          # NUL-terminated entries back to back: read each up to its own NUL
+            name = C.string_at(addr)
+            addr += len(name) + 1
+            out[name.decode()] = float(ms[i])
+        return out
 
 
 class ProverData:
@@ -292,7 +301,7 @@ class TraceBatch:
     pinned=True places the Montgomery matrices in cudaHostAlloc'd memory (the e2e path of bench.py)."""
 
     def __init__(self, ctx: Context, traces, pubs, pinned: bool = False, p2_ops: dict | None = None,
-                 alu_ops: dict | None = None):
+                 alu_ops: dict | None = None, insts=None):
         """p2_ops: {instance index: Poseidon2Ops}, alu_ops: {instance index: airs.alu.AluTableOps}; those instances' traces
         are generated on the device from the operation lists and their entry in `traces` may be None."""
         self.ctx = ctx
@@ -301,21 +310,22 @@ class TraceBatch:
                      if (p2_ops or alu_ops) else None)
         skip = set(p2_ops or {}) | set(alu_ops or {})
         traces = [None if k in skip else t for k, t in enumerate(traces)]
-        if pinned:
-            arr = (abi.MatrixU32 * len(traces))()
-            self._bufs = []
-            for k, t in enumerate(traces):
-                if t is None:
-                    arr[k] = abi.MatrixU32(None, 0, 0)
-                    continue
+        # Montgomery row-major host matrices by instance (pinned=True: cudaHostAlloc'd); write_rows patches them in place
+        arr = (abi.MatrixU32 * len(traces))()
+        self._host = {}
+        for k, t in enumerate(traces):
+            if t is None:
+                arr[k] = abi.MatrixU32(None, 0, 0)
+                continue
+            if pinned:
                 buf = ctx.pinned_empty(t.shape)
                 buf[...] = ctx.field.to_monty(t)
-                self._bufs.append(buf)
-                arr[k] = abi.MatrixU32(abi.as_u32p(buf), t.shape[0], t.shape[1])
-            self.tm = arr
-        else:
-            self.tm = self.m.matrices(traces)
-        self.pv = self.m.public_values(pubs)
+            else:
+                buf = self.m.u32(ctx.field.to_monty(t))
+            self._host[k] = buf
+            arr[k] = abi.MatrixU32(abi.as_u32p(buf), t.shape[0], t.shape[1])
+        self.tm = arr
+        self.pv = self.m.public_values(pubs, insts)   # insts given: lengths checked against n_public
         self.h2d_bytes = int(sum(int(t.size) * 4 for t in traces if t is not None))
         if p2_ops:
             self.h2d_bytes += int(sum(o.n * (64 + 4 + 1) for o in p2_ops.values()))
@@ -329,6 +339,19 @@ class TraceBatch:
         self.ctx._check(self.ctx.lib.p3r_traces_upload_ops(self.ctx.h, prover_data.h, self.tm, self.tops, C.byref(h)))
         self.resident = h
         return self
+
+    def write_rows(self, prover_data, inst: int, row0: int, rows_canonical: np.ndarray):
+        """Overwrite rows [row0, row0 + n) of instance `inst`'s main trace: in the resident copy (p3r_traces_write_rows) when
+        uploaded, and in the host (pinned) matrix when this batch carries one for that instance."""
+        rows = np.ascontiguousarray(self.ctx.field.to_monty(np.asarray(rows_canonical, dtype=np.uint32)))
+        if rows.ndim != 2 or rows.shape[1] != prover_data.insts[inst].main_width:
+            raise ValueError("write_rows: rows must be (n, main_width)")
+        if self.resident is not None:
+            self.ctx._check(self.ctx.lib.p3r_traces_write_rows(self.ctx.h, prover_data.h, self.resident, inst, row0,
+                                                               rows.shape[0], abi.as_u32p(rows)))
+        host = self._host.get(inst)
+        if host is not None:
+            host[row0:row0 + rows.shape[0]] = rows
 
     def download(self, prover_data, inst: int) -> np.ndarray:
         """Main trace of instance `inst` as held on the device (canonical, row-major) — parity checks of the GPU table fill."""
@@ -348,32 +371,35 @@ class BatchStarkProver:
 
     def __init__(self, ctx: Context, pinned_output: bool = False):
         self.ctx = ctx
+        self._pinned_output = pinned_output
         self._buf = ctx.pinned_empty((1 << 22,)) if pinned_output else np.zeros(1 << 22, dtype=np.uint32)
         self.last_proof_words = 0
 
     def prove_resident(self, traces: "TraceBatch", prover_data: ProverData, copy: bool = True):
         """Prove from device-resident traces (TraceBatch.upload)."""
         ctx = self.ctx
-        n = C.c_size_t(0)
-        ctx._check(ctx.lib.p3r_prove_resident(ctx.h, prover_data.h, traces.resident, traces.pv, abi.as_u32p(self._buf),
-                                              C.c_size_t(self._buf.size), C.byref(n)))
-        self.last_proof_words = n.value
-        return self._buf[: n.value].copy() if copy else self._buf[: n.value]
+        n = self._call_growing(lambda n: ctx.lib.p3r_prove_resident(
+            ctx.h, prover_data.h, traces.resident, traces.pv, abi.as_u32p(self._buf), C.c_size_t(self._buf.size), C.byref(n)))
+        return self._buf[:n].copy() if copy else self._buf[:n]
 
-    def prove_all_tables(self, traces, prover_data: ProverData, public_values=None) -> np.ndarray:
+    def _call_growing(self, call) -> int:
+        """Run a prove entry point; on P3R_ERR_BUFFER (needed size in n) grow the proof buffer once and retry."""
+        n = C.c_size_t(0)
+        rc = call(n)
+        if rc == 6 and n.value > self._buf.size:
+            self._buf = (self.ctx.pinned_empty((n.value,)) if self._pinned_output else np.zeros(n.value, dtype=np.uint32))
+            rc = call(n)
+        self.ctx._check(rc)
+        self.last_proof_words = n.value
+        return n.value
+
+    def prove_all_tables(self, traces, prover_data: ProverData, public_values=None, copy: bool = True) -> np.ndarray:
         """traces: list of canonical (h, w) uint32 matrices in instance order, or a TraceBatch.
         Returns the flat proof blob (DESIGN.md "Proof blob")."""
         ctx = self.ctx
         if not isinstance(traces, TraceBatch):
             pubs = public_values if public_values is not None else [None] * len(traces)
-            traces = TraceBatch(ctx, traces, pubs)
-        n = C.c_size_t(0)
-        rc = ctx.lib.p3r_prove_ops(ctx.h, prover_data.h, traces.tm, traces.tops, traces.pv, abi.as_u32p(self._buf),
-                                   C.c_size_t(self._buf.size), C.byref(n))
-        if rc == 6 and n.value > self._buf.size:  # P3R_ERR_BUFFER: grow once
-            self._buf = np.zeros(n.value, dtype=np.uint32)
-            rc = ctx.lib.p3r_prove_ops(ctx.h, prover_data.h, traces.tm, traces.tops, traces.pv, abi.as_u32p(self._buf),
-                                       C.c_size_t(self._buf.size), C.byref(n))
-        ctx._check(rc)
-        self.last_proof_words = n.value
-        return self._buf[: n.value].copy()
+            traces = TraceBatch(ctx, traces, pubs, insts=prover_data.insts)
+        n = self._call_growing(lambda n: ctx.lib.p3r_prove_ops(
+            ctx.h, prover_data.h, traces.tm, traces.tops, traces.pv, abi.as_u32p(self._buf), C.c_size_t(self._buf.size), C.byref(n)))
+        return self._buf[:n].copy() if copy else self._buf[:n]

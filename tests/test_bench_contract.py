@@ -12,7 +12,7 @@ def _run(extra_env=None, args=()):
     env = dict(os.environ)
     env.update(extra_env or {})
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
-                          *args], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+                          "--scale", "0.0625", *args], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     return out.stdout
 
@@ -26,7 +26,9 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
         assert key in d, key
     assert d["steps"] == 1 and d["warmup"] == 1 and d["value"] > 0 and d["vs_baseline"] is None
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "scale" in cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "no size extrapolation" in cb["sample"]
+    # the test runs a 1/16-size layer to stay fast: the line itself must say that it is not the headline configuration
+    assert d["same_config"] is False and d["same_steps"] is True and d["extrapolated"] is False
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
 

@@ -514,8 +514,6 @@ def test_full_size_layer_is_accepted_by_the_oracle_verifier():
     ctx.close()
 
 
-@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: first run is the round-end suite; the "
-                                        "oracle side of the same systems is covered by test_table_packing_variants on CPU")
 @pytest.mark.parametrize("public_lanes,alu_lanes,horner_k", [(2, 2, 4), (2, 4, 3), (4, 3, 2)])
 def test_table_packing_variants_bit_identical(pair, public_lanes, alu_lanes, horner_k):
     """Other `TablePacking` shapes (public lanes, ALU lanes, packed-Horner depth): interpreter kernels for every table."""
@@ -528,3 +526,82 @@ def test_table_packing_variants_bit_identical(pair, public_lanes, alu_lanes, hor
     assert np.array_equal(proof, orc.prove(L.insts, L.preps, L.traces, L.pubs))
     orc.verify(L.insts, pd.preprocessed_commitment, L.pubs, proof)
     pd.close()
+
+
+AGG_FRI = dict(log_blowup=2, log_final_poly_len=6, max_log_arity=2, num_queries=5, commit_pow_bits=0, query_pow_bits=5, cap_height=0)
+
+
+@pytest.mark.parametrize("field_name", FIELDS)
+@pytest.mark.parametrize("public_lanes,alu_lanes", [(1, 2), (1, 1), (2, 2)])
+def test_reference_example_packings_bit_identical(field_name, public_lanes, alu_lanes):
+    """The packings BASELINE configs[2]/[3] use: `TablePacking::new(1, 2)` (recursion/examples/recursive_keccak.rs:562),
+    `new(1, 1)` for base proofs and `new(2, 2)` for aggregation level 1 (recursive_aggregation.rs:632,666) — default packed
+    Horner depth 2 (batch_stark_prover/packing.rs:28-30) — with the aggregation example's `log_final_poly_len` 6
+    (recursive_aggregation.rs:83), hence min_trace_height 2^(6+2+1) = 512 (packing.rs:100-106)."""
+    wl = importlib.import_module("plonky3-recursion_b200.workload")
+    ctx = lib.Context(field_name, AGG_FRI)
+    orc = make_oracle(field_name, AGG_FRI)
+    L = wl.synthetic_layer(ctx.field, 17, n_const=12, n_public=40, n_alu=700, n_perms=30, n_recompose=6, min_height=512,
+                           public_lanes=public_lanes, alu_lanes=alu_lanes, horner_k=2)
+    pd = lib.ProverData.from_airs_and_degrees(ctx, L.insts, L.preps)
+    proof = lib.BatchStarkProver(ctx).prove_all_tables(L.traces, pd, L.pubs)
+    assert np.array_equal(proof, orc.prove(L.insts, L.preps, L.traces, L.pubs))
+    orc.verify(L.insts, pd.preprocessed_commitment, L.pubs, proof)
+    pd.close()
+    ctx.close()
+
+
+def test_contexts_with_different_poseidon2_constants_are_refused():
+    """The thread-per-permutation kernels read the round constants from one `__constant__` slot per (device, field): a second
+    live context of the same field with other constants must fail loudly (P3R_ERR_UNSUPPORTED) instead of corrupting the
+    first one's hashes; the same constants share the slot; after the first context is gone the other constants load."""
+    p2mod = importlib.import_module("plonky3-recursion_b200.poseidon2_params")
+    F = field_mod.get_field("koala-bear")
+    a = lib.Context("koala-bear", SMALL_FRI)
+    orc = make_oracle("koala-bear", SMALL_FRI)
+    st = F.rand(np.random.default_rng(5), (33, 16))
+    want = orc.poseidon2_permute(st)
+    other = p2mod.Poseidon2Params(F.field_id)
+    other.external_rc = other.external_rc.copy()
+    other.external_rc[0] = (int(other.external_rc[0]) + 1) % F.p
+    with pytest.raises(lib.P3RError) as ei:
+        lib.Context("koala-bear", SMALL_FRI, poseidon2=other)
+    assert ei.value.code == 5
+    b = lib.Context("koala-bear", SMALL_FRI)              # same constants: shares the slot
+    assert np.array_equal(a.poseidon2_permute(st), want) and np.array_equal(b.poseidon2_permute(st), want)
+    a.close()
+    b.close()
+    c = lib.Context("koala-bear", SMALL_FRI, poseidon2=other)   # nobody else alive: the other constants load
+    got = c.poseidon2_permute(st)
+    assert not np.array_equal(got, want)
+    assert np.array_equal(got, other.permute(st))
+    c.close()
+    d = lib.Context("koala-bear", SMALL_FRI)
+    assert np.array_equal(d.poseidon2_permute(st), want)
+    d.close()
+
+
+def test_missing_public_values_are_an_invalid_argument():
+    """n_public > 0 with a NULL public-values pointer is P3R_ERR_INVALID_ARG at the C ABI (not a host crash)."""
+    import ctypes as C
+    abi = importlib.import_module("plonky3-recursion_b200.abi")
+    fib = importlib.import_module("plonky3-recursion_b200.airs.fibonacci")
+    air_mod = importlib.import_module("plonky3-recursion_b200.air")
+    ctx = lib.Context("koala-bear", SMALL_FRI)
+    F = ctx.field
+    inst = air_mod.build_instance("fib", fib.eval_air, F.p, 5, 2, 0, 3, air_mod.BusRegistry())
+    pd = lib.ProverData.from_airs_and_degrees(ctx, [inst], [None])
+    trace, _ = fib.trace(F.p, 5)
+    with pytest.raises(ValueError):
+        lib.BatchStarkProver(ctx).prove_all_tables([trace], pd, [None])      # the Python mirror checks lengths first
+    m = abi.Marshal(F)
+    tm = m.matrices([trace])
+    pv = (abi.u32p * 1)()                                                      # NULL entry
+    buf = np.zeros(1 << 16, dtype=np.uint32)
+    n = C.c_size_t(0)
+    rc = ctx.lib.p3r_prove(ctx.h, pd.h, tm, pv, abi.as_u32p(buf), C.c_size_t(buf.size), C.byref(n))
+    assert rc == 1 and b"public values" in ctx.lib.p3r_last_error(ctx.h)
+    rc = ctx.lib.p3r_prove(ctx.h, pd.h, tm, None, abi.as_u32p(buf), C.c_size_t(buf.size), C.byref(n))
+    assert rc == 1
+    pd.close()
+    ctx.close()
