@@ -222,6 +222,10 @@ class Lane:
             host = lib.TraceBatch(self.ctx, L.traces, L.pubs, pinned=True, p2_ops=L.p2_ops, alu_ops=L.alu_ops)
             w = L.insts[PUBLIC_INST].main_width
             rows = max(1, PATCH_WORDS // w)
+            # the patched rows must be padding of the Public table: index 0, multiplicity 0 in its preprocessed columns, so
+            # that their values are free (the WitnessChecks bus ignores them) while still being committed
+            if np.any(L.preps[PUBLIC_INST][-rows:] != 0) or np.any(L.traces[PUBLIC_INST][-rows:] != 0):
+                raise ValueError(f"shape '{name}': the last {rows} rows of the Public table are not padding")
             self.kind[name] = (pd, res, host, (1 << L.insts[PUBLIC_INST].log_height) - rows, rows, w)
 
     def prove(self, name, patch_words, host_buffers: bool):

@@ -347,6 +347,44 @@ int p3r_last_phase_times(p3r_ctx* ctx, const char** names_out, float* ms_out, ui
  *   bit 2  set   : DISABLE the device-side transcript of the FRI commit rounds in p3r_prove* (one host round trip per round). */
 int p3r_set_specialization(p3r_ctx* ctx, int enable);
 
+/* ---- proof wire format: flat proof blob <-> postcard bytes of the reference's `BatchStarkProof<SC>`
+ * (circuit-prover/src/batch_stark_prover.rs:613-640; `postcard::to_allocvec`, recursion/examples/common/mod.rs:144-147).
+ * Host-only (no CUDA call). The field mapping is documented at the top of csrc/wire.cpp. ---- */
+typedef struct {                    /* NonPrimitiveTableEntry, batch_stark_prover.rs:274-290 */
+    const char* op_type;            /* NpoTypeId string, e.g. "poseidon2_perm/koala_bear_d4_w16", "recompose" */
+    uint64_t rows, lanes;
+    const uint32_t* public_values;  /* Montgomery words */
+    uint32_t n_public_values;
+    uint32_t air_variant;           /* AirVariant: 0 Baseline, 1 Optimized (batch_stark_prover.rs:254-260) */
+} p3r_npo_entry;
+typedef struct {                    /* the BatchStarkProof fields next to `proof` (batch_stark_prover.rs:1598-1641) */
+    uint64_t public_lanes, alu_lanes;             /* TablePacking, batch_stark_prover/packing.rs:9-27 */
+    const char* const* npo_lane_ops;              /* npo_lanes: Vec<(NpoTypeId, usize)> */
+    const uint64_t* npo_lane_counts;
+    uint32_t n_npo_lanes;
+    uint64_t min_trace_height, horner_packed_steps;
+    uint64_t rows[3];                             /* RowCounts: const, public, alu */
+    uint32_t alu_variant;
+    uint64_t ext_degree;                          /* w_binomial = Some(field.w) iff ext_degree > 1 */
+    uint32_t alu_quintic_trinomial;
+    const p3r_npo_entry* non_primitives;
+    uint32_t n_non_primitives;
+    const uint32_t* prep_cap;                     /* stark_common: the preprocessed commitment (p3r_prep_commit's cap), or NULL */
+} p3r_proof_meta;
+enum {
+    P3R_WIRE_CANONICAL = 1,   /* field elements as canonical u32 (default: the Montgomery word, p3's in-memory form) — SURVEY.md B5 */
+    P3R_WIRE_BARE_ROOT = 2    /* cap_height 0: commitments as the bare [F; 8] root instead of a one-entry Vec<[F; 8]> cap */
+};
+/* `descs` are the instances the proof was made for (widths, lookups, quotient chunks); *n_bytes receives the size (also on
+ * P3R_ERR_BUFFER); *proof_bytes_out (optional) the length of the leading `proof: BatchProof` field. */
+int p3r_proof_serialize(const p3r_field_desc* field, const p3r_fri_params* fri, uint32_t n_inst, const p3r_instance_desc* descs,
+                        const uint32_t* blob, size_t n_words, const p3r_proof_meta* meta, uint32_t flags, uint8_t* out,
+                        size_t cap_bytes, size_t* n_bytes, size_t* proof_bytes_out);
+/* Inverse of the `proof` field: postcard bytes -> flat blob (the metadata that follows is skipped; *proof_bytes = its offset). */
+int p3r_proof_deserialize(const p3r_field_desc* field, const p3r_fri_params* fri, const uint8_t* bytes, size_t n_bytes,
+                          uint32_t flags, uint32_t* blob_out, size_t cap_words, size_t* n_words, size_t* proof_bytes);
+const char* p3r_wire_last_error(void);
+
 /* How host threads wait for the GPU (process-wide): 1 = poll + sched_yield with device->host results staged through pinned
  * memory (default: a waiting thread yields its core to a thread that has kernels to launch; best throughput with several
  * proofs in flight per GPU and few host cores per GPU), 0 = spin inside the driver (cudaStreamSynchronize, direct copies),

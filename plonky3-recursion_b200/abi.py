@@ -72,6 +72,19 @@ class InstanceDesc(C.Structure):
                 ("interactions", C.POINTER(InteractionC)), ("n_interactions", u32)]
 
 
+class NpoEntryC(C.Structure):
+    _fields_ = [("op_type", C.c_char_p), ("rows", C.c_uint64), ("lanes", C.c_uint64), ("public_values", u32p),
+                ("n_public_values", u32), ("air_variant", u32)]
+
+
+class ProofMetaC(C.Structure):
+    _fields_ = [("public_lanes", C.c_uint64), ("alu_lanes", C.c_uint64), ("npo_lane_ops", C.POINTER(C.c_char_p)),
+                ("npo_lane_counts", C.POINTER(C.c_uint64)), ("n_npo_lanes", u32), ("min_trace_height", C.c_uint64),
+                ("horner_packed_steps", C.c_uint64), ("rows", C.c_uint64 * 3), ("alu_variant", u32), ("ext_degree", C.c_uint64),
+                ("alu_quintic_trinomial", u32), ("non_primitives", C.POINTER(NpoEntryC)), ("n_non_primitives", u32),
+                ("prep_cap", u32p)]
+
+
 def as_u32p(a: np.ndarray):
     assert a.dtype == np.uint32 and a.flags["C_CONTIGUOUS"]
     return a.ctypes.data_as(u32p)
@@ -189,6 +202,26 @@ class Marshal:
             st = self.keep(AluOpsC(t.lanes, t.d, t.k_max, kind.size, as_u32p(kind), as_u32p(first), t.values.shape[0], as_u32p(vals)))
             arr[i].alu = C.pointer(st)
         return self.keep(arr)
+
+    def proof_meta(self, meta: dict) -> ProofMetaC:
+        """dict with the BatchStarkProof metadata (include/p3r.h p3r_proof_meta): public_lanes, alu_lanes, npo_lanes
+        [(op_type, lanes)], min_trace_height, horner_packed_steps, rows (const, public, alu), ext_degree, non_primitives
+        [(op_type, rows, lanes, canonical public values, air_variant)], prep_cap (Montgomery words or None)."""
+        lanes = meta.get("npo_lanes", [])
+        ops = (C.c_char_p * max(1, len(lanes)))(*[o.encode() for o, _ in lanes])
+        cnt = (C.c_uint64 * max(1, len(lanes)))(*[int(n) for _, n in lanes])
+        nps = meta.get("non_primitives", [])
+        ents = (NpoEntryC * max(1, len(nps)))()
+        for k, (op, rows, ln, pv, variant) in enumerate(nps):
+            a = self.u32(self.field.to_monty(np.asarray(pv, dtype=np.uint32))) if len(pv) else self.u32(np.zeros(1))
+            ents[k] = NpoEntryC(op.encode(), int(rows), int(ln), as_u32p(a), len(pv), int(variant))
+        cap = meta.get("prep_cap")
+        capa = self.u32(cap) if cap is not None else None
+        self.keep((ops, cnt, ents))
+        return ProofMetaC(int(meta["public_lanes"]), int(meta["alu_lanes"]), ops, cnt, len(lanes), int(meta["min_trace_height"]),
+                          int(meta["horner_packed_steps"]), (C.c_uint64 * 3)(*[int(x) for x in meta["rows"]]),
+                          int(meta.get("alu_variant", 0)), int(meta["ext_degree"]), int(meta.get("alu_quintic_trinomial", 0)),
+                          ents, len(nps), as_u32p(capa) if capa is not None else None)
 
     def public_values(self, pubs, insts=None) -> C.Array:
         """pubs[k]: canonical public values of instance k (None / empty when it has none). With `insts` the lengths are

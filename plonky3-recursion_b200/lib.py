@@ -83,7 +83,46 @@ EXPORTS = ["p3r_abi_version", "p3r_build_info", "p3r_ctx_create", "p3r_ctx_destr
            "p3r_reset_kernel_stats", "p3r_kernel_stats", "p3r_set_specialization", "p3r_prove_ex", "p3r_traces_upload_ex",
            "p3r_traces_download", "p3r_kernel_perms", "p3r_bench_fri_round", "p3r_prove_ops",
            "p3r_traces_upload_ops", "p3r_set_wait_mode", "p3r_host_hasher_create", "p3r_host_hasher_permute",
-           "p3r_host_hasher_free", "p3r_traces_write_rows"]
+           "p3r_host_hasher_free", "p3r_traces_write_rows", "p3r_proof_serialize", "p3r_proof_deserialize",
+           "p3r_wire_last_error"]
+
+WIRE_CANONICAL, WIRE_BARE_ROOT = 1, 2
+
+
+def serialize_proof(field, fri: dict, insts, blob: np.ndarray, meta: dict, flags: int = 0):
+    """Flat proof blob -> postcard bytes of the reference's `BatchStarkProof` (p3r_proof_serialize; host-only, no GPU needed).
+    Returns (bytes, length of the leading `proof: BatchProof` field)."""
+    lib = load()
+    lib.p3r_wire_last_error.restype = C.c_char_p
+    F = get_field(field) if isinstance(field, str) else field
+    m = abi.Marshal(F)
+    fd, fp, descs, mc = m.field_desc(), m.fri(fri), m.instances(insts), m.proof_meta(meta)
+    blob = np.ascontiguousarray(blob, dtype=np.uint32)
+    out = np.zeros(blob.size * 5 + 4096, dtype=np.uint8)
+    n, pb = C.c_size_t(0), C.c_size_t(0)
+    rc = lib.p3r_proof_serialize(C.byref(fd), C.byref(fp), len(insts), descs, abi.as_u32p(blob), C.c_size_t(blob.size), C.byref(mc),
+                                 flags, out.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_size_t(out.size), C.byref(n), C.byref(pb))
+    if rc != 0:
+        raise P3RError(rc, lib.p3r_wire_last_error().decode())
+    return out[: n.value].tobytes(), pb.value
+
+
+def deserialize_proof(field, fri: dict, data: bytes, flags: int = 0):
+    """postcard bytes -> (flat proof blob, offset at which the BatchStarkProof metadata starts) (p3r_proof_deserialize)."""
+    lib = load()
+    lib.p3r_wire_last_error.restype = C.c_char_p
+    F = get_field(field) if isinstance(field, str) else field
+    m = abi.Marshal(F)
+    fd, fp = m.field_desc(), m.fri(fri)
+    buf = np.frombuffer(data, dtype=np.uint8)
+    out = np.zeros(len(data) + 64, dtype=np.uint32)
+    n, pb = C.c_size_t(0), C.c_size_t(0)
+    rc = lib.p3r_proof_deserialize(C.byref(fd), C.byref(fp), buf.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_size_t(buf.size), flags,
+                                   abi.as_u32p(out), C.c_size_t(out.size), C.byref(n), C.byref(pb))
+    if rc != 0:
+        raise P3RError(rc, lib.p3r_wire_last_error().decode())
+    return out[: n.value].copy(), pb.value
+
 
 KERNEL_CLASSES = ["ntt_lde", "hash_rows", "compress", "logup", "quotient", "open", "reduced_openings", "fri_fold", "transpose",
                   "misc"]

@@ -17,9 +17,9 @@ pytestmark = pytest.mark.gpu
 
 def _shapes(F):
     return {"leaf": wl.base_layer_fibonacci(F, 50, min_height=32),
-            "l1": wl.synthetic_layer(F, 2, n_const=10, n_public=25, n_alu=150, n_perms=20, n_recompose=5, min_height=32,
+            "l1": wl.synthetic_layer(F, 2, n_const=10, n_public=40, n_alu=150, n_perms=20, n_recompose=5, min_height=32,
                                      public_lanes=2, alu_lanes=2, horner_k=2),
-            "node": wl.synthetic_layer(F, 1, n_const=12, n_public=30, n_alu=200, n_perms=40, n_recompose=6, min_height=32)}
+            "node": wl.synthetic_layer(F, 1, n_const=12, n_public=40, n_alu=200, n_perms=40, n_recompose=6, min_height=32)}
 
 
 def test_tree_roots_depend_on_every_leaf_and_match_a_serial_run():
