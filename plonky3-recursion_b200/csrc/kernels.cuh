@@ -341,6 +341,44 @@ __global__ void __launch_bounds__(128) k_hash_rows(const HashJob* __restrict__ j
     o[0] = make_uint4(st[0], st[1], st[2], st[3]);
     o[1] = make_uint4(st[4], st[5], st[6], st[7]);
 }
+// Same result through a work queue: a work item is 32 consecutive rows of one job (one warp), items are numbered with the
+// longest sponges first and every warp of a machine-filling grid takes the next item from an atomic counter when it finishes
+// its current one (longest-processing-time-first list scheduling). With one CTA per 128 rows the hardware dispatches the 512
+// long-row CTAs of the recursion layer in the first wave, 3 or 4 per SM, and nothing later can even that out: the launch ran at
+// 4.07 permutations/ns against 5.1 for the same permutation code on uniform work.
+struct HashQueue {
+    uint32_t n_jobs, n_items;
+    uint32_t counter;        // zero when the launch starts (uploaded with the descriptor)
+    uint32_t pad;
+};
+template <class F>
+__global__ void __launch_bounds__(128) k_hash_rows_queue(const HashJob* __restrict__ jobs, HashQueue* __restrict__ q) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_jobs = q->n_jobs, n_items = q->n_items;
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(&q->counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) return;
+        uint32_t j = 0;
+        while (j + 1 < n_jobs && item >= __ldg(&jobs[j + 1].cta_begin)) j++;   // cta_begin = first item of the job here
+        const HashJob job = jobs[j];
+        const uint32_t r = (item - job.cta_begin) * 32u + lane;
+        if (r >= job.n_rows) continue;
+        uint32_t st[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) st[i] = 0;
+        for (uint32_t c0 = 0; c0 < job.ncols; c0 += 8) {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (c0 + k < job.ncols) st[k] = __ldg(job.colptr[c0 + k] + r);
+            poseidon2_permute<F>(st);
+        }
+        uint4* o = reinterpret_cast<uint4*>(job.out + (size_t)r * 8);
+        o[0] = make_uint4(st[0], st[1], st[2], st[3]);
+        o[1] = make_uint4(st[4], st[5], st[6], st[7]);
+    }
+}
 // Rows of a row-major matrix of `w` words (ExtensionMmcs rows of the FRI commit phase, recursion/src/pcs/mmcs.rs:434-441).
 template <class F>
 __global__ void __launch_bounds__(128) k_hash_rows_rowmajor(const uint32_t* __restrict__ data, uint32_t w, uint32_t n_rows,

@@ -142,6 +142,8 @@ struct p3r_ctx {
     uint32_t* tw = nullptr;   // = tws + 2^(logT-1) - 1: half table of omega_T
     void (*host_permute)(uint32_t*, const Poseidon2Consts&) = nullptr;  // transcript permutation (AVX2 or scalar), set at creation
     bool dev_fri_transcript = true;  // FRI commit rounds without host round trips (p3r_set_specialization bit 2 turns it off)
+    bool use_hash_queue = true;  // work-queue row hashing (p3r_set_specialization bit 3 turns it off: one CTA per 128 rows)
+    uint32_t n_sms = 148;
     bool use_col_ntt = true;  // whole-column LDE kernels for 2^5..2^15 rows (p3r_set_specialization bit 1 turns them off)
     uint32_t logT = 0;
     uint32_t r4 = 0, r8 = 0, r8_3 = 0;
@@ -512,7 +514,12 @@ static int get_gtable(p3r_ctx* ctx, uint32_t log_n, GTable* out) {
 // scratch_coef: n*w words; scratch_tmp: N*w words (only touched when log_n > TILE_LOG).
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t TILE_LOG = 13;
-constexpr uint32_t STAGE_MAX_NODES = 1u << 13;  // Merkle levels up to this size go through the fused k_merkle_stage launches
+// Merkle levels up to this many nodes go through the fused k_merkle_stage launches (P3R_STAGE_MAX_LOG overrides the log2)
+static const uint32_t STAGE_MAX_NODES = [] {
+    const char* e = getenv("P3R_STAGE_MAX_LOG");
+    uint32_t l = e ? (uint32_t)atoi(e) : 13u;
+    return 1u << std::max(8u, std::min(l, 16u));
+}();
 struct PassPlan {
     uint32_t s0, r, log_cw;
 };
@@ -974,12 +981,33 @@ static int commit_tree(p3r_ctx* ctx, const std::vector<MatRef>& mats, Tree* t, u
         jobs.push_back(j);
     }
     std::stable_sort(jobs.begin(), jobs.end(), [](const HashJob& a, const HashJob& b) { return a.ncols > b.ncols; });
-    uint32_t cta = 0;
-    for (auto& j : jobs) {
-        j.cta_begin = cta;
-        cta += (j.n_rows + 127) / 128;
-    }
-    {
+    if (ctx->use_hash_queue) {
+        // work queue: items of 32 rows, longest sponges first, taken by the warps of a machine-filling grid
+        uint32_t items = 0;
+        for (auto& j : jobs) {
+            j.cta_begin = items;
+            items += (j.n_rows + 31) / 32;
+        }
+        std::vector<uint8_t> blob(sizeof(HashQueue) + jobs.size() * sizeof(HashJob));
+        HashQueue hq{(uint32_t)jobs.size(), items, 0u, 0u};
+        std::memcpy(blob.data(), &hq, sizeof hq);
+        std::memcpy(blob.data() + sizeof hq, jobs.data(), jobs.size() * sizeof(HashJob));
+        char* d_blob = (char*)upload_small(ctx, blob.data(), blob.size());
+        if (!d_blob) {
+            set_err(ctx, "staging exhausted");
+            return P3R_ERR_OOM;
+        }
+        const uint32_t grid = std::min((items + 3) / 4, ctx->n_sms * 16u);
+        KT kt(ctx, KC_HASH, hash_bytes);
+        k_hash_rows_queue<F><<<grid, 128, 0, ctx->stream>>>(reinterpret_cast<const HashJob*>(d_blob + sizeof hq),
+                                                          reinterpret_cast<HashQueue*>(d_blob));
+        LAUNCH_CHECK_C(KC_HASH);
+    } else {
+        uint32_t cta = 0;
+        for (auto& j : jobs) {
+            j.cta_begin = cta;
+            cta += (j.n_rows + 127) / 128;
+        }
         const HashJob* d_jobs = upload_vec(ctx, jobs);
         if (!d_jobs) {
             set_err(ctx, "staging exhausted");
@@ -1978,8 +2006,9 @@ static int fri_fold_impl(p3r_session* s, uint32_t round, const uint32_t beta_w[4
     return P3R_OK;
 }
 
+// Enqueues the final-polynomial kernel and the copy of its coefficients to `coeffs_out`; the caller waits (ctx_wait).
 template <class F>
-static int fri_final_poly_impl(p3r_session* s, uint32_t* coeffs_out) {
+static int fri_final_poly_enqueue(p3r_session* s, uint32_t* coeffs_out) {
     p3r_ctx* ctx = s->ctx;
     if (s->phase != PH_FRI) {
         set_err(ctx, "fri_final_poly: wrong phase");
@@ -1991,6 +2020,12 @@ static int fri_final_poly_impl(p3r_session* s, uint32_t* coeffs_out) {
     k_final_poly<F><<<(n + 63) / 64, 64, 0, ctx->stream>>>(s->final_vec, d_c, lf, ctx->tw, ctx->logT);
     LAUNCH_CHECK();
     CUDA_TRY(d2h_async(ctx, coeffs_out, d_c, (size_t)n * 16));
+    return P3R_OK;
+}
+template <class F>
+static int fri_final_poly_impl(p3r_session* s, uint32_t* coeffs_out) {
+    p3r_ctx* ctx = s->ctx;
+    TRY(fri_final_poly_enqueue<F>(s, coeffs_out));
     CUDA_TRY(ctx_wait(ctx));
     return P3R_OK;
 }
@@ -2237,6 +2272,8 @@ static int prove_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* 
     TRY(fri_begin_impl<F>(s, alpha_fri, &n_rounds, log_arities));
     pt.mark("fri_reduce");
     std::vector<uint32_t> fri_caps(n_rounds * capw), commit_pow(n_rounds);
+    std::vector<uint32_t> final_poly((size_t)4 << ctx->fri.log_final_poly_len);
+    bool final_poly_done = false;
     if (ctx->fri.commit_pow_bits == 0 && ctx->dev_fri_transcript && n_rounds > 0) {
         // No commit-phase PoW: the rounds' caps are observed and the betas sampled by a one-warp kernel, so all rounds are
         // enqueued without a host round trip; afterwards the host challenger replays the same operations on the caps.
@@ -2264,6 +2301,9 @@ static int prove_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* 
         }
         std::vector<Ext4> dev_betas(n_rounds);
         CUDA_TRY(d2h_async(ctx, dev_betas.data(), d_beta, n_rounds * sizeof(Ext4)));
+        // the final polynomial depends only on the last fold: same wait as the caps and betas (one host round trip less)
+        TRY(fri_final_poly_enqueue<F>(s, final_poly.data()));
+        final_poly_done = true;
         CUDA_TRY(ctx_wait(ctx));
         for (uint32_t r = 0; r < n_rounds; r++) {
             ch.observe_words(fri_caps.data() + r * capw, capw);
@@ -2285,8 +2325,7 @@ static int prove_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* 
             TRY(fri_fold_impl<F>(s, r, beta));
         }
     }
-    std::vector<uint32_t> final_poly((size_t)4 << ctx->fri.log_final_poly_len);
-    TRY(fri_final_poly_impl<F>(s, final_poly.data()));
+    if (!final_poly_done) TRY(fri_final_poly_impl<F>(s, final_poly.data()));
     pt.mark("fri_commit_phase");
     ch.observe_words(final_poly.data(), final_poly.size());
     for (uint32_t r = 0; r < n_rounds; r++) ch.observe(to_monty<F>(log_arities[r]));
@@ -2545,6 +2584,10 @@ int p3r_ctx_create(int device, const p3r_field_desc* field, const p3r_poseidon2_
         ctx->gen_m = to_monty<BabyBear>(field->generator);
         ctx->inv2_m = finv<BabyBear>(to_monty<BabyBear>(2));
     }
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->n_sms = (uint32_t)sms;
+    }
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ctx->pin_size = ctx->dstage_size = (size_t)8 << 20;
     ok = ok && cudaHostAlloc((void**)&ctx->pin, ctx->pin_size, cudaHostAllocDefault) == cudaSuccess;
@@ -2800,6 +2843,7 @@ int p3r_set_specialization(p3r_ctx* ctx, int enable) {
     ctx->use_spec = (enable & 1) != 0;
     ctx->use_col_ntt = (enable & 2) == 0;
     ctx->dev_fri_transcript = (enable & 4) == 0;
+    ctx->use_hash_queue = (enable & 8) == 0;
     return P3R_OK;
 }
 int p3r_timer_start(p3r_ctx* ctx) {

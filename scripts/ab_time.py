@@ -14,6 +14,8 @@ F = fm.get_field(field)
 L = wl.synthetic_layer(F, 1, n_const=int(1500 * scale), n_public=int(43000 * scale), n_alu=int(60000 * scale),
                        n_perms=int(12000 * scale), n_recompose=int(4000 * scale), min_height=256)
 ctx = lib.Context(field)
+spec = int(os.environ.get("P3R_SPEC", "1"))
+ctx.lib.p3r_set_specialization(ctx.h, spec)
 pd = lib.ProverData.from_airs_and_degrees(ctx, L.insts, L.preps)
 prover = lib.BatchStarkProver(ctx, pinned_output=True)
 tb = lib.TraceBatch(ctx, L.traces, L.pubs).upload(pd)
@@ -29,7 +31,8 @@ ctx.set_kernel_timing(lib.KERNEL_CLASSES)
 for _ in range(4):
     prover.prove_resident(tb, pd, copy=False)
 st = ctx.kernel_stats()
-print(json.dumps({"lib": os.path.basename(os.environ.get("P3R_LIB", "libp3r_b200.so")), "field": field, "scale": scale,
+print(json.dumps({"lib": os.path.basename(os.environ.get("P3R_LIB", "libp3r_b200.so")), "spec": spec,
+                  "stage_max_log": os.environ.get("P3R_STAGE_MAX_LOG"), "field": field, "scale": scale,
                   "ms_median": float(np.median(ms)), "ms_min": float(min(ms)),
                   "digest": int(proof.astype(np.uint64).sum() % (1 << 61)),
                   "phases": {k: round(v, 3) for k, v in ctx.last_phase_times().items()},
