@@ -343,9 +343,11 @@ __global__ void __launch_bounds__(128) k_hash_rows(const HashJob* __restrict__ j
 }
 // Same result through a work queue: a work item is 32 consecutive rows of one job (one warp), items are numbered with the
 // longest sponges first and every warp of a machine-filling grid takes the next item from an atomic counter when it finishes
-// its current one (longest-processing-time-first list scheduling). With one CTA per 128 rows the hardware dispatches the 512
-// long-row CTAs of the recursion layer in the first wave, 3 or 4 per SM, and nothing later can even that out: the launch ran at
-// 4.07 permutations/ns against 5.1 for the same permutation code on uniform work.
+// its current one (longest-processing-time-first list scheduling). Kept as the second schedule for the parity tests
+// (p3r_set_specialization bit 3): on B200 it is SLOWER than k_hash_rows (hash class 1.44 ms against 1.18 ms per layer proof):
+// ptxas gives the persistent loop 40 registers (48 resident warps instead of 64) and puts 48 instead of 28 of a full round's
+// additions on the multiplier pipe (478 against 436 multiplier-pipe cycles per round and warp, scripts/sass_pipe_model.py).
+// The load imbalance it was written for is handled by the CTA size of k_hash_rows instead (64 rows, p3r.cu commit_tree).
 struct HashQueue {
     uint32_t n_jobs, n_items;
     uint32_t counter;        // zero when the launch starts (uploaded with the descriptor)
@@ -427,6 +429,26 @@ __global__ void __launch_bounds__(128) k_compress(const uint32_t* __restrict__ p
     uint4* o = reinterpret_cast<uint4*>(next + (size_t)i * 8);
     o[0] = make_uint4(st[0], st[1], st[2], st[3]);
     o[1] = make_uint4(st[4], st[5], st[6], st[7]);
+}
+// One level, 16 lanes per node (cooperative permutation): for the mid-size levels (2^13 .. 2^15 nodes), where one thread per
+// node leaves most of the machine idle for a full 10^4-cycle permutation (2^15 threads are 11 % of the resident-thread
+// capacity) while 16 lanes per node fill it and finish in one or two cooperative-permutation latencies.
+template <class F>
+__global__ void __launch_bounds__(256) k_compress_coop(const uint32_t* __restrict__ prev, uint32_t* __restrict__ next, uint32_t n_next,
+                                                        const uint32_t* __restrict__ inj, const Poseidon2Consts* __restrict__ gk) {
+    const uint32_t lane = threadIdx.x & 31u, l16 = lane & 15u;
+    const P2Lane c = p2_lane_consts<F>(gk, l16);
+    const uint32_t node = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool live = node < n_next;
+    if (!__ballot_sync(0xffffffffu, live)) return;
+    const uint32_t i = live ? node : 0;
+    uint32_t x = prev[(size_t)i * 16 + l16];   // left digest || right digest
+    x = p2_coop_permute<F>(x, lane, c);
+    if (inj) {
+        if (l16 >= 8) x = __ldg(inj + (size_t)i * 8 + (l16 - 8));
+        x = p2_coop_permute<F>(x, lane, c);
+    }
+    if (live && l16 < 8) next[(size_t)i * 8 + l16] = x;
 }
 // ---- cooperative (16 lanes per permutation) Merkle kernel for the small levels ---------------------------------------
 // Several consecutive Merkle levels in ONE launch. CTA b owns the subtree rooted at node b of the stage's last level:

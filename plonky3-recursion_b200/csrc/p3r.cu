@@ -142,7 +142,7 @@ struct p3r_ctx {
     uint32_t* tw = nullptr;   // = tws + 2^(logT-1) - 1: half table of omega_T
     void (*host_permute)(uint32_t*, const Poseidon2Consts&) = nullptr;  // transcript permutation (AVX2 or scalar), set at creation
     bool dev_fri_transcript = true;  // FRI commit rounds without host round trips (p3r_set_specialization bit 2 turns it off)
-    bool use_hash_queue = true;  // work-queue row hashing (p3r_set_specialization bit 3 turns it off: one CTA per 128 rows)
+    bool use_hash_queue = false;  // work-queue row hashing (p3r_set_specialization bit 3 turns it ON; measured slower, see kernels.cuh)
     uint32_t n_sms = 148;
     bool use_col_ntt = true;  // whole-column LDE kernels for 2^5..2^15 rows (p3r_set_specialization bit 1 turns them off)
     uint32_t logT = 0;
@@ -517,8 +517,14 @@ constexpr uint32_t TILE_LOG = 13;
 // Merkle levels up to this many nodes go through the fused k_merkle_stage launches (P3R_STAGE_MAX_LOG overrides the log2)
 static const uint32_t STAGE_MAX_NODES = [] {
     const char* e = getenv("P3R_STAGE_MAX_LOG");
-    uint32_t l = e ? (uint32_t)atoi(e) : 13u;
+    uint32_t l = e ? (uint32_t)atoi(e) : 12u;   // measured: compress class 1.03 ms at 2^12 against 1.06 at 2^13, 1.17 at 2^14
     return 1u << std::max(8u, std::min(l, 16u));
+}();
+// Levels with at most this many nodes (and more than STAGE_MAX_NODES) use k_compress_coop (P3R_COOP_MAX_LOG overrides; 0 = off)
+static const uint32_t COOP_LEVEL_MAX_NODES = [] {
+    const char* e = getenv("P3R_COOP_MAX_LOG");
+    uint32_t l = e ? (uint32_t)atoi(e) : 15u;
+    return l == 0 ? 0u : 1u << std::min(l, 20u);
 }();
 struct PassPlan {
     uint32_t s0, r, log_cw;
@@ -902,7 +908,11 @@ static int build_tree(p3r_ctx* ctx, const uint32_t* leaf_rows, uint32_t leaf_w, 
         if (leaves_done && n_next > STAGE_MAX_NODES) {
             const uint32_t* inj = inj_at(l);
             if (inj) ctx->kstats.bytes[KC_COMPRESS] += 32ull * n_next, ctx->kstats.perms[KC_COMPRESS] += n_next;
-            k_compress<F><<<(n_next + 127) / 128, 128, 0, ctx->stream>>>(digests + level_off(l - 1), digests + level_off(l), n_next, inj);
+            if (n_next > COOP_LEVEL_MAX_NODES)   // throughput-bound: one thread per permutation
+                k_compress<F><<<(n_next + 127) / 128, 128, 0, ctx->stream>>>(digests + level_off(l - 1), digests + level_off(l), n_next, inj);
+            else                                  // latency-bound: 16 lanes per permutation, one level per launch
+                k_compress_coop<F><<<(n_next * 16 + 255) / 256, 256, 0, ctx->stream>>>(digests + level_off(l - 1), digests + level_off(l),
+                                                                                       n_next, inj, ctx->d_p2);
             LAUNCH_CHECK_C(KC_COMPRESS);
             cur = l;
             continue;
@@ -1003,10 +1013,17 @@ static int commit_tree(p3r_ctx* ctx, const std::vector<MatRef>& mats, Tree* t, u
                                                           reinterpret_cast<HashQueue*>(d_blob));
         LAUNCH_CHECK_C(KC_HASH);
     } else {
+        // CTA size (P3R_HASH_CTA = 32 / 64 / 128): the long-sponge CTAs all land in the first wave, round-robin over the SMs, so
+        // small CTAs spread them evenly. Measured per layer proof (hash class): 128 rows 1.18 ms, 64 rows 1.18 ms, 32 rows 1.13 ms.
+        static const uint32_t hash_cta = [] {
+            const char* e = getenv("P3R_HASH_CTA");
+            uint32_t v = e ? (uint32_t)atoi(e) : 32u;
+            return (v == 32 || v == 64 || v == 128) ? v : 32u;
+        }();
         uint32_t cta = 0;
         for (auto& j : jobs) {
             j.cta_begin = cta;
-            cta += (j.n_rows + 127) / 128;
+            cta += (j.n_rows + hash_cta - 1) / hash_cta;
         }
         const HashJob* d_jobs = upload_vec(ctx, jobs);
         if (!d_jobs) {
@@ -1014,7 +1031,7 @@ static int commit_tree(p3r_ctx* ctx, const std::vector<MatRef>& mats, Tree* t, u
             return P3R_ERR_OOM;
         }
         KT kt(ctx, KC_HASH, hash_bytes);
-        k_hash_rows<F><<<cta, 128, 0, ctx->stream>>>(d_jobs, (uint32_t)jobs.size());
+        k_hash_rows<F><<<cta, hash_cta, 0, ctx->stream>>>(d_jobs, (uint32_t)jobs.size());
         LAUNCH_CHECK_C(KC_HASH);
     }
     return build_tree<F>(ctx, nullptr, 0, lmax, digests, [&](uint32_t level) { return inj_digests[level]; });
@@ -2843,7 +2860,7 @@ int p3r_set_specialization(p3r_ctx* ctx, int enable) {
     ctx->use_spec = (enable & 1) != 0;
     ctx->use_col_ntt = (enable & 2) == 0;
     ctx->dev_fri_transcript = (enable & 4) == 0;
-    ctx->use_hash_queue = (enable & 8) == 0;
+    ctx->use_hash_queue = (enable & 8) != 0;
     return P3R_OK;
 }
 int p3r_timer_start(p3r_ctx* ctx) {

@@ -608,16 +608,17 @@ def test_missing_public_values_are_an_invalid_argument():
 
 
 def test_work_queue_row_hashing_matches_one_cta_per_rows(pair):
-    """k_hash_rows_queue (32-row work items taken from an atomic counter, longest sponges first) and k_hash_rows (one CTA per
-    128 rows) are two schedules of the same sponge: identical mixed-height commitments, both equal to the oracle's."""
+    """k_hash_rows (one CTA per 64 rows, the product path) and k_hash_rows_queue (32-row work items taken from an atomic
+    counter, longest sponges first) are two schedules of the same sponge: identical mixed-height commitments, both equal to
+    the oracle's."""
     ctx, orc = pair
     rng = np.random.default_rng(77)
     mats = [ctx.field.rand(rng, (1 << lh, w)) for lh, w in [(12, 3), (11, 70), (10, 170), (12, 9), (7, 5), (3, 33)]]
     want = orc.mmcs_commit(mats)
-    got_queue = ctx.mmcs_commit(mats)
+    got_cta = ctx.mmcs_commit(mats)
     ctx.set_specialization(1 | 8)
     try:
-        got_cta = ctx.mmcs_commit(mats)
+        got_queue = ctx.mmcs_commit(mats)
     finally:
         ctx.set_specialization(1)
     assert np.array_equal(got_queue, want) and np.array_equal(got_cta, want)
