@@ -338,6 +338,8 @@ void poseidon2_permute(Fp* s) {
     }
 }
 
+#include "direct_airs.inc"   // independent, hard-coded ALU / Poseidon2 constraint evaluators (checked against the bytecode)
+
 struct Digest {
     Fp d[8];
 };
@@ -1697,6 +1699,65 @@ int orc_verify(uint32_t n_inst, const p3r_instance_desc* descs, const uint32_t* 
 // semantics (is_first = row 0, is_last = row n-1, is_transition = not last) and report the first violated
 // constraint: the analogue of p3's debug `check_constraints` (book/src/advanced_topics/debugging.md).
 // Programs with E_* perm/challenge inputs are not supported here (AIR-only check). Returns 0 when satisfied.
+// ---- constraint values of ONE (local, next) row pair: through the bytecode program, and through the hard-coded evaluators of
+// direct_airs.inc. `main2` / `prep2`: two rows (local then next) of Montgomery words. Output: Montgomery words.
+int orc_eval_air_rows(const p3r_instance_desc* desc, const uint32_t* main2, const uint32_t* prep2, const uint32_t* public_values,
+                      const uint32_t sel[3], uint32_t* out, uint32_t cap_constraints, uint32_t* n_out) {
+    ORC_GUARD({
+        Inst s = load_inst(*desc);
+        std::vector<Fp> m(2 * (size_t)s.main_w), p(2 * (size_t)s.prep_w), pub;
+        for (size_t k = 0; k < m.size(); k++) m[k] = from_monty(main2[k]);
+        for (size_t k = 0; k < p.size(); k++) p[k] = from_monty(prep2[k]);
+        for (uint32_t k = 0; k < s.n_pub; k++) pub.push_back(from_monty(public_values[k]));
+        std::vector<Ext> zero_ch(2 * s.lookups.size() + 2, ext_zero()), zperm(s.aux_w() + 1, ext_zero());
+        Ext zt = ext_zero();
+        RowCtx<Fp> rc;
+        rc.main[0] = m.data();
+        rc.main[1] = m.data() + s.main_w;
+        rc.prep[0] = p.data();
+        rc.prep[1] = p.data() + s.prep_w;
+        rc.perm[0] = rc.perm[1] = zperm.data();
+        rc.pub = pub.data();
+        for (int k = 0; k < 3; k++) rc.sel[k] = from_monty(sel[k]);
+        rc.chal = zero_ch.data();
+        rc.pval = &zt;
+        std::vector<Ext> cons(s.cons.n_constraints, ext_zero());
+        run_program<Fp>(s.cons, rc, &cons, nullptr);
+        *n_out = (uint32_t)cons.size();
+        if (cons.size() > cap_constraints) throw std::runtime_error("eval_air_rows: output too small");
+        for (size_t k = 0; k < cons.size(); k++)
+            for (int c = 0; c < 4; c++) out[4 * k + c] = to_monty(cons[k].c[c]);
+    })
+}
+int orc_alu_eval_direct(uint32_t d, uint32_t lanes, uint32_t k_max, const uint32_t* main2, uint32_t main_w, const uint32_t* prep2,
+                        uint32_t prep_w, uint32_t* out, uint32_t cap, uint32_t* n_out) {
+    ORC_GUARD({
+        std::vector<Fp> m(2 * (size_t)main_w), p(2 * (size_t)prep_w);
+        for (size_t k = 0; k < m.size(); k++) m[k] = from_monty(main2[k]);
+        for (size_t k = 0; k < p.size(); k++) p[k] = from_monty(prep2[k]);
+        std::vector<Fp> c = direct::alu_constraints_direct(d, lanes, k_max, Fp{Wnr}, m.data(), m.data() + main_w, main_w, p.data(),
+                                                           p.data() + prep_w, prep_w);
+        *n_out = (uint32_t)c.size();
+        if (c.size() > cap) throw std::runtime_error("alu_eval_direct: output too small");
+        for (size_t k = 0; k < c.size(); k++) out[k] = to_monty(c[k]);
+    })
+}
+int orc_poseidon2_eval_direct(uint32_t sbox_registers, const uint32_t* main2, uint32_t main_w, const uint32_t* prep2, uint32_t prep_w,
+                              uint32_t is_transition, uint32_t* out, uint32_t cap, uint32_t* n_out) {
+    ORC_GUARD({
+        std::vector<Fp> m(2 * (size_t)main_w), p(2 * (size_t)prep_w);
+        for (size_t k = 0; k < m.size(); k++) m[k] = from_monty(main2[k]);
+        for (size_t k = 0; k < p.size(); k++) p[k] = from_monty(prep2[k]);
+        direct::P2Params pp{P2.sbox, sbox_registers, P2.rf / 2, P2.rp, P2.ext_rc.data(), P2.int_rc.data(), P2.diag.data()};
+        const uint32_t want_w = 16 + 2 * (P2.rf / 2) * (16 * sbox_registers + 16) + P2.rp * (sbox_registers + 1) + 2;
+        if (main_w != want_w || prep_w != 24) throw std::runtime_error("poseidon2_eval_direct: widths do not match the parameters");
+        std::vector<Fp> c = direct::poseidon2_constraints_direct(pp, m.data(), m.data() + main_w, p.data() + prep_w, from_monty(is_transition));
+        *n_out = (uint32_t)c.size();
+        if (c.size() > cap) throw std::runtime_error("poseidon2_eval_direct: output too small");
+        for (size_t k = 0; k < c.size(); k++) out[k] = to_monty(c[k]);
+    })
+}
+
 int orc_check_constraints(const p3r_instance_desc* desc, const p3r_matrix_u32* prep, const p3r_matrix_u32* trace,
                           const uint32_t* public_values, int64_t* bad_row, int64_t* bad_constraint) {
     ORC_GUARD({

@@ -21,7 +21,8 @@ def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
     src = os.path.join(_HERE, "oracle.cpp")
     hdr = os.path.join(_HERE, "..", "include", "p3r.h")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    inc = os.path.join(_HERE, "direct_airs.inc")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(inc)):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
 
@@ -115,6 +116,47 @@ class Oracle:
         proof = np.ascontiguousarray(proof, dtype=np.uint32)
         pc = abi.as_u32p(np.ascontiguousarray(prep_cap_monty, dtype=np.uint32)) if prep_cap_monty is not None else None
         self._check(self.lib.orc_verify(len(insts), descs, pc, pv, abi.as_u32p(proof), C.c_size_t(proof.size)))
+
+    # ---- one (local, next) row pair: constraint values through the bytecode and through the hard-coded evaluators ----
+    def _two_rows(self, local, nxt):
+        return np.ascontiguousarray(self.field.to_monty(np.stack([np.asarray(local), np.asarray(nxt)]).astype(np.uint32)))
+
+    def eval_air_rows(self, inst, local, nxt, prep_local, prep_next, sel, pub=None) -> np.ndarray:
+        """AIR-only constraint values (canonical, one per constraint) of the instance's bytecode on this row pair."""
+        import copy
+        s = copy.copy(inst)
+        s.constraints = inst.air_only_constraints
+        s.lookups, s.interactions, s.lookup_inputs = [], [], None
+        m = abi.Marshal(self.field)
+        descs = m.instances([s])
+        m2, p2 = self._two_rows(local, nxt), self._two_rows(prep_local, prep_next)
+        pv = m.u32(self.field.to_monty(np.asarray(pub if pub is not None else [0], dtype=np.uint32)))
+        sl = m.u32(self.field.to_monty(np.asarray(sel, dtype=np.uint32)))
+        n_c = s.constraints.n_constraints
+        out = np.zeros(4 * n_c, dtype=np.uint32)
+        n = C.c_uint32(0)
+        self._check(self.lib.orc_eval_air_rows(C.byref(descs[0]), abi.as_u32p(m2), abi.as_u32p(p2), abi.as_u32p(pv), abi.as_u32p(sl),
+                                               abi.as_u32p(out), n_c, C.byref(n)))
+        vals = self.field.from_monty(out).reshape(-1, 4)
+        assert not vals[:, 1:].any()          # base-field constraints only
+        return vals[:, 0]
+
+    def alu_eval_direct(self, d, lanes, k_max, local, nxt, prep_local, prep_next) -> np.ndarray:
+        m2, p2 = self._two_rows(local, nxt), self._two_rows(prep_local, prep_next)
+        out = np.zeros(4096, dtype=np.uint32)
+        n = C.c_uint32(0)
+        self._check(self.lib.orc_alu_eval_direct(d, lanes, k_max, abi.as_u32p(m2), m2.shape[1], abi.as_u32p(p2), p2.shape[1],
+                                                 abi.as_u32p(out), out.size, C.byref(n)))
+        return self.field.from_monty(out[: n.value])
+
+    def poseidon2_eval_direct(self, sbox_registers, local, nxt, prep_local, prep_next, is_transition) -> np.ndarray:
+        m2, p2 = self._two_rows(local, nxt), self._two_rows(prep_local, prep_next)
+        out = np.zeros(4096, dtype=np.uint32)
+        n = C.c_uint32(0)
+        it = int(self.field.to_monty(np.array([is_transition], dtype=np.uint32))[0])
+        self._check(self.lib.orc_poseidon2_eval_direct(sbox_registers, abi.as_u32p(m2), m2.shape[1], abi.as_u32p(p2), p2.shape[1], it,
+                                                       abi.as_u32p(out), out.size, C.byref(n)))
+        return self.field.from_monty(out[: n.value])
 
     def check_constraints(self, inst, prep_mat, trace, pub):
         """AIR-only constraint check on the trace domain; returns (bad_row, bad_constraint) or None."""

@@ -430,26 +430,6 @@ __global__ void __launch_bounds__(128) k_compress(const uint32_t* __restrict__ p
     o[0] = make_uint4(st[0], st[1], st[2], st[3]);
     o[1] = make_uint4(st[4], st[5], st[6], st[7]);
 }
-// One level, 16 lanes per node (cooperative permutation): for the mid-size levels (2^13 .. 2^15 nodes), where one thread per
-// node leaves most of the machine idle for a full 10^4-cycle permutation (2^15 threads are 11 % of the resident-thread
-// capacity) while 16 lanes per node fill it and finish in one or two cooperative-permutation latencies.
-template <class F>
-__global__ void __launch_bounds__(256) k_compress_coop(const uint32_t* __restrict__ prev, uint32_t* __restrict__ next, uint32_t n_next,
-                                                        const uint32_t* __restrict__ inj, const Poseidon2Consts* __restrict__ gk) {
-    const uint32_t lane = threadIdx.x & 31u, l16 = lane & 15u;
-    const P2Lane c = p2_lane_consts<F>(gk, l16);
-    const uint32_t node = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-    const bool live = node < n_next;
-    if (!__ballot_sync(0xffffffffu, live)) return;
-    const uint32_t i = live ? node : 0;
-    uint32_t x = prev[(size_t)i * 16 + l16];   // left digest || right digest
-    x = p2_coop_permute<F>(x, lane, c);
-    if (inj) {
-        if (l16 >= 8) x = __ldg(inj + (size_t)i * 8 + (l16 - 8));
-        x = p2_coop_permute<F>(x, lane, c);
-    }
-    if (live && l16 < 8) next[(size_t)i * 8 + l16] = x;
-}
 // ---- cooperative (16 lanes per permutation) Merkle kernel for the small levels ---------------------------------------
 // Several consecutive Merkle levels in ONE launch. CTA b owns the subtree rooted at node b of the stage's last level:
 // with K = n_levels it produces 2^(K-1-j) nodes of level first_level + j (j < K), keeps them in shared memory for the

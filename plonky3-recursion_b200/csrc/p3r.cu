@@ -520,12 +520,6 @@ static const uint32_t STAGE_MAX_NODES = [] {
     uint32_t l = e ? (uint32_t)atoi(e) : 12u;   // measured: compress class 1.03 ms at 2^12 against 1.06 at 2^13, 1.17 at 2^14
     return 1u << std::max(8u, std::min(l, 16u));
 }();
-// Levels with at most this many nodes (and more than STAGE_MAX_NODES) use k_compress_coop (P3R_COOP_MAX_LOG overrides; 0 = off)
-static const uint32_t COOP_LEVEL_MAX_NODES = [] {
-    const char* e = getenv("P3R_COOP_MAX_LOG");
-    uint32_t l = e ? (uint32_t)atoi(e) : 15u;
-    return l == 0 ? 0u : 1u << std::min(l, 20u);
-}();
 struct PassPlan {
     uint32_t s0, r, log_cw;
 };
@@ -908,11 +902,10 @@ static int build_tree(p3r_ctx* ctx, const uint32_t* leaf_rows, uint32_t leaf_w, 
         if (leaves_done && n_next > STAGE_MAX_NODES) {
             const uint32_t* inj = inj_at(l);
             if (inj) ctx->kstats.bytes[KC_COMPRESS] += 32ull * n_next, ctx->kstats.perms[KC_COMPRESS] += n_next;
-            if (n_next > COOP_LEVEL_MAX_NODES)   // throughput-bound: one thread per permutation
-                k_compress<F><<<(n_next + 127) / 128, 128, 0, ctx->stream>>>(digests + level_off(l - 1), digests + level_off(l), n_next, inj);
-            else                                  // latency-bound: 16 lanes per permutation, one level per launch
-                k_compress_coop<F><<<(n_next * 16 + 255) / 256, 256, 0, ctx->stream>>>(digests + level_off(l - 1), digests + level_off(l),
-                                                                                       n_next, inj, ctx->d_p2);
+            // one thread per permutation. (A one-level kernel with 16 lanes per node for the 2^13..2^15-node levels was measured
+            // and dropped: compress class 1.03 -> 1.13 / 1.23 ms with it up to 2^14 / 2^15 nodes — the cooperative permutation has
+            // an eighth of the throughput, and these levels already need it.)
+            k_compress<F><<<(n_next + 127) / 128, 128, 0, ctx->stream>>>(digests + level_off(l - 1), digests + level_off(l), n_next, inj);
             LAUNCH_CHECK_C(KC_COMPRESS);
             cur = l;
             continue;
