@@ -216,6 +216,19 @@ int p3r_ctx_create(int device, const p3r_field_desc* field, const p3r_poseidon2_
 void p3r_ctx_destroy(p3r_ctx* ctx);
 const char* p3r_last_error(const p3r_ctx* ctx);
 
+/* Protocol conventions that live in the crates.io p3-* 0.6 crates and NOT in the reference tree ([P3-EXT]): each is
+ * a named, run-time selectable choice in the library and, identically, in the oracle, so that pinning against real reference
+ * output (tools/ref_golden) is a flag flip, not a rewrite. Defaults (all zero) are the choices DESIGN.md §2 argues for.
+ * LogUp denominator of a tuple (f_0 .. f_{n-1}) on a bus:  bus_prefix + s * sum_k beta^{e(k)} * f_k  with
+ *   s = -1 if logup_negate else +1;   e(k) = first_power + (logup_descending ? n - 1 - k : k).
+ * The constraint bytecode the caller supplies must encode the same choice (symbolic.LOGUP_CONVENTIONS on the Python side). */
+typedef struct {
+    uint32_t logup_negate;        /* 0: prefix + sum, 1: prefix - sum                                  */
+    uint32_t logup_first_power;   /* 0: powers start at beta^0, 1: at beta^1                           */
+    uint32_t logup_descending;    /* 0: f_0 gets the lowest power, 1: the highest (all tuples of one length) */
+} p3r_conventions;
+int p3r_ctx_set_conventions(p3r_ctx* ctx, const p3r_conventions* conv);
+
 /* Replaces ProverData::from_airs_and_degrees (recursion/src/recursion.rs:376): uploads the
  * instance descriptions (bytecode, lookups), LDEs + commits all preprocessed matrices into one
  * global MMCS tree that stays device-resident, and writes its cap (8 << cap_height words).

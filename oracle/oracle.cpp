@@ -532,6 +532,8 @@ struct Challenger {
 // ------------------------------------------------------------------------------------------------
 // Instances + constraint bytecode interpreter (format: include/p3r.h).
 // ------------------------------------------------------------------------------------------------
+p3r_conventions CONV{0, 0, 0};   // orc_set_conventions: the [P3-EXT] choices, same names as the library's
+
 struct Program {
     std::vector<p3r_insn> insns;
     uint32_t nb = 0, ne = 0, n_constraints = 0, n_outputs = 0;
@@ -702,10 +704,11 @@ Mat logup_trace(const Inst& s, const Mat& main, const Mat* prep, const Fp* pub, 
             Ext frac = ext_zero();
             for (uint32_t j = 0; j < l.n_interactions; j++) {
                 const auto& it = s.inter[l.first_interaction + j];
-                Ext den = prefix, bp = ext_one();
+                Ext den = prefix;   // prefix + s * sum_k beta^{e(k)} f_k, see p3r_conventions
                 for (uint32_t k = 0; k < it.n_elems; k++) {
-                    den = den + bp * outs[it.elem_out_first + k];
-                    bp = bp * beta;
+                    const uint32_t e = CONV.logup_first_power + (CONV.logup_descending ? it.n_elems - 1 - k : k);
+                    const Ext term = epow(beta, e) * outs[it.elem_out_first + k];
+                    den = CONV.logup_negate ? den - term : den + term;
                 }
                 Fp m = outs[it.mult_out];
                 if (m.v != 0) frac = frac + einv(den) * m;
@@ -1565,6 +1568,10 @@ int orc_init(const p3r_field_desc* field, const p3r_poseidon2_consts* p2, const 
         return 1;                                        \
     }
 
+int orc_set_conventions(const p3r_conventions* conv) {
+    CONV = *conv;
+    return 0;
+}
 int orc_poseidon2_permute(uint32_t* states, uint32_t n) {
     ORC_GUARD({
         for (uint32_t i = 0; i < n; i++) {

@@ -40,6 +40,12 @@ class Oracle:
         if rc != 0:
             raise RuntimeError(self.lib.orc_last_error().decode())
 
+    def set_conventions(self, **conv):
+        """Same names and meaning as the library's p3r_conventions (process-wide in the oracle)."""
+        c = abi.ConventionsC(int(conv.get("logup_negate", 0)), int(conv.get("logup_first_power", 0)),
+                             int(conv.get("logup_descending", 0)))
+        self._check(self.lib.orc_set_conventions(C.byref(c)))
+
     def poseidon2_permute(self, states_canonical: np.ndarray) -> np.ndarray:
         s = np.ascontiguousarray(self.field.to_monty(states_canonical).reshape(-1, 16))
         self._check(self.lib.orc_poseidon2_permute(abi.as_u32p(s), s.shape[0]))

@@ -72,6 +72,10 @@ class InstanceDesc(C.Structure):
                 ("interactions", C.POINTER(InteractionC)), ("n_interactions", u32)]
 
 
+class ConventionsC(C.Structure):
+    _fields_ = [("logup_negate", u32), ("logup_first_power", u32), ("logup_descending", u32)]
+
+
 class NpoEntryC(C.Structure):
     _fields_ = [("op_type", C.c_char_p), ("rows", C.c_uint64), ("lanes", C.c_uint64), ("public_values", u32p),
                 ("n_public_values", u32), ("air_variant", u32)]

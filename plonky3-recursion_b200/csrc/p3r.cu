@@ -142,6 +142,7 @@ struct p3r_ctx {
     uint32_t* tw = nullptr;   // = tws + 2^(logT-1) - 1: half table of omega_T
     void (*host_permute)(uint32_t*, const Poseidon2Consts&) = nullptr;  // transcript permutation (AVX2 or scalar), set at creation
     bool dev_fri_transcript = true;  // FRI commit rounds without host round trips (p3r_set_specialization bit 2 turns it off)
+    p3r_conventions conv{0, 0, 0};  // p3r_ctx_set_conventions
     bool use_hash_queue = false;  // work-queue row hashing (p3r_set_specialization bit 3 turns it ON; measured slower, see kernels.cuh)
     uint32_t n_sms = 148;
     bool use_col_ntt = true;  // whole-column LDE kernels for 2^5..2^15 rows (p3r_set_specialization bit 1 turns them off)
@@ -1475,9 +1476,24 @@ static int commit_perm_impl(p3r_session* s, const uint32_t alpha[4], const uint3
             chal.push_back(b);
         }
     }
-    std::vector<Ext4> bp(8);
-    bp[0] = ext_one<F>();
-    for (int k = 1; k < 8; k++) bp[k] = emul<F>(bp[k - 1], b, wnr);
+    // coefficient of tuple element k in a denominator (p3r_conventions): s * beta^(first_power + k), or with the powers in
+    // descending order over the tuple (then every tuple must have the same length, the widest one)
+    const p3r_conventions& cv = ctx->conv;
+    if (cv.logup_descending)
+        for (auto& d : pp->inst)
+            for (auto& it : d.inter)
+                if (it.n_elems != pp->max_msg_w) {
+                    set_err(ctx, "logup_descending needs every lookup tuple to have the same length");
+                    return P3R_ERR_UNSUPPORTED;
+                }
+    std::vector<Ext4> pw(9), bp(8);
+    pw[0] = ext_one<F>();
+    for (int k = 1; k < 9; k++) pw[k] = emul<F>(pw[k - 1], b, wnr);
+    for (uint32_t k = 0; k < 8; k++) {
+        const uint32_t e = cv.logup_first_power + (cv.logup_descending ? (k < pp->max_msg_w ? pp->max_msg_w - 1 - k : 0) : k);
+        bp[k] = pw[std::min(e, 8u)];
+        if (cv.logup_negate) bp[k] = eneg<F>(bp[k]);
+    }
     s->d_chal = upload_vec(ctx, chal);
     Ext4* d_bp = upload_vec(ctx, bp);
     if (!s->d_chal || !d_bp || !s->d_terminals) return P3R_ERR_OOM;
@@ -2653,6 +2669,11 @@ int p3r_prep_commit(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_desc* desc
     if (!ctx || !descs || !out || n_inst == 0) return P3R_ERR_INVALID_ARG;
     cudaSetDevice(ctx->device);
     return DISPATCH(ctx, prep_commit_impl<F>(ctx, n_inst, descs, prep, out, cap_out, has_prep_out));
+}
+int p3r_ctx_set_conventions(p3r_ctx* ctx, const p3r_conventions* conv) {
+    if (!ctx || !conv || conv->logup_negate > 1 || conv->logup_first_power > 1 || conv->logup_descending > 1) return P3R_ERR_INVALID_ARG;
+    ctx->conv = *conv;
+    return P3R_OK;
 }
 void p3r_set_wait_mode(int mode) { g_wait_mode.store(mode < 0 || mode > 2 ? 1 : mode, std::memory_order_relaxed); }
 void p3r_prep_free(p3r_prep* prep) {

@@ -84,7 +84,7 @@ EXPORTS = ["p3r_abi_version", "p3r_build_info", "p3r_ctx_create", "p3r_ctx_destr
            "p3r_traces_download", "p3r_kernel_perms", "p3r_bench_fri_round", "p3r_prove_ops",
            "p3r_traces_upload_ops", "p3r_set_wait_mode", "p3r_host_hasher_create", "p3r_host_hasher_permute",
            "p3r_host_hasher_free", "p3r_traces_write_rows", "p3r_proof_serialize", "p3r_proof_deserialize",
-           "p3r_wire_last_error"]
+           "p3r_wire_last_error", "p3r_ctx_set_conventions"]
 
 WIRE_CANONICAL, WIRE_BARE_ROOT = 1, 2
 
@@ -243,6 +243,13 @@ class Context:
     def set_wait_mode(self, mode: str):
         """'spin' | 'yield' | 'block' (process-wide, p3r_set_wait_mode)."""
         self.lib.p3r_set_wait_mode({"spin": 0, "yield": 1, "block": 2}[mode])
+
+    def set_conventions(self, **conv):
+        """[P3-EXT] protocol conventions (include/p3r.h p3r_conventions): logup_negate, logup_first_power, logup_descending.
+        The instances must have been built under the same symbolic.LOGUP_CONVENTIONS."""
+        c = abi.ConventionsC(int(conv.get("logup_negate", 0)), int(conv.get("logup_first_power", 0)),
+                             int(conv.get("logup_descending", 0)))
+        self._check(self.lib.p3r_ctx_set_conventions(self.h, C.byref(c)))
 
     def set_specialization(self, enable: bool):
         self._check(self.lib.p3r_set_specialization(self.h, int(enable)))

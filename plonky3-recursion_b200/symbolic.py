@@ -314,22 +314,31 @@ def pack_same_bus(interactions, budget):
     return groups
 
 
+# [P3-EXT] LogUp denominator convention (include/p3r.h p3r_conventions): prefix + s * sum_k beta^{e(k)} f_k with s = -1 if
+# `negate`, e(k) = first_power + (n - 1 - k if descending else k). Must match Context.set_conventions / Oracle.set_conventions.
+LOGUP_CONVENTIONS = dict(logup_negate=0, logup_first_power=0, logup_descending=0)
+
+
 def logup_constraints(b: AirBuilder, groups):
     """Append the LogUp constraints for `groups` (list of lists of Interaction) to builder `b`."""
     ctx = b.ctx
     if not groups:
         return
+    cv = LOGUP_CONVENTIONS
     fracs = []
     for c, group in enumerate(groups):
         prefix, beta = ctx.chal(2 * c), ctx.chal(2 * c + 1)
         dens = []
         for it in group:
+            n = len(it.fields)
+            pows = [None]                    # pows[e] = beta^e as an expression (None = 1)
+            for _ in range(n + 1):
+                pows.append(beta if pows[-1] is None else pows[-1] * beta)
             den = prefix
-            bp = None
             for k, f in enumerate(it.fields):
-                term = f if k == 0 else bp * f
-                den = den + term
-                bp = beta if bp is None else bp * beta
+                e = cv["logup_first_power"] + ((n - 1 - k) if cv["logup_descending"] else k)
+                term = f if pows[e] is None else pows[e] * f    # default convention: the same nodes as ever (program hash)
+                den = (den - term) if cv["logup_negate"] else (den + term)
             dens.append(den)
         frac = ctx.perm(c + 1, 0)
         fracs.append(frac)
