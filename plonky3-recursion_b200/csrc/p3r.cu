@@ -123,6 +123,7 @@ struct p3r_ctx {
     cudaEvent_t timer_ev[2] = {nullptr, nullptr};
     uint32_t time_mask = 0;  // bit per KClass: record CUDA events around launches of that class
     std::vector<cudaEvent_t> ev_pool;
+    std::vector<cudaEvent_t> phase_ev;  // PhaseTimer's events
     size_t ev_used = 0;
     std::vector<std::pair<int, size_t>> ev_pending;  // (class, index of start event)
     KernelStats kstats;
@@ -153,7 +154,10 @@ struct p3r_ctx {
     Arena arena;
     // pinned staging for small uploads/downloads
     char* pin = nullptr;
-    size_t pin_size = 0, pin_used = 0;
+    size_t pin_size = 0, pin_used = 0, pin_top_used = 0;
+    size_t mirror_valid = 0;        // dstage[0, mirror_valid) == pin[0, mirror_valid): see upload_small
+    bool skip_equal_uploads = true; // P3R_UPLOAD_SKIP=0 turns the skipping off (A/B)
+    uint64_t uploads_skipped = 0;
     // D2H staging for the yield / block wait modes (d2h_async, ctx_wait)
     char* pin_out = nullptr;
     size_t pin_out_size = 0, pin_out_used = 0;
@@ -252,14 +256,38 @@ static cudaError_t ctx_wait(p3r_ctx* ctx) {
     return e;
 }
 // Copy a small host blob to the device through the pinned staging area (valid until the next session begins).
-static void* upload_small(p3r_ctx* ctx, const void* src, size_t bytes) {
-    size_t b = (bytes + 255) & ~(size_t)255;
-    if (ctx->pin_used + b > ctx->pin_size) return nullptr;
-    char* h = ctx->pin + ctx->pin_used;
-    char* d = ctx->dstage + ctx->pin_used;
-    ctx->pin_used += b;
+// The ring is reset at the start of every session and a circuit shape allocates it in the same order every time, so a slot
+// usually receives the bytes it already holds (job descriptors, column pointers, twiddle tables: everything that does not depend
+// on the proof's challenges). The pinned copy of the previous session doubles as the record of what the device mirror holds:
+// inside the prefix [0, mirror_valid) the mirror is known to equal the pinned ring, and when the new bytes equal the pinned ones
+// the host-to-device copy is skipped (most of the ~40 small copies of a layer proof, each a stream operation of its own between
+// two kernels). `device_mutable`: a kernel writes to the device copy (challenger state, queue counters); those slots come from
+// the top of the ring, are always copied and never trusted.
+static void ring_reset(p3r_ctx* ctx) {
+    ctx->pin_used = 0;
+    ctx->pin_top_used = 0;
+}
+static void* upload_small(p3r_ctx* ctx, const void* src, size_t bytes, bool device_mutable = false) {
+    const size_t b = (bytes + 255) & ~(size_t)255;
+    if (ctx->pin_used + ctx->pin_top_used + b > ctx->pin_size) return nullptr;
+    size_t off;
+    if (device_mutable) {
+        ctx->pin_top_used += b;
+        off = ctx->pin_size - ctx->pin_top_used;
+    } else {
+        off = ctx->pin_used;
+        ctx->pin_used += b;
+        if (ctx->skip_equal_uploads && off + b <= ctx->mirror_valid && std::memcmp(ctx->pin + off, src, bytes) == 0) {
+            ctx->uploads_skipped++;
+            return ctx->dstage + off;
+        }
+    }
+    char* h = ctx->pin + off;
+    char* d = ctx->dstage + off;
     std::memcpy(h, src, bytes);
     if (cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return nullptr;
+    if (!device_mutable && off <= ctx->mirror_valid) ctx->mirror_valid = std::max(ctx->mirror_valid, off + b);
+    if (device_mutable) ctx->mirror_valid = std::min(ctx->mirror_valid, off);   // (only if the two ends ever met)
     return d;
 }
 template <class T>
@@ -996,7 +1024,7 @@ static int commit_tree(p3r_ctx* ctx, const std::vector<MatRef>& mats, Tree* t, u
         HashQueue hq{(uint32_t)jobs.size(), items, 0u, 0u};
         std::memcpy(blob.data(), &hq, sizeof hq);
         std::memcpy(blob.data() + sizeof hq, jobs.data(), jobs.size() * sizeof(HashJob));
-        char* d_blob = (char*)upload_small(ctx, blob.data(), blob.size());
+        char* d_blob = (char*)upload_small(ctx, blob.data(), blob.size(), /*device_mutable=*/true);
         if (!d_blob) {
             set_err(ctx, "staging exhausted");
             return P3R_ERR_OOM;
@@ -1174,7 +1202,7 @@ static int prep_commit_impl(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_de
         return r;
     };
     ctx->arena.reset();
-    ctx->pin_used = 0;
+    ring_reset(ctx);
     const bool trace_prep = getenv("P3R_TRACE_PREP") != nullptr;
     auto t_prev = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) {
@@ -1339,7 +1367,7 @@ static int prove_begin_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix
                             const uint32_t* const* public_values, p3r_session** out, const p3r_traces* resident = nullptr,
                             const p3r_table_ops* tops = nullptr) {
     ctx->arena.reset();
-    ctx->pin_used = 0;
+    ring_reset(ctx);
     auto* s = new p3r_session();
     s->ctx = ctx;
     s->prep = prep;
@@ -2152,28 +2180,28 @@ static int grind_impl(p3r_ctx* ctx, const uint32_t state[16], const uint32_t* pe
 // ------------------------------------------------------------------------------------------------
 // One-shot prove: host transcript (SURVEY.md A1/A2/A7 order) over the phases. Blob layout: DESIGN.md "Proof blob".
 // ------------------------------------------------------------------------------------------------
-struct PhaseTimer {
+struct PhaseTimer {   // CUDA events on the session stream, taken from a pool owned by the context (no create/destroy per proof)
     p3r_ctx* ctx;
-    std::vector<cudaEvent_t> ev;
+    size_t used = 0;
     std::vector<std::string> names;
     explicit PhaseTimer(p3r_ctx* c) : ctx(c) { mark("start"); }
     void mark(const char* name) {
-        cudaEvent_t e;
-        cudaEventCreate(&e);
-        cudaEventRecord(e, ctx->stream);
-        ev.push_back(e);
+        if (used == ctx->phase_ev.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ctx->phase_ev.push_back(e);
+        }
+        cudaEventRecord(ctx->phase_ev[used++], ctx->stream);
         names.push_back(name);
     }
     void finish() {
-        cudaEventSynchronize(ev.back());
+        cudaEventSynchronize(ctx->phase_ev[used - 1]);
         ctx->phase_times.clear();
-        for (size_t i = 1; i < ev.size(); i++) {
+        for (size_t i = 1; i < used; i++) {
             float ms = 0;
-            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            cudaEventElapsedTime(&ms, ctx->phase_ev[i - 1], ctx->phase_ev[i]);
             ctx->phase_times.push_back({names[i], ms});
         }
-        for (auto e : ev) cudaEventDestroy(e);
-        ev.clear();
     }
 };
 
@@ -2309,7 +2337,7 @@ static int prove_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* 
         std::memcpy(hc.out, ch.out, sizeof hc.out);
         hc.n_in = (uint32_t)ch.n_in;
         hc.n_out = (uint32_t)ch.n_out;
-        DevChallenger* d_ch = reinterpret_cast<DevChallenger*>(upload_small(ctx, &hc, sizeof hc));
+        DevChallenger* d_ch = reinterpret_cast<DevChallenger*>(upload_small(ctx, &hc, sizeof hc, /*device_mutable=*/true));
         Ext4* d_beta = arena_alloc<Ext4>(ctx, n_rounds);
         if (!d_ch || !d_beta) return P3R_ERR_OOM;
         for (uint32_t r = 0; r < n_rounds; r++) {
@@ -2407,7 +2435,7 @@ static int coset_lde_host_impl(p3r_ctx* ctx, const p3r_matrix_u32* in, uint32_t 
         return P3R_ERR_INVALID_ARG;
     }
     ctx->arena.reset();
-    ctx->pin_used = 0;
+    ring_reset(ctx);
     uint32_t log_n = ilog2(in->height);
     size_t n = in->height, N = n << log_blowup, w = in->width;
     uint32_t* rm = arena_alloc<uint32_t>(ctx, N * w);
@@ -2428,7 +2456,7 @@ static int coset_lde_host_impl(p3r_ctx* ctx, const p3r_matrix_u32* in, uint32_t 
 template <class F>
 static int mmcs_commit_host_impl(p3r_ctx* ctx, uint32_t n_mats, const p3r_matrix_u32* mats, uint32_t* cap_out) {
     ctx->arena.reset();
-    ctx->pin_used = 0;
+    ring_reset(ctx);
     std::vector<MatRef> refs;
     uint32_t lmax = 0;
     for (uint32_t i = 0; i < n_mats; i++) {
@@ -2465,7 +2493,7 @@ static int permute_host_impl(p3r_ctx* ctx, uint32_t* states, uint32_t n) {
 template <class F>
 static int bench_commit_impl(p3r_ctx* ctx, uint32_t log_height, uint32_t width, uint32_t iters, uint64_t seed, float* ms_out) {
     ctx->arena.reset();
-    ctx->pin_used = 0;
+    ring_reset(ctx);
     const uint32_t lb = ctx->fri.log_blowup;
     size_t n = (size_t)1 << log_height, N = n << lb, w = width;
     uint32_t* cm = arena_alloc<uint32_t>(ctx, n * w);
@@ -2614,6 +2642,7 @@ int p3r_ctx_create(int device, const p3r_field_desc* field, const p3r_poseidon2_
         int sms = 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->n_sms = (uint32_t)sms;
     }
+    if (const char* e = getenv("P3R_UPLOAD_SKIP")) ctx->skip_equal_uploads = atoi(e) != 0;
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ctx->pin_size = ctx->dstage_size = (size_t)8 << 20;
     ok = ok && cudaHostAlloc((void**)&ctx->pin, ctx->pin_size, cudaHostAllocDefault) == cudaSuccess;
@@ -2646,6 +2675,7 @@ void p3r_ctx_destroy(p3r_ctx* ctx) {
         cudaFree(kv.second.hi);
     }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    for (auto e : ctx->phase_ev) cudaEventDestroy(e);
     if (ctx->tws) cudaFree(ctx->tws);
     if (ctx->d_p2) cudaFree(ctx->d_p2);
     if (ctx->pin) cudaFreeHost(ctx->pin);
@@ -2846,7 +2876,7 @@ int p3r_traces_write_rows(p3r_ctx* ctx, const p3r_prep* prep, p3r_traces* traces
     }
     cudaSetDevice(ctx->device);
     CUDA_TRY(ctx_wait(ctx));   // staging is about to be reused from its start
-    ctx->pin_used = 0;
+    ring_reset(ctx);
     const uint32_t* d_rows = (const uint32_t*)upload_small(ctx, rows, (size_t)n_rows * d.main_w * 4);
     if (!d_rows) return P3R_ERR_OOM;
     const uint32_t words = n_rows * d.main_w;
@@ -2954,7 +2984,7 @@ int p3r_poseidon2_permute(p3r_ctx* ctx, uint32_t* states, uint32_t n) {
 template <class F>
 static int bench_fri_round_impl(p3r_ctx* ctx, uint32_t log_len, uint32_t log_arity, uint32_t iters, uint64_t seed, float* ms_out) {
     ctx->arena.reset();
-    ctx->pin_used = 0;
+    ring_reset(ctx);
     if (log_arity < 1 || log_arity > 4 || log_len < 2 * log_arity + ctx->fri.cap_height) return P3R_ERR_INVALID_ARG;
     TRY(ensure_twiddles<F>(ctx, log_len));
     const size_t L = (size_t)1 << log_len;

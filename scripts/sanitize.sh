@@ -14,7 +14,7 @@ for tool in memcheck racecheck synccheck; do
     timeout 900 compute-sanitizer --tool "$tool" --print-limit 20 --error-exitcode 86 \
         python -m pytest $sel -m gpu -x -q -k "koala or not baby" > "$log" 2>&1
     rc=$?
-    verdict=$(grep -E "passed|failed|error" "$log" | tail -1)
+    verdict=$(grep -E "[0-9]+ (passed|failed)" "$log" | tail -1)
     errs=$(grep -E "ERROR SUMMARY|RACECHECK SUMMARY" "$log" | tail -1)
     echo "$tool: rc=$rc | pytest: ${verdict:-none} | ${errs:-no summary line}" | tee -a "${prefix}_summary.txt"
 done
