@@ -143,6 +143,7 @@ struct p3r_ctx {
     uint32_t* tw = nullptr;   // = tws + 2^(logT-1) - 1: half table of omega_T
     void (*host_permute)(uint32_t*, const Poseidon2Consts&) = nullptr;  // transcript permutation (AVX2 or scalar), set at creation
     bool dev_fri_transcript = true;  // FRI commit rounds without host round trips (p3r_set_specialization bit 2 turns it off)
+    uint32_t lde_streams = 4;       // job groups (streams) of one batched LDE, 1..N_AUX (P3R_LDE_STREAMS)
     p3r_conventions conv{0, 0, 0};  // p3r_ctx_set_conventions
     bool use_hash_queue = false;  // work-queue row hashing (p3r_set_specialization bit 3 turns it ON; measured slower, see kernels.cuh)
     uint32_t n_sms = 148;
@@ -698,7 +699,7 @@ static int coset_lde_cols(p3r_ctx* ctx, const std::vector<LdeJob>& jobs, uint32_
     std::vector<size_t> order(jobs.size());
     for (size_t i = 0; i < order.size(); i++) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return jobs[x].log_n > jobs[y].log_n; });
-    auto launch_top = [&](const LdeJob& j, size_t qi, bool fwd) -> int {
+    auto launch_top = [&](const LdeJob& j, size_t qi, bool fwd, cudaStream_t st) -> int {
         const uint32_t T = j.log_n - COL_MAX_LOG;                 // stages above the shared-memory kernel
         const uint32_t n_pass = (T + 3) / 4;
         std::vector<uint32_t> qs(n_pass, T / n_pass);
@@ -726,9 +727,9 @@ static int coset_lde_cols(p3r_ctx* ctx, const std::vector<LdeJob>& jobs, uint32_
                 b.dst_coset_stride = fwd ? (uint64_t)j.w * n : 0;
             }
             dim3 grid((unsigned)((n >> Q) / 256), j.w, fwd ? n_cosets : 1);
-#define P3R_TOP(QQ)                                                                                   \
-    if (fwd) k_ntt_top<F, QQ, true><<<grid, 256, 0, ctx->stream>>>(b, jj, last_fwd ? 1u : 0u);       \
-    else k_ntt_top<F, QQ, false><<<grid, 256, 0, ctx->stream>>>(b, jj, 0u)
+#define P3R_TOP(QQ)                                                                       \
+    if (fwd) k_ntt_top<F, QQ, true><<<grid, 256, 0, st>>>(b, jj, last_fwd ? 1u : 0u);    \
+    else k_ntt_top<F, QQ, false><<<grid, 256, 0, st>>>(b, jj, 0u)
             if (Q == 1) { P3R_TOP(1); }
             else if (Q == 2) { P3R_TOP(2); }
             else if (Q == 3) { P3R_TOP(3); }
@@ -739,64 +740,84 @@ static int coset_lde_cols(p3r_ctx* ctx, const std::vector<LdeJob>& jobs, uint32_
         }
         return P3R_OK;
     };
-    for (int dir = 0; dir < 2; dir++) {
-        if (dir == 0)
-            for (size_t qi : order)
-                if (jobs[qi].log_n > COL_MAX_LOG) TRY(launch_top(jobs[qi], qi, false));
-        std::vector<ColJob> level;
-        uint32_t cta = 0;
-        for (size_t qi : order) {
-            const LdeJob& j = jobs[qi];
-            const size_t n = (size_t)1 << j.log_n, N = n << log_blowup;
-            const bool big = j.log_n > COL_MAX_LOG;
-            const uint32_t sub_log = big ? COL_MAX_LOG : j.log_n;   // rows handled inside one CTA column
-            const size_t sub_n = (size_t)1 << sub_log;
-            ColJob b = base;
-            b.log_n = sub_log;
-            b.n_cols = j.w << (j.log_n - sub_log);                   // virtual columns = sub-blocks of 2^15 rows
-            b.cols_per_cta = 1u << (COL_MAX_LOG - sub_log);
-            col_plan(sub_log, b.q);
-            b.n_inv = finv<F>(to_monty<F>(1u << j.log_n));
-            if (dir == 0) {
-                b.src = big ? j.tmp : j.src;
-                b.dst = j.coef;
-                b.src_col_stride = b.dst_col_stride = sub_n;         // == n for ordinary jobs; sub-blocks are contiguous
-                b.dst_coset_stride = 0;
-                b.n_cosets = 1;
-                b.ctab = d_ctab;
-            } else {
-                b.src = j.coef;
-                b.src_col_stride = sub_n;
-                b.n_cosets = n_cosets;
-                b.ctab = d_ctab + job_ctab[qi];
-                if (big) {
-                    b.dst = j.tmp;                                   // [coset][column][n], natural order
-                    b.dst_col_stride = sub_n;
-                    b.dst_coset_stride = (uint64_t)j.w * n;
-                    b.natural_out = 1;
-                } else {
-                    b.dst = j.dst;
-                    b.dst_col_stride = N;
-                    b.dst_coset_stride = n;
-                }
-            }
-            b.cta_begin = cta;
-            cta += ((b.n_cols + b.cols_per_cta - 1) / b.cols_per_cta) * b.n_cosets;
-            level.push_back(b);
+    // The kernel holds 128 KB of shared memory, so one CTA per SM: a launch of C CTAs takes ceil(C / 148) waves of ~30 us, and the
+    // inverse launch of a commit (173 CTAs for the layer's main traces: two waves, the second 17 % full) is followed by a forward
+    // launch that cannot start before it ends. The jobs are therefore split into up to N_AUX groups of similar size, each with its
+    // own inverse -> forward chain on its own stream: a group's forward CTAs fill the SMs another group's inverse tail leaves idle.
+    const uint32_t n_groups = (uint32_t)std::min<size_t>(ctx->lde_streams, order.size());
+    std::vector<std::vector<size_t>> groups(std::max(1u, n_groups));
+    {
+        std::vector<uint64_t> load(groups.size(), 0);
+        for (size_t qi : order) {   // largest first, to the lightest group
+            size_t g = std::min_element(load.begin(), load.end()) - load.begin();
+            groups[g].push_back(qi);
+            load[g] += (uint64_t)jobs[qi].w << jobs[qi].log_n;
         }
-        const ColJob* d_jobs = upload_vec(ctx, level);
-        if (!d_jobs) {
-            set_err(ctx, "staging exhausted");
-            return P3R_ERR_OOM;
-        }
-        const size_t smem = (size_t)4 << COL_MAX_LOG;
-        if (dir == 0) k_ntt_col<F, false><<<cta, 512, smem, ctx->stream>>>(d_jobs, (uint32_t)level.size());
-        else k_ntt_col<F, true><<<cta, 512, smem, ctx->stream>>>(d_jobs, (uint32_t)level.size());
-        LAUNCH_CHECK_C(KC_NTT);
-        if (dir == 1)
-            for (size_t qi : order)
-                if (jobs[qi].log_n > COL_MAX_LOG) TRY(launch_top(jobs[qi], qi, true));
     }
+    const bool multi = groups.size() > 1;
+    if (multi) TRY(fork_streams(ctx));
+    for (size_t g = 0; g < groups.size(); g++) {
+        cudaStream_t st = multi ? ctx->aux[g % p3r_ctx::N_AUX] : ctx->stream;
+        for (int dir = 0; dir < 2; dir++) {
+            if (dir == 0)
+                for (size_t qi : groups[g])
+                    if (jobs[qi].log_n > COL_MAX_LOG) TRY(launch_top(jobs[qi], qi, false, st));
+            std::vector<ColJob> level;
+            uint32_t cta = 0;
+            for (size_t qi : groups[g]) {
+                const LdeJob& j = jobs[qi];
+                const size_t n = (size_t)1 << j.log_n, N = n << log_blowup;
+                const bool big = j.log_n > COL_MAX_LOG;
+                const uint32_t sub_log = big ? COL_MAX_LOG : j.log_n;   // rows handled inside one CTA column
+                const size_t sub_n = (size_t)1 << sub_log;
+                ColJob b = base;
+                b.log_n = sub_log;
+                b.n_cols = j.w << (j.log_n - sub_log);                   // virtual columns = sub-blocks of 2^15 rows
+                b.cols_per_cta = 1u << (COL_MAX_LOG - sub_log);
+                col_plan(sub_log, b.q);
+                b.n_inv = finv<F>(to_monty<F>(1u << j.log_n));
+                if (dir == 0) {
+                    b.src = big ? j.tmp : j.src;
+                    b.dst = j.coef;
+                    b.src_col_stride = b.dst_col_stride = sub_n;         // == n for ordinary jobs; sub-blocks are contiguous
+                    b.dst_coset_stride = 0;
+                    b.n_cosets = 1;
+                    b.ctab = d_ctab;
+                } else {
+                    b.src = j.coef;
+                    b.src_col_stride = sub_n;
+                    b.n_cosets = n_cosets;
+                    b.ctab = d_ctab + job_ctab[qi];
+                    if (big) {
+                        b.dst = j.tmp;                                   // [coset][column][n], natural order
+                        b.dst_col_stride = sub_n;
+                        b.dst_coset_stride = (uint64_t)j.w * n;
+                        b.natural_out = 1;
+                    } else {
+                        b.dst = j.dst;
+                        b.dst_col_stride = N;
+                        b.dst_coset_stride = n;
+                    }
+                }
+                b.cta_begin = cta;
+                cta += ((b.n_cols + b.cols_per_cta - 1) / b.cols_per_cta) * b.n_cosets;
+                level.push_back(b);
+            }
+            const ColJob* d_jobs = upload_vec(ctx, level);
+            if (!d_jobs) {
+                set_err(ctx, "staging exhausted");
+                return P3R_ERR_OOM;
+            }
+            const size_t smem = (size_t)4 << COL_MAX_LOG;
+            if (dir == 0) k_ntt_col<F, false><<<cta, 512, smem, st>>>(d_jobs, (uint32_t)level.size());
+            else k_ntt_col<F, true><<<cta, 512, smem, st>>>(d_jobs, (uint32_t)level.size());
+            LAUNCH_CHECK_C(KC_NTT);
+            if (dir == 1)
+                for (size_t qi : groups[g])
+                    if (jobs[qi].log_n > COL_MAX_LOG) TRY(launch_top(jobs[qi], qi, true, st));
+        }
+    }
+    if (multi) TRY(join_streams(ctx));
     return P3R_OK;
 }
 
@@ -2643,6 +2664,7 @@ int p3r_ctx_create(int device, const p3r_field_desc* field, const p3r_poseidon2_
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->n_sms = (uint32_t)sms;
     }
     if (const char* e = getenv("P3R_UPLOAD_SKIP")) ctx->skip_equal_uploads = atoi(e) != 0;
+    if (const char* e = getenv("P3R_LDE_STREAMS")) ctx->lde_streams = (uint32_t)std::max(1, std::min(atoi(e), (int)p3r_ctx::N_AUX));
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ctx->pin_size = ctx->dstage_size = (size_t)8 << 20;
     ok = ok && cudaHostAlloc((void**)&ctx->pin, ctx->pin_size, cudaHostAllocDefault) == cudaSuccess;
