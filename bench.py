@@ -295,7 +295,11 @@ def run_ours(args):
     sampler.start()
     barrier()
     t_res = 0.0
-    for _ in range(args.steps):
+    H_pub = 1 << L.insts[PUBLIC_INST].log_height
+    for step in range(args.steps):
+        # a different proof every step (the Public table's padding rows carry the step number), so that challenges, openings
+        # and every challenge-dependent descriptor differ from the previous proof as they do in a real chain of layers
+        tb_res.write_rows(pd, PUBLIC_INST, H_pub - 1, np.full((1, L.insts[PUBLIC_INST].main_width), step + 1, dtype=np.uint32))
         flush_l2()
         ctx.timer_start()
         prover.prove_resident(tb_res, pd, copy=False)

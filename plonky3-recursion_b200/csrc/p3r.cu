@@ -755,13 +755,11 @@ static int coset_lde_cols(p3r_ctx* ctx, const std::vector<LdeJob>& jobs, uint32_
         }
     }
     const bool multi = groups.size() > 1;
-    if (multi) TRY(fork_streams(ctx));
+    // descriptors first (their copies are queued on the main stream), then the fork, then the launches on the group streams
+    std::vector<const ColJob*> d_levels(groups.size() * 2, nullptr);
+    std::vector<uint32_t> n_levels(groups.size() * 2, 0), n_ctas(groups.size() * 2, 0);
     for (size_t g = 0; g < groups.size(); g++) {
-        cudaStream_t st = multi ? ctx->aux[g % p3r_ctx::N_AUX] : ctx->stream;
         for (int dir = 0; dir < 2; dir++) {
-            if (dir == 0)
-                for (size_t qi : groups[g])
-                    if (jobs[qi].log_n > COL_MAX_LOG) TRY(launch_top(jobs[qi], qi, false, st));
             std::vector<ColJob> level;
             uint32_t cta = 0;
             for (size_t qi : groups[g]) {
@@ -808,14 +806,23 @@ static int coset_lde_cols(p3r_ctx* ctx, const std::vector<LdeJob>& jobs, uint32_
                 set_err(ctx, "staging exhausted");
                 return P3R_ERR_OOM;
             }
-            const size_t smem = (size_t)4 << COL_MAX_LOG;
-            if (dir == 0) k_ntt_col<F, false><<<cta, 512, smem, st>>>(d_jobs, (uint32_t)level.size());
-            else k_ntt_col<F, true><<<cta, 512, smem, st>>>(d_jobs, (uint32_t)level.size());
-            LAUNCH_CHECK_C(KC_NTT);
-            if (dir == 1)
-                for (size_t qi : groups[g])
-                    if (jobs[qi].log_n > COL_MAX_LOG) TRY(launch_top(jobs[qi], qi, true, st));
+            d_levels[2 * g + dir] = d_jobs;
+            n_levels[2 * g + dir] = (uint32_t)level.size();
+            n_ctas[2 * g + dir] = cta;
         }
+    }
+    if (multi) TRY(fork_streams(ctx));
+    for (size_t g = 0; g < groups.size(); g++) {
+        cudaStream_t st = multi ? ctx->aux[g % p3r_ctx::N_AUX] : ctx->stream;
+        const size_t smem = (size_t)4 << COL_MAX_LOG;
+        for (size_t qi : groups[g])
+            if (jobs[qi].log_n > COL_MAX_LOG) TRY(launch_top(jobs[qi], qi, false, st));
+        k_ntt_col<F, false><<<n_ctas[2 * g], 512, smem, st>>>(d_levels[2 * g], n_levels[2 * g]);
+        LAUNCH_CHECK_C(KC_NTT);
+        k_ntt_col<F, true><<<n_ctas[2 * g + 1], 512, smem, st>>>(d_levels[2 * g + 1], n_levels[2 * g + 1]);
+        LAUNCH_CHECK_C(KC_NTT);
+        for (size_t qi : groups[g])
+            if (jobs[qi].log_n > COL_MAX_LOG) TRY(launch_top(jobs[qi], qi, true, st));
     }
     if (multi) TRY(join_streams(ctx));
     return P3R_OK;
