@@ -143,7 +143,8 @@ struct p3r_ctx {
     uint32_t* tw = nullptr;   // = tws + 2^(logT-1) - 1: half table of omega_T
     void (*host_permute)(uint32_t*, const Poseidon2Consts&) = nullptr;  // transcript permutation (AVX2 or scalar), set at creation
     bool dev_fri_transcript = true;  // FRI commit rounds without host round trips (p3r_set_specialization bit 2 turns it off)
-    uint32_t lde_streams = 4;       // job groups (streams) of one batched LDE, 1..N_AUX (P3R_LDE_STREAMS)
+    uint32_t lde_streams = 2;       // job groups (streams) of one batched LDE, 1..N_AUX (P3R_LDE_STREAMS); measured best: 2
+    bool lde_small_cta = true;      // 2^14-element CTAs for columns of up to 2^14 rows (P3R_LDE_SMALL_CTA=0 turns it off)
     p3r_conventions conv{0, 0, 0};  // p3r_ctx_set_conventions
     bool use_hash_queue = false;  // work-queue row hashing (p3r_set_specialization bit 3 turns it ON; measured slower, see kernels.cuh)
     uint32_t n_sms = 148;
@@ -744,15 +745,31 @@ static int coset_lde_cols(p3r_ctx* ctx, const std::vector<LdeJob>& jobs, uint32_
     // inverse launch of a commit (173 CTAs for the layer's main traces: two waves, the second 17 % full) is followed by a forward
     // launch that cannot start before it ends. The jobs are therefore split into up to N_AUX groups of similar size, each with its
     // own inverse -> forward chain on its own stream: a group's forward CTAs fill the SMs another group's inverse tail leaves idle.
-    const uint32_t n_groups = (uint32_t)std::min<size_t>(ctx->lde_streams, order.size());
-    std::vector<std::vector<size_t>> groups(std::max(1u, n_groups));
+    // Grouping: columns of up to 2^14 rows form their own group and run in CTAs of 2^14 elements (256 threads, 64 KB): two of
+    // those fit an SM, so one CTA's copy-in / copy-out overlaps the other's butterflies, which a single 2^15-element CTA per SM
+    // cannot do. Taller columns need the 2^15-element CTA. Within a size class the jobs are spread over the remaining streams.
+    std::vector<std::vector<size_t>> groups;
+    std::vector<uint32_t> group_cta_log;
     {
-        std::vector<uint64_t> load(groups.size(), 0);
-        for (size_t qi : order) {   // largest first, to the lightest group
-            size_t g = std::min_element(load.begin(), load.end()) - load.begin();
-            groups[g].push_back(qi);
-            load[g] += (uint64_t)jobs[qi].w << jobs[qi].log_n;
-        }
+        std::vector<size_t> small, large;
+        for (size_t qi : order) (ctx->lde_small_cta && jobs[qi].log_n <= COL_MAX_LOG - 1 ? small : large).push_back(qi);
+        auto spread = [&](const std::vector<size_t>& js, uint32_t n, uint32_t cta_log) {
+            if (js.empty()) return;
+            n = (uint32_t)std::max<size_t>(1, std::min<size_t>(n, js.size()));
+            const size_t g0 = groups.size();
+            std::vector<uint64_t> load(n, 0);
+            groups.resize(g0 + n);
+            group_cta_log.resize(g0 + n, cta_log);
+            for (size_t qi : js) {   // largest first, to the lightest group
+                size_t g = std::min_element(load.begin(), load.end()) - load.begin();
+                groups[g0 + g].push_back(qi);
+                load[g] += (uint64_t)jobs[qi].w << jobs[qi].log_n;
+            }
+        };
+        const uint32_t streams = ctx->lde_streams;
+        const uint32_t n_small = small.empty() ? 0 : std::max(1u, streams / 2), n_large = std::max(1u, streams - n_small);
+        spread(large, n_large, COL_MAX_LOG);
+        spread(small, std::max(1u, n_small), COL_MAX_LOG - 1);
     }
     const bool multi = groups.size() > 1;
     // descriptors first (their copies are queued on the main stream), then the fork, then the launches on the group streams
@@ -771,7 +788,7 @@ static int coset_lde_cols(p3r_ctx* ctx, const std::vector<LdeJob>& jobs, uint32_
                 ColJob b = base;
                 b.log_n = sub_log;
                 b.n_cols = j.w << (j.log_n - sub_log);                   // virtual columns = sub-blocks of 2^15 rows
-                b.cols_per_cta = 1u << (COL_MAX_LOG - sub_log);
+                b.cols_per_cta = 1u << (group_cta_log[g] - sub_log);
                 col_plan(sub_log, b.q);
                 b.n_inv = finv<F>(to_monty<F>(1u << j.log_n));
                 if (dir == 0) {
@@ -814,12 +831,13 @@ static int coset_lde_cols(p3r_ctx* ctx, const std::vector<LdeJob>& jobs, uint32_
     if (multi) TRY(fork_streams(ctx));
     for (size_t g = 0; g < groups.size(); g++) {
         cudaStream_t st = multi ? ctx->aux[g % p3r_ctx::N_AUX] : ctx->stream;
-        const size_t smem = (size_t)4 << COL_MAX_LOG;
+        const size_t smem = (size_t)4 << group_cta_log[g];
+        const uint32_t threads = group_cta_log[g] == COL_MAX_LOG ? 512u : 256u;
         for (size_t qi : groups[g])
             if (jobs[qi].log_n > COL_MAX_LOG) TRY(launch_top(jobs[qi], qi, false, st));
-        k_ntt_col<F, false><<<n_ctas[2 * g], 512, smem, st>>>(d_levels[2 * g], n_levels[2 * g]);
+        k_ntt_col<F, false><<<n_ctas[2 * g], threads, smem, st>>>(d_levels[2 * g], n_levels[2 * g]);
         LAUNCH_CHECK_C(KC_NTT);
-        k_ntt_col<F, true><<<n_ctas[2 * g + 1], 512, smem, st>>>(d_levels[2 * g + 1], n_levels[2 * g + 1]);
+        k_ntt_col<F, true><<<n_ctas[2 * g + 1], threads, smem, st>>>(d_levels[2 * g + 1], n_levels[2 * g + 1]);
         LAUNCH_CHECK_C(KC_NTT);
         for (size_t qi : groups[g])
             if (jobs[qi].log_n > COL_MAX_LOG) TRY(launch_top(jobs[qi], qi, true, st));
@@ -2671,6 +2689,7 @@ int p3r_ctx_create(int device, const p3r_field_desc* field, const p3r_poseidon2_
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->n_sms = (uint32_t)sms;
     }
     if (const char* e = getenv("P3R_UPLOAD_SKIP")) ctx->skip_equal_uploads = atoi(e) != 0;
+    if (const char* e = getenv("P3R_LDE_SMALL_CTA")) ctx->lde_small_cta = atoi(e) != 0;
     if (const char* e = getenv("P3R_LDE_STREAMS")) ctx->lde_streams = (uint32_t)std::max(1, std::min(atoi(e), (int)p3r_ctx::N_AUX));
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ctx->pin_size = ctx->dstage_size = (size_t)8 << 20;
