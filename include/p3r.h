@@ -59,16 +59,16 @@ typedef struct {
     uint32_t generator;     /* F::GENERATOR = coset shift of every LDE        */
 } p3r_field_desc;
 
-/* Poseidon2 width-16 parameters (round constants are injected, Montgomery form).
+/* Poseidon2 parameters, width 16 (context permutation) or 24 (leaf hasher); round constants are injected, Montgomery form.
  * Reference: poseidon2-circuit-air/src/public_types.rs:48-53,99-104,220-226,272-278. */
 typedef struct {
-    uint32_t width;                 /* 16                                           */
+    uint32_t width;                 /* 16 (24 for p3r_ctx_set_leaf_hasher / p3r_poseidon2_permute_w) */
     uint32_t sbox_degree;           /* 3 (KoalaBear) or 7 (BabyBear)                */
     uint32_t rounds_f;              /* 8 (4 initial + 4 terminal)                   */
     uint32_t rounds_p;              /* 20 (KoalaBear) or 13 (BabyBear)              */
-    const uint32_t* external_rc;    /* rounds_f * 16 words: initial rounds then terminal rounds */
+    const uint32_t* external_rc;    /* rounds_f * width words: initial rounds then terminal rounds */
     const uint32_t* internal_rc;    /* rounds_p words                                */
-    const uint32_t* internal_diag;  /* 16 words V: s_i <- V_i * s_i + sum(s)         */
+    const uint32_t* internal_diag;  /* width words V: s_i <- V_i * s_i + sum(s)      */
 } p3r_poseidon2_consts;
 
 /* FRI / MMCS parameters (recursion/examples/common/mod.rs:464-486, circuit-prover/src/config.rs:129-136). */
@@ -228,6 +228,15 @@ typedef struct {
     uint32_t logup_descending;    /* 0: f_0 gets the lowest power, 1: the highest (all tuples of one length) */
 } p3r_conventions;
 int p3r_ctx_set_conventions(p3r_ctx* ctx, const p3r_conventions* conv);
+
+/* Width-24 leaf hashing: with `w24` (width 24 constants of the context's field: 21 / 23 partial rounds for BabyBear / KoalaBear,
+ * circuit/src/ops/poseidon2_perm/config.rs:77-86,124-133) every MMCS leaf row — trace, quotient and FRI commit-phase matrices — is
+ * hashed with PaddingFreeSponge<Perm24, 24, 16, 8> instead of the width-16 sponge; the 2-to-1 compression and the challenger stay on
+ * the context's width-16 permutation (the `Config<F, PermHash, PermCompress, HASH_PERM_WIDTH, ..>` shape of
+ * circuit-prover/src/config.rs:59-74 with PermHash = Poseidon2<24>). NULL switches back to width 16. Call between proofs. */
+int p3r_ctx_set_leaf_hasher(p3r_ctx* ctx, const p3r_poseidon2_consts* w24);
+/* Poseidon2 permutation of n states of consts->width (16 or 24) words, in place, with the GIVEN constants (isolated kernel). */
+int p3r_poseidon2_permute_w(p3r_ctx* ctx, const p3r_poseidon2_consts* consts, uint32_t* states, uint32_t n);
 
 /* Replaces ProverData::from_airs_and_degrees (recursion/src/recursion.rs:376): uploads the
  * instance descriptions (bytecode, lookups), LDEs + commits all preprocessed matrices into one

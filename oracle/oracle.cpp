@@ -344,7 +344,74 @@ struct Digest {
     Fp d[8];
 };
 // PaddingFreeSponge<Perm,16,8,8> in overwrite mode (recursion/src/pcs/mmcs.rs:16-24).
+// Generic-width permutation with explicit constants (width 16 or 24): the leaf hasher of the
+// PaddingFreeSponge<Perm24, 24, 16, 8> configurations (circuit/src/ops/poseidon2_perm/config.rs:77-86,124-133).
+struct Poseidon2W {
+    uint32_t width = 0, sbox = 0, rf = 0, rp = 0;
+    std::vector<Fp> ext_rc, int_rc, diag;
+};
+bool HASH_W_SET = false;
+Poseidon2W HASH_W;   // orc_set_leaf_hasher: when set, MMCS leaf rows use this sponge (rate 16) instead of the width-16 one
+void external_linear_w(Fp* s, uint32_t w) {
+    const Fp two{2}, three{3};
+    for (uint32_t k = 0; k < w / 4; k++) {
+        Fp a = s[4 * k], b = s[4 * k + 1], c = s[4 * k + 2], d = s[4 * k + 3];
+        s[4 * k] = two * a + three * b + c + d;
+        s[4 * k + 1] = a + two * b + three * c + d;
+        s[4 * k + 2] = a + b + two * c + three * d;
+        s[4 * k + 3] = three * a + b + c + two * d;
+    }
+    Fp sums[4];
+    for (int j = 0; j < 4; j++) {
+        sums[j] = Fp{0};
+        for (uint32_t k = 0; k < w / 4; k++) sums[j] = sums[j] + s[4 * k + j];
+    }
+    for (uint32_t i = 0; i < w; i++) s[i] = s[i] + sums[i % 4];
+}
+void poseidon2_permute_w(const Poseidon2W& q, Fp* s) {
+    auto sb = [&](Fp x) { return fpow(x, q.sbox); };
+    const uint32_t w = q.width, half = q.rf / 2;
+    external_linear_w(s, w);
+    for (uint32_t r = 0; r < half; r++) {
+        for (uint32_t i = 0; i < w; i++) s[i] = sb(s[i] + q.ext_rc[w * r + i]);
+        external_linear_w(s, w);
+    }
+    for (uint32_t r = 0; r < q.rp; r++) {
+        s[0] = sb(s[0] + q.int_rc[r]);
+        Fp sum{0};
+        for (uint32_t i = 0; i < w; i++) sum = sum + s[i];
+        for (uint32_t i = 0; i < w; i++) s[i] = sum + q.diag[i] * s[i];
+    }
+    for (uint32_t r = half; r < q.rf; r++) {
+        for (uint32_t i = 0; i < w; i++) s[i] = sb(s[i] + q.ext_rc[w * r + i]);
+        external_linear_w(s, w);
+    }
+}
+Poseidon2W load_p2w(const p3r_poseidon2_consts* c) {
+    if (!c || (c->width != 16 && c->width != 24)) throw std::runtime_error("oracle: width 16 or 24 expected");
+    Poseidon2W q;
+    q.width = c->width;
+    q.sbox = c->sbox_degree;
+    q.rf = c->rounds_f;
+    q.rp = c->rounds_p;
+    for (uint32_t i = 0; i < c->rounds_f * c->width; i++) q.ext_rc.push_back(from_monty(c->external_rc[i]));
+    for (uint32_t i = 0; i < c->rounds_p; i++) q.int_rc.push_back(from_monty(c->internal_rc[i]));
+    for (uint32_t i = 0; i < c->width; i++) q.diag.push_back(from_monty(c->internal_diag[i]));
+    return q;
+}
+
 Digest sponge_hash(const std::vector<Fp>& in) {
+    if (HASH_W_SET) {   // PaddingFreeSponge<PermW, width, 16, 8>, overwrite mode
+        std::vector<Fp> st(HASH_W.width, Fp{0});
+        for (size_t off = 0; off < in.size(); off += 16) {
+            size_t n = std::min<size_t>(16, in.size() - off);
+            for (size_t i = 0; i < n; i++) st[i] = in[off + i];
+            poseidon2_permute_w(HASH_W, st.data());
+        }
+        Digest dg;
+        for (int i = 0; i < 8; i++) dg.d[i] = st[i];
+        return dg;
+    }
     Fp st[16];
     for (auto& x : st) x = Fp{0};
     for (size_t off = 0; off < in.size(); off += 8) {
@@ -1568,6 +1635,27 @@ int orc_init(const p3r_field_desc* field, const p3r_poseidon2_consts* p2, const 
         return 1;                                        \
     }
 
+int orc_set_leaf_hasher(const p3r_poseidon2_consts* w24) {
+    ORC_GUARD({
+        HASH_W_SET = false;
+        if (w24) {
+            HASH_W = load_p2w(w24);
+            if (HASH_W.width != 24) throw std::runtime_error("oracle: leaf hasher must be width 24");
+            HASH_W_SET = true;
+        }
+    })
+}
+int orc_poseidon2_permute_w(const p3r_poseidon2_consts* consts, uint32_t* states, uint32_t n) {
+    ORC_GUARD({
+        Poseidon2W q = load_p2w(consts);
+        std::vector<Fp> st(q.width);
+        for (uint32_t i = 0; i < n; i++) {
+            for (uint32_t k = 0; k < q.width; k++) st[k] = from_monty(states[(size_t)q.width * i + k]);
+            poseidon2_permute_w(q, st.data());
+            for (uint32_t k = 0; k < q.width; k++) states[(size_t)q.width * i + k] = to_monty(st[k]);
+        }
+    })
+}
 int orc_set_conventions(const p3r_conventions* conv) {
     CONV = *conv;
     return 0;

@@ -46,6 +46,22 @@ class Oracle:
                              int(conv.get("logup_descending", 0)))
         self._check(self.lib.orc_set_conventions(C.byref(c)))
 
+    def set_leaf_hasher(self, params24=None):
+        """Width-24 leaf sponge (rate 16) for every MMCS leaf row, or None for the width-16 sponge (process-wide)."""
+        if params24 is None:
+            self._check(self.lib.orc_set_leaf_hasher(None))
+            return
+        m = abi.Marshal(self.field)
+        pc = m.poseidon2(params24)
+        self._check(self.lib.orc_set_leaf_hasher(C.byref(pc)))
+
+    def poseidon2_permute_w(self, params, states_canonical: np.ndarray) -> np.ndarray:
+        m = abi.Marshal(self.field)
+        pc = m.poseidon2(params)
+        s = np.ascontiguousarray(self.field.to_monty(states_canonical).reshape(-1, params.width))
+        self._check(self.lib.orc_poseidon2_permute_w(C.byref(pc), abi.as_u32p(s), s.shape[0]))
+        return self.field.from_monty(s)
+
     def poseidon2_permute(self, states_canonical: np.ndarray) -> np.ndarray:
         s = np.ascontiguousarray(self.field.to_monty(states_canonical).reshape(-1, 16))
         self._check(self.lib.orc_poseidon2_permute(abi.as_u32p(s), s.shape[0]))

@@ -401,6 +401,58 @@ __global__ void __launch_bounds__(128) k_hash_rows_rowmajor(const uint32_t* __re
     o[0] = make_uint4(st[0], st[1], st[2], st[3]);
     o[1] = make_uint4(st[4], st[5], st[6], st[7]);
 }
+// ---- width-24 leaf hasher: PaddingFreeSponge<Perm24, 24, 16, 8> (overwrite mode, rate 16, digest = first 8 words) ----
+template <class F>
+__global__ void __launch_bounds__(128) k_hash_rows_w24(const HashJob* __restrict__ jobs, uint32_t n_jobs,
+                                                        const Poseidon2ConstsW* __restrict__ k) {
+    uint32_t j = 0;
+    while (j + 1 < n_jobs && blockIdx.x >= jobs[j + 1].cta_begin) j++;
+    const HashJob job = jobs[j];
+    uint32_t r = (blockIdx.x - job.cta_begin) * blockDim.x + threadIdx.x;
+    if (r >= job.n_rows) return;
+    uint32_t st[24];
+#pragma unroll
+    for (int i = 0; i < 24; i++) st[i] = 0;
+    for (uint32_t c0 = 0; c0 < job.ncols; c0 += 16) {
+#pragma unroll
+        for (int q = 0; q < 16; q++)
+            if (c0 + q < job.ncols) st[q] = __ldg(job.colptr[c0 + q] + r);
+        poseidon2_permute_w<F, 24>(st, k);
+    }
+    uint4* o = reinterpret_cast<uint4*>(job.out + (size_t)r * 8);
+    o[0] = make_uint4(st[0], st[1], st[2], st[3]);
+    o[1] = make_uint4(st[4], st[5], st[6], st[7]);
+}
+template <class F>
+__global__ void __launch_bounds__(128) k_hash_rows_rowmajor_w24(const uint32_t* __restrict__ data, uint32_t w, uint32_t n_rows,
+                                                                 uint32_t* __restrict__ out, const Poseidon2ConstsW* __restrict__ k) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    uint32_t st[24];
+#pragma unroll
+    for (int i = 0; i < 24; i++) st[i] = 0;
+    const uint32_t* row = data + (size_t)r * w;
+    for (uint32_t c0 = 0; c0 < w; c0 += 16) {
+#pragma unroll
+        for (int q = 0; q < 16; q++)
+            if (c0 + q < w) st[q] = row[c0 + q];
+        poseidon2_permute_w<F, 24>(st, k);
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + (size_t)r * 8);
+    o[0] = make_uint4(st[0], st[1], st[2], st[3]);
+    o[1] = make_uint4(st[4], st[5], st[6], st[7]);
+}
+template <class F, int W>
+__global__ void k_permute_states_w(uint32_t* states, uint32_t n, const Poseidon2ConstsW* __restrict__ k) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t st[W];
+#pragma unroll
+    for (int q = 0; q < W; q++) st[q] = states[(size_t)i * W + q];
+    poseidon2_permute_w<F, W>(st, k);
+#pragma unroll
+    for (int q = 0; q < W; q++) states[(size_t)i * W + q] = st[q];
+}
 // next[i] = compress(prev[2i], prev[2i+1]); with inj != nullptr additionally next[i] = compress(next[i], inj[i]) where inj
 // holds the digests of the rows injected at this level.
 template <class F>

@@ -144,13 +144,15 @@ struct p3r_ctx {
     void (*host_permute)(uint32_t*, const Poseidon2Consts&) = nullptr;  // transcript permutation (AVX2 or scalar), set at creation
     bool dev_fri_transcript = true;  // FRI commit rounds without host round trips (p3r_set_specialization bit 2 turns it off)
     uint32_t lde_streams = 2;       // job groups (streams) of one batched LDE, 1..N_AUX (P3R_LDE_STREAMS); measured best: 2
-    bool lde_small_cta = true;      // 2^14-element CTAs for columns of up to 2^14 rows (P3R_LDE_SMALL_CTA=0 turns it off)
+    bool lde_small_cta = false;     // 2^14-element CTAs (two per SM) for columns of up to 2^14 rows: P3R_LDE_SMALL_CTA=1; measured
+                                    // neutral (LDE class 0.398 vs 0.392 ms per layer proof), so the single CTA shape stays the default
     p3r_conventions conv{0, 0, 0};  // p3r_ctx_set_conventions
     bool use_hash_queue = false;  // work-queue row hashing (p3r_set_specialization bit 3 turns it ON; measured slower, see kernels.cuh)
     uint32_t n_sms = 148;
     bool use_col_ntt = true;  // whole-column LDE kernels for 2^5..2^15 rows (p3r_set_specialization bit 1 turns them off)
     uint32_t logT = 0;
     uint32_t r4 = 0, r8 = 0, r8_3 = 0;
+    Poseidon2ConstsW* d_p2w = nullptr;  // width-24 leaf hasher (p3r_ctx_set_leaf_hasher), nullptr = width-16 sponge
     Poseidon2Consts* d_p2 = nullptr;  // global-memory copy of the Poseidon2 constants (per-lane reads of the cooperative kernels)
     std::map<uint32_t, GTable> gtables;
     Arena arena;
@@ -963,6 +965,12 @@ static int build_tree(p3r_ctx* ctx, const uint32_t* leaf_rows, uint32_t leaf_w, 
     ctx->kstats.perms[KC_COMPRESS] += ((uint64_t)rows - ((uint64_t)1 << cap));   // one compression per internal node
     if (leaf_rows) ctx->kstats.perms[rows > STAGE_MAX_NODES ? KC_HASH : KC_COMPRESS] += (uint64_t)rows * ((leaf_w + 7) / 8);
     bool leaves_done = leaf_rows == nullptr;
+    if (!leaves_done && ctx->d_p2w) {   // width-24 leaf hasher: always its own launch (the fused stage kernel is width 16)
+        KT kt(ctx, KC_HASH, (uint64_t)rows * (4ull * leaf_w + 32));
+        k_hash_rows_rowmajor_w24<F><<<(rows + 127) / 128, 128, 0, ctx->stream>>>(leaf_rows, leaf_w, rows, digests, ctx->d_p2w);
+        LAUNCH_CHECK_C(KC_HASH);
+        leaves_done = true;
+    }
     if (!leaves_done && rows > STAGE_MAX_NODES) {
         KT kt(ctx, KC_HASH, (uint64_t)rows * (4ull * leaf_w + 32));
         k_hash_rows_rowmajor<F><<<(rows + 127) / 128, 128, 0, ctx->stream>>>(leaf_rows, leaf_w, rows, digests);
@@ -1059,7 +1067,7 @@ static int commit_tree(p3r_ctx* ctx, const std::vector<MatRef>& mats, Tree* t, u
         jobs.push_back(j);
     }
     std::stable_sort(jobs.begin(), jobs.end(), [](const HashJob& a, const HashJob& b) { return a.ncols > b.ncols; });
-    if (ctx->use_hash_queue) {
+    if (ctx->use_hash_queue && !ctx->d_p2w) {
         // work queue: items of 32 rows, longest sponges first, taken by the warps of a machine-filling grid
         uint32_t items = 0;
         for (auto& j : jobs) {
@@ -1099,7 +1107,8 @@ static int commit_tree(p3r_ctx* ctx, const std::vector<MatRef>& mats, Tree* t, u
             return P3R_ERR_OOM;
         }
         KT kt(ctx, KC_HASH, hash_bytes);
-        k_hash_rows<F><<<cta, hash_cta, 0, ctx->stream>>>(d_jobs, (uint32_t)jobs.size());
+        if (ctx->d_p2w) k_hash_rows_w24<F><<<cta, hash_cta, 0, ctx->stream>>>(d_jobs, (uint32_t)jobs.size(), ctx->d_p2w);
+        else k_hash_rows<F><<<cta, hash_cta, 0, ctx->stream>>>(d_jobs, (uint32_t)jobs.size());
         LAUNCH_CHECK_C(KC_HASH);
     }
     return build_tree<F>(ctx, nullptr, 0, lmax, digests, [&](uint32_t level) { return inj_digests[level]; });
@@ -2537,6 +2546,21 @@ static int permute_host_impl(p3r_ctx* ctx, uint32_t* states, uint32_t n) {
     return P3R_OK;
 }
 template <class F>
+static int permute_w_impl(p3r_ctx* ctx, const Poseidon2ConstsW& k, uint32_t* states, uint32_t n) {
+    ctx->arena.reset();
+    uint32_t* d = arena_alloc<uint32_t>(ctx, (size_t)n * k.width);
+    Poseidon2ConstsW* dk = arena_alloc<Poseidon2ConstsW>(ctx, 1);
+    if (!d || !dk) return P3R_ERR_OOM;
+    CUDA_TRY(cudaMemcpyAsync(dk, &k, sizeof k, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d, states, (size_t)n * k.width * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (k.width == 24) k_permute_states_w<F, 24><<<(n + 127) / 128, 128, 0, ctx->stream>>>(d, n, dk);
+    else k_permute_states_w<F, 16><<<(n + 127) / 128, 128, 0, ctx->stream>>>(d, n, dk);
+    LAUNCH_CHECK();
+    CUDA_TRY(d2h_async(ctx, states, d, (size_t)n * k.width * 4));
+    CUDA_TRY(ctx_wait(ctx));   // `k` (pageable source of the first copy) must outlive it
+    return P3R_OK;
+}
+template <class F>
 static int bench_commit_impl(p3r_ctx* ctx, uint32_t log_height, uint32_t width, uint32_t iters, uint64_t seed, float* ms_out) {
     ctx->arena.reset();
     ring_reset(ctx);
@@ -2726,6 +2750,7 @@ void p3r_ctx_destroy(p3r_ctx* ctx) {
     for (auto e : ctx->phase_ev) cudaEventDestroy(e);
     if (ctx->tws) cudaFree(ctx->tws);
     if (ctx->d_p2) cudaFree(ctx->d_p2);
+    if (ctx->d_p2w) cudaFree(ctx->d_p2w);
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
     if (ctx->dstage) cudaFree(ctx->dstage);
@@ -2747,6 +2772,49 @@ int p3r_prep_commit(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_desc* desc
     if (!ctx || !descs || !out || n_inst == 0) return P3R_ERR_INVALID_ARG;
     cudaSetDevice(ctx->device);
     return DISPATCH(ctx, prep_commit_impl<F>(ctx, n_inst, descs, prep, out, cap_out, has_prep_out));
+}
+static int load_consts_w(const p3r_ctx* ctx, const p3r_poseidon2_consts* c, Poseidon2ConstsW* out) {
+    const uint32_t sb = ctx->field_id == P3R_FIELD_KOALABEAR ? KoalaBear::SBOX : BabyBear::SBOX;
+    if (!c || !c->external_rc || !c->internal_rc || !c->internal_diag || (c->width != 16 && c->width != 24) || c->rounds_f != 8 ||
+        c->rounds_p == 0 || c->rounds_p > 32 || c->sbox_degree != sb)
+        return P3R_ERR_UNSUPPORTED;
+    std::memset(out, 0, sizeof *out);
+    out->width = c->width;
+    out->rounds_p = c->rounds_p;
+    std::memcpy(out->ext_rc, c->external_rc, (size_t)8 * c->width * 4);
+    std::memcpy(out->int_rc, c->internal_rc, (size_t)c->rounds_p * 4);
+    std::memcpy(out->diag, c->internal_diag, (size_t)c->width * 4);
+    return P3R_OK;
+}
+int p3r_ctx_set_leaf_hasher(p3r_ctx* ctx, const p3r_poseidon2_consts* w24) {
+    if (!ctx) return P3R_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    CUDA_TRY(ctx_wait(ctx));
+    if (!w24) {
+        if (ctx->d_p2w) cudaFree(ctx->d_p2w);
+        ctx->d_p2w = nullptr;
+        return P3R_OK;
+    }
+    Poseidon2ConstsW k;
+    int rc = load_consts_w(ctx, w24, &k);
+    if (rc != P3R_OK || k.width != 24) {
+        set_err(ctx, "set_leaf_hasher: width-24 Poseidon2 constants of this field expected");
+        return P3R_ERR_UNSUPPORTED;
+    }
+    if (!ctx->d_p2w) CUDA_TRY(cudaMalloc((void**)&ctx->d_p2w, sizeof k));
+    CUDA_TRY(cudaMemcpy(ctx->d_p2w, &k, sizeof k, cudaMemcpyHostToDevice));
+    return P3R_OK;
+}
+int p3r_poseidon2_permute_w(p3r_ctx* ctx, const p3r_poseidon2_consts* consts, uint32_t* states, uint32_t n) {
+    if (!ctx || !states) return P3R_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    Poseidon2ConstsW k;
+    int rc = load_consts_w(ctx, consts, &k);
+    if (rc != P3R_OK) {
+        set_err(ctx, "poseidon2_permute_w: width 16 or 24 constants of this field expected");
+        return rc;
+    }
+    return DISPATCH(ctx, permute_w_impl<F>(ctx, k, states, n));
 }
 int p3r_ctx_set_conventions(p3r_ctx* ctx, const p3r_conventions* conv) {
     if (!ctx || !conv || conv->logup_negate > 1 || conv->logup_first_power > 1 || conv->logup_descending > 1) return P3R_ERR_INVALID_ARG;

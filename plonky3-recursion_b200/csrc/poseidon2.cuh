@@ -281,6 +281,58 @@ __device__ __forceinline__ uint32_t p2_coop_permute(uint32_t x, uint32_t lane, c
 }
 #endif
 
+// ---- generic width (16 or 24): the leaf hasher of the `PaddingFreeSponge<Perm24, 24, 16, 8>` configurations
+// (circuit/src/ops/poseidon2_perm/config.rs:77-86,124-133: BABY_BEAR_D4_W24 / KOALA_BEAR_D4_W24; the reference's `Config` is generic
+// over the hash permutation's width and rate, circuit-prover/src/config.rs:59-74). Constants come from global memory (per
+// context, no __constant__ slot), the diagonal is applied with general products: this path serves the width-24 leaf hashing,
+// the width-16 hot path keeps its specialised code above.
+struct Poseidon2ConstsW {
+    uint32_t width, rounds_p;
+    uint32_t ext_rc[8 * 24];
+    uint32_t int_rc[32];
+    uint32_t diag[24];
+};
+template <class F, int W>
+P3R_HD void external_linear_w(uint32_t* s) {
+#pragma unroll
+    for (int k = 0; k < W / 4; k++) m4<F>(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3], 0u);
+    uint32_t sums[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint32_t t = s[j];
+#pragma unroll
+        for (int k = 1; k < W / 4; k++) t = fadd<F>(t, s[4 * k + j]);
+        sums[j] = t;
+    }
+#pragma unroll
+    for (int i = 0; i < W; i++) s[i] = fadd<F>(s[i], sums[i & 3]);
+}
+template <class F, int W>
+P3R_HD void poseidon2_permute_w(uint32_t* s, const Poseidon2ConstsW* __restrict__ k) {
+    external_linear_w<F, W>(s);
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < W; i++) s[i] = sbox<F>(fadd<F>(s[i], k->ext_rc[W * r + i]));
+        external_linear_w<F, W>(s);
+    }
+#pragma unroll 1
+    for (uint32_t r = 0; r < k->rounds_p; r++) {
+        s[0] = sbox<F>(fadd<F>(s[0], k->int_rc[r]));
+        uint32_t sum = s[0];
+#pragma unroll
+        for (int i = 1; i < W; i++) sum = fadd<F>(sum, s[i]);
+#pragma unroll
+        for (int i = 0; i < W; i++) s[i] = fadd<F>(sum, fmul<F>(k->diag[i], s[i]));
+    }
+#pragma unroll 1
+    for (int r = 4; r < 8; r++) {
+#pragma unroll
+        for (int i = 0; i < W; i++) s[i] = sbox<F>(fadd<F>(s[i], k->ext_rc[W * r + i]));
+        external_linear_w<F, W>(s);
+    }
+}
+
 #if defined(__CUDACC__)
 template <class F>
 __device__ __forceinline__ void poseidon2_permute(uint32_t* s) {

@@ -84,7 +84,7 @@ EXPORTS = ["p3r_abi_version", "p3r_build_info", "p3r_ctx_create", "p3r_ctx_destr
            "p3r_traces_download", "p3r_kernel_perms", "p3r_bench_fri_round", "p3r_prove_ops",
            "p3r_traces_upload_ops", "p3r_set_wait_mode", "p3r_host_hasher_create", "p3r_host_hasher_permute",
            "p3r_host_hasher_free", "p3r_traces_write_rows", "p3r_proof_serialize", "p3r_proof_deserialize",
-           "p3r_wire_last_error", "p3r_ctx_set_conventions"]
+           "p3r_wire_last_error", "p3r_ctx_set_conventions", "p3r_ctx_set_leaf_hasher", "p3r_poseidon2_permute_w"]
 
 WIRE_CANONICAL, WIRE_BARE_ROOT = 1, 2
 
@@ -243,6 +243,23 @@ class Context:
     def set_wait_mode(self, mode: str):
         """'spin' | 'yield' | 'block' (process-wide, p3r_set_wait_mode)."""
         self.lib.p3r_set_wait_mode({"spin": 0, "yield": 1, "block": 2}[mode])
+
+    def set_leaf_hasher(self, params24: Poseidon2Params | None):
+        """Width-24 leaf hashing (p3r_ctx_set_leaf_hasher): PaddingFreeSponge<Perm24, 24, 16, 8> for every MMCS leaf row;
+        None = back to the width-16 sponge."""
+        if params24 is None:
+            self._check(self.lib.p3r_ctx_set_leaf_hasher(self.h, None))
+            return
+        pc = self._m.poseidon2(params24)
+        self._check(self.lib.p3r_ctx_set_leaf_hasher(self.h, C.byref(pc)))
+
+    def poseidon2_permute_w(self, params: Poseidon2Params, states_canonical: np.ndarray) -> np.ndarray:
+        """Isolated permutation kernel of width params.width (16 or 24) with the given constants."""
+        m = abi.Marshal(self.field)
+        pc = m.poseidon2(params)
+        s = np.ascontiguousarray(self.field.to_monty(states_canonical).reshape(-1, params.width))
+        self._check(self.lib.p3r_poseidon2_permute_w(self.h, C.byref(pc), abi.as_u32p(s), s.shape[0]))
+        return self.field.from_monty(s)
 
     def set_conventions(self, **conv):
         """[P3-EXT] protocol conventions (include/p3r.h p3r_conventions): logup_negate, logup_first_power, logup_descending.
