@@ -229,6 +229,14 @@ typedef struct {
 } p3r_conventions;
 int p3r_ctx_set_conventions(p3r_ctx* ctx, const p3r_conventions* conv);
 
+/* Uni-STARK mode (the base layer of recursive_keccak, `p3_uni_stark::prove(&config_0, &keccak_air, trace, &pis)`,
+ * recursion/examples/recursive_keccak.rs:520-530): the one-shot provers (p3r_prove*) prove ONE table without lookups with the
+ * uni-stark transcript head — degree_bits, degree_bits - is_zk, preprocessed width as single base elements, trace commitment,
+ * preprocessed commitment, public values (restated in-tree at recursion/src/types/challenges.rs:44-54,100-140) — instead of the
+ * batch head; everything after it (alpha, quotient, zeta, openings at zeta and zeta*g, FRI) is shared with the batch prover, which
+ * is why the same kernels serve the wide single-table shape (KeccakAir: ~2 600 columns). The proof blob layout is unchanged. */
+int p3r_ctx_set_uni_stark(p3r_ctx* ctx, int on);
+
 /* Width-24 leaf hashing: with `w24` (width 24 constants of the context's field: 21 / 23 partial rounds for BabyBear / KoalaBear,
  * circuit/src/ops/poseidon2_perm/config.rs:77-86,124-133) every MMCS leaf row — trace, quotient and FRI commit-phase matrices — is
  * hashed with PaddingFreeSponge<Perm24, 24, 16, 8> instead of the width-16 sponge; the 2-to-1 compression and the challenger stay on

@@ -947,8 +947,24 @@ Common load_common(uint32_t n, const p3r_instance_desc* descs) {
 }
 
 // Transcript head (recursion/src/verifier/batch_stark.rs:521-578).
+bool UNI_STARK = false;   // orc_set_uni_stark: single-table proofs with p3-uni-stark's transcript head
 void transcript_head(Challenger& ch, const Common& cm, const std::vector<Digest>& main_cap,
                      const std::vector<std::vector<Fp>>& pubs, const std::vector<Digest>* prep_cap) {
+    if (UNI_STARK) {
+        // p3_uni_stark::prove / verify, order restated in-tree at recursion/src/types/challenges.rs:44-54,100-140: degree_bits,
+        // degree_bits - is_zk, preprocessed_width (single base elements), trace commitment, preprocessed commitment (if any),
+        // public values; then alpha, the quotient commitment and zeta as in the batch prover.
+        if (cm.insts.size() != 1 || !cm.insts[0].lookups.empty())
+            throw std::runtime_error("uni-stark mode: exactly one table without lookups");
+        const Inst& s = cm.insts[0];
+        ch.observe(Fp{s.log_h});
+        ch.observe(Fp{s.log_h});
+        ch.observe(Fp{s.prep_w});
+        ch.observe_cap(main_cap);
+        if (prep_cap) ch.observe_cap(*prep_cap);
+        for (auto v : pubs[0]) ch.observe(v);
+        return;
+    }
     ch.observe_lifted(cm.insts.size());
     for (auto& s : cm.insts) {
         ch.observe_lifted(s.log_h);                      // ext_degree_bits (non-ZK: equal)
@@ -1635,6 +1651,10 @@ int orc_init(const p3r_field_desc* field, const p3r_poseidon2_consts* p2, const 
         return 1;                                        \
     }
 
+int orc_set_uni_stark(int on) {
+    UNI_STARK = on != 0;
+    return 0;
+}
 int orc_set_leaf_hasher(const p3r_poseidon2_consts* w24) {
     ORC_GUARD({
         HASH_W_SET = false;

@@ -46,6 +46,9 @@ class Oracle:
                              int(conv.get("logup_descending", 0)))
         self._check(self.lib.orc_set_conventions(C.byref(c)))
 
+    def set_uni_stark(self, on: bool):
+        self._check(self.lib.orc_set_uni_stark(int(bool(on))))
+
     def set_leaf_hasher(self, params24=None):
         """Width-24 leaf sponge (rate 16) for every MMCS leaf row, or None for the width-16 sponge (process-wide)."""
         if params24 is None:

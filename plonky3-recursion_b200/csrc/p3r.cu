@@ -146,6 +146,7 @@ struct p3r_ctx {
     uint32_t lde_streams = 2;       // job groups (streams) of one batched LDE, 1..N_AUX (P3R_LDE_STREAMS); measured best: 2
     bool lde_small_cta = false;     // 2^14-element CTAs (two per SM) for columns of up to 2^14 rows: P3R_LDE_SMALL_CTA=1; measured
                                     // neutral (LDE class 0.398 vs 0.392 ms per layer proof), so the single CTA shape stays the default
+    bool uni_stark = false;         // p3r_ctx_set_uni_stark: single-table proofs with p3-uni-stark's transcript head
     p3r_conventions conv{0, 0, 0};  // p3r_ctx_set_conventions
     bool use_hash_queue = false;  // work-queue row hashing (p3r_set_specialization bit 3 turns it ON; measured slower, see kernels.cuh)
     uint32_t n_sms = 148;
@@ -2293,20 +2294,35 @@ static int prove_impl(p3r_ctx* ctx, const p3r_prep* prep, const p3r_matrix_u32* 
     HostChallenger<F> ch(&ctx->p2, ctx->host_permute);
 
     std::vector<uint32_t> main_cap(capw), perm_cap(capw), quot_cap(capw);
+    if (ctx->uni_stark && (n_inst != 1 || prep->has_perm || !prep->inst[0].uses_next)) {
+        set_err(ctx, "uni-stark mode: exactly one table, no lookups, main trace opened at zeta and zeta*g");
+        return P3R_ERR_INVALID_ARG;
+    }
     TRY(commit_main_impl<F>(s, main_cap.data()));
     pt.mark("commit_main");
-    ch.observe_lifted((uint32_t)n_inst);
-    for (auto& d : prep->inst) {
-        ch.observe_lifted(d.log_h);
-        ch.observe_lifted(d.log_h);
-        ch.observe_lifted(d.main_w);
-        ch.observe_lifted(1u << d.log_qc);
+    if (ctx->uni_stark) {
+        // p3_uni_stark::prove's transcript head (restated in-tree: recursion/src/types/challenges.rs:44-54,100-140)
+        const InstDev& d = prep->inst[0];
+        ch.observe(to_monty<F>(d.log_h));
+        ch.observe(to_monty<F>(d.log_h));
+        ch.observe(to_monty<F>(d.prep_w));
+        ch.observe_words(main_cap.data(), capw);
+        if (prep->has_prep) ch.observe_words(prep->prep_cap.data(), capw);
+        if (d.n_pub) ch.observe_words(public_values[0], d.n_pub);
+    } else {
+        ch.observe_lifted((uint32_t)n_inst);
+        for (auto& d : prep->inst) {
+            ch.observe_lifted(d.log_h);
+            ch.observe_lifted(d.log_h);
+            ch.observe_lifted(d.main_w);
+            ch.observe_lifted(1u << d.log_qc);
+        }
+        ch.observe_words(main_cap.data(), capw);
+        for (size_t i = 0; i < n_inst; i++)
+            if (prep->inst[i].n_pub) ch.observe_words(public_values[i], prep->inst[i].n_pub);
+        for (auto& d : prep->inst) ch.observe_lifted(d.prep_w);
+        if (prep->has_prep) ch.observe_words(prep->prep_cap.data(), capw);
     }
-    ch.observe_words(main_cap.data(), capw);
-    for (size_t i = 0; i < n_inst; i++)
-        if (prep->inst[i].n_pub) ch.observe_words(public_values[i], prep->inst[i].n_pub);
-    for (auto& d : prep->inst) ch.observe_lifted(d.prep_w);
-    if (prep->has_prep) ch.observe_words(prep->prep_cap.data(), capw);
 
     size_t n_perm_inst = 0;
     for (auto& d : prep->inst) n_perm_inst += !d.lookups.empty();
@@ -2815,6 +2831,11 @@ int p3r_poseidon2_permute_w(p3r_ctx* ctx, const p3r_poseidon2_consts* consts, ui
         return rc;
     }
     return DISPATCH(ctx, permute_w_impl<F>(ctx, k, states, n));
+}
+int p3r_ctx_set_uni_stark(p3r_ctx* ctx, int on) {
+    if (!ctx) return P3R_ERR_INVALID_ARG;
+    ctx->uni_stark = on != 0;
+    return P3R_OK;
 }
 int p3r_ctx_set_conventions(p3r_ctx* ctx, const p3r_conventions* conv) {
     if (!ctx || !conv || conv->logup_negate > 1 || conv->logup_first_power > 1 || conv->logup_descending > 1) return P3R_ERR_INVALID_ARG;

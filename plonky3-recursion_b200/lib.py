@@ -84,7 +84,7 @@ EXPORTS = ["p3r_abi_version", "p3r_build_info", "p3r_ctx_create", "p3r_ctx_destr
            "p3r_traces_download", "p3r_kernel_perms", "p3r_bench_fri_round", "p3r_prove_ops",
            "p3r_traces_upload_ops", "p3r_set_wait_mode", "p3r_host_hasher_create", "p3r_host_hasher_permute",
            "p3r_host_hasher_free", "p3r_traces_write_rows", "p3r_proof_serialize", "p3r_proof_deserialize",
-           "p3r_wire_last_error", "p3r_ctx_set_conventions", "p3r_ctx_set_leaf_hasher", "p3r_poseidon2_permute_w"]
+           "p3r_wire_last_error", "p3r_ctx_set_conventions", "p3r_ctx_set_leaf_hasher", "p3r_poseidon2_permute_w", "p3r_ctx_set_uni_stark"]
 
 WIRE_CANONICAL, WIRE_BARE_ROOT = 1, 2
 
@@ -243,6 +243,10 @@ class Context:
     def set_wait_mode(self, mode: str):
         """'spin' | 'yield' | 'block' (process-wide, p3r_set_wait_mode)."""
         self.lib.p3r_set_wait_mode({"spin": 0, "yield": 1, "block": 2}[mode])
+
+    def set_uni_stark(self, on: bool):
+        """One-table proofs with p3-uni-stark's transcript head (p3r_ctx_set_uni_stark)."""
+        self._check(self.lib.p3r_ctx_set_uni_stark(self.h, int(bool(on))))
 
     def set_leaf_hasher(self, params24: Poseidon2Params | None):
         """Width-24 leaf hashing (p3r_ctx_set_leaf_hasher): PaddingFreeSponge<Perm24, 24, 16, 8> for every MMCS leaf row;
