@@ -366,19 +366,23 @@ def run_ours(args):
     r_e2e = tree_region(n_trees, True)
     clocks = sampler.stop()
 
+    common_trees = 2 * args.steps        # the trees every N proves (N = 1 proves exactly these): comparable across N
+
     def roots_sum(r):
         s = 0
         for t, pr in r["roots"].items():
-            s += int(proof_checksum(pr, p).astype(np.uint64).sum()) * (2 * (t - first_timed) + 1)
+            if t - first_timed < common_trees:
+                s += int(proof_checksum(pr, p).astype(np.uint64).sum()) * (2 * (t - first_timed) + 1)
         return s
-    stats = torch.tensor([t_res, r_res["ms"], r_e2e["ms"], r_res["wall_ms"], r_e2e["wall_ms"]], dtype=torch.float64, device=dev)
+    stats = torch.tensor([t_res, r_res["ms"], r_e2e["ms"], r_res["wall_ms"], r_e2e["wall_ms"],
+                          sum(r_res["idle_s"]) / len(lanes) / (r_res["wall_ms"] / 1e3)], dtype=torch.float64, device=dev)
     sums = torch.tensor([r_res["sent_bytes"], r_e2e["sent_bytes"], r_res["launches"], r_e2e["launches"],
                          roots_sum(r_res) % (1 << 59), roots_sum(r_e2e) % (1 << 59),
                          sum(r_res["proved"].values()), int(1e6 * sum(r_res["idle_s"]) / len(lanes))], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    t_res, ms_res, ms_e2e, wall_res, wall_e2e = (float(x) for x in stats)
+    t_res, ms_res, ms_e2e, wall_res, wall_e2e, idle_worst = (float(x) for x in stats)
     sent_res, sent_e2e, launches_res, launches_e2e, rsum_res, rsum_e2e, proved_total, idle_us = (int(x) for x in sums)
 
     if rank == 0:
@@ -454,6 +458,10 @@ def run_ours(args):
                      "all_proofs": proved_total, "all_proofs_per_s": proved_total / (ms_res / 1e3),
                      "p2p_bytes_resident_region": sent_res, "p2p_bytes_e2e_region": sent_e2e,
                      "roots_checksum": rsum_res, "roots_checksum_e2e": rsum_e2e, "roots_match": rsum_res == rsum_e2e,
+                     "roots_checksum_scope": f"weighted sum of the root-proof checksums of the first {common_trees} trees of the "
+                                             "timed region (the trees every N proves): equal at every N iff every child proof "
+                                             "reached its parent",
+                     "lane_idle_fraction_worst_rank": idle_worst,
                      "wall_ms_per_step": wall_res / args.steps, "lane_idle_fraction": idle_us / 1e6 / world / (wall_res / 1e3),
                      "critical_path_speedup_one_tree": agg.critical_path_speedup(args.leaves, world)},
             "gpu_launches": launches_res,
