@@ -272,7 +272,10 @@ def run_ours(args):
 
     # ======== part 1: latency of ONE prove_next_layer proof alone (recursive_fibonacci parameters: log_final_poly_len 5) ========
     ctx = lib.Context(args.field, lib.DEFAULT_FRI, device=local)
-    wait_mode = args.wait or os.environ.get("P3R_WAIT", "yield")
+    # host wait of the prover threads: pure yield-polling while every proving thread can have a core of its own, the sleeping
+    # poll once the node's proving threads (ranks x lanes) reach the number of host cores (p3r_set_wait_mode)
+    cores_avail = len(os.sched_getaffinity(0))
+    wait_mode = args.wait or os.environ.get("P3R_WAIT") or ("sleep" if world * args.inflight >= cores_avail else "yield")
     ctx.set_wait_mode(wait_mode)
     L = shapes["node"]
     pd = lib.ProverData.from_airs_and_degrees(ctx, L.insts, L.preps)
@@ -496,12 +499,12 @@ def main():
     ap.add_argument("--field", default="koala-bear", choices=["koala-bear", "baby-bear"])
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--wait", choices=["spin", "yield", "block"], default=None,
+    ap.add_argument("--wait", choices=["spin", "yield", "block", "sleep"], default=None,
                     help="host wait mode of the prover threads (default: the library default, yield)")
     ap.add_argument("--inflight", type=int, default=4, help="concurrent proofs (lanes) per GPU")
     ap.add_argument("--leaves", type=int, default=8, help="base proofs per aggregation tree (power of two)")
     ap.add_argument("--trees-per-step", type=int, default=0, help="default 2 per GPU")
-    ap.add_argument("--skew", type=int, default=3, help="wave skew of the hand-off posting order (aggregation.message_plan)")
+    ap.add_argument("--skew", type=int, default=6, help="wave skew of the hand-off posting order (aggregation.message_plan)")
     ap.add_argument("--tree-timeout-s", type=float, default=300.0)
     ap.add_argument("--cpu-budget-s", type=float, default=240.0, help="--impl reference: wall-clock budget of the whole run")
     ap.add_argument("--cpu-baseline-budget-s", type=float, default=30.0)

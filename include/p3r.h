@@ -421,8 +421,9 @@ const char* p3r_wire_last_error(void);
 /* How host threads wait for the GPU (process-wide): 1 = poll + sched_yield with device->host results staged through pinned
  * memory (default: a waiting thread yields its core to a thread that has kernels to launch; best throughput with several
  * proofs in flight per GPU and few host cores per GPU), 0 = spin inside the driver (cudaStreamSynchronize, direct copies),
- * 2 = block on an event (the thread sleeps; least CPU, highest latency). Also settable with the environment variable
- * P3R_WAIT=spin|yield|block. No reference counterpart (rayon owns the reference's threads). */
+ * 2 = block on an event (the thread sleeps; least CPU, highest latency), 3 = poll with a 20 us yielding phase and then 30 us
+ * sleeps (for hosts with fewer cores than proving threads, e.g. 8 ranks x 4 proofs in flight on 32 cores). Also settable with the
+ * environment variable P3R_WAIT=spin|yield|block|sleep. No reference counterpart (rayon owns the reference's threads). */
 void p3r_set_wait_mode(int mode);
 
 /* CUDA-event stopwatch on the ctx stream (the stream every kernel of this ctx is launched on): start synchronises the

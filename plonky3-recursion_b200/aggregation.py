@@ -101,7 +101,7 @@ def rotated_owner(node: Node, n_leaves: int, world: int, tree: int) -> int:
     return (owner(node, n_leaves, world) + tree) % world
 
 
-def message_plan(n_leaves: int, world: int, n_trees: int, skew: int = 3):
+def message_plan(n_leaves: int, world: int, n_trees: int, skew: int = 6):
     """Every cross-rank child-proof transfer of `n_trees` trees as (wave, tree, parent level, child index, src, dst), in the
     ONE global order all ranks post their sends / receives in. wave = tree + skew * parent level: a proof depends only on
     messages of smaller waves (its own children's), which makes in-order posting deadlock-free even when a rank's transfers
@@ -134,7 +134,7 @@ class TreeExecutor:
     """
 
     def __init__(self, rank: int, world: int, n_leaves: int, n_lanes: int, prove_leaf, prove_node, transport=None,
-                 sizes=None, skew: int = 3, timeout_s: float = 600.0):
+                 sizes=None, skew: int = 6, timeout_s: float = 600.0):
         self.rank, self.world, self.n_leaves, self.n_lanes = rank, world, n_leaves, n_lanes
         self.depth = n_leaves.bit_length() - 1
         self.prove_leaf, self.prove_node, self.transport = prove_leaf, prove_node, transport

@@ -241,8 +241,8 @@ class Context:
         return {"fold_ms": t[0], "commit_ms": t[1]}
 
     def set_wait_mode(self, mode: str):
-        """'spin' | 'yield' | 'block' (process-wide, p3r_set_wait_mode)."""
-        self.lib.p3r_set_wait_mode({"spin": 0, "yield": 1, "block": 2}[mode])
+        """'spin' | 'yield' | 'block' | 'sleep' (process-wide, p3r_set_wait_mode)."""
+        self.lib.p3r_set_wait_mode({"spin": 0, "yield": 1, "block": 2, "sleep": 3}[mode])
 
     def set_uni_stark(self, on: bool):
         """One-table proofs with p3-uni-stark's transcript head (p3r_ctx_set_uni_stark)."""
