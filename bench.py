@@ -327,9 +327,12 @@ def run_ours(args):
         transport = agg.TorchTransport(dist, torch, dev, agg.MSG_HEADER_WORDS + max(sizes.values()), max_outstanding=48)
     mode = {"host": False}
 
+    region_base = [0]     # first tree of the current region: a leaf's identity is its tree's index WITHIN the region, so the
+                          # k-th timed tree is the same tree (same root proof) at every N
+
     def prove_leaf(k, t, i):
         ident = np.zeros(PATCH_WORDS, dtype=np.uint32)
-        ident[0], ident[1] = t % p, i
+        ident[0], ident[1] = (t - region_base[0]) % p, i
         return lanes[k].prove("leaf", ident, mode["host"])
 
     def prove_node(k, t, nd, left, right):
@@ -345,6 +348,7 @@ def run_ours(args):
     def tree_region(n_trees, host_buffers):
         """n_trees trees, no barrier between them; CUDA events on every lane's stream, time = max over lanes."""
         mode["host"] = host_buffers
+        region_base[0] = next_tree[0]
         barrier()
         l0 = sum(ln.ctx.launch_count() for ln in lanes)
         for ln in lanes:
@@ -504,7 +508,7 @@ def main():
     ap.add_argument("--inflight", type=int, default=4, help="concurrent proofs (lanes) per GPU")
     ap.add_argument("--leaves", type=int, default=8, help="base proofs per aggregation tree (power of two)")
     ap.add_argument("--trees-per-step", type=int, default=0, help="default 2 per GPU")
-    ap.add_argument("--skew", type=int, default=6, help="wave skew of the hand-off posting order (aggregation.message_plan)")
+    ap.add_argument("--skew", type=int, default=8, help="wave skew of the hand-off posting order (aggregation.message_plan)")
     ap.add_argument("--tree-timeout-s", type=float, default=300.0)
     ap.add_argument("--cpu-budget-s", type=float, default=240.0, help="--impl reference: wall-clock budget of the whole run")
     ap.add_argument("--cpu-baseline-budget-s", type=float, default=30.0)
