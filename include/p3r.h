@@ -360,6 +360,11 @@ void p3r_host_hasher_free(p3r_host_hasher* h);
 int p3r_bench_commit(p3r_ctx* ctx, uint32_t log_height, uint32_t width, uint32_t iters, uint64_t seed,
                      float* times_ms_out);
 
+/* Same for a MIXED-HEIGHT batch (heights {2^k, 2^(k-1), 2^(k-3)}): one batched LDE and one MMCS commit over
+ * n_mats synthetic matrices. times_ms_out: [lde, commit]. */
+int p3r_bench_commit_multi(p3r_ctx* ctx, uint32_t n_mats, const uint32_t* log_heights, const uint32_t* widths, uint32_t iters,
+                           uint64_t seed, float* times_ms_out);
+
 /* Device-resident benchmark of one FRI commit round on a synthetic extension-field vector of 2^log_len elements: fold by
  * 2^log_arity (k_fri_fold) and Merkle-commit the folded vector as rows of 2^log_arity elements. times_ms_out: [fold, commit]. */
 int p3r_bench_fri_round(p3r_ctx* ctx, uint32_t log_len, uint32_t log_arity, uint32_t iters, uint64_t seed, float* times_ms_out);

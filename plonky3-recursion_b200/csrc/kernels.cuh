@@ -1188,9 +1188,20 @@ __global__ void __launch_bounds__(128) k_fri_fold(const Ext4* __restrict__ in, E
         uint32_t half = arity >> (step + 1);   // outputs this thread produces at this step
         for (uint32_t j = 0; j < half; j++) {
             uint32_t gi = i * half + j;        // index in the folded vector (length 2^(lg-1))
-            uint32_t e = bitrev32(gi, lg - 1);
-            // 1/x0 = w_{2^lg}^{-e}
-            uint32_t xinv = root_pow<F>(tw, logT, (((uint64_t)1 << lg) - e) << (logT - lg));
+            // 1/x0 = w_{2^lg}^{-e}, e = bitrev(gi, lg-1). Looked up directly, the bit-reversed index makes every lane of a warp
+            // read a different cache line of the twiddle table (the kernel ran at 8-35 % of HBM on that gather alone). Split
+            // instead: e = (rev5(gi & 31) << (lg-6)) + bitrev(gi >> 5, lg-6), so w^-e = w_64^-rev5(gi & 31) * w_{2^lg}^-bitrev(gi >> 5):
+            // the first factor comes from 32 fixed table entries, the second is one address per 32 consecutive outputs.
+            uint32_t xinv;
+            if (lg >= 7) {
+                const uint32_t f1 = root_pow<F>(tw, logT, (uint64_t)(64u - (__brev(gi & 31u) >> 27)) << (logT - 6));
+                const uint32_t e_hi = bitrev32(gi >> 5, lg - 6);
+                const uint32_t f2 = root_pow<F>(tw, logT, (((uint64_t)1 << lg) - e_hi) << (logT - lg));
+                xinv = fmul<F>(f1, f2);
+            } else {
+                uint32_t e = bitrev32(gi, lg - 1);
+                xinv = root_pow<F>(tw, logT, (((uint64_t)1 << lg) - e) << (logT - lg));
+            }
             Ext4 e0 = v[2 * j], e1 = v[2 * j + 1];
             Ext4 sum = eadd<F>(e0, e1);
             Ext4 dif = emul_base<F>(esub<F>(e0, e1), xinv);

@@ -2600,6 +2600,61 @@ static int permute_w_impl(p3r_ctx* ctx, const Poseidon2ConstsW& k, uint32_t* sta
     CUDA_TRY(ctx_wait(ctx));   // `k` (pageable source of the first copy) must outlive it
     return P3R_OK;
 }
+// Mixed-height version of the commit benchmark: one batched LDE + one MMCS commit over several synthetic matrices.
+template <class F>
+static int bench_commit_multi_impl(p3r_ctx* ctx, uint32_t n_mats, const uint32_t* log_heights, const uint32_t* widths, uint32_t iters,
+                                   uint64_t seed, float* ms_out) {
+    ctx->arena.reset();
+    ring_reset(ctx);
+    const uint32_t lb = ctx->fri.log_blowup;
+    std::vector<LdeJob> jobs;
+    std::vector<MatRef> mats;
+    uint32_t lmax = 0;
+    for (uint32_t i = 0; i < n_mats; i++) {
+        const size_t n = (size_t)1 << log_heights[i], N = n << lb, w = widths[i];
+        uint32_t* cm = arena_alloc<uint32_t>(ctx, n * w);
+        uint32_t* coef = arena_alloc<uint32_t>(ctx, n * w);
+        uint32_t* lde = arena_alloc<uint32_t>(ctx, N * w);
+        uint32_t* tmp = log_heights[i] > TILE_LOG ? arena_alloc<uint32_t>(ctx, N * w) : nullptr;
+        if (!cm || !coef || !lde || (log_heights[i] > TILE_LOG && !tmp)) return P3R_ERR_OOM;
+        k_fill_random<F><<<(unsigned)((n * w + 255) / 256), 256, 0, ctx->stream>>>(cm, n * w, seed + i);
+        LAUNCH_CHECK();
+        jobs.push_back({cm, lde, log_heights[i], widths[i], true, 0, coef, tmp});
+        mats.push_back({lde, log_heights[i] + lb, widths[i]});
+        lmax = std::max(lmax, log_heights[i] + lb);
+    }
+    uint32_t* dg = arena_alloc<uint32_t>(ctx, tree_digest_words(lmax));
+    if (!dg) return P3R_ERR_OOM;
+    TRY(coset_lde_batch<F>(ctx, jobs, lb));   // warm-up (tables, attributes)
+    cudaEvent_t e0, e1, e2;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventCreate(&e2);
+    float t_lde = 0, t_tree = 0;
+    for (uint32_t it = 0; it < iters; it++) {
+        size_t pin_mark = ctx->pin_used;
+        cudaEventRecord(e0, ctx->stream);
+        TRY(coset_lde_batch<F>(ctx, jobs, lb));
+        cudaEventRecord(e1, ctx->stream);
+        Tree t;
+        TRY(commit_tree<F>(ctx, mats, &t, dg));
+        cudaEventRecord(e2, ctx->stream);
+        CUDA_TRY(cudaEventSynchronize(e2));
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, e0, e1);
+        cudaEventElapsedTime(&b, e1, e2);
+        t_lde += a;
+        t_tree += b;
+        ctx->pin_used = pin_mark;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    kstats_collect(ctx);
+    ms_out[0] = t_lde / iters;
+    ms_out[1] = t_tree / iters;
+    return P3R_OK;
+}
 template <class F>
 static int bench_commit_impl(p3r_ctx* ctx, uint32_t log_height, uint32_t width, uint32_t iters, uint64_t seed, float* ms_out) {
     ctx->arena.reset();
@@ -3191,6 +3246,12 @@ int p3r_bench_fri_round(p3r_ctx* ctx, uint32_t log_len, uint32_t log_arity, uint
     if (!ctx || !times_ms_out || !iters) return P3R_ERR_INVALID_ARG;
     cudaSetDevice(ctx->device);
     return DISPATCH(ctx, bench_fri_round_impl<F>(ctx, log_len, log_arity, iters, seed, times_ms_out));
+}
+int p3r_bench_commit_multi(p3r_ctx* ctx, uint32_t n_mats, const uint32_t* log_heights, const uint32_t* widths, uint32_t iters,
+                           uint64_t seed, float* times_ms_out) {
+    if (!ctx || !times_ms_out || !iters || !n_mats || !log_heights || !widths) return P3R_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    return DISPATCH(ctx, bench_commit_multi_impl<F>(ctx, n_mats, log_heights, widths, iters, seed, times_ms_out));
 }
 int p3r_bench_commit(p3r_ctx* ctx, uint32_t log_height, uint32_t width, uint32_t iters, uint64_t seed, float* times_ms_out) {
     if (!ctx || !times_ms_out || !iters) return P3R_ERR_INVALID_ARG;

@@ -84,7 +84,7 @@ EXPORTS = ["p3r_abi_version", "p3r_build_info", "p3r_ctx_create", "p3r_ctx_destr
            "p3r_traces_download", "p3r_kernel_perms", "p3r_bench_fri_round", "p3r_prove_ops",
            "p3r_traces_upload_ops", "p3r_set_wait_mode", "p3r_host_hasher_create", "p3r_host_hasher_permute",
            "p3r_host_hasher_free", "p3r_traces_write_rows", "p3r_proof_serialize", "p3r_proof_deserialize",
-           "p3r_wire_last_error", "p3r_ctx_set_conventions", "p3r_ctx_set_leaf_hasher", "p3r_poseidon2_permute_w", "p3r_ctx_set_uni_stark"]
+           "p3r_wire_last_error", "p3r_ctx_set_conventions", "p3r_ctx_set_leaf_hasher", "p3r_poseidon2_permute_w", "p3r_ctx_set_uni_stark", "p3r_bench_commit_multi"]
 
 WIRE_CANONICAL, WIRE_BARE_ROOT = 1, 2
 
@@ -233,6 +233,13 @@ class Context:
     def bench_commit(self, log_height: int, width: int, iters: int = 5, seed: int = 0xB200):
         t = (C.c_float * 3)()
         self._check(self.lib.p3r_bench_commit(self.h, log_height, width, iters, C.c_uint64(seed), t))
+        return {"lde_ms": t[0], "merkle_ms": t[1]}
+
+    def bench_commit_multi(self, log_heights, widths, iters: int = 3, seed: int = 0xB200):
+        lh = (C.c_uint32 * len(log_heights))(*log_heights)
+        wd = (C.c_uint32 * len(widths))(*widths)
+        t = (C.c_float * 2)()
+        self._check(self.lib.p3r_bench_commit_multi(self.h, len(log_heights), lh, wd, iters, C.c_uint64(seed), t))
         return {"lde_ms": t[0], "merkle_ms": t[1]}
 
     def bench_fri_round(self, log_len: int, log_arity: int, iters: int = 5, seed: int = 0xB200):
