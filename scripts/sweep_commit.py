@@ -22,13 +22,14 @@ def product_bound_gbs(log_n, B):
 
 
 rows = (18, 20) if quick else (18, 20, 22, 24)
+TWO_ADICITY = {"koala-bear": 24, "baby-bear": 27}[field]   # 2^24-row LDEs exist only for BabyBear (KoalaBear: 2^24 is the largest domain)
 for log_blowup in (1, 2, 3):
     B = 1 << log_blowup
     fri = dict(lib.DEFAULT_FRI)
     fri["log_blowup"] = log_blowup
     for log_n in rows:
         for cols in (64, 128, 256, 512):
-            if (cols << (log_n + log_blowup)) > (1 << 32):
+            if (cols << (log_n + log_blowup)) > (1 << 32) or log_n + log_blowup > TWO_ADICITY:
                 continue
             ctx = lib.Context(field, fri)
             r = ctx.bench_commit(log_n, cols, iters=2 if log_n >= 22 else 3)
@@ -60,6 +61,8 @@ for log_blowup in (1, 2, 3):
         for log_n in (18, 20) if quick else (18, 20, 22, 24):
             for log_arity in (1, 2, 3):
                 log_len = log_n + log_blowup
+                if log_len > TWO_ADICITY:
+                    continue
                 r = ctx.bench_fri_round(log_len, log_arity, iters=3)
                 L = 1 << log_len
                 fold_bytes = 16.0 * (L + (L >> log_arity))
