@@ -347,6 +347,24 @@ int p3r_mmcs_commit(p3r_ctx* ctx, uint32_t n_mats, const p3r_matrix_u32* mats, u
 /* Poseidon2 permutation of n states of 16 words (in place). */
 int p3r_poseidon2_permute(p3r_ctx* ctx, uint32_t* states, uint32_t n);
 
+/* Runner assist: the Poseidon2 permutation operations of `CircuitRunner::execute_all`
+ * (circuit/src/tables/runner.rs:256-308 -> circuit/src/ops/poseidon_perm/executor.rs:924-975) as chains on the device. Per row, in
+ * table order: state = zeros (new_start) or the previous row's output (sponge mode: all four limbs; arity-2 Merkle mode: the
+ * first two limbs); on Merkle rows words 8..15 of `values` (the private sibling digest) fill limbs 2, 3; limbs whose bit is set in
+ * witness_mask are overwritten with `values` (CTL-exposed witnesses); Merkle rows with mmcs_bit swap the two halves; permute.
+ * Rows from a new_start row to the next one form a chain (sequential); chains run in parallel. Writes the resolved input state
+ * (what `Poseidon2CircuitRow::input_values` / p3r_poseidon2_ops.input_values holds) and the output state of every row, 16
+ * Montgomery words each. D = 4, width 16. At most 32 768 rows per call. */
+typedef struct {
+    uint32_t n_rows;
+    const uint8_t* new_start;      /* row 0 starts a chain whatever its flag says */
+    const uint8_t* merkle_path;
+    const uint8_t* mmcs_bit;
+    const uint8_t* witness_mask;   /* bit l = limb l (words 4l..4l+3) comes from `values` */
+    const uint32_t* values;        /* n_rows x 16 Montgomery words */
+} p3r_poseidon2_chain_ops;
+int p3r_poseidon2_run_chains(p3r_ctx* ctx, const p3r_poseidon2_chain_ops* ops, uint32_t* inputs_out, uint32_t* outputs_out);
+
 /* Host-only Poseidon2 (no CUDA call, usable without a GPU): the permutation the prover's host transcript uses (AVX2 when the
  * CPU has it, checked against the scalar twin at creation), for host code that must hash exactly like the prover — the
  * circuit runner's Poseidon2 rows (circuit/src/ops/poseidon_perm/executor.rs) when a GPU batch is not worth a round trip, and

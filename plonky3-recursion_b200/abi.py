@@ -72,6 +72,11 @@ class InstanceDesc(C.Structure):
                 ("interactions", C.POINTER(InteractionC)), ("n_interactions", u32)]
 
 
+class Poseidon2ChainOpsC(C.Structure):
+    _fields_ = [("n_rows", u32), ("new_start", C.POINTER(C.c_uint8)), ("merkle_path", C.POINTER(C.c_uint8)),
+                ("mmcs_bit", C.POINTER(C.c_uint8)), ("witness_mask", C.POINTER(C.c_uint8)), ("values", u32p)]
+
+
 class ConventionsC(C.Structure):
     _fields_ = [("logup_negate", u32), ("logup_first_power", u32), ("logup_descending", u32)]
 

@@ -1414,6 +1414,67 @@ __global__ void __launch_bounds__(128) k_poseidon2_table_fill(P2FillArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Runner assist: the Poseidon2 permutation rows of `CircuitRunner::execute_all`
+// (/root/reference circuit/src/tables/runner.rs:256-308 -> circuit/src/ops/poseidon_perm/executor.rs:924-975) executed as CHAINS on
+// the device. The host runner does, per operation in order: state = zeros (new_start) or the previous output (sponge mode: the
+// whole state; arity-2 Merkle mode: the first RATE_EXT limbs) :111-139, sibling limbs into [RATE_EXT, WIDTH_EXT) on Merkle rows
+// :171-208, CTL-exposed witness limbs overwrite :214-225, rate halves swapped when the direction bit is set :233-240, permute.
+// A chain (new_start row .. next new_start row) is sequential, chains are independent: one thread per chain. D = 4, width 16
+// (WIDTH_EXT 4, RATE_EXT 2). "Previous output" is the previous ROW's output — what the AIR's chaining constraints bind
+// (poseidon2-circuit-air/src/air.rs:1024-1081); the executor keeps one slot per mode, which is the same thing whenever the
+// rows of a chain are adjacent. Writes the resolved input state and the output state of every row.
+// ------------------------------------------------------------------------------------------------
+struct P2ChainArgs {
+    const uint8_t* new_start;
+    const uint8_t* merkle_path;
+    const uint8_t* mmcs_bit;
+    const uint8_t* witness_mask;   // bit l: limb l (4 words) is a CTL-exposed witness taken from `values`
+    const uint32_t* values;        // n_rows x 16: witness limbs where masked; on Merkle rows words 8..15 = the sibling digest
+    uint32_t n_rows;
+    uint32_t* inputs_out;          // n_rows x 16
+    uint32_t* outputs_out;         // n_rows x 16
+};
+template <class F>
+__global__ void __launch_bounds__(64) k_poseidon2_chains(P2ChainArgs a) {
+    const uint32_t r0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r0 >= a.n_rows || !(a.new_start[r0] || r0 == 0)) return;
+    uint32_t prev[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) prev[i] = 0;
+    for (uint32_t r = r0; r < a.n_rows && (r == r0 || !a.new_start[r]); r++) {
+        const bool fresh = a.new_start[r] != 0, merkle = a.merkle_path[r] != 0, bit = a.mmcs_bit[r] != 0;
+        const uint32_t mask = a.witness_mask[r];
+        const uint32_t* v = a.values + (size_t)r * 16;
+        uint32_t st[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) st[i] = fresh ? 0u : ((merkle && i >= 8) ? 0u : prev[i]);
+        if (merkle) {
+#pragma unroll
+            for (int i = 8; i < 16; i++) st[i] = v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            if ((mask >> (i >> 2)) & 1u) st[i] = v[i];
+        if (merkle && bit) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t t = st[i];
+                st[i] = st[8 + i];
+                st[8 + i] = t;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) a.inputs_out[(size_t)r * 16 + i] = st[i];
+        poseidon2_permute<F>(st);
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            a.outputs_out[(size_t)r * 16 + i] = st[i];
+            prev[i] = st[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // ALU table fill (AluAir::trace_to_matrix, /root/reference circuit-prover/src/air/alu_air.rs:497-608; layout :22-58,
 // columns air/alu_columns.rs:8-46). One thread per table row. Slot (row, lane) holds nothing, one operation [a, b, c, out], or
 // (lane 0 only) a packed Horner run of k operations: a, b, c of the first, out of the last, plus the intermediate

@@ -2600,6 +2600,28 @@ static int permute_w_impl(p3r_ctx* ctx, const Poseidon2ConstsW& k, uint32_t* sta
     CUDA_TRY(ctx_wait(ctx));   // `k` (pageable source of the first copy) must outlive it
     return P3R_OK;
 }
+template <class F>
+static int run_chains_impl(p3r_ctx* ctx, const p3r_poseidon2_chain_ops* ops, uint32_t* inputs_out, uint32_t* outputs_out) {
+    ctx->arena.reset();
+    const size_t n = ops->n_rows;
+    if (n == 0) return P3R_OK;
+    uint8_t* d_flags = arena_alloc<uint8_t>(ctx, 4 * n);
+    uint32_t* d_val = arena_alloc<uint32_t>(ctx, n * 16);
+    uint32_t* d_io = arena_alloc<uint32_t>(ctx, n * 32);
+    if (!d_flags || !d_val || !d_io) return P3R_ERR_OOM;
+    CUDA_TRY(cudaMemcpyAsync(d_flags, ops->new_start, n, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_flags + n, ops->merkle_path, n, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_flags + 2 * n, ops->mmcs_bit, n, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_flags + 3 * n, ops->witness_mask, n, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_val, ops->values, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+    P2ChainArgs a{d_flags, d_flags + n, d_flags + 2 * n, d_flags + 3 * n, d_val, (uint32_t)n, d_io, d_io + n * 16};
+    k_poseidon2_chains<F><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(a);
+    LAUNCH_CHECK_C(KC_MISC);
+    CUDA_TRY(d2h_async(ctx, inputs_out, d_io, n * 64));
+    CUDA_TRY(d2h_async(ctx, outputs_out, d_io + n * 16, n * 64));
+    CUDA_TRY(ctx_wait(ctx));
+    return P3R_OK;
+}
 // Mixed-height version of the commit benchmark: one batched LDE + one MMCS commit over several synthetic matrices.
 template <class F>
 static int bench_commit_multi_impl(p3r_ctx* ctx, uint32_t n_mats, const uint32_t* log_heights, const uint32_t* widths, uint32_t iters,
@@ -3246,6 +3268,16 @@ int p3r_bench_fri_round(p3r_ctx* ctx, uint32_t log_len, uint32_t log_arity, uint
     if (!ctx || !times_ms_out || !iters) return P3R_ERR_INVALID_ARG;
     cudaSetDevice(ctx->device);
     return DISPATCH(ctx, bench_fri_round_impl<F>(ctx, log_len, log_arity, iters, seed, times_ms_out));
+}
+int p3r_poseidon2_run_chains(p3r_ctx* ctx, const p3r_poseidon2_chain_ops* ops, uint32_t* inputs_out, uint32_t* outputs_out) {
+    if (!ctx || !ops || !inputs_out || !outputs_out) return P3R_ERR_INVALID_ARG;
+    if (ops->n_rows && (!ops->new_start || !ops->merkle_path || !ops->mmcs_bit || !ops->witness_mask || !ops->values)) return P3R_ERR_INVALID_ARG;
+    if ((size_t)ops->n_rows * 64 > ctx->pin_out_size / 2) {
+        set_err(ctx, "run_chains: at most " + std::to_string(ctx->pin_out_size / 128) + " rows per call");
+        return P3R_ERR_INVALID_ARG;
+    }
+    cudaSetDevice(ctx->device);
+    return DISPATCH(ctx, run_chains_impl<F>(ctx, ops, inputs_out, outputs_out));
 }
 int p3r_bench_commit_multi(p3r_ctx* ctx, uint32_t n_mats, const uint32_t* log_heights, const uint32_t* widths, uint32_t iters,
                            uint64_t seed, float* times_ms_out) {

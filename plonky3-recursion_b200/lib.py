@@ -84,7 +84,7 @@ EXPORTS = ["p3r_abi_version", "p3r_build_info", "p3r_ctx_create", "p3r_ctx_destr
            "p3r_traces_download", "p3r_kernel_perms", "p3r_bench_fri_round", "p3r_prove_ops",
            "p3r_traces_upload_ops", "p3r_set_wait_mode", "p3r_host_hasher_create", "p3r_host_hasher_permute",
            "p3r_host_hasher_free", "p3r_traces_write_rows", "p3r_proof_serialize", "p3r_proof_deserialize",
-           "p3r_wire_last_error", "p3r_ctx_set_conventions", "p3r_ctx_set_leaf_hasher", "p3r_poseidon2_permute_w", "p3r_ctx_set_uni_stark", "p3r_bench_commit_multi"]
+           "p3r_wire_last_error", "p3r_ctx_set_conventions", "p3r_ctx_set_leaf_hasher", "p3r_poseidon2_permute_w", "p3r_ctx_set_uni_stark", "p3r_bench_commit_multi", "p3r_poseidon2_run_chains"]
 
 WIRE_CANONICAL, WIRE_BARE_ROOT = 1, 2
 
@@ -250,6 +250,18 @@ class Context:
     def set_wait_mode(self, mode: str):
         """'spin' | 'yield' | 'block' | 'sleep' (process-wide, p3r_set_wait_mode)."""
         self.lib.p3r_set_wait_mode({"spin": 0, "yield": 1, "block": 2, "sleep": 3}[mode])
+
+    def poseidon2_run_chains(self, new_start, merkle_path, mmcs_bit, witness_mask, values_canonical):
+        """Runner assist (p3r_poseidon2_run_chains): returns (inputs, outputs), canonical (n, 16) arrays."""
+        u8 = lambda a: np.ascontiguousarray(a, dtype=np.uint8)
+        ns, mp, mb, wm = u8(new_start), u8(merkle_path), u8(mmcs_bit), u8(witness_mask)
+        v = np.ascontiguousarray(self.field.to_monty(np.asarray(values_canonical, dtype=np.uint32).reshape(-1, 16)))
+        n = v.shape[0]
+        p8 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint8))
+        ops = abi.Poseidon2ChainOpsC(n, p8(ns), p8(mp), p8(mb), p8(wm), abi.as_u32p(v))
+        ins, outs = np.zeros((n, 16), dtype=np.uint32), np.zeros((n, 16), dtype=np.uint32)
+        self._check(self.lib.p3r_poseidon2_run_chains(self.h, C.byref(ops), abi.as_u32p(ins), abi.as_u32p(outs)))
+        return self.field.from_monty(ins), self.field.from_monty(outs)
 
     def set_uni_stark(self, on: bool):
         """One-table proofs with p3-uni-stark's transcript head (p3r_ctx_set_uni_stark)."""
