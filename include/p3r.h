@@ -400,7 +400,9 @@ int p3r_last_phase_times(p3r_ctx* ctx, const char** names_out, float* ms_out, ui
  *   bit 2  set   : DISABLE the device-side transcript of the FRI commit rounds in p3r_prove* (one host round trip per round).
  *   bit 3  set   : ENABLE the work-queue row hashing (k_hash_rows_queue) instead of one CTA per 64 rows (k_hash_rows); a second
  *                  schedule of the same sponge for the parity tests (measured slower on B200: ptxas gives the persistent loop 40
- *                  registers and a worse pipe mix). */
+ *                  registers and a worse pipe mix).
+ *   bit 4  set   : DISABLE the constraint-group schedule of the bytecode interpreter (k_quotient_grouped): one thread per row
+ *                  runs the whole program (k_quotient). */
 int p3r_set_specialization(p3r_ctx* ctx, int enable);
 
 /* ---- proof wire format: flat proof blob <-> postcard bytes of the reference's `BatchStarkProof<SC>`

@@ -341,6 +341,28 @@ __global__ void __launch_bounds__(128) k_hash_rows(const HashJob* __restrict__ j
     o[0] = make_uint4(st[0], st[1], st[2], st[3]);
     o[1] = make_uint4(st[4], st[5], st[6], st[7]);
 }
+// Few rows, many columns (the uni-stark base layer: 16 384 LDE rows x 2 600 columns = 325 dependent permutations per row): one
+// thread per row leaves 95 % of the machine idle for 325 x 5.3 us. Here a row is hashed by 16 lanes with the cooperative
+// permutation (2.8 us each, 16x the threads). Lanes 0..7 of a group load the next eight columns of their row.
+template <class F>
+__global__ void __launch_bounds__(256) k_hash_rows_coop(const HashJob* __restrict__ jobs, uint32_t n_jobs,
+                                                         const Poseidon2Consts* __restrict__ gk) {
+    uint32_t j = 0;
+    while (j + 1 < n_jobs && blockIdx.x >= jobs[j + 1].cta_begin) j++;
+    const HashJob job = jobs[j];
+    const uint32_t lane = threadIdx.x & 31u, l16 = lane & 15u;
+    const P2Lane c = p2_lane_consts<F>(gk, l16);
+    const uint32_t row = (blockIdx.x - job.cta_begin) * (blockDim.x >> 4) + (threadIdx.x >> 4);
+    const bool live = row < job.n_rows;
+    if (!__ballot_sync(0xffffffffu, live)) return;
+    const uint32_t r = live ? row : 0;
+    uint32_t x = 0;
+    for (uint32_t c0 = 0; c0 < job.ncols; c0 += 8) {
+        if (l16 < 8 && c0 + l16 < job.ncols) x = __ldg(job.colptr[c0 + l16] + r);
+        x = p2_coop_permute<F>(x, lane, c);
+    }
+    if (live && l16 < 8) job.out[(size_t)row * 8 + l16] = x;
+}
 // Same result through a work queue: a work item is 32 consecutive rows of one job (one warp), items are numbered with the
 // longest sponges first and every warp of a machine-filling grid takes the next item from an atomic counter when it finishes
 // its current one (longest-processing-time-first list scheduling). Kept as the second schedule for the parity tests
@@ -898,6 +920,53 @@ __global__ void __launch_bounds__(128) k_quotient(QuotientArgs a) {
     uint32_t c = i & ((1u << a.log_qc) - 1), r = i >> a.log_qc;
 #pragma unroll
     for (int k = 0; k < 4; k++) a.chunks[((size_t)c * 4 + k) * n + r] = q.c[k];
+}
+// Interpreter with constraint groups: the program is cut into QG_GROUPS sub-programs at preparation time (p3r.cu slice_program:
+// the constraints of a group plus, by backward liveness over the slot-allocated code, exactly the instructions they need), a
+// CTA is 32 rows x QG_GROUPS warps, warp g folds group g and the partial sums meet in shared memory — the schedule of the
+// generated kernels (k_quotient_spec_*) for programs that have none (other packings, conventions, the wide uni-stark table,
+// whose 13 000-instruction program took 4.1 ms at one thread per row whatever the number of rows).
+constexpr int QG_GROUPS = 8;
+struct QuotientGroups {
+    const uint4* insns;             // the sub-programs back to back
+    uint32_t off[QG_GROUPS + 1];    // instruction range of group g: [off[g], off[g + 1])
+};
+template <class F>
+__global__ void __launch_bounds__(32 * QG_GROUPS) k_quotient_grouped(QuotientArgs a, QuotientGroups gr) {
+    __shared__ Ext4 part[QG_GROUPS][32];
+    const uint32_t lq = a.log_n + a.log_qc, NQ = 1u << lq, n = 1u << a.log_n;
+    const uint32_t g = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t s_raw = blockIdx.x * 32 + lane;
+    const uint32_t s = s_raw < NQ ? s_raw : NQ - 1;   // out-of-range lanes recompute the last row and drop it
+    const uint32_t i = bitrev32(s, lq);
+    const uint32_t inext = (i + (1u << a.log_qc)) & (NQ - 1);
+    RowSrc rs;
+    rs.main = a.main;
+    rs.prep = a.prep;
+    rs.perm = a.perm;
+    rs.main_cs = rs.prep_cs = rs.perm_cs = (uint64_t)n << a.log_blowup;
+    rs.row[0] = s;
+    rs.row[1] = bitrev32(inext, lq);
+    rs.pub = a.pub;
+    rs.sel[0] = a.sel[s];
+    rs.sel[1] = a.sel[NQ + s];
+    rs.sel[2] = a.sel[2 * NQ + s];
+    rs.chal = a.chal;
+    rs.pval = a.pval;
+    rs.econst = a.econst;
+    FoldSink<F> sink{a.alpha_pows, a.wnr, ext_zero()};
+    run_program<F>(gr.insns + gr.off[g], gr.off[g + 1] - gr.off[g], rs, a.wnr, sink);
+    part[g][lane] = sink.acc;
+    __syncthreads();
+    if (g == 0 && s_raw < NQ) {
+        Ext4 tot = part[0][lane];
+#pragma unroll
+        for (int k = 1; k < QG_GROUPS; k++) tot = eadd<F>(tot, part[k][lane]);
+        const Ext4 q = emul_base<F>(tot, a.inv_van[i & ((1u << a.log_qc) - 1)]);
+        const uint32_t c = i & ((1u << a.log_qc) - 1), r = i >> a.log_qc;
+#pragma unroll
+        for (int k = 0; k < 4; k++) a.chunks[((size_t)c * 4 + k) * n + r] = q.c[k];
+    }
 }
 // Selector arrays for (log_n, log_qc) in storage order + inv_vanishing per coset class.
 template <class F>

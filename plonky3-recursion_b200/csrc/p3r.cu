@@ -167,6 +167,8 @@ struct p3r_ctx {
     uint32_t* tw = nullptr;   // = tws + 2^(logT-1) - 1: half table of omega_T
     void (*host_permute)(uint32_t*, const Poseidon2Consts&) = nullptr;  // transcript permutation (AVX2 or scalar), set at creation
     bool dev_fri_transcript = true;  // FRI commit rounds without host round trips (p3r_set_specialization bit 2 turns it off)
+    bool use_grouped_interp = true; // k_quotient_grouped for long programs without a generated kernel (p3r_set_specialization bit 4 off)
+    bool coop_wide_rows = true;     // k_hash_rows_coop for commits of few, wide rows (P3R_COOP_ROWS=0 turns it off)
     uint32_t lde_streams = 2;       // job groups (streams) of one batched LDE, 1..N_AUX (P3R_LDE_STREAMS); measured best: 2
     bool lde_small_cta = false;     // 2^14-element CTAs (two per SM) for columns of up to 2^14 rows: P3R_LDE_SMALL_CTA=1; measured
                                     // neutral (LDE class 0.398 vs 0.392 ms per layer proof), so the single CTA shape stays the default
@@ -372,6 +374,8 @@ struct InstDev {
     uint32_t* prep_lde = nullptr;
     uint32_t* sel = nullptr;
     uint32_t* inv_van = nullptr;
+    uint4* gcons = nullptr;             // the constraint program cut into QG_GROUPS sub-programs (programs of >= 256 instructions)
+    uint32_t goff[QG_GROUPS + 1] = {0};
     SpecQuotientKernel spec = nullptr;  // build-time specialised quotient kernel whose program hash matches, if any
     SpecLogupKernel spec_logup = nullptr;  // same for the LogUp trace rows
     uint32_t aux_w() const { return lookups.empty() ? 0 : (uint32_t)lookups.size() + 1; }
@@ -1092,7 +1096,25 @@ static int commit_tree(p3r_ctx* ctx, const std::vector<MatRef>& mats, Tree* t, u
         jobs.push_back(j);
     }
     std::stable_sort(jobs.begin(), jobs.end(), [](const HashJob& a, const HashJob& b) { return a.ncols > b.ncols; });
-    if (ctx->use_hash_queue && !ctx->d_p2w) {
+    uint64_t total_rows = 0;
+    uint32_t widest = 0;
+    for (auto& j : jobs) total_rows += j.n_rows, widest = std::max(widest, j.ncols);
+    if (!ctx->d_p2w && ctx->coop_wide_rows && widest >= 256 && total_rows * 16 <= (uint64_t)ctx->n_sms * 2048) {
+        // few long rows: 16 lanes per row (k_hash_rows_coop)
+        uint32_t cta = 0;
+        for (auto& j : jobs) {
+            j.cta_begin = cta;
+            cta += (j.n_rows + 15) / 16;
+        }
+        const HashJob* d_jobs = upload_vec(ctx, jobs);
+        if (!d_jobs) {
+            set_err(ctx, "staging exhausted");
+            return P3R_ERR_OOM;
+        }
+        KT kt(ctx, KC_HASH, hash_bytes);
+        k_hash_rows_coop<F><<<cta, 256, 0, ctx->stream>>>(d_jobs, (uint32_t)jobs.size(), ctx->d_p2);
+        LAUNCH_CHECK_C(KC_HASH);
+    } else if (ctx->use_hash_queue && !ctx->d_p2w) {
         // work queue: items of 32 rows, longest sponges first, taken by the warps of a machine-filling grid
         uint32_t items = 0;
         for (auto& j : jobs) {
@@ -1242,6 +1264,49 @@ static int fill_from_ops(p3r_ctx* ctx, const InstDev& d, const p3r_table_ops& t,
     return t.poseidon2 ? fill_poseidon2_table<F>(ctx, d, *t.poseidon2, d_colmajor) : fill_alu_table<F>(ctx, d, *t.alu, d_colmajor);
 }
 
+// Cut a constraint program into QG_GROUPS sub-programs for k_quotient_grouped. Group g takes the constraints whose ASSERT lies in
+// the g-th part of the instruction stream (the lowering emits a constraint's instructions just before its ASSERT, so equal
+// instruction ranges are roughly equal work) and, by one backward liveness pass over the slot-allocated code, the instructions
+// those constraints depend on: an instruction is kept iff the slot it writes is live (needed by a kept later instruction and
+// not overwritten in between). Shared subexpressions are recomputed by every group that needs them.
+static void slice_program(const p3r_insn* insns, uint32_t n, std::vector<p3r_insn>* out, uint32_t off[QG_GROUPS + 1]) {
+    auto is_ext_dst = [](uint32_t op) { return op >= P3R_OP_E_PERM && op <= P3R_OP_E_SUBB; };
+    out->clear();
+    for (int g = 0; g < QG_GROUPS; g++) {
+        const uint32_t lo = (uint32_t)((uint64_t)n * g / QG_GROUPS), hi = (uint32_t)((uint64_t)n * (g + 1) / QG_GROUPS);
+        std::vector<uint8_t> live_b(MAX_B_SLOTS, 0), live_e(MAX_E_SLOTS, 0), keep(n, 0);
+        for (uint32_t k = n; k-- > 0;) {
+            const p3r_insn& in = insns[k];
+            bool need = false;
+            if (in.op == P3R_OP_ASSERT_B || in.op == P3R_OP_ASSERT_E) {
+                need = k >= lo && k < hi;
+            } else if (in.op == P3R_OP_OUT_B) {
+                need = false;
+            } else if (is_ext_dst(in.op)) {
+                need = in.dst < (uint32_t)MAX_E_SLOTS && live_e[in.dst];
+                if (need) live_e[in.dst] = 0;
+            } else {
+                need = in.dst < (uint32_t)MAX_B_SLOTS && live_b[in.dst];
+                if (need) live_b[in.dst] = 0;
+            }
+            if (!need) continue;
+            keep[k] = 1;
+            switch (in.op) {
+                case P3R_OP_B_ADD: case P3R_OP_B_SUB: case P3R_OP_B_MUL: live_b[in.a] = live_b[in.b] = 1; break;
+                case P3R_OP_B_NEG: case P3R_OP_ASSERT_B: case P3R_OP_E_FROMB: live_b[in.a] = 1; break;
+                case P3R_OP_E_ADD: case P3R_OP_E_SUB: case P3R_OP_E_MUL: live_e[in.a] = live_e[in.b] = 1; break;
+                case P3R_OP_E_NEG: case P3R_OP_ASSERT_E: live_e[in.a] = 1; break;
+                case P3R_OP_E_MULB: case P3R_OP_E_ADDB: case P3R_OP_E_SUBB: live_e[in.a] = 1; live_b[in.b] = 1; break;
+                default: break;   // leaves: no slot operands
+            }
+        }
+        off[g] = (uint32_t)out->size();
+        for (uint32_t k = 0; k < n; k++)
+            if (keep[k]) out->push_back(insns[k]);
+    }
+    off[QG_GROUPS] = (uint32_t)out->size();
+}
+
 static bool is_pow2(uint32_t x) { return x && !(x & (x - 1)); }
 static uint32_t ilog2(uint32_t x) {
     uint32_t l = 0;
@@ -1341,6 +1406,15 @@ static int prep_commit_impl(p3r_ctx* ctx, uint32_t n_inst, const p3r_instance_de
         s.n_constraints = d.constraints.n_constraints;
         s.cons = (uint4*)up(d.constraints.insns, (size_t)d.constraints.n_insns * 16);
         s.cons_econst = (Ext4*)up(d.constraints.ext_consts, (size_t)d.constraints.n_ext_consts * 16);
+        if (d.constraints.n_insns >= 256) {
+            std::vector<p3r_insn> sliced;
+            slice_program(d.constraints.insns, d.constraints.n_insns, &sliced, s.goff);
+            s.gcons = (uint4*)up(sliced.data(), sliced.size() * sizeof(p3r_insn));
+            if (!s.gcons) {
+                set_err(ctx, "device allocation failed");
+                return fail(P3R_ERR_OOM);
+            }
+        }
         s.n_lk_insns = d.lookup_inputs.n_insns;
         s.n_lk_outs = d.lookup_inputs.n_outputs;
         s.lk = (uint4*)up(d.lookup_inputs.insns, (size_t)d.lookup_inputs.n_insns * 16);
@@ -1777,7 +1851,12 @@ static int commit_quotient_impl(p3r_session* s, const uint32_t alpha[4], uint32_
             ctx->kstats.bytes[KC_QUOTIENT] += (uint64_t)NQ * (8ull * (d.main_w + d.prep_w + d.aux_w() * 4) + 16);
             if (d.spec && ctx->use_spec)
                 p3r_spec_launch(d.spec, qa, (NQ + 31) / 32, p3r_spec_threads(), qs);  // 32 rows x constraint groups per CTA
-            else
+            else if (d.gcons && ctx->use_grouped_interp) {
+                QuotientGroups gr{};
+                gr.insns = d.gcons;
+                for (int g = 0; g <= QG_GROUPS; g++) gr.off[g] = d.goff[g];
+                k_quotient_grouped<F><<<(NQ + 31) / 32, 32 * QG_GROUPS, 0, qs>>>(qa, gr);
+            } else
                 k_quotient<F><<<(NQ + 127) / 128, 128, 0, qs>>>(qa);
             LAUNCH_CHECK_C(KC_QUOTIENT);
         }
@@ -2830,6 +2909,7 @@ int p3r_ctx_create(int device, const p3r_field_desc* field, const p3r_poseidon2_
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->n_sms = (uint32_t)sms;
     }
     if (const char* e = getenv("P3R_UPLOAD_SKIP")) ctx->skip_equal_uploads = atoi(e) != 0;
+    if (const char* e = getenv("P3R_COOP_ROWS")) ctx->coop_wide_rows = atoi(e) != 0;
     if (const char* e = getenv("P3R_LDE_SMALL_CTA")) ctx->lde_small_cta = atoi(e) != 0;
     if (const char* e = getenv("P3R_LDE_STREAMS")) ctx->lde_streams = (uint32_t)std::max(1, std::min(atoi(e), (int)p3r_ctx::N_AUX));
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -3143,6 +3223,7 @@ int p3r_set_specialization(p3r_ctx* ctx, int enable) {
     ctx->use_col_ntt = (enable & 2) == 0;
     ctx->dev_fri_transcript = (enable & 4) == 0;
     ctx->use_hash_queue = (enable & 8) != 0;
+    ctx->use_grouped_interp = (enable & 16) == 0;
     return P3R_OK;
 }
 int p3r_timer_start(p3r_ctx* ctx) {

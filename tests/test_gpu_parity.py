@@ -360,8 +360,8 @@ def test_large_lde_properties(pair, log_n, width):
 
 
 def test_specialized_and_interpreted_quotient_agree(pair):
-    """The build-time specialised quotient kernels (ALU / Poseidon2 programs) and the bytecode interpreter must produce the
-    same proof; both equal the oracle's."""
+    """The build-time specialised quotient kernels (ALU / Poseidon2 programs) and the bytecode interpreter — in its
+    constraint-group schedule and with one thread per row — must produce the same proof; all equal the oracle's."""
     wl = importlib.import_module("plonky3-recursion_b200.workload")
     ctx, orc = pair
     L = wl.synthetic_layer(ctx.field, 31, n_const=10, n_public=40, n_alu=300, n_perms=60, n_recompose=5, min_height=32)
@@ -369,10 +369,12 @@ def test_specialized_and_interpreted_quotient_agree(pair):
     prover = lib.BatchStarkProver(ctx)
     ctx.set_specialization(True)
     a = prover.prove_all_tables(L.traces, pd, L.pubs)
-    ctx.set_specialization(False)
+    ctx.set_specialization(False)          # interpreter with constraint groups (k_quotient_grouped) for the long programs
     b = prover.prove_all_tables(L.traces, pd, L.pubs)
+    ctx.set_specialization(16)             # interpreter, one thread per row (k_quotient)
+    c = prover.prove_all_tables(L.traces, pd, L.pubs)
     ctx.set_specialization(True)
-    assert np.array_equal(a, b)
+    assert np.array_equal(a, b) and np.array_equal(a, c)
     assert np.array_equal(a, orc.prove(L.insts, L.preps, L.traces, L.pubs))
     pd.close()
 
@@ -622,3 +624,13 @@ def test_work_queue_row_hashing_matches_one_cta_per_rows(pair):
     finally:
         ctx.set_specialization(1)
     assert np.array_equal(got_queue, want) and np.array_equal(got_cta, want)
+
+
+def test_wide_short_matrices_use_the_cooperative_row_hasher(pair):
+    """Commits of few, wide rows (>= 256 columns, <= 18 944 rows in total) go through k_hash_rows_coop (16 lanes per row): same
+    mixed-height commitment as the oracle, including a partial last chunk and an injected shorter matrix."""
+    ctx, orc = pair
+    rng = np.random.default_rng(91)
+    for shapes in ([(10, 300)], [(9, 517), (7, 33), (9, 2)], [(4, 260), (2, 1)]):
+        mats = [ctx.field.rand(rng, (1 << lh, w)) for lh, w in shapes]
+        assert np.array_equal(ctx.mmcs_commit(mats), orc.mmcs_commit(mats))
