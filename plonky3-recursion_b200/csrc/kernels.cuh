@@ -341,28 +341,6 @@ __global__ void __launch_bounds__(128) k_hash_rows(const HashJob* __restrict__ j
     o[0] = make_uint4(st[0], st[1], st[2], st[3]);
     o[1] = make_uint4(st[4], st[5], st[6], st[7]);
 }
-// Few rows, many columns (the uni-stark base layer: 16 384 LDE rows x 2 600 columns = 325 dependent permutations per row): one
-// thread per row leaves 95 % of the machine idle for 325 x 5.3 us. Here a row is hashed by 16 lanes with the cooperative
-// permutation (2.8 us each, 16x the threads). Lanes 0..7 of a group load the next eight columns of their row.
-template <class F>
-__global__ void __launch_bounds__(256) k_hash_rows_coop(const HashJob* __restrict__ jobs, uint32_t n_jobs,
-                                                         const Poseidon2Consts* __restrict__ gk) {
-    uint32_t j = 0;
-    while (j + 1 < n_jobs && blockIdx.x >= jobs[j + 1].cta_begin) j++;
-    const HashJob job = jobs[j];
-    const uint32_t lane = threadIdx.x & 31u, l16 = lane & 15u;
-    const P2Lane c = p2_lane_consts<F>(gk, l16);
-    const uint32_t row = (blockIdx.x - job.cta_begin) * (blockDim.x >> 4) + (threadIdx.x >> 4);
-    const bool live = row < job.n_rows;
-    if (!__ballot_sync(0xffffffffu, live)) return;
-    const uint32_t r = live ? row : 0;
-    uint32_t x = 0;
-    for (uint32_t c0 = 0; c0 < job.ncols; c0 += 8) {
-        if (l16 < 8 && c0 + l16 < job.ncols) x = __ldg(job.colptr[c0 + l16] + r);
-        x = p2_coop_permute<F>(x, lane, c);
-    }
-    if (live && l16 < 8) job.out[(size_t)row * 8 + l16] = x;
-}
 // Same result through a work queue: a work item is 32 consecutive rows of one job (one warp), items are numbered with the
 // longest sponges first and every warp of a machine-filling grid takes the next item from an atomic counter when it finishes
 // its current one (longest-processing-time-first list scheduling). Kept as the second schedule for the parity tests

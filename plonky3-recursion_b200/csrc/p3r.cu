@@ -168,7 +168,6 @@ struct p3r_ctx {
     void (*host_permute)(uint32_t*, const Poseidon2Consts&) = nullptr;  // transcript permutation (AVX2 or scalar), set at creation
     bool dev_fri_transcript = true;  // FRI commit rounds without host round trips (p3r_set_specialization bit 2 turns it off)
     bool use_grouped_interp = true; // k_quotient_grouped for long programs without a generated kernel (p3r_set_specialization bit 4 off)
-    bool coop_wide_rows = true;     // k_hash_rows_coop for commits of few, wide rows (P3R_COOP_ROWS=0 turns it off)
     uint32_t lde_streams = 2;       // job groups (streams) of one batched LDE, 1..N_AUX (P3R_LDE_STREAMS); measured best: 2
     bool lde_small_cta = false;     // 2^14-element CTAs (two per SM) for columns of up to 2^14 rows: P3R_LDE_SMALL_CTA=1; measured
                                     // neutral (LDE class 0.398 vs 0.392 ms per layer proof), so the single CTA shape stays the default
@@ -1096,25 +1095,7 @@ static int commit_tree(p3r_ctx* ctx, const std::vector<MatRef>& mats, Tree* t, u
         jobs.push_back(j);
     }
     std::stable_sort(jobs.begin(), jobs.end(), [](const HashJob& a, const HashJob& b) { return a.ncols > b.ncols; });
-    uint64_t total_rows = 0;
-    uint32_t widest = 0;
-    for (auto& j : jobs) total_rows += j.n_rows, widest = std::max(widest, j.ncols);
-    if (!ctx->d_p2w && ctx->coop_wide_rows && widest >= 256 && total_rows * 16 <= (uint64_t)ctx->n_sms * 2048) {
-        // few long rows: 16 lanes per row (k_hash_rows_coop)
-        uint32_t cta = 0;
-        for (auto& j : jobs) {
-            j.cta_begin = cta;
-            cta += (j.n_rows + 15) / 16;
-        }
-        const HashJob* d_jobs = upload_vec(ctx, jobs);
-        if (!d_jobs) {
-            set_err(ctx, "staging exhausted");
-            return P3R_ERR_OOM;
-        }
-        KT kt(ctx, KC_HASH, hash_bytes);
-        k_hash_rows_coop<F><<<cta, 256, 0, ctx->stream>>>(d_jobs, (uint32_t)jobs.size(), ctx->d_p2);
-        LAUNCH_CHECK_C(KC_HASH);
-    } else if (ctx->use_hash_queue && !ctx->d_p2w) {
+    if (ctx->use_hash_queue && !ctx->d_p2w) {
         // work queue: items of 32 rows, longest sponges first, taken by the warps of a machine-filling grid
         uint32_t items = 0;
         for (auto& j : jobs) {
@@ -2909,7 +2890,6 @@ int p3r_ctx_create(int device, const p3r_field_desc* field, const p3r_poseidon2_
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->n_sms = (uint32_t)sms;
     }
     if (const char* e = getenv("P3R_UPLOAD_SKIP")) ctx->skip_equal_uploads = atoi(e) != 0;
-    if (const char* e = getenv("P3R_COOP_ROWS")) ctx->coop_wide_rows = atoi(e) != 0;
     if (const char* e = getenv("P3R_LDE_SMALL_CTA")) ctx->lde_small_cta = atoi(e) != 0;
     if (const char* e = getenv("P3R_LDE_STREAMS")) ctx->lde_streams = (uint32_t)std::max(1, std::min(atoi(e), (int)p3r_ctx::N_AUX));
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;

@@ -625,12 +625,3 @@ def test_work_queue_row_hashing_matches_one_cta_per_rows(pair):
         ctx.set_specialization(1)
     assert np.array_equal(got_queue, want) and np.array_equal(got_cta, want)
 
-
-def test_wide_short_matrices_use_the_cooperative_row_hasher(pair):
-    """Commits of few, wide rows (>= 256 columns, <= 18 944 rows in total) go through k_hash_rows_coop (16 lanes per row): same
-    mixed-height commitment as the oracle, including a partial last chunk and an injected shorter matrix."""
-    ctx, orc = pair
-    rng = np.random.default_rng(91)
-    for shapes in ([(10, 300)], [(9, 517), (7, 33), (9, 2)], [(4, 260), (2, 1)]):
-        mats = [ctx.field.rand(rng, (1 << lh, w)) for lh, w in shapes]
-        assert np.array_equal(ctx.mmcs_commit(mats), orc.mmcs_commit(mats))
