@@ -454,6 +454,152 @@ std::vector<Fp> concat_rows(const std::vector<const Mat*>& ms, size_t row) {
         for (size_t c = 0; c < m->w; c++) v.push_back(m->at(row, c));
     return v;
 }
+// ------------------------------------------------------------------------------------------------
+// Eight permutations at once (one per lane) for the commitment loops: the same width-16 permutation in Montgomery arithmetic on
+// 32-bit lanes, written as plain lane loops that GCC vectorises; compiled for AVX2 too and picked at orc_init when the CPU has
+// it and the batch reproduces the scalar code on a probe (P2X8.ok). Only the CPU arm's speed depends on it: every caller falls
+// back to the scalar functions above, and the results are identical either way (tests/test_oracle_kat.py, golden vectors).
+// ------------------------------------------------------------------------------------------------
+struct P2X8Consts {
+    uint32_t ext_rc[8 * 16], int_rc[32], diag[16];   // Montgomery form
+    uint32_t p = 0, mu_neg = 0, r2 = 0, rp = 0, sbox = 0;
+    bool ok = false;
+} P2X8;
+#define P2X8_BODY                                                                                         \
+    const uint32_t P_ = k.p, MU = k.mu_neg;                                                               \
+    auto mm = [&](uint32_t a, uint32_t b) -> uint32_t {                                                   \
+        uint64_t t = (uint64_t)a * b;                                                                     \
+        uint32_t m = (uint32_t)t * MU;                                                                    \
+        uint32_t r = (uint32_t)((t + (uint64_t)m * P_) >> 32);                                            \
+        return r >= P_ ? r - P_ : r;                                                                      \
+    };                                                                                                    \
+    auto add = [&](uint32_t a, uint32_t b) -> uint32_t {                                                  \
+        uint32_t x = a + b;                                                                               \
+        return x >= P_ ? x - P_ : x;                                                                      \
+    };                                                                                                    \
+    auto sb = [&](uint32_t x) -> uint32_t {                                                               \
+        uint32_t x2 = mm(x, x), x3 = mm(x2, x);                                                           \
+        if (k.sbox == 3) return x3;                                                                       \
+        return mm(mm(x2, x2), x3);                                                                        \
+    };                                                                                                    \
+    auto external = [&]() {                                                                               \
+        for (int q = 0; q < 4; q++)                                                                       \
+            for (int l = 0; l < 8; l++) {                                                                 \
+                uint32_t a = s[4 * q][l], b = s[4 * q + 1][l], c = s[4 * q + 2][l], d = s[4 * q + 3][l];  \
+                uint32_t t = add(add(a, b), add(c, d));                                                   \
+                s[4 * q][l] = add(add(t, a), add(b, b));                                                  \
+                s[4 * q + 1][l] = add(add(t, b), add(c, c));                                              \
+                s[4 * q + 2][l] = add(add(t, c), add(d, d));                                              \
+                s[4 * q + 3][l] = add(add(t, d), add(a, a));                                              \
+            }                                                                                             \
+        for (int j = 0; j < 4; j++)                                                                       \
+            for (int l = 0; l < 8; l++) {                                                                 \
+                uint32_t sum = add(add(s[j][l], s[4 + j][l]), add(s[8 + j][l], s[12 + j][l]));            \
+                for (int q = 0; q < 4; q++) s[4 * q + j][l] = add(s[4 * q + j][l], sum);                  \
+            }                                                                                             \
+    };                                                                                                    \
+    external();                                                                                           \
+    for (uint32_t r = 0; r < 4; r++) {                                                                    \
+        for (int i = 0; i < 16; i++)                                                                      \
+            for (int l = 0; l < 8; l++) s[i][l] = sb(add(s[i][l], k.ext_rc[16 * r + i]));                 \
+        external();                                                                                       \
+    }                                                                                                     \
+    for (uint32_t r = 0; r < k.rp; r++) {                                                                 \
+        uint32_t sum[8];                                                                                  \
+        for (int l = 0; l < 8; l++) {                                                                     \
+            s[0][l] = sb(add(s[0][l], k.int_rc[r]));                                                      \
+            sum[l] = s[0][l];                                                                             \
+        }                                                                                                 \
+        for (int i = 1; i < 16; i++)                                                                      \
+            for (int l = 0; l < 8; l++) sum[l] = add(sum[l], s[i][l]);                                    \
+        for (int i = 0; i < 16; i++)                                                                      \
+            for (int l = 0; l < 8; l++) s[i][l] = add(sum[l], mm(k.diag[i], s[i][l]));                    \
+    }                                                                                                     \
+    for (uint32_t r = 4; r < 8; r++) {                                                                    \
+        for (int i = 0; i < 16; i++)                                                                      \
+            for (int l = 0; l < 8; l++) s[i][l] = sb(add(s[i][l], k.ext_rc[16 * r + i]));                 \
+        external();                                                                                       \
+    }
+#if defined(__x86_64__)
+__attribute__((target("avx2"), optimize("O3"))) void permute_x8_avx2(uint32_t (*s)[8], const P2X8Consts& k) { P2X8_BODY }
+#endif
+__attribute__((optimize("O3"))) void permute_x8_plain(uint32_t (*s)[8], const P2X8Consts& k) { P2X8_BODY }
+void (*permute_x8)(uint32_t (*)[8], const P2X8Consts&) = permute_x8_plain;
+// canonical <-> Montgomery for the batch code
+inline uint32_t x8_to_monty(Fp a) {
+    uint64_t t = (uint64_t)a.v * P2X8.r2;
+    uint32_t m = (uint32_t)t * P2X8.mu_neg;
+    uint32_t r = (uint32_t)((t + (uint64_t)m * P2X8.p) >> 32);
+    return r >= P2X8.p ? r - P2X8.p : r;
+}
+inline Fp x8_from_monty(uint32_t a) {
+    uint32_t m = a * P2X8.mu_neg;
+    uint32_t r = (uint32_t)(((uint64_t)a + (uint64_t)m * P2X8.p) >> 32);
+    return Fp{r >= P2X8.p ? r - P2X8.p : r};
+}
+void p2x8_init() {
+    P2X8 = P2X8Consts();
+    if (P2.rf != 8 || P2.rp > 32 || (P2.sbox != 3 && P2.sbox != 7)) return;
+    P2X8.p = P;
+    uint32_t inv = P;
+    for (int i = 0; i < 5; i++) inv *= 2u - P * inv;
+    P2X8.mu_neg = 0u - inv;
+    uint64_t r = ((uint64_t)1 << 32) % P;
+    P2X8.r2 = (uint32_t)((r * r) % P);
+    P2X8.rp = P2.rp;
+    P2X8.sbox = P2.sbox;
+    for (int i = 0; i < 8 * 16; i++) P2X8.ext_rc[i] = x8_to_monty(P2.ext_rc[i]);
+    for (uint32_t i = 0; i < P2.rp; i++) P2X8.int_rc[i] = x8_to_monty(P2.int_rc[i]);
+    for (int i = 0; i < 16; i++) P2X8.diag[i] = x8_to_monty(P2.diag[i]);
+    permute_x8 = permute_x8_plain;
+#if defined(__x86_64__)
+    if (__builtin_cpu_supports("avx2")) permute_x8 = permute_x8_avx2;
+#endif
+    // probe: the batch must reproduce the scalar permutation, or it is not used
+    uint32_t s[16][8];
+    Fp ref[8][16];
+    for (int l = 0; l < 8; l++)
+        for (int i = 0; i < 16; i++) {
+            ref[l][i] = mk((uint64_t)(l * 16 + i + 1) * 0x9E3779B1ull);
+            s[i][l] = x8_to_monty(ref[l][i]);
+        }
+    permute_x8(s, P2X8);
+    bool ok = true;
+    for (int l = 0; l < 8; l++) {
+        poseidon2_permute(ref[l]);
+        for (int i = 0; i < 16; i++) ok = ok && x8_from_monty(s[i][l]) == ref[l][i];
+    }
+    P2X8.ok = ok;
+}
+// Sponge digests of rows r0 .. r0+7 of the concatenation of `ms` (all of one height), and eight 2-to-1 compressions.
+void sponge_hash_x8(const std::vector<const Mat*>& ms, size_t r0, Digest* out) {
+    uint32_t s[16][8];
+    std::memset(s, 0, sizeof s);
+    int k = 0;
+    for (auto* m : ms)
+        for (size_t c = 0; c < m->w; c++) {
+            for (int l = 0; l < 8; l++) s[k][l] = x8_to_monty(m->at(r0 + l, c));
+            if (++k == 8) {
+                permute_x8(s, P2X8);
+                k = 0;
+            }
+        }
+    if (k) permute_x8(s, P2X8);
+    for (int l = 0; l < 8; l++)
+        for (int i = 0; i < 8; i++) out[l].d[i] = x8_from_monty(s[i][l]);
+}
+void compress2_x8(const Digest* left, size_t lstride, const Digest* right, size_t rstride, Digest* out) {
+    uint32_t s[16][8];
+    for (int l = 0; l < 8; l++)
+        for (int i = 0; i < 8; i++) {
+            s[i][l] = x8_to_monty(left[l * lstride].d[i]);
+            s[8 + i][l] = x8_to_monty(right[l * rstride].d[i]);
+        }
+    permute_x8(s, P2X8);
+    for (int l = 0; l < 8; l++)
+        for (int i = 0; i < 8; i++) out[l].d[i] = x8_from_monty(s[i][l]);
+}
+
 MerkleTree mmcs_commit(const std::vector<const Mat*>& mats) {
     MerkleTree t;
     t.mats = mats;
@@ -469,19 +615,37 @@ MerkleTree mmcs_commit(const std::vector<const Mat*>& mats) {
     };
     auto tallest = at_height(max_h);
     std::vector<Digest> layer(max_h);
+    const bool x8 = P2X8.ok && !HASH_W_SET;   // eight rows / nodes per call (width-16 sponge only)
+    if (x8 && max_h >= 8) {
 #pragma omp parallel for
-    for (size_t r = 0; r < max_h; r++) layer[r] = sponge_hash(concat_rows(tallest, r));
+        for (size_t r = 0; r < max_h; r += 8) sponge_hash_x8(tallest, r, &layer[r]);
+    } else {
+#pragma omp parallel for
+        for (size_t r = 0; r < max_h; r++) layer[r] = sponge_hash(concat_rows(tallest, r));
+    }
     t.layers.push_back(layer);
     while (t.layers.back().size() > ((size_t)1 << CAP_HEIGHT)) {
         const auto& prev = t.layers.back();
         size_t n = prev.size() / 2;
         auto inject = at_height(n);
         std::vector<Digest> next(n);
+        if (x8 && n >= 8) {
 #pragma omp parallel for
-        for (size_t i = 0; i < n; i++) {
-            Digest d = compress2(prev[2 * i], prev[2 * i + 1]);
-            if (!inject.empty()) d = compress2(d, sponge_hash(concat_rows(inject, i)));
-            next[i] = d;
+            for (size_t i = 0; i < n; i += 8) {
+                compress2_x8(&prev[2 * i], 2, &prev[2 * i + 1], 2, &next[i]);
+                if (!inject.empty()) {
+                    Digest inj[8];
+                    sponge_hash_x8(inject, i, inj);
+                    compress2_x8(&next[i], 1, inj, 1, &next[i]);
+                }
+            }
+        } else {
+#pragma omp parallel for
+            for (size_t i = 0; i < n; i++) {
+                Digest d = compress2(prev[2 * i], prev[2 * i + 1]);
+                if (!inject.empty()) d = compress2(d, sponge_hash(concat_rows(inject, i)));
+                next[i] = d;
+            }
         }
         t.layers.push_back(next);
     }
@@ -1673,6 +1837,7 @@ int orc_init(const p3r_field_desc* field, const p3r_poseidon2_consts* p2, const 
         for (uint32_t i = 0; i < 16; i++) P2.diag.push_back(from_monty(p2->internal_diag[i]));
         FRI = *fri;
         CAP_HEIGHT = fri->cap_height;
+        p2x8_init();
         g_init = true;
         return 0;
     } catch (std::exception& e) {
