@@ -255,6 +255,12 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if world > 1 and args.pin_cores:
+        # one contiguous slice of the host cores per rank: the ranks' polling and launching threads stop migrating onto each other
+        avail = sorted(os.sched_getaffinity(0))
+        per = len(avail) // world
+        if per >= 1:
+            os.sched_setaffinity(0, avail[local * per:(local + 1) * per])
     lib = importlib.import_module("plonky3-recursion_b200.lib")
     agg = importlib.import_module("plonky3-recursion_b200.aggregation")
     F, shapes = tree_workloads(args.field, args.scale)
@@ -274,7 +280,7 @@ def run_ours(args):
     ctx = lib.Context(args.field, lib.DEFAULT_FRI, device=local)
     # host wait of the prover threads: pure yield-polling while every proving thread can have a core of its own, the sleeping
     # poll once the node's proving threads (ranks x lanes) reach the number of host cores (p3r_set_wait_mode)
-    cores_avail = len(os.sched_getaffinity(0))
+    cores_avail = len(os.sched_getaffinity(0)) * (world if (world > 1 and args.pin_cores) else 1)
     wait_mode = args.wait or os.environ.get("P3R_WAIT") or ("sleep" if world * args.inflight >= cores_avail else "yield")
     ctx.set_wait_mode(wait_mode)
     L = shapes["node"]
@@ -510,6 +516,7 @@ def main():
     ap.add_argument("--trees-per-step", type=int, default=0, help="default 2 per GPU")
     ap.add_argument("--skew", type=int, default=8, help="wave skew of the hand-off posting order (aggregation.message_plan)")
     ap.add_argument("--tree-timeout-s", type=float, default=300.0)
+    ap.add_argument("--pin-cores", type=int, default=0, help="1: give every rank its own slice of the host cores (sched_setaffinity)")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0, help="--impl reference: wall-clock budget of the whole run")
     ap.add_argument("--cpu-baseline-budget-s", type=float, default=30.0)
     args = ap.parse_args()
