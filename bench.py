@@ -360,9 +360,11 @@ def run_ours(args):
         for ln in lanes:
             ln.ctx.timer_start()
         w0 = time.perf_counter()
+        c0 = time.process_time()
         out = ex.run(n_trees, first_tree=next_tree[0])
         ms = max(ln.ctx.timer_stop() for ln in lanes)
         out["wall_ms"] = (time.perf_counter() - w0) * 1e3
+        out["cpu_s"] = time.process_time() - c0       # user + system time of every thread of this rank
         out["launches"] = sum(ln.ctx.launch_count() for ln in lanes) - l0
         next_tree[0] += n_trees
         barrier()
@@ -388,14 +390,15 @@ def run_ours(args):
                 s += int(proof_checksum(pr, p).astype(np.uint64).sum()) * (2 * (t - first_timed) + 1)
         return s
     stats = torch.tensor([t_res, r_res["ms"], r_e2e["ms"], r_res["wall_ms"], r_e2e["wall_ms"],
-                          sum(r_res["idle_s"]) / len(lanes) / (r_res["wall_ms"] / 1e3)], dtype=torch.float64, device=dev)
+                          sum(r_res["idle_s"]) / len(lanes) / (r_res["wall_ms"] / 1e3),
+                          r_res["cpu_s"] / (r_res["wall_ms"] / 1e3)], dtype=torch.float64, device=dev)
     sums = torch.tensor([r_res["sent_bytes"], r_e2e["sent_bytes"], r_res["launches"], r_e2e["launches"],
                          roots_sum(r_res) % (1 << 59), roots_sum(r_e2e) % (1 << 59),
                          sum(r_res["proved"].values()), int(1e6 * sum(r_res["idle_s"]) / len(lanes))], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    t_res, ms_res, ms_e2e, wall_res, wall_e2e, idle_worst = (float(x) for x in stats)
+    t_res, ms_res, ms_e2e, wall_res, wall_e2e, idle_worst, host_cores_busy = (float(x) for x in stats)
     sent_res, sent_e2e, launches_res, launches_e2e, rsum_res, rsum_e2e, proved_total, idle_us = (int(x) for x in sums)
 
     if rank == 0:
@@ -474,7 +477,7 @@ def run_ours(args):
                      "roots_checksum_scope": f"weighted sum of the root-proof checksums of the first {common_trees} trees of the "
                                              "timed region (the trees every N proves): equal at every N iff every child proof "
                                              "reached its parent",
-                     "lane_idle_fraction_worst_rank": idle_worst,
+                     "lane_idle_fraction_worst_rank": idle_worst, "host_cores_busy_worst_rank": host_cores_busy,
                      "wall_ms_per_step": wall_res / args.steps, "lane_idle_fraction": idle_us / 1e6 / world / (wall_res / 1e3),
                      "critical_path_speedup_one_tree": agg.critical_path_speedup(args.leaves, world)},
             "gpu_launches": launches_res,
