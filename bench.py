@@ -101,9 +101,9 @@ def proof_checksum(proof: np.ndarray, p: int) -> np.ndarray:
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
 
-    def __init__(self, device: int):
+    def __init__(self, device: int, period_s: float = 0.005):
         super().__init__(daemon=True)
-        self.device, self.rows, self._stop_ev = device, [], threading.Event()
+        self.device, self.rows, self._stop_ev, self.period_s = device, [], threading.Event(), period_s
 
     def run(self):
         # NVML in-process (a sample costs ~0.1 ms, so short timed regions still get many samples); nvidia-smi as fallback
@@ -121,7 +121,7 @@ class ClockSampler(threading.Thread):
                 for bit, pos in bits:
                     row[pos] = "Active" if reasons & bit else "Not Active"
                 self.rows.append(row)
-                self._stop_ev.wait(0.005)
+                self._stop_ev.wait(self.period_s)
             return
         except Exception:
             pass
@@ -212,36 +212,61 @@ def run_reference(args):
 class Lane:
     """One proving context (stream, arena, host thread) with the three circuit shapes of the tree prepared on it."""
 
-    def __init__(self, lib, field, fri, device, shapes):
-        self.ctx = lib.Context(field, fri, device=device)
-        self.prover = lib.BatchStarkProver(self.ctx, pinned_output=True)
+    def __init__(self, lib, field, fri, device, shapes, priority_shapes=()):
+        # the shapes named in `priority_shapes` are proved on a second context of this lane whose streams have high CUDA
+        # priority (p3r_ctx_set_stream_priority): the short dependent kernels of a small proof do not queue behind the
+        # pending blocks of the full-size proofs of the other lanes
+        self.ctxs = [lib.Context(field, fri, device=device)]
+        provers = [lib.BatchStarkProver(self.ctxs[0], pinned_output=True)]
+        if any(n in priority_shapes for n in shapes):
+            self.ctxs.append(lib.Context(field, fri, device=device))
+            self.ctxs[1].set_stream_priority(True)
+            provers.append(lib.BatchStarkProver(self.ctxs[1], pinned_output=True))
         self.kind = {}
+        self.log = []                     # (shape, start, end) of every proof of this lane, host clock
         for name, L in shapes.items():
-            pd = lib.ProverData.from_airs_and_degrees(self.ctx, L.insts, L.preps)
-            res = lib.TraceBatch(self.ctx, L.traces, L.pubs).upload(pd)
-            host = lib.TraceBatch(self.ctx, L.traces, L.pubs, pinned=True, p2_ops=L.p2_ops, alu_ops=L.alu_ops)
+            which = 1 if name in priority_shapes else 0
+            ctx = self.ctxs[which]
+            pd = lib.ProverData.from_airs_and_degrees(ctx, L.insts, L.preps)
+            res = lib.TraceBatch(ctx, L.traces, L.pubs).upload(pd)
+            host = lib.TraceBatch(ctx, L.traces, L.pubs, pinned=True, p2_ops=L.p2_ops, alu_ops=L.alu_ops)
             w = L.insts[PUBLIC_INST].main_width
             rows = max(1, PATCH_WORDS // w)
             # the patched rows must be padding of the Public table: index 0, multiplicity 0 in its preprocessed columns, so
             # that their values are free (the WitnessChecks bus ignores them) while still being committed
             if np.any(L.preps[PUBLIC_INST][-rows:] != 0) or np.any(L.traces[PUBLIC_INST][-rows:] != 0):
                 raise ValueError(f"shape '{name}': the last {rows} rows of the Public table are not padding")
-            self.kind[name] = (pd, res, host, (1 << L.insts[PUBLIC_INST].log_height) - rows, rows, w)
+            self.kind[name] = (pd, res, host, (1 << L.insts[PUBLIC_INST].log_height) - rows, rows, w, provers[which])
 
     def prove(self, name, patch_words, host_buffers: bool):
         """One proof of shape `name` whose Public table carries `patch_words` in its last (padding, multiplicity-0) rows."""
-        pd, res, host, row0, rows, w = self.kind[name]
+        pd, res, host, row0, rows, w, prover = self.kind[name]
         tb = host if host_buffers else res
+        t0 = time.perf_counter()
         tb.write_rows(pd, PUBLIC_INST, row0, np.asarray(patch_words, dtype=np.uint32)[: rows * w].reshape(rows, w))
         if host_buffers:
-            return self.prover.prove_all_tables(tb, pd, copy=False).copy()
-        return self.prover.prove_resident(tb, pd, copy=False).copy()
+            out = prover.prove_all_tables(tb, pd, copy=False).copy()
+        else:
+            out = prover.prove_resident(tb, pd, copy=False).copy()
+        self.log.append((name, t0, time.perf_counter()))
+        return out
 
     def close(self):
         for pd, res, host, *_ in self.kind.values():
             res.close()
             pd.close()
-        self.ctx.close()
+        for c in self.ctxs:
+            c.close()
+
+    def launch_count(self):
+        return sum(c.launch_count() for c in self.ctxs)
+
+    def timer_start(self):
+        for c in self.ctxs:
+            c.timer_start()
+
+    def timer_stop(self):
+        return max(c.timer_stop() for c in self.ctxs)
 
 
 def run_ours(args):
@@ -300,7 +325,7 @@ def run_ours(args):
     # live timing, inside the timed region, of the dominant kernel class and of the LDE (the HBM-roofline kernel)
     ctx.set_kernel_timing(sorted({dominant, "ntt_lde"}))
     ctx.reset_kernel_stats()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, args.clock_sample_ms / 1e3)
     sampler.start()
     barrier()
     t_res = 0.0
@@ -322,7 +347,8 @@ def run_ours(args):
     pd.close()
 
     # ======== part 2: the aggregation tree ========
-    lanes = [Lane(lib, args.field, fri_params(lib, 6), local, shapes) for _ in range(args.inflight)]
+    prio = tuple(x for x in args.priority_shapes.split(",") if x)
+    lanes = [Lane(lib, args.field, fri_params(lib, 6), local, shapes, prio) for _ in range(args.inflight)]
     kind_of_level = lambda lvl: "leaf" if lvl == 0 else ("l1" if lvl == 1 else "node")
     depth = args.leaves.bit_length() - 1
     sizes = {}
@@ -346,7 +372,7 @@ def run_ours(args):
         return lanes[k].prove(kind_of_level(nd.level), patch, mode["host"])
 
     ex = agg.TreeExecutor(rank, world, args.leaves, args.inflight, prove_leaf, prove_node, transport, sizes, skew=args.skew,
-                          timeout_s=args.tree_timeout_s)
+                          timeout_s=args.tree_timeout_s, comm_poll_s=args.comm_poll_us / 1e6, order=args.order)
     trees_per_step = args.trees_per_step or 2 * world
     n_agg = args.leaves - 1
     next_tree = [0]
@@ -356,19 +382,35 @@ def run_ours(args):
         mode["host"] = host_buffers
         region_base[0] = next_tree[0]
         barrier()
-        l0 = sum(ln.ctx.launch_count() for ln in lanes)
+        l0 = sum(ln.launch_count() for ln in lanes)
         for ln in lanes:
-            ln.ctx.timer_start()
+            ln.log.clear()
+            ln.timer_start()
         w0 = time.perf_counter()
         c0 = time.process_time()
         out = ex.run(n_trees, first_tree=next_tree[0])
-        ms = max(ln.ctx.timer_stop() for ln in lanes)
+        ms = max(ln.timer_stop() for ln in lanes)
         out["wall_ms"] = (time.perf_counter() - w0) * 1e3
         out["cpu_s"] = time.process_time() - c0       # user + system time of every thread of this rank
-        out["launches"] = sum(ln.ctx.launch_count() for ln in lanes) - l0
+        out["launches"] = sum(ln.launch_count() for ln in lanes) - l0
         next_tree[0] += n_trees
         barrier()
         out["ms"] = ms
+        # host-clock duration of the proofs by shape, and how many full-size node proofs were in flight at once (time-weighted)
+        ev, by = [], {}
+        for ln in lanes:
+            for name, a, b in ln.log:
+                by.setdefault(name, []).append(b - a)
+                if name == "node":
+                    ev += [(a, 1), (b, -1)]
+        out["proof_ms"] = {k: round(1e3 * float(np.mean(v)), 3) for k, v in by.items()}
+        hist, cur, last = [0.0] * (len(lanes) + 1), 0, None
+        for tt, d in sorted(ev):
+            if last is not None:
+                hist[cur] += tt - last
+            cur, last = cur + d, tt
+        tot = sum(hist) or 1.0
+        out["nodes_in_flight"] = [round(h / tot, 3) for h in hist]
         return out
 
     warm_trees = max(world, 2)           # every rank plays every role once: all NCCL peer channels are set up
@@ -395,9 +437,16 @@ def run_ours(args):
     sums = torch.tensor([r_res["sent_bytes"], r_e2e["sent_bytes"], r_res["launches"], r_e2e["launches"],
                          roots_sum(r_res) % (1 << 59), roots_sum(r_e2e) % (1 << 59),
                          sum(r_res["proved"].values()), int(1e6 * sum(r_res["idle_s"]) / len(lanes))], dtype=torch.int64, device=dev)
+    mine = torch.tensor([r_res["ms"], r_e2e["ms"], float(clocks.get("sm_mhz") or 0.0), r_res["cpu_s"] / (r_res["wall_ms"] / 1e3),
+                         sum(r_res["idle_s"]) / len(lanes) / (r_res["wall_ms"] / 1e3), float(sum(r_res["proved"].values()))],
+                        dtype=torch.float64, device=dev)
+    per_rank = [mine]
     if world > 1:
+        per_rank = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(per_rank, mine)
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    per_rank = [[round(float(x), 3) for x in t] for t in per_rank]
     t_res, ms_res, ms_e2e, wall_res, wall_e2e, idle_worst, host_cores_busy = (float(x) for x in stats)
     sent_res, sent_e2e, launches_res, launches_e2e, rsum_res, rsum_e2e, proved_total, idle_us = (int(x) for x in sums)
 
@@ -463,8 +512,10 @@ def run_ours(args):
                              "pipeline) — the proofs in flight stream > 500 MB of LDE / digest data per GPU, 4x the 126 MB L2",
                        "parallelism": f"{world} GPU(s) x {args.inflight} proofs in flight; nodes of a tree on different ranks "
                                       f"(block partition rotated per tree); child proofs by NCCL send/recv, posting order = "
-                                      f"wave (tree + {args.skew} x level)",
+                                      + (f"wave (tree + {args.skew} x level)" if args.order == "wave" else
+                                         f"blocks of {args.skew} trees, bucket = block + level, higher levels first inside a bucket"),
                        "proofs_per_step": trees_per_step * (2 * args.leaves - 1), "host_wait": wait_mode,
+                       "high_priority_shapes": list(prio),
                        "host_cores": len(os.sched_getaffinity(0)), "proof_words": sizes, "layer_proof_words": proof_words,
                        "prep_commit_ms": prep_commit_ms, "launches_per_layer_proof": launches_per_proof},
             "e2e": {"value": e2e_value, "unit": "aggregation proofs/s", "ms_per_step": ms_e2e / args.steps,
@@ -478,6 +529,9 @@ def run_ours(args):
                                              "timed region (the trees every N proves): equal at every N iff every child proof "
                                              "reached its parent",
                      "lane_idle_fraction_worst_rank": idle_worst, "host_cores_busy_worst_rank": host_cores_busy,
+                     "proof_ms_by_shape_rank0": r_res["proof_ms"], "node_proofs_in_flight_hist_rank0": r_res["nodes_in_flight"],
+                     "per_rank": {"columns": ["ms_resident", "ms_e2e", "sm_mhz", "host_cores_busy", "lane_idle_fraction", "proofs"],
+                                  "rows": per_rank},
                      "wall_ms_per_step": wall_res / args.steps, "lane_idle_fraction": idle_us / 1e6 / world / (wall_res / 1e3),
                      "critical_path_speedup_one_tree": agg.critical_path_speedup(args.leaves, world)},
             "gpu_launches": launches_res,
@@ -519,6 +573,10 @@ def main():
     ap.add_argument("--trees-per-step", type=int, default=0, help="default 2 per GPU")
     ap.add_argument("--skew", type=int, default=8, help="wave skew of the hand-off posting order (aggregation.message_plan)")
     ap.add_argument("--tree-timeout-s", type=float, default=300.0)
+    ap.add_argument("--clock-sample-ms", type=float, default=5.0, help="period of the NVML clock / throttle-reason samples")
+    ap.add_argument("--comm-poll-us", type=float, default=200.0, help="idle period of the hand-off thread's poll")
+    ap.add_argument("--priority-shapes", default="", help="comma list of tree shapes (leaf,l1,node) proved on high-priority streams")
+    ap.add_argument("--order", default="wave", choices=["wave", "block"], help="task / hand-off order (aggregation.order_key)")
     ap.add_argument("--pin-cores", type=int, default=0, help="1: give every rank its own slice of the host cores (sched_setaffinity)")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0, help="--impl reference: wall-clock budget of the whole run")
     ap.add_argument("--cpu-baseline-budget-s", type=float, default=30.0)

@@ -101,7 +101,22 @@ def rotated_owner(node: Node, n_leaves: int, world: int, tree: int) -> int:
     return (owner(node, n_leaves, world) + tree) % world
 
 
-def message_plan(n_leaves: int, world: int, n_trees: int, skew: int = 6):
+def order_key(tree: int, level: int, index: int, skew: int, order: str = "wave"):
+    """Priority of the proof of node (level, index) of tree `tree` — and of the message that carries it to its parent.
+    "wave": tree + skew * (level + 1), older trees first inside a wave. "block": the trees are taken in blocks of `skew`;
+    bucket = block + level + 1, and inside a bucket the HIGHER levels come first, then tree order. Both orders give a proof a
+    larger key than the proofs (and messages) it depends on — children sit one bucket / `skew` waves earlier — which is all
+    in-order posting needs. "block" keeps proofs of one shape together on a rank (root, level-2, level-1, leaves of eight
+    trees) whatever the number of ranks: small latency-bound proofs run among themselves instead of beside full-size
+    ones."""
+    if order == "block":
+        return (tree // skew + level + 1, -level, tree, index)
+    if order != "wave":
+        raise ValueError(f"unknown order {order!r}")
+    return (tree + skew * (level + 1), tree, level, index)
+
+
+def message_plan(n_leaves: int, world: int, n_trees: int, skew: int = 6, order: str = "wave"):
     """Every cross-rank child-proof transfer of `n_trees` trees as (wave, tree, parent level, child index, src, dst), in the
     ONE global order all ranks post their sends / receives in. wave = tree + skew * parent level: a proof depends only on
     messages of smaller waves (its own children's), which makes in-order posting deadlock-free even when a rank's transfers
@@ -117,7 +132,7 @@ def message_plan(n_leaves: int, world: int, n_trees: int, skew: int = 6):
                 for c in nd.children():
                     cown = rotated_owner(c, n_leaves, world, t)
                     if cown != own:
-                        msgs.append((t + skew * lvl, t, lvl, c.index, cown, own))
+                        msgs.append((order_key(t, lvl - 1, c.index, skew, order), t, lvl, c.index, cown, own))
     msgs.sort()
     return msgs
 
@@ -134,16 +149,18 @@ class TreeExecutor:
     """
 
     def __init__(self, rank: int, world: int, n_leaves: int, n_lanes: int, prove_leaf, prove_node, transport=None,
-                 sizes=None, skew: int = 6, timeout_s: float = 600.0):
+                 sizes=None, skew: int = 6, timeout_s: float = 600.0, comm_poll_s: float = 0.0002, order: str = "wave"):
         self.rank, self.world, self.n_leaves, self.n_lanes = rank, world, n_leaves, n_lanes
         self.depth = n_leaves.bit_length() - 1
         self.prove_leaf, self.prove_node, self.transport = prove_leaf, prove_node, transport
-        self.sizes, self.skew, self.timeout_s = sizes or {}, skew, timeout_s
+        self.sizes, self.skew, self.timeout_s, self.comm_poll_s = sizes or {}, skew, timeout_s, comm_poll_s
+        self.order = order
+        order_key(0, 0, 0, skew, order)
         if world > 1 and transport is None:
             raise ValueError("world > 1 needs a transport")
 
-    def _wave(self, tree, level):
-        return tree + self.skew * (level + 1)   # wave of the message that carries this proof to its parent
+    def _key(self, tree, level, index):
+        return order_key(tree, level, index, self.skew, self.order)
 
     def run(self, n_trees: int, first_tree: int = 0):
         """Returns {"roots": {tree: proof} (trees whose root this rank proved), "proved": {level: count}, "sent_bytes",
@@ -161,8 +178,8 @@ class TreeExecutor:
                     if rotated_owner(Node(lvl, i), L, world, t) == rank:
                         state["left"] += 1
                         if lvl == 0:
-                            heapq.heappush(ready, (self._wave(t, 0), t, 0, i))
-        msgs = [m for m in message_plan(L, world, first_tree + n_trees, self.skew)
+                            heapq.heappush(ready, (self._key(t, 0, i), t, 0, i))
+        msgs = [m for m in message_plan(L, world, first_tree + n_trees, self.skew, self.order)
                 if m[1] >= first_tree and rank in (m[4], m[5])] if world > 1 else []
         deadline = time.monotonic() + self.timeout_s
 
@@ -171,7 +188,7 @@ class TreeExecutor:
             slot = arrived.setdefault((t, parent), [None, None])
             slot[child.index & 1] = proof
             if slot[0] is not None and slot[1] is not None:
-                heapq.heappush(ready, (self._wave(t, parent.level), t, parent.level, parent.index))
+                heapq.heappush(ready, (self._key(t, parent.level, parent.index), t, parent.level, parent.index))
                 lock.notify_all()
 
         def complete(t, nd: Node, proof):
@@ -257,7 +274,7 @@ class TreeExecutor:
                         if time.monotonic() > deadline:
                             raise TimeoutError(f"rank {rank}: proof hand-off timed out at message {i}/{len(msgs)}")
                         with lock:
-                            lock.wait(timeout=0.0002)
+                            lock.wait(timeout=self.comm_poll_s)
             except BaseException as e:   # noqa: BLE001
                 fail(e)
 

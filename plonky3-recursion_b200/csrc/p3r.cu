@@ -162,6 +162,7 @@ struct p3r_ctx {
     // disjoint data): fork_streams() makes them wait for everything queued on `stream`, join_streams() the reverse.
     static constexpr int N_AUX = 4;
     cudaStream_t aux[N_AUX] = {nullptr, nullptr, nullptr, nullptr};
+    int stream_prio = 0;      // CUDA priority of `stream` and the side streams (p3r_ctx_set_stream_priority)
     cudaEvent_t aux_ev[N_AUX + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     uint32_t* tws = nullptr;  // per-stage compact twiddle tables, 2^logT - 1 entries
     uint32_t* tw = nullptr;   // = tws + 2^(logT-1) - 1: half table of omega_T
@@ -329,7 +330,7 @@ static T* upload_vec(p3r_ctx* ctx, const std::vector<T>& v) {
 static int fork_streams(p3r_ctx* ctx) {
     for (int i = 0; i < p3r_ctx::N_AUX; i++)
         if (!ctx->aux[i]) {
-            CUDA_TRY(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
+            CUDA_TRY(cudaStreamCreateWithPriority(&ctx->aux[i], cudaStreamNonBlocking, ctx->stream_prio));
             CUDA_TRY(cudaEventCreateWithFlags(&ctx->aux_ev[i], cudaEventDisableTiming));
         }
     if (!ctx->aux_ev[p3r_ctx::N_AUX]) CUDA_TRY(cudaEventCreateWithFlags(&ctx->aux_ev[p3r_ctx::N_AUX], cudaEventDisableTiming));
@@ -2941,6 +2942,28 @@ void p3r_ctx_destroy(p3r_ctx* ctx) {
     cudaStreamDestroy(ctx->stream);
     p2_registry_release(ctx->device, ctx->field_id);
     delete ctx;
+}
+int p3r_ctx_set_stream_priority(p3r_ctx* ctx, int high) {
+    if (!ctx) return P3R_ERR_INVALID_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx_wait(ctx));
+    int least = 0, greatest = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    const int prio = high ? greatest : least;
+    if (prio == ctx->stream_prio) return P3R_OK;
+    cudaStream_t fresh = nullptr;
+    CUDA_TRY(cudaStreamCreateWithPriority(&fresh, cudaStreamNonBlocking, prio));
+    cudaStreamDestroy(ctx->stream);
+    ctx->stream = fresh;
+    ctx->stream_prio = prio;
+    for (int i = 0; i < p3r_ctx::N_AUX; i++)       // the side streams are re-created at the next fork with the new priority
+        if (ctx->aux[i]) {
+            cudaStreamDestroy(ctx->aux[i]);
+            ctx->aux[i] = nullptr;
+            cudaEventDestroy(ctx->aux_ev[i]);
+            ctx->aux_ev[i] = nullptr;
+        }
+    return P3R_OK;
 }
 const char* p3r_last_error(const p3r_ctx* ctx) { return ctx ? ctx->err.c_str() : g_noctx_err.c_str(); }
 

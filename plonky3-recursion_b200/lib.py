@@ -82,7 +82,7 @@ EXPORTS = ["p3r_abi_version", "p3r_build_info", "p3r_ctx_create", "p3r_ctx_destr
            "p3r_host_alloc", "p3r_host_free", "p3r_timer_start", "p3r_timer_stop", "p3r_set_kernel_timing",
            "p3r_reset_kernel_stats", "p3r_kernel_stats", "p3r_set_specialization", "p3r_prove_ex", "p3r_traces_upload_ex",
            "p3r_traces_download", "p3r_kernel_perms", "p3r_bench_fri_round", "p3r_prove_ops",
-           "p3r_traces_upload_ops", "p3r_set_wait_mode", "p3r_host_hasher_create", "p3r_host_hasher_permute",
+           "p3r_traces_upload_ops", "p3r_set_wait_mode", "p3r_ctx_set_stream_priority", "p3r_host_hasher_create", "p3r_host_hasher_permute",
            "p3r_host_hasher_free", "p3r_traces_write_rows", "p3r_proof_serialize", "p3r_proof_deserialize",
            "p3r_wire_last_error", "p3r_ctx_set_conventions", "p3r_ctx_set_leaf_hasher", "p3r_poseidon2_permute_w", "p3r_ctx_set_uni_stark", "p3r_bench_commit_multi", "p3r_poseidon2_run_chains"]
 
@@ -250,6 +250,10 @@ class Context:
     def set_wait_mode(self, mode: str):
         """'spin' | 'yield' | 'block' | 'sleep' (process-wide, p3r_set_wait_mode)."""
         self.lib.p3r_set_wait_mode({"spin": 0, "yield": 1, "block": 2, "sleep": 3}[mode])
+
+    def set_stream_priority(self, high: bool):
+        """Schedule this context's kernels ahead of default-priority contexts (p3r_ctx_set_stream_priority)."""
+        self._check(self.lib.p3r_ctx_set_stream_priority(self.h, 1 if high else 0))
 
     def poseidon2_run_chains(self, new_start, merkle_path, mmcs_bit, witness_mask, values_canonical):
         """Runner assist (p3r_poseidon2_run_chains): returns (inputs, outputs), canonical (n, 16) arrays."""

@@ -118,8 +118,8 @@ def test_message_plan_is_balanced_and_ordered():
     for world in (2, 4, 8):
         msgs = agg.message_plan(8, world, 2 * world, skew=3)
         assert msgs == sorted(msgs)
-        for wave, t, lvl, ci, src, dst in msgs:
-            assert src != dst and wave == t + 3 * lvl
+        for key, t, lvl, ci, src, dst in msgs:
+            assert src != dst and key[0] == t + 3 * lvl
             assert src == agg.rotated_owner(agg.Node(lvl - 1, ci), 8, world, t)
             assert dst == agg.rotated_owner(agg.Node(lvl, ci // 2), 8, world, t)
         # a proof's own children arrive in strictly earlier waves than the message that carries it onwards
@@ -133,9 +133,29 @@ def test_message_plan_is_balanced_and_ordered():
         assert len(set(load.values())) == 1 and len(load) == world   # every rank proves the same number of nodes
 
 
+@pytest.mark.parametrize("order", ["wave", "block"])
+def test_order_key_puts_children_before_parents(order):
+    """What in-order posting needs: the key of a proof (= of the message that carries it on) is larger than the keys of both
+    child proofs, for every tree, level and skew."""
+    for skew in (1, 3, 8):
+        for t in range(20):
+            for lvl in range(1, 4):
+                for i in range(8 >> lvl):
+                    k = agg.order_key(t, lvl, i, skew, order)
+                    assert agg.order_key(t, lvl - 1, 2 * i, skew, order) < k
+                    assert agg.order_key(t, lvl - 1, 2 * i + 1, skew, order) < k
+    # block order: inside one bucket a rank sees the higher levels first
+    ks = sorted(agg.order_key(t, lvl, 0, 8, "block") + (lvl,) for t in range(32) for lvl in range(4))
+    in_bucket = [k[-1] for k in ks if k[0] == 4]
+    assert in_bucket == sorted(in_bucket, reverse=True) and set(in_bucket) == {0, 1, 2, 3}
+    with pytest.raises(ValueError):
+        agg.order_key(0, 0, 0, 8, "nope")
+
+
+@pytest.mark.parametrize("order", ["wave", "block"])
 @pytest.mark.parametrize("lanes", [1, 4])
-def test_executor_single_rank_many_trees(lanes):
-    ex = agg.TreeExecutor(0, 1, 8, lanes, _x_leaf, _x_node)
+def test_executor_single_rank_many_trees(lanes, order):
+    ex = agg.TreeExecutor(0, 1, 8, lanes, _x_leaf, _x_node, order=order, skew=2)
     out = ex.run(5)
     assert out["proved"] == {0: 40, 1: 20, 2: 10, 3: 5} and out["sent_bytes"] == 0
     for t in range(5):
@@ -151,14 +171,14 @@ def test_executor_propagates_prover_errors():
         agg.TreeExecutor(0, 1, 4, 3, _x_leaf, bad_node).run(2)
 
 
-def _x_worker(rank, world, port, n_leaves, n_trees, lanes, out_dir):
+def _x_worker(rank, world, port, n_leaves, n_trees, lanes, out_dir, order="wave", skew=6):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     tr = agg.TorchTransport(dist, torch, torch.device("cpu"), agg.MSG_HEADER_WORDS + max(PROOF_WORDS.values()), 8)
-    ex = agg.TreeExecutor(rank, world, n_leaves, lanes, _x_leaf, _x_node, tr, PROOF_WORDS, timeout_s=120)
+    ex = agg.TreeExecutor(rank, world, n_leaves, lanes, _x_leaf, _x_node, tr, PROOF_WORDS, timeout_s=120, order=order, skew=skew)
     out = ex.run(n_trees)
     for t, proof in out["roots"].items():
         np.save(os.path.join(out_dir, f"root{t}.npy"), proof)
@@ -168,15 +188,17 @@ def _x_worker(rank, world, port, n_leaves, n_trees, lanes, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n_leaves,n_trees,lanes", [(2, 8, 6, 3), (4, 8, 8, 2), (2, 2, 5, 2)])
-def test_executor_over_gloo_ranks(tmp_path, world, n_leaves, n_trees, lanes):
+@pytest.mark.parametrize("world,n_leaves,n_trees,lanes,order,skew",
+                         [(2, 8, 6, 3, "wave", 6), (4, 8, 8, 2, "wave", 6), (2, 2, 5, 2, "wave", 6),
+                          (2, 8, 7, 3, "block", 2), (4, 8, 9, 2, "block", 4)])
+def test_executor_over_gloo_ranks(tmp_path, world, n_leaves, n_trees, lanes, order, skew):
     """Same roots as the serial loop of the reference (recursive_aggregation.rs:676-704) for every tree, every node proved
     exactly once, and real bytes on the wire in both directions (the rotation makes every rank send and receive)."""
     import torch.multiprocessing as mp
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_x_worker, args=(world, port, n_leaves, n_trees, lanes, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_x_worker, args=(world, port, n_leaves, n_trees, lanes, str(tmp_path), order, skew), nprocs=world, join=True)
     for t in range(n_trees):
         assert np.array_equal(np.load(tmp_path / f"root{t}.npy"), _x_serial_root(t, n_leaves))
     stats = np.array([np.load(tmp_path / f"stats{r}.npy") for r in range(world)])
