@@ -576,7 +576,7 @@ def main():
     ap.add_argument("--clock-sample-ms", type=float, default=5.0, help="period of the NVML clock / throttle-reason samples")
     ap.add_argument("--comm-poll-us", type=float, default=200.0, help="idle period of the hand-off thread's poll")
     ap.add_argument("--priority-shapes", default="", help="comma list of tree shapes (leaf,l1,node) proved on high-priority streams")
-    ap.add_argument("--order", default="wave", choices=["wave", "block"], help="task / hand-off order (aggregation.order_key)")
+    ap.add_argument("--order", default="block", choices=["wave", "block"], help="task / hand-off order (aggregation.order_key)")
     ap.add_argument("--pin-cores", type=int, default=0, help="1: give every rank its own slice of the host cores (sched_setaffinity)")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0, help="--impl reference: wall-clock budget of the whole run")
     ap.add_argument("--cpu-baseline-budget-s", type=float, default=30.0)

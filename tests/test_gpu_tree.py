@@ -93,3 +93,49 @@ def test_write_rows_matches_a_fresh_upload():
     tb.close()
     pd.close()
     ctx.close()
+
+
+def test_block_order_and_priority_streams_give_the_same_roots():
+    """The task order and the CUDA stream priority are scheduling only: trees proved in block order, with the leaf and level-1
+    shapes on high-priority contexts (p3r_ctx_set_stream_priority), have the same root proofs as the wave-order run."""
+    F = field_mod.get_field("koala-bear")
+    shapes = _shapes(F)
+    kind = lambda lvl: "leaf" if lvl == 0 else ("l1" if lvl == 1 else "node")
+    roots = []
+    for order, prio in (("wave", ()), ("block", ("leaf", "l1"))):
+        lanes = [bench.Lane(lib, "koala-bear", SMALL_FRI, 0, shapes, prio) for _ in range(3)]
+        assert all(len(ln.ctxs) == (2 if prio else 1) for ln in lanes)
+
+        def leaf(k, t, i):
+            ident = np.zeros(bench.PATCH_WORDS, dtype=np.uint32)
+            ident[0], ident[1] = t, i
+            return lanes[k].prove("leaf", ident, False)
+
+        def node(k, t, nd, left, right):
+            patch = np.concatenate([bench.proof_checksum(left, F.p), bench.proof_checksum(right, F.p)])
+            return lanes[k].prove(kind(nd.level), patch, False)
+
+        out = agg.TreeExecutor(0, 1, 8, 3, leaf, node, order=order, skew=2).run(5)
+        roots.append(out["roots"])
+        for ln in lanes:
+            ln.close()
+    for t in range(5):
+        assert np.array_equal(roots[0][t], roots[1][t])
+
+
+def test_stream_priority_can_be_switched_between_proofs():
+    F = field_mod.get_field("koala-bear")
+    L = wl.synthetic_layer(F, 7, n_const=10, n_public=20, n_alu=100, n_perms=20, n_recompose=4, min_height=32)
+    ctx = lib.Context("koala-bear", SMALL_FRI)
+    pd = lib.ProverData.from_airs_and_degrees(ctx, L.insts, L.preps)
+    tb = lib.TraceBatch(ctx, L.traces, L.pubs).upload(pd)
+    prover = lib.BatchStarkProver(ctx)
+    a = prover.prove_resident(tb, pd)
+    ctx.set_stream_priority(True)
+    b = prover.prove_resident(tb, pd)
+    ctx.set_stream_priority(False)
+    c = prover.prove_resident(tb, pd)
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+    tb.close()
+    pd.close()
+    ctx.close()
