@@ -20,11 +20,15 @@
 
 #include <algorithm>
 #include <cassert>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include <chrono>
 #include <cstdint>
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <functional>
 #include <type_traits>
 #include <map>
@@ -521,7 +525,59 @@ struct P2X8Consts {
         external();                                                                                       \
     }
 #if defined(__x86_64__)
-__attribute__((target("avx2"), optimize("O3"))) void permute_x8_avx2(uint32_t (*s)[8], const P2X8Consts& k) { P2X8_BODY }
+// AVX2 by hand (GCC does not vectorise the 64-bit products of the lane loops above): one permutation per 32-bit lane, the
+// 32x32 -> 64 products taken on the even and the odd lanes separately (vpmuludq), Montgomery reduction with mu = -P^-1.
+#define X8_FN __attribute__((target("avx2"), always_inline)) inline
+X8_FN __m256i x8_add(__m256i a, __m256i b, __m256i p) {
+    __m256i s = _mm256_add_epi32(a, b);
+    return _mm256_min_epu32(s, _mm256_sub_epi32(s, p));
+}
+X8_FN __m256i x8_mul(__m256i a, __m256i b, __m256i p, __m256i mu) {
+    __m256i te = _mm256_mul_epu32(a, b);
+    __m256i to = _mm256_mul_epu32(_mm256_srli_epi64(a, 32), _mm256_srli_epi64(b, 32));
+    __m256i ue = _mm256_add_epi64(te, _mm256_mul_epu32(_mm256_mul_epu32(te, mu), p));
+    __m256i uo = _mm256_add_epi64(to, _mm256_mul_epu32(_mm256_mul_epu32(to, mu), p));
+    __m256i r = _mm256_blend_epi32(_mm256_srli_epi64(ue, 32), uo, 0xAA);
+    return _mm256_min_epu32(r, _mm256_sub_epi32(r, p));
+}
+X8_FN __m256i x8_sbox(__m256i x, __m256i p, __m256i mu, bool cube) {
+    __m256i x2 = x8_mul(x, x, p, mu), x3 = x8_mul(x2, x, p, mu);
+    if (cube) return x3;
+    return x8_mul(x8_mul(x2, x2, p, mu), x3, p, mu);
+}
+X8_FN void x8_external(__m256i* v, __m256i p) {
+    for (int q = 0; q < 4; q++) {
+        __m256i a = v[4 * q], b = v[4 * q + 1], c = v[4 * q + 2], d = v[4 * q + 3];
+        __m256i t = x8_add(x8_add(a, b, p), x8_add(c, d, p), p);
+        v[4 * q] = x8_add(x8_add(t, a, p), x8_add(b, b, p), p);
+        v[4 * q + 1] = x8_add(x8_add(t, b, p), x8_add(c, c, p), p);
+        v[4 * q + 2] = x8_add(x8_add(t, c, p), x8_add(d, d, p), p);
+        v[4 * q + 3] = x8_add(x8_add(t, d, p), x8_add(a, a, p), p);
+    }
+    for (int j = 0; j < 4; j++) {
+        __m256i sum = x8_add(x8_add(v[j], v[4 + j], p), x8_add(v[8 + j], v[12 + j], p), p);
+        for (int q = 0; q < 4; q++) v[4 * q + j] = x8_add(v[4 * q + j], sum, p);
+    }
+}
+__attribute__((target("avx2"), optimize("O3"))) void permute_x8_avx2(uint32_t (*s)[8], const P2X8Consts& k) {
+    const __m256i p = _mm256_set1_epi32((int)k.p), mu = _mm256_set1_epi32((int)k.mu_neg);
+    const bool cube = k.sbox == 3;
+    __m256i v[16];
+    for (int i = 0; i < 16; i++) v[i] = _mm256_loadu_si256((const __m256i*)s[i]);
+    x8_external(v, p);
+    for (uint32_t r = 0; r < 8; r++) {
+        if (r == 4)
+            for (uint32_t q = 0; q < k.rp; q++) {
+                v[0] = x8_sbox(x8_add(v[0], _mm256_set1_epi32((int)k.int_rc[q]), p), p, mu, cube);
+                __m256i sum = v[0];
+                for (int i = 1; i < 16; i++) sum = x8_add(sum, v[i], p);
+                for (int i = 0; i < 16; i++) v[i] = x8_add(sum, x8_mul(_mm256_set1_epi32((int)k.diag[i]), v[i], p, mu), p);
+            }
+        for (int i = 0; i < 16; i++) v[i] = x8_sbox(x8_add(v[i], _mm256_set1_epi32((int)k.ext_rc[16 * r + i]), p), p, mu, cube);
+        x8_external(v, p);
+    }
+    for (int i = 0; i < 16; i++) _mm256_storeu_si256((__m256i*)s[i], v[i]);
+}
 #endif
 __attribute__((optimize("O3"))) void permute_x8_plain(uint32_t (*s)[8], const P2X8Consts& k) { P2X8_BODY }
 void (*permute_x8)(uint32_t (*)[8], const P2X8Consts&) = permute_x8_plain;
@@ -599,6 +655,9 @@ void compress2_x8(const Digest* left, size_t lstride, const Digest* right, size_
     for (int l = 0; l < 8; l++)
         for (int i = 0; i < 8; i++) out[l].d[i] = x8_from_monty(s[i][l]);
 }
+
+bool GRIND_PARALLEL = false;   // Challenger::grind; set with the other CPU-arm fast paths (ff_init)
+#include "fast_paths.inc"   // strip-wise AVX2 interpolation / evaluation used by prove() when FF.ok (the CPU arm's speed)
 
 MerkleTree mmcs_commit(const std::vector<const Mat*>& mats) {
     MerkleTree t;
@@ -750,6 +809,23 @@ struct Challenger {
     // GrindingChallenger::grind, made deterministic: smallest witness.
     Fp grind(uint32_t bits) {
         if (bits == 0) return Fp{0};
+        if (GRIND_PARALLEL) {   // same answer (the smallest witness), candidates tried in blocks by all threads
+            const uint32_t block = 4096;
+            for (uint32_t base = 0; base < P; base += block) {
+                uint32_t best = P;
+                const uint32_t end = (uint32_t)std::min<uint64_t>(P, (uint64_t)base + block);
+#pragma omp parallel for reduction(min : best)
+                for (uint32_t w = base; w < end; w++) {
+                    Challenger c = *this;
+                    if (c.check_witness(bits, Fp{w}) && w < best) best = w;
+                }
+                if (best != P) {
+                    check_witness(bits, Fp{best});
+                    return Fp{best};
+                }
+            }
+            throw std::runtime_error("oracle: no PoW witness");
+        }
         for (uint32_t w = 0; w < P; w++) {
             Challenger c = *this;
             if (c.check_witness(bits, Fp{w})) {
@@ -823,9 +899,19 @@ struct RowCtx {
 // Runs `p`; constraints land in cons_b/cons_e style single vector `cons` (as Ext) at their fold position;
 // OUT_B values land in `outs`.
 template <class BT>
-void run_program(const Program& p, const RowCtx<BT>& rc, std::vector<Ext>* cons, std::vector<BT>* outs) {
-    std::vector<BT> B(p.nb);
-    std::vector<Ext> E(p.ne, ext_zero());
+struct ProgramScratch {   // register files of the interpreter, reusable across rows (a row loop would allocate them per row)
+    std::vector<BT> B;
+    std::vector<Ext> E;
+};
+template <class BT>
+void run_program(const Program& p, const RowCtx<BT>& rc, std::vector<Ext>* cons, std::vector<BT>* outs,
+                 ProgramScratch<BT>* scratch = nullptr) {
+    ProgramScratch<BT> local;
+    ProgramScratch<BT>& sc = scratch ? *scratch : local;
+    sc.B.resize(p.nb);
+    sc.E.assign(p.ne, ext_zero());
+    std::vector<BT>& B = sc.B;
+    std::vector<Ext>& E = sc.E;
     for (const auto& in : p.insns) {
         switch (in.op) {
             case P3R_OP_B_MAIN: B[in.dst] = rc.main[in.b][in.a]; break;
@@ -1004,6 +1090,18 @@ std::vector<Ext> fold_once(const std::vector<Ext>& v, const Ext& beta) {
     uint32_t lg = log2_strict(L);
     Fp g = two_adic_gen(lg);
     std::vector<Ext> out(L / 2);
+    if (FF.ok && L >= 4) {
+        // x0 = g^j and 1 / (x1 - x0) = 1 / (-2 x0) = (-1/2) * g^-j from two power tables (j = bitrev(i)): no inversion and no
+        // exponentiation per element
+        std::vector<Fp> gp = fp_powers(g, L / 2), gi = fp_powers(finv(g), L / 2, -finv(Fp{2}));
+#pragma omp parallel for
+        for (size_t i = 0; i < L / 2; i++) {
+            size_t j = bitrev((uint32_t)i, lg - 1);
+            Ext e0 = v[2 * i], e1 = v[2 * i + 1];
+            out[i] = e0 + (beta - gp[j]) * ((e1 - e0) * gi[j]);
+        }
+        return out;
+    }
     for (size_t i = 0; i < L / 2; i++) {
         Fp x0 = fpow(g, bitrev((uint32_t)i, lg - 1));
         Ext e0 = v[2 * i], e1 = v[2 * i + 1];
@@ -1252,6 +1350,27 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
         t_prev = now;
     };
 
+    // LDEs of the matrices picked by `want` (evaluations over H_n -> GENERATOR * H_{n << lb}, rows bit-reversed). The plain
+    // route is coset_lde() per matrix; with FF.ok the strips are interpolated once (coefficients kept for the quotient domain
+    // and the openings) and evaluated on the cosets, every (matrix, strip) of the commit in one parallel loop.
+    auto commit_ldes = [&](const std::vector<Mat>& src, std::vector<Strips>& coef, std::vector<Mat>& lde,
+                           const std::function<bool(size_t)>& want) {
+        if (!FF.ok) {
+            for (size_t i = 0; i < src.size(); i++)
+                if (want(i)) lde[i] = coset_lde(src[i], lb, Fp{1});
+            return;
+        }
+        std::vector<InterpJob> ij;
+        std::vector<EvalJob> ej;
+        for (size_t i = 0; i < src.size(); i++)
+            if (want(i)) {
+                ij.push_back({&src[i], Fp{1}, &coef[i]});
+                ej.push_back({&coef[i], lb, Fp{GEN}, false, &lde[i]});
+            }
+        interpolate_strips(ij);
+        evaluate_strips(ej);
+    };
+
     // -- preprocessed (ProverData::from_airs_and_degrees) --
     // Computed once per circuit shape and kept, as the reference keeps it in NextLayerPrepCache / CircuitProverData
     // (recursion/src/recursion.rs:295-298,376) and the CUDA path in p3r_prep: a prove call on the same preprocessed matrices
@@ -1260,13 +1379,14 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
     struct PrepCache {
         std::vector<Mat> src;        // the preprocessed matrices the entry was built from
         uint32_t lb = 0, cap_height = 0, p = 0;
-        bool hash_w = false;
+        bool hash_w = false, fast = false;
         std::vector<Mat> lde;
+        std::vector<Strips> coef;    // FF.ok: coefficients of the preprocessed columns (quotient domain, openings)
         MerkleTree tree;
     };
     static PrepCache cache;
     bool hit = cache.lb == lb && cache.cap_height == CAP_HEIGHT && cache.p == P && cache.hash_w == HASH_W_SET && !HASH_W_SET &&
-               cache.src.size() == n_inst;
+               cache.fast == FF.ok && cache.src.size() == n_inst;
     for (size_t i = 0; hit && i < n_inst; i++) {
         const bool has = cm.insts[i].prep_w != 0;
         hit = has ? (cache.src[i].h == prep[i].h && cache.src[i].w == prep[i].w &&
@@ -1279,27 +1399,31 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
         cache.cap_height = CAP_HEIGHT;
         cache.p = P;
         cache.hash_w = HASH_W_SET;
+        cache.fast = FF.ok;
         cache.src.resize(n_inst);
         cache.lde.resize(n_inst);
+        cache.coef.resize(n_inst);
         std::vector<const Mat*> ptrs;
         for (size_t i = 0; i < n_inst; i++)
             if (cm.insts[i].prep_w) {
                 cache.src[i] = prep[i];
-                cache.lde[i] = coset_lde(prep[i], lb, Fp{1});
                 ptrs.push_back(&cache.lde[i]);
             }
+        commit_ldes(cache.src, cache.coef, cache.lde, [&](size_t i) { return cm.insts[i].prep_w != 0; });
         if (cm.has_prep) cache.tree = mmcs_commit(ptrs);
     }
+    if (cache.fast != FF.ok) throw std::runtime_error("oracle: fast-path setting changed under the preprocessed cache");
     const MerkleTree& prep_tree = cache.tree;
+    const std::vector<Strips>& prep_coef = cache.coef;
 
     lap("preprocessed");
     // -- main commit --
     std::vector<Mat> main_lde(n_inst);
+    std::vector<Strips> main_coef(n_inst);
     std::vector<const Mat*> main_ptrs;
-    for (size_t i = 0; i < n_inst; i++) {
-        main_lde[i] = coset_lde(traces[i], lb, Fp{1});
-        main_ptrs.push_back(&main_lde[i]);
-    }
+    commit_ldes(traces, main_coef, main_lde, [](size_t) { return true; });
+    for (size_t i = 0; i < n_inst; i++) main_ptrs.push_back(&main_lde[i]);
+    lap("  main lde");
     MerkleTree main_tree = mmcs_commit(main_ptrs);
     std::vector<Digest> prep_cap;
     if (cm.has_prep) prep_cap = prep_tree.cap();
@@ -1309,6 +1433,7 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
     // -- permutation --
     std::vector<std::vector<Ext>> chal(n_inst);
     std::vector<Mat> perm(n_inst), perm_lde(n_inst);
+    std::vector<Strips> perm_coef(n_inst);
     std::vector<Ext> terminals(n_inst, ext_zero());
     MerkleTree perm_tree;
     if (cm.has_perm) {
@@ -1320,9 +1445,11 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
             if (!cm.insts[i].lookups.empty()) {
                 perm[i] = logup_trace(cm.insts[i], traces[i], cm.insts[i].prep_w ? &prep[i] : nullptr,
                                       pubs[i].data(), chal[i], &terminals[i]);
-                perm_lde[i] = coset_lde(perm[i], lb, Fp{1});
                 ptrs.push_back(&perm_lde[i]);
             }
+        lap("  logup trace");
+        commit_ldes(perm, perm_coef, perm_lde, [&](size_t i) { return !cm.insts[i].lookups.empty(); });
+        lap("  logup lde");
         perm_tree = mmcs_commit(ptrs);
         ch.observe_cap(perm_tree.cap());
         for (size_t i = 0; i < n_inst; i++)
@@ -1334,6 +1461,7 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
     // -- quotient --
     std::vector<std::vector<Mat>> qchunk_lde(n_inst);
     std::vector<std::vector<Mat>> qchunk(n_inst);
+    std::vector<std::vector<Strips>> qchunk_coef(n_inst);
     for (size_t i = 0; i < n_inst; i++) {
         const Inst& s = cm.insts[i];
         size_t n = (size_t)1 << s.log_h;
@@ -1354,13 +1482,80 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
             }
             return o;
         };
-        Mat mq = on_qdomain(traces[i]);
-        Mat pq, rq;
-        if (s.prep_w) pq = on_qdomain(prep[i]);
-        if (!s.lookups.empty()) rq = on_qdomain(perm[i]);
+        Mat mq, pq, rq;
+        if (FF.ok) {   // from the coefficients the commits left behind
+            std::vector<EvalJob> ej;
+            ej.push_back({&main_coef[i], s.log_qc, Fp{GEN}, true, &mq});
+            if (s.prep_w) ej.push_back({&prep_coef[i], s.log_qc, Fp{GEN}, true, &pq});
+            if (!s.lookups.empty()) ej.push_back({&perm_coef[i], s.log_qc, Fp{GEN}, true, &rq});
+            evaluate_strips(ej);
+        } else {
+            mq = on_qdomain(traces[i]);
+            if (s.prep_w) pq = on_qdomain(prep[i]);
+            if (!s.lookups.empty()) rq = on_qdomain(perm[i]);
+        }
+        lap("    qdomain evals");
         std::vector<Ext> Q(NQ);
         Fp wq = two_adic_gen(lq);
         uint32_t aux = s.aux_w();
+        if (FF.ok) {
+            // Same values as the plain loop below. x_r = GEN * wq^r runs along a chunk; x_r^n = GEN^n * (wq^n)^r takes only qc
+            // values (wq^n has order qc), so the vanishing polynomial and its inverse are tabulated; the two selector
+            // denominators of a chunk share one inversion; the interpreter's register files are per thread, not per row.
+            const Fp ginv = finv(two_adic_gen(s.log_h));
+            const Fp gn = fpow(Fp{GEN}, n), wqn = fpow(wq, n);
+            std::vector<Fp> zval(qc), zinv(qc);
+            for (size_t c = 0; c < qc; c++) {
+                zval[c] = gn * fpow(wqn, c) - Fp{1};
+                zinv[c] = finv(zval[c]);
+            }
+            const size_t CH = 256;
+#pragma omp parallel
+            {
+                ProgramScratch<Fp> sc;
+                std::vector<Ext> pl(aux), pn(aux), cons(s.cons.n_constraints);
+                std::vector<Fp> xs(CH), den(2 * CH), tmp(2 * CH);
+#pragma omp for schedule(dynamic)
+                for (size_t r0 = 0; r0 < NQ; r0 += CH) {
+                    const size_t cnt = std::min(CH, NQ - r0);
+                    Fp x = Fp{GEN} * fpow(wq, r0);
+                    for (size_t j = 0; j < cnt; j++) {
+                        xs[j] = x;
+                        den[2 * j] = x - Fp{1};
+                        den[2 * j + 1] = x - ginv;
+                        x = x * wq;
+                    }
+                    batch_finv(den.data(), 2 * cnt, tmp.data());
+                    for (size_t j = 0; j < cnt; j++) {
+                        const size_t r = r0 + j, rn = (r + qc) % NQ;
+                        const Fp z = zval[r % qc];
+                        RowCtx<Fp> rc;
+                        rc.main[0] = &mq.d[r * mq.w];
+                        rc.main[1] = &mq.d[rn * mq.w];
+                        if (s.prep_w) {
+                            rc.prep[0] = &pq.d[r * pq.w];
+                            rc.prep[1] = &pq.d[rn * pq.w];
+                        }
+                        for (uint32_t c = 0; c < aux; c++)
+                            for (int k = 0; k < 4; k++) {
+                                pl[c].c[k] = rq.at(r, 4 * c + k);
+                                pn[c].c[k] = rq.at(rn, 4 * c + k);
+                            }
+                        rc.perm[0] = pl.data();
+                        rc.perm[1] = pn.data();
+                        rc.pub = pubs[i].data();
+                        rc.sel[0] = z * den[2 * j];
+                        rc.sel[1] = z * den[2 * j + 1];
+                        rc.sel[2] = xs[j] - ginv;
+                        rc.chal = chal[i].data();
+                        rc.pval = &terminals[i];
+                        cons.assign(s.cons.n_constraints, ext_zero());
+                        run_program<Fp>(s.cons, rc, &cons, nullptr, &sc);
+                        Q[r] = fold_constraints(cons, alpha) * zinv[r % qc];
+                    }
+                }
+            }
+        } else
 #pragma omp parallel for
         for (size_t r = 0; r < NQ; r++) {
             size_t rn = (r + qc) % NQ;
@@ -1392,17 +1587,34 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
             Q[r] = fold_constraints(cons, alpha) * sel.inv_vanishing;
         }
         // split_evals: chunk c row r = Q[r*qc + c]; chunk domain shift = GEN * wq^c
+        lap("    constraint rows");
+        qchunk[i].resize(qc);
+        qchunk_lde[i].resize(qc);
+        qchunk_coef[i].resize(qc);
         for (size_t c = 0; c < qc; c++) {
-            Mat m;
+            Mat& m = qchunk[i][c];
             m.h = n;
             m.w = 4;
             m.d.resize(n * 4);
             for (size_t r = 0; r < n; r++)
                 for (int k = 0; k < 4; k++) m.at(r, k) = Q[r * qc + c].c[k];
-            qchunk_lde[i].push_back(coset_lde(m, lb, Fp{GEN} * fpow(wq, c)));
-            qchunk[i].push_back(m);
+            if (!FF.ok) qchunk_lde[i][c] = coset_lde(m, lb, Fp{GEN} * fpow(wq, c));
         }
     }
+    if (FF.ok) {   // the chunk LDEs of every instance in one batch
+        std::vector<InterpJob> ij;
+        std::vector<EvalJob> ej;
+        for (size_t i = 0; i < n_inst; i++) {
+            Fp wq = two_adic_gen(cm.insts[i].log_h + cm.insts[i].log_qc);
+            for (size_t c = 0; c < qchunk[i].size(); c++) {
+                ij.push_back({&qchunk[i][c], Fp{GEN} * fpow(wq, c), &qchunk_coef[i][c]});
+                ej.push_back({&qchunk_coef[i][c], lb, Fp{GEN}, false, &qchunk_lde[i][c]});
+            }
+        }
+        interpolate_strips(ij);
+        evaluate_strips(ej);
+    }
+    lap("  quotient values + lde");
     std::vector<const Mat*> qptrs;
     for (size_t i = 0; i < n_inst; i++)
         for (auto& m : qchunk_lde[i]) qptrs.push_back(&m);
@@ -1423,9 +1635,30 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
         return out;
     };
     std::vector<OpenedInst> ov(n_inst);
+    ExtPowers zeta_pw;
+    if (FF.ok) {
+        size_t nmax = 1;
+        for (auto& s : cm.insts) nmax = std::max(nmax, (size_t)1 << s.log_h);
+        zeta_pw = ext_powers(zeta, nmax);
+    }
     for (size_t i = 0; i < n_inst; i++) {
         const Inst& s = cm.insts[i];
         Ext zn = zeta * two_adic_gen(s.log_h);
+        if (FF.ok) {   // sum_k c_k z^k on the stored coefficients, powers of z tabulated once per point
+            ExtPowers zn_pw = ext_powers(zn, (size_t)1 << s.log_h);
+            ov[i].main_local = eval_strips_at(main_coef[i], zeta_pw);
+            if (s.uses_next) ov[i].main_next = eval_strips_at(main_coef[i], zn_pw);
+            if (s.prep_w) {
+                ov[i].prep_local = eval_strips_at(prep_coef[i], zeta_pw);
+                ov[i].prep_next = eval_strips_at(prep_coef[i], zn_pw);
+            }
+            if (!s.lookups.empty()) {
+                ov[i].perm_local = eval_strips_at(perm_coef[i], zeta_pw);
+                ov[i].perm_next = eval_strips_at(perm_coef[i], zn_pw);
+            }
+            for (size_t c = 0; c < qchunk[i].size(); c++) ov[i].qchunks.push_back(eval_strips_at(qchunk_coef[i][c], zeta_pw));
+            continue;
+        }
         ov[i].main_local = eval_cols(traces[i], Fp{1}, zeta);
         if (s.uses_next) ov[i].main_next = eval_cols(traces[i], Fp{1}, zn);
         if (s.prep_w) {
@@ -1451,6 +1684,32 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
     if (cm.has_perm) trees.push_back(&perm_tree);
     std::map<uint32_t, std::vector<Ext>, std::greater<uint32_t>> ro;
     std::map<uint32_t, Ext> apow;
+    struct InvDen {
+        uint32_t log_h;
+        Ext point;
+        std::vector<Ext> inv;   // 1 / (point - x) at every (bit-reversed) position of the height-2^log_h LDE domain
+    };
+    std::deque<InvDen> inv_cache;
+    auto inv_den = [&](uint32_t log_h, const Ext& pt) -> const std::vector<Ext>& {
+        for (auto& e : inv_cache)
+            if (e.log_h == log_h && e.point == pt) return e.inv;
+        inv_cache.push_back({log_h, pt, {}});
+        std::vector<Ext>& v = inv_cache.back().inv;
+        const size_t N = (size_t)1 << log_h, CH = 1024;
+        v.resize(N);
+        const Fp g = two_adic_gen(log_h);
+#pragma omp parallel for
+        for (size_t k0 = 0; k0 < N; k0 += CH) {
+            Fp x = Fp{GEN} * fpow(g, k0);
+            for (size_t k = k0; k < std::min(N, k0 + CH); k++) {
+                v[bitrev((uint32_t)k, log_h)] = pt - x;
+                x = x * g;
+            }
+        }
+#pragma omp parallel for
+        for (size_t k0 = 0; k0 < N; k0 += CH) batch_einv(v.data() + k0, std::min(CH, N - k0));
+        return v;
+    };
     for (size_t ri = 0; ri < rounds.size(); ri++) {
         for (size_t mi = 0; mi < rounds[ri].size(); mi++) {
             const MatOpen& mo = rounds[ri][mi];
@@ -1479,6 +1738,18 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
                 Ext t = ext_zero();
                 for (size_t c = 0; c < lde.w; c++) t = t + pw[c] * mo.values[pi][c];
                 cp[pi] = t;
+            }
+            if (FF.ok) {   // 1 / (z - x) once per (height, point) instead of once per matrix, the inversions batched
+                std::vector<const std::vector<Ext>*> inv(mo.points.size());
+                for (size_t pi = 0; pi < mo.points.size(); pi++) inv[pi] = &inv_den(mo.log_h, mo.points[pi]);
+#pragma omp parallel for
+                for (size_t sidx = 0; sidx < N; sidx++) {
+                    Ext row = ext_zero();
+                    for (size_t c = 0; c < lde.w; c++) row = row + pw[c] * lde.at(sidx, c);
+                    for (size_t pi = 0; pi < mo.points.size(); pi++)
+                        acc[sidx] = acc[sidx] + ap0[pi] * (cp[pi] - row) * (*inv[pi])[sidx];
+                }
+                continue;
             }
 #pragma omp parallel for
             for (size_t sidx = 0; sidx < N; sidx++) {
@@ -1838,6 +2109,7 @@ int orc_init(const p3r_field_desc* field, const p3r_poseidon2_consts* p2, const 
         FRI = *fri;
         CAP_HEIGHT = fri->cap_height;
         p2x8_init();
+        ff_init();
         g_init = true;
         return 0;
     } catch (std::exception& e) {
@@ -1856,6 +2128,16 @@ int orc_init(const p3r_field_desc* field, const p3r_poseidon2_consts* p2, const 
         return 1;                                        \
     }
 
+// The CPU-arm fast routes (fast_paths.inc) on / off; returns 1 when they are in effect afterwards (0: off, or no AVX2).
+// ORACLE_SIMPLE=1 in the environment has the effect of orc_set_fast_paths(0) at every orc_init.
+int orc_set_fast_paths(int on) {
+    ff_init();
+    if (!on) {
+        FF.ok = false;
+        GRIND_PARALLEL = false;
+    }
+    return FF.ok ? 1 : 0;
+}
 int orc_set_uni_stark(int on) {
     UNI_STARK = on != 0;
     return 0;
@@ -1901,6 +2183,24 @@ int orc_coset_lde(const p3r_matrix_u32* in, uint32_t log_blowup, uint32_t* out) 
         Mat m = mat_from_abi(*in);
         Mat o = coset_lde(m, log_blowup, Fp{1});
         for (size_t i = 0; i < o.d.size(); i++) out[i] = to_monty(o.d[i]);
+    })
+}
+
+// The same LDE through the strip route of fast_paths.inc (fails where that route does not exist): lets the tests compare the
+// two on matrices of any width, and the quotient-domain flavour (natural row order, log_ext extra bits) as well.
+int orc_coset_lde_strips(const p3r_matrix_u32* in, uint32_t log_ext, int natural, uint32_t* out) {
+    ORC_GUARD({
+        ff_init();
+        if (!FF.ok) throw std::runtime_error("oracle: strip route unavailable (no AVX2 or ORACLE_SIMPLE)");
+#if defined(__x86_64__)
+        Mat m = mat_from_abi(*in), o;
+        Strips coef;
+        std::vector<InterpJob> ij{{&m, Fp{1}, &coef}};
+        interpolate_strips(ij);
+        std::vector<EvalJob> ej{{&coef, log_ext, Fp{GEN}, natural != 0, &o}};
+        evaluate_strips(ej);
+        for (size_t i = 0; i < o.d.size(); i++) out[i] = to_monty(o.d[i]);
+#endif
     })
 }
 

@@ -46,6 +46,11 @@ class Oracle:
                              int(conv.get("logup_descending", 0)))
         self._check(self.lib.orc_set_conventions(C.byref(c)))
 
+    def set_fast_paths(self, on: bool) -> bool:
+        """prove() through the strip-wise AVX2 / batched-inverse routes of fast_paths.inc (default where the CPU has AVX2)
+        or through the plain per-column routines. Returns whether the fast routes are in effect. Same proofs either way."""
+        return bool(self.lib.orc_set_fast_paths(int(bool(on))))
+
     def set_uni_stark(self, on: bool):
         self._check(self.lib.orc_set_uni_stark(int(bool(on))))
 
@@ -75,6 +80,15 @@ class Oracle:
         mm = m.matrix(mat_canonical)
         out = np.zeros((mat_canonical.shape[0] << log_blowup, mat_canonical.shape[1]), dtype=np.uint32)
         self._check(self.lib.orc_coset_lde(C.byref(mm), log_blowup, abi.as_u32p(out)))
+        return self.field.from_monty(out)
+
+    def coset_lde_strips(self, mat_canonical: np.ndarray, log_ext: int, natural: bool = False) -> np.ndarray:
+        """coset_lde through the eight-column strip route (fast_paths.inc); natural=True: rows in natural order (the
+        quotient-domain flavour). Raises where the route does not exist (no AVX2)."""
+        m = abi.Marshal(self.field)
+        mm = m.matrix(mat_canonical)
+        out = np.zeros((mat_canonical.shape[0] << log_ext, mat_canonical.shape[1]), dtype=np.uint32)
+        self._check(self.lib.orc_coset_lde_strips(C.byref(mm), log_ext, int(natural), abi.as_u32p(out)))
         return self.field.from_monty(out)
 
     def mmcs_commit(self, mats_canonical) -> np.ndarray:
