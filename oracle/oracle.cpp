@@ -467,7 +467,7 @@ std::vector<Fp> concat_rows(const std::vector<const Mat*>& ms, size_t row) {
 struct P2X8Consts {
     uint32_t ext_rc[8 * 16], int_rc[32], diag[16];   // Montgomery form
     uint32_t p = 0, mu_neg = 0, r2 = 0, rp = 0, sbox = 0;
-    bool ok = false;
+    bool ok = false, ok16 = false;   // ok16: the AVX-512 sixteen-lane routine exists here and passed its probe
 } P2X8;
 #define P2X8_BODY                                                                                         \
     const uint32_t P_ = k.p, MU = k.mu_neg;                                                               \
@@ -569,14 +569,72 @@ __attribute__((target("avx2"), optimize("O3"))) void permute_x8_avx2(uint32_t (*
         if (r == 4)
             for (uint32_t q = 0; q < k.rp; q++) {
                 v[0] = x8_sbox(x8_add(v[0], _mm256_set1_epi32((int)k.int_rc[q]), p), p, mu, cube);
-                __m256i sum = v[0];
-                for (int i = 1; i < 16; i++) sum = x8_add(sum, v[i], p);
+                __m256i s01 = x8_add(v[0], v[1], p), s23 = x8_add(v[2], v[3], p), s45 = x8_add(v[4], v[5], p),
+                        s67 = x8_add(v[6], v[7], p), s89 = x8_add(v[8], v[9], p), sab = x8_add(v[10], v[11], p),
+                        scd = x8_add(v[12], v[13], p), sef = x8_add(v[14], v[15], p);
+                __m256i sum = x8_add(x8_add(x8_add(s01, s23, p), x8_add(s45, s67, p), p),
+                                     x8_add(x8_add(s89, sab, p), x8_add(scd, sef, p), p), p);
                 for (int i = 0; i < 16; i++) v[i] = x8_add(sum, x8_mul(_mm256_set1_epi32((int)k.diag[i]), v[i], p, mu), p);
             }
         for (int i = 0; i < 16; i++) v[i] = x8_sbox(x8_add(v[i], _mm256_set1_epi32((int)k.ext_rc[16 * r + i]), p), p, mu, cube);
         x8_external(v, p);
     }
     for (int i = 0; i < 16; i++) _mm256_storeu_si256((__m256i*)s[i], v[i]);
+}
+// AVX-512: sixteen permutations per call, the whole state and the constants in the 32 vector registers.
+#define X16_FN __attribute__((target("avx512f"), always_inline)) inline
+X16_FN __m512i x16_add(__m512i a, __m512i b, __m512i p) {
+    __m512i s = _mm512_add_epi32(a, b);
+    return _mm512_min_epu32(s, _mm512_sub_epi32(s, p));
+}
+X16_FN __m512i x16_mul(__m512i a, __m512i b, __m512i p, __m512i mu) {
+    __m512i te = _mm512_mul_epu32(a, b);
+    __m512i to = _mm512_mul_epu32(_mm512_srli_epi64(a, 32), _mm512_srli_epi64(b, 32));
+    __m512i ue = _mm512_add_epi64(te, _mm512_mul_epu32(_mm512_mul_epu32(te, mu), p));
+    __m512i uo = _mm512_add_epi64(to, _mm512_mul_epu32(_mm512_mul_epu32(to, mu), p));
+    __m512i r = _mm512_mask_blend_epi32((__mmask16)0xAAAA, _mm512_srli_epi64(ue, 32), uo);
+    return _mm512_min_epu32(r, _mm512_sub_epi32(r, p));
+}
+X16_FN __m512i x16_sbox(__m512i x, __m512i p, __m512i mu, bool cube) {
+    __m512i x2 = x16_mul(x, x, p, mu), x3 = x16_mul(x2, x, p, mu);
+    if (cube) return x3;
+    return x16_mul(x16_mul(x2, x2, p, mu), x3, p, mu);
+}
+X16_FN void x16_external(__m512i* v, __m512i p) {
+    for (int q = 0; q < 4; q++) {
+        __m512i a = v[4 * q], b = v[4 * q + 1], c = v[4 * q + 2], d = v[4 * q + 3];
+        __m512i t = x16_add(x16_add(a, b, p), x16_add(c, d, p), p);
+        v[4 * q] = x16_add(x16_add(t, a, p), x16_add(b, b, p), p);
+        v[4 * q + 1] = x16_add(x16_add(t, b, p), x16_add(c, c, p), p);
+        v[4 * q + 2] = x16_add(x16_add(t, c, p), x16_add(d, d, p), p);
+        v[4 * q + 3] = x16_add(x16_add(t, d, p), x16_add(a, a, p), p);
+    }
+    for (int j = 0; j < 4; j++) {
+        __m512i sum = x16_add(x16_add(v[j], v[4 + j], p), x16_add(v[8 + j], v[12 + j], p), p);
+        for (int q = 0; q < 4; q++) v[4 * q + j] = x16_add(v[4 * q + j], sum, p);
+    }
+}
+__attribute__((target("avx512f"), optimize("O3"))) void permute_x16_avx512(uint32_t (*s)[16], const P2X8Consts& k) {
+    const __m512i p = _mm512_set1_epi32((int)k.p), mu = _mm512_set1_epi32((int)k.mu_neg);
+    const bool cube = k.sbox == 3;
+    __m512i v[16];
+    for (int i = 0; i < 16; i++) v[i] = _mm512_loadu_si512((const void*)s[i]);
+    x16_external(v, p);
+    for (uint32_t r = 0; r < 8; r++) {
+        if (r == 4)
+            for (uint32_t q = 0; q < k.rp; q++) {
+                v[0] = x16_sbox(x16_add(v[0], _mm512_set1_epi32((int)k.int_rc[q]), p), p, mu, cube);
+                __m512i s01 = x16_add(v[0], v[1], p), s23 = x16_add(v[2], v[3], p), s45 = x16_add(v[4], v[5], p),
+                        s67 = x16_add(v[6], v[7], p), s89 = x16_add(v[8], v[9], p), sab = x16_add(v[10], v[11], p),
+                        scd = x16_add(v[12], v[13], p), sef = x16_add(v[14], v[15], p);
+                __m512i sum = x16_add(x16_add(x16_add(s01, s23, p), x16_add(s45, s67, p), p),
+                                      x16_add(x16_add(s89, sab, p), x16_add(scd, sef, p), p), p);
+                for (int i = 0; i < 16; i++) v[i] = x16_add(sum, x16_mul(_mm512_set1_epi32((int)k.diag[i]), v[i], p, mu), p);
+            }
+        for (int i = 0; i < 16; i++) v[i] = x16_sbox(x16_add(v[i], _mm512_set1_epi32((int)k.ext_rc[16 * r + i]), p), p, mu, cube);
+        x16_external(v, p);
+    }
+    for (int i = 0; i < 16; i++) _mm512_storeu_si512((void*)s[i], v[i]);
 }
 #endif
 __attribute__((optimize("O3"))) void permute_x8_plain(uint32_t (*s)[8], const P2X8Consts& k) { P2X8_BODY }
@@ -626,34 +684,67 @@ void p2x8_init() {
         for (int i = 0; i < 16; i++) ok = ok && x8_from_monty(s[i][l]) == ref[l][i];
     }
     P2X8.ok = ok;
+#if defined(__x86_64__)
+    if (ok && __builtin_cpu_supports("avx512f") && !getenv("ORACLE_NO_AVX512")) {
+        uint32_t s16[16][16];
+        Fp ref16[16][16];
+        for (int l = 0; l < 16; l++)
+            for (int i = 0; i < 16; i++) {
+                ref16[l][i] = mk((uint64_t)(l * 16 + i + 7) * 0x85EBCA6Bull);
+                s16[i][l] = x8_to_monty(ref16[l][i]);
+            }
+        permute_x16_avx512(s16, P2X8);
+        bool ok16 = true;
+        for (int l = 0; l < 16; l++) {
+            poseidon2_permute(ref16[l]);
+            for (int i = 0; i < 16; i++) ok16 = ok16 && x8_from_monty(s16[i][l]) == ref16[l][i];
+        }
+        P2X8.ok16 = ok16;
+    }
+#endif
 }
-// Sponge digests of rows r0 .. r0+7 of the concatenation of `ms` (all of one height), and eight 2-to-1 compressions.
-void sponge_hash_x8(const std::vector<const Mat*>& ms, size_t r0, Digest* out) {
-    uint32_t s[16][8];
+// Sponge digests of rows r0 .. r0+L-1 of the concatenation of `ms` (all of one height), and L 2-to-1 compressions; L = 8
+// (AVX2 or plain lane loops) or 16 (AVX-512).
+template <int L>
+inline void permute_lanes(uint32_t (*s)[L]);
+template <>
+inline void permute_lanes<8>(uint32_t (*s)[8]) { permute_x8(s, P2X8); }
+#if defined(__x86_64__)
+template <>
+inline void permute_lanes<16>(uint32_t (*s)[16]) { permute_x16_avx512(s, P2X8); }
+#endif
+template <int L>
+void sponge_hash_lanes(const std::vector<const Mat*>& ms, size_t r0, Digest* out) {
+    uint32_t s[16][L];
     std::memset(s, 0, sizeof s);
     int k = 0;
     for (auto* m : ms)
         for (size_t c = 0; c < m->w; c++) {
-            for (int l = 0; l < 8; l++) s[k][l] = x8_to_monty(m->at(r0 + l, c));
+            for (int l = 0; l < L; l++) s[k][l] = x8_to_monty(m->at(r0 + l, c));
             if (++k == 8) {
-                permute_x8(s, P2X8);
+                permute_lanes<L>(s);
                 k = 0;
             }
         }
-    if (k) permute_x8(s, P2X8);
-    for (int l = 0; l < 8; l++)
+    if (k) permute_lanes<L>(s);
+    for (int l = 0; l < L; l++)
         for (int i = 0; i < 8; i++) out[l].d[i] = x8_from_monty(s[i][l]);
 }
-void compress2_x8(const Digest* left, size_t lstride, const Digest* right, size_t rstride, Digest* out) {
-    uint32_t s[16][8];
-    for (int l = 0; l < 8; l++)
+template <int L>
+void compress2_lanes(const Digest* left, size_t lstride, const Digest* right, size_t rstride, Digest* out) {
+    uint32_t s[16][L];
+    for (int l = 0; l < L; l++)
         for (int i = 0; i < 8; i++) {
             s[i][l] = x8_to_monty(left[l * lstride].d[i]);
             s[8 + i][l] = x8_to_monty(right[l * rstride].d[i]);
         }
-    permute_x8(s, P2X8);
-    for (int l = 0; l < 8; l++)
+    permute_lanes<L>(s);
+    for (int l = 0; l < L; l++)
         for (int i = 0; i < 8; i++) out[l].d[i] = x8_from_monty(s[i][l]);
+}
+void sponge_hash_x8(const std::vector<const Mat*>& ms, size_t r0, Digest* out) { sponge_hash_lanes<8>(ms, r0, out); }
+void compress2_x8(const Digest* left, size_t lstride, const Digest* right, size_t rstride, Digest* out) {
+    compress2_lanes<8>(left, lstride, right, rstride, out);
 }
 
 bool GRIND_PARALLEL = false;   // Challenger::grind; set with the other CPU-arm fast paths (ff_init)
@@ -674,8 +765,14 @@ MerkleTree mmcs_commit(const std::vector<const Mat*>& mats) {
     };
     auto tallest = at_height(max_h);
     std::vector<Digest> layer(max_h);
-    const bool x8 = P2X8.ok && !HASH_W_SET;   // eight rows / nodes per call (width-16 sponge only)
-    if (x8 && max_h >= 8) {
+    const bool x8 = P2X8.ok && !HASH_W_SET;   // eight (sixteen with AVX-512) rows / nodes per call (width-16 sponge only)
+    const bool x16 = x8 && P2X8.ok16;
+    if (x16 && max_h >= 16) {
+#if defined(__x86_64__)
+#pragma omp parallel for
+        for (size_t r = 0; r < max_h; r += 16) sponge_hash_lanes<16>(tallest, r, &layer[r]);
+#endif
+    } else if (x8 && max_h >= 8) {
 #pragma omp parallel for
         for (size_t r = 0; r < max_h; r += 8) sponge_hash_x8(tallest, r, &layer[r]);
     } else {
@@ -688,7 +785,19 @@ MerkleTree mmcs_commit(const std::vector<const Mat*>& mats) {
         size_t n = prev.size() / 2;
         auto inject = at_height(n);
         std::vector<Digest> next(n);
-        if (x8 && n >= 8) {
+        if (x16 && n >= 16) {
+#if defined(__x86_64__)
+#pragma omp parallel for
+            for (size_t i = 0; i < n; i += 16) {
+                compress2_lanes<16>(&prev[2 * i], 2, &prev[2 * i + 1], 2, &next[i]);
+                if (!inject.empty()) {
+                    Digest inj[16];
+                    sponge_hash_lanes<16>(inject, i, inj);
+                    compress2_lanes<16>(&next[i], 1, inj, 1, &next[i]);
+                }
+            }
+#endif
+        } else if (x8 && n >= 8) {
 #pragma omp parallel for
             for (size_t i = 0; i < n; i += 8) {
                 compress2_x8(&prev[2 * i], 2, &prev[2 * i + 1], 2, &next[i]);
@@ -956,6 +1065,8 @@ Ext fold_constraints(const std::vector<Ext>& cons, const Ext& alpha) {
     return acc;
 }
 
+#include "fast_interp.inc"   // the same interpreter over eight rows per instruction (AVX2), for prove()'s quotient loop
+
 // ------------------------------------------------------------------------------------------------
 // LogUp challenges layout (recursion/src/verifier/batch_stark.rs:1031-1110): gamma = beta^W with W the
 // widest message over all lookups of all instances; bus_prefix[b] = alpha + (b+1)*gamma; per lookup the
@@ -1000,6 +1111,85 @@ Mat logup_trace(const Inst& s, const Mat& main, const Mat* prep, const Fp* pub, 
     out.w = aux * 4;
     out.d.assign(n * out.w, Fp{0});
     std::vector<Ext> rowsum(n, ext_zero());
+    if (FF.ok) {
+        // Same values as the plain loop below: the powers of beta are tabulated per lookup, the interpreter's register files
+        // are per thread, and the denominators of a chunk of rows are inverted together (batch_einv).
+        uint32_t max_e = 0;
+        for (auto& it : s.inter) max_e = std::max(max_e, CONV.logup_first_power + it.n_elems);
+        std::vector<std::vector<Ext>> bpow(s.lookups.size());
+        for (size_t c = 0; c < s.lookups.size(); c++) {
+            bpow[c].resize(max_e + 1);
+            Ext run = ext_one();
+            for (uint32_t e = 0; e <= max_e; e++) {
+                bpow[c][e] = run;
+                run = run * chal[2 * c + 1];
+            }
+        }
+        const size_t CH = 64;
+#pragma omp parallel
+        {
+            ProgramScratch<Fp> sc;
+            std::vector<Fp> outs(CH * (size_t)s.lk.n_outputs);
+            std::vector<Ext> dens;
+#pragma omp for schedule(dynamic)
+            for (size_t r0 = 0; r0 < n; r0 += CH) {
+                const size_t cnt = std::min(CH, n - r0);
+                dens.clear();
+                std::vector<Fp> row_outs(s.lk.n_outputs);
+                for (size_t j = 0; j < cnt; j++) {
+                    const size_t r = r0 + j;
+                    RowCtx<Fp> rc;
+                    rc.main[0] = &main.d[r * main.w];
+                    rc.main[1] = &main.d[((r + 1) % n) * main.w];
+                    if (prep) {
+                        rc.prep[0] = &prep->d[r * prep->w];
+                        rc.prep[1] = &prep->d[((r + 1) % n) * prep->w];
+                    }
+                    rc.pub = pub;
+                    rc.sel[0] = Fp{r == 0};
+                    rc.sel[1] = Fp{r == n - 1};
+                    rc.sel[2] = Fp{r != n - 1};
+                    std::fill(row_outs.begin(), row_outs.end(), Fp{0});
+                    run_program<Fp>(s.lk, rc, nullptr, &row_outs, &sc);
+                    Fp* o = &outs[j * s.lk.n_outputs];
+                    std::copy(row_outs.begin(), row_outs.end(), o);
+                    for (size_t c = 0; c < s.lookups.size(); c++) {
+                        const auto& l = s.lookups[c];
+                        for (uint32_t q = 0; q < l.n_interactions; q++) {
+                            const auto& it = s.inter[l.first_interaction + q];
+                            if (o[it.mult_out].v == 0) continue;
+                            Ext den = chal[2 * c];
+                            for (uint32_t k = 0; k < it.n_elems; k++) {
+                                const uint32_t e = CONV.logup_first_power + (CONV.logup_descending ? it.n_elems - 1 - k : k);
+                                const Ext term = bpow[c][e] * o[it.elem_out_first + k];
+                                den = CONV.logup_negate ? den - term : den + term;
+                            }
+                            dens.push_back(den);
+                        }
+                    }
+                }
+                batch_einv(dens.data(), dens.size());
+                size_t at = 0;
+                for (size_t j = 0; j < cnt; j++) {
+                    const size_t r = r0 + j;
+                    const Fp* o = &outs[j * s.lk.n_outputs];
+                    Ext total = ext_zero();
+                    for (size_t c = 0; c < s.lookups.size(); c++) {
+                        const auto& l = s.lookups[c];
+                        Ext frac = ext_zero();
+                        for (uint32_t q = 0; q < l.n_interactions; q++) {
+                            const auto& it = s.inter[l.first_interaction + q];
+                            Fp m = o[it.mult_out];
+                            if (m.v != 0) frac = frac + dens[at++] * m;
+                        }
+                        for (int k = 0; k < 4; k++) out.at(r, 4 * (c + 1) + k) = frac.c[k];
+                        total = total + frac;
+                    }
+                    rowsum[r] = total;
+                }
+            }
+        }
+    } else
 #pragma omp parallel for
     for (size_t r = 0; r < n; r++) {
         RowCtx<Fp> rc;
@@ -1510,9 +1700,13 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
                 zinv[c] = finv(zval[c]);
             }
             const size_t CH = 256;
+            const bool rows8 = NQ % 8 == 0 && NQ * std::max<size_t>({mq.w, pq.w, rq.w}) < ((size_t)1 << 31);
+            std::vector<uint32_t> zinv_m(qc);
+            for (size_t c = 0; c < qc; c++) zinv_m[c] = ff_to(zinv[c]);
 #pragma omp parallel
             {
                 ProgramScratch<Fp> sc;
+                Scratch8 sc8;
                 std::vector<Ext> pl(aux), pn(aux), cons(s.cons.n_constraints);
                 std::vector<Fp> xs(CH), den(2 * CH), tmp(2 * CH);
 #pragma omp for schedule(dynamic)
@@ -1526,6 +1720,42 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
                         x = x * wq;
                     }
                     batch_finv(den.data(), 2 * cnt, tmp.data());
+                    if (rows8) {   // eight rows per interpreter instruction (fast_interp.inc)
+                        for (size_t j = 0; j < cnt; j += 8) {
+                            uint32_t rl[8], rnx[8], s0[8], s1[8], s2[8], iv[8];
+                            for (size_t l = 0; l < 8; l++) {
+                                const size_t r = r0 + j + l;
+                                const Fp z = zval[r % qc];
+                                rl[l] = (uint32_t)r;
+                                rnx[l] = (uint32_t)((r + qc) % NQ);
+                                s0[l] = (z * den[2 * (j + l)]).v;
+                                s1[l] = (z * den[2 * (j + l) + 1]).v;
+                                s2[l] = (xs[j + l] - ginv).v;
+                                iv[l] = zinv_m[r % qc];
+                            }
+                            Row8 rc;
+                            rc.main = &mq.d[0].v;
+                            rc.main_w = (int)mq.w;
+                            if (s.prep_w) {
+                                rc.prep = &pq.d[0].v;
+                                rc.prep_w = (int)pq.w;
+                            }
+                            if (aux) {
+                                rc.perm = &rq.d[0].v;
+                                rc.perm_w = (int)rq.w;
+                            }
+                            std::memcpy(rc.row[0], rl, 32);
+                            std::memcpy(rc.row[1], rnx, 32);
+                            std::memcpy(rc.sel[0], s0, 32);
+                            std::memcpy(rc.sel[1], s1, 32);
+                            std::memcpy(rc.sel[2], s2, 32);
+                            rc.pub = pubs[i].data();
+                            rc.chal = chal[i].data();
+                            rc.pval = &terminals[i];
+                            quotient_rows_x8(s.cons, rc, sc8, alpha, iv, &Q[r0 + j]);
+                        }
+                        continue;
+                    }
                     for (size_t j = 0; j < cnt; j++) {
                         const size_t r = r0 + j, rn = (r + qc) % NQ;
                         const Fp z = zval[r % qc];
@@ -1742,10 +1972,15 @@ ProveOut prove(const Common& cm, const std::vector<Mat>& prep, const std::vector
             if (FF.ok) {   // 1 / (z - x) once per (height, point) instead of once per matrix, the inversions batched
                 std::vector<const std::vector<Ext>*> inv(mo.points.size());
                 for (size_t pi = 0; pi < mo.points.size(); pi++) inv[pi] = &inv_den(mo.log_h, mo.points[pi]);
+                std::vector<uint32_t> pwm[4];
+                for (int j = 0; j < 4; j++) {
+                    pwm[j].resize(lde.w);
+                    for (size_t c = 0; c < lde.w; c++) pwm[j][c] = ff_to(pw[c].c[j]);
+                }
+                const uint32_t* const pwp[4] = {pwm[0].data(), pwm[1].data(), pwm[2].data(), pwm[3].data()};
 #pragma omp parallel for
                 for (size_t sidx = 0; sidx < N; sidx++) {
-                    Ext row = ext_zero();
-                    for (size_t c = 0; c < lde.w; c++) row = row + pw[c] * lde.at(sidx, c);
+                    Ext row = ff_row_dot(&lde.d[sidx * lde.w].v, lde.w, pwp);
                     for (size_t pi = 0; pi < mo.points.size(); pi++)
                         acc[sidx] = acc[sidx] + ap0[pi] * (cp[pi] - row) * (*inv[pi])[sidx];
                 }
