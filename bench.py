@@ -157,6 +157,8 @@ def time_oracle(field, fri, L, steps, warmup, budget_s):
     so (never an extrapolation in size). Returns (seconds per proof, steps run, warm-ups run)."""
     from common import make_oracle
     orc = make_oracle(field, fri)
+    orc.set_threads(len(os.sched_getaffinity(0)))   # OMP_NUM_THREADS may have been read (as 1, under torchrun) long ago
+    orc.set_fast_paths(True)
     run = orc.prepare(L.insts, L.preps, L.traces, L.pubs)
     t0 = time.perf_counter()
     run()
@@ -175,8 +177,10 @@ def time_oracle(field, fri, L, steps, warmup, budget_s):
 def run_reference(args):
     """CPU arm: the oracle port (kind "port": the Rust reference cannot be built in this image — no cargo / rustc) with all
     host threads, on the full-size aggregation-node layer, one proof per step. The published Rust number (other hardware) is
-    quoted beside it; the oracle is a plain restatement (canonical residues, textbook NTT, Horner openings), not a packed-field
-    rayon prover, so the driver's ratio to this line is an upper bound on the speed-up over the real reference."""
+    quoted beside it. The oracle runs its CPU-arm routes here (oracle/fast_paths.inc: AVX2 / AVX-512 Poseidon2, eight-column
+    strips interpolated once and shared by the LDE, the quotient domain and the openings, an eight-row constraint interpreter,
+    batched inversions, OpenMP over all host cores) — the layout of a packed-field CPU prover, still a port and not the tuned
+    Rust code, so the driver's ratio to this line remains an upper bound on the speed-up over the real reference."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -191,7 +195,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": args.gpus, "steps": n,
         "warmup": w, "ms_per_step": dt * 1e3, "ms_per_layer": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u32 (31-bit field, degree-4 extension; canonical residues on the CPU)", "data": "synthetic",
+        "vs_baseline": None, "dtype": "u32 (31-bit field, degree-4 extension; Montgomery AVX2/AVX-512 lanes on the CPU)", "data": "synthetic",
         "steps_requested": args.steps, "same_steps": n == args.steps, "same_config": args.scale == 1.0, "extrapolated": False,
         "config": {"workload": f"one full-size aggregation-node layer proof per step ({args.field}, scale {args.scale}): the CPU arm "
                                "is charged only the level >= 2 node proofs; the leaf and level-1 proofs the GPU arm also proves "

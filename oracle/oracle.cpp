@@ -14,8 +14,14 @@
 // semantics, each restated from the in-tree recursive verifier cited at every function below; (c) the AIR
 // column-count goldens of circuit-prover/src/air/shape_golden.rs:33-68 (tests/test_airs.py).
 //
-// Arithmetic here is deliberately naive: canonical residues, `%` reduction, textbook NTT, Horner evaluation,
-// so that it shares no code or algorithmic shortcut with the Montgomery/CUDA implementation it checks.
+// Arithmetic in this file is deliberately plain: canonical residues, `%` reduction, textbook NTT, Horner evaluation,
+// one inversion where the formula has one, so that it reads like the protocol and shares no code or algorithmic
+// shortcut with the Montgomery/CUDA implementation it checks. Because bench.py also TIMES this library as its CPU arm,
+// prove() has a second route through the same mathematics laid out the way a CPU prover lays it out (fast_paths.inc,
+// fast_interp.inc: eight-column AVX2 strips interpolated once, an eight-row interpreter, batched inversions, AVX2 /
+// AVX-512 Poseidon2 for the commitment loops). The two routes are exact and give the same words
+// (tests/test_oracle_fast_paths.py compares whole proofs); orc_set_fast_paths(0) / ORACLE_SIMPLE=1 selects the plain
+// one, the verifier and the unit-level entry points (orc_coset_lde, orc_poseidon2_permute, ...) are plain only.
 // At the C boundary every field word is Montgomery (R = 2^32) exactly as in include/p3r.h.
 
 #include <algorithm>
@@ -37,6 +43,9 @@
 #include <vector>
 
 #include "../include/p3r.h"
+#if defined(_OPENMP)
+#include <omp.h>
+#endif
 
 namespace {
 
@@ -2363,6 +2372,17 @@ int orc_init(const p3r_field_desc* field, const p3r_poseidon2_consts* p2, const 
         return 1;                                        \
     }
 
+// Number of OpenMP threads of the parallel loops (0: leave as is). OMP_NUM_THREADS is read once, when libgomp is first loaded
+// — under torchrun that is 1 and long before the CPU arm runs — so bench.py sets the count explicitly. Returns the count in
+// effect.
+int orc_set_threads(int n) {
+#if defined(_OPENMP)
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
 // The CPU-arm fast routes (fast_paths.inc) on / off; returns 1 when they are in effect afterwards (0: off, or no AVX2).
 // ORACLE_SIMPLE=1 in the environment has the effect of orc_set_fast_paths(0) at every orc_init.
 int orc_set_fast_paths(int on) {

@@ -46,6 +46,10 @@ class Oracle:
                              int(conv.get("logup_descending", 0)))
         self._check(self.lib.orc_set_conventions(C.byref(c)))
 
+    def set_threads(self, n: int = 0) -> int:
+        """OpenMP threads of the oracle's parallel loops (0: query only). Returns the count in effect."""
+        return int(self.lib.orc_set_threads(int(n)))
+
     def set_fast_paths(self, on: bool) -> bool:
         """prove() through the strip-wise AVX2 / batched-inverse routes of fast_paths.inc (default where the CPU has AVX2)
         or through the plain per-column routines. Returns whether the fast routes are in effect. Same proofs either way."""
