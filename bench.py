@@ -169,9 +169,12 @@ def time_oracle(field, fri, L, steps, warmup, budget_s):
         w_done += 1
     n = max(1, min(steps, int(budget_s / first) - w_done))
     t0 = time.perf_counter()
+    last = None
     for _ in range(n):
-        run()
-    return (time.perf_counter() - t0) / n, n, w_done
+        last = run()
+    dt = (time.perf_counter() - t0) / n
+    time_oracle.last_proof = np.array(last, copy=True)    # bench.py compares the GPU proof of the same inputs with it
+    return dt, n, w_done
 
 
 def run_reference(args):
@@ -548,6 +551,14 @@ def run_ours(args):
             cores = len(os.sched_getaffinity(0))
             os.environ["OMP_NUM_THREADS"] = str(cores)
             dt, n, _ = time_oracle(args.field, fri_params(lib, 6), shapes["node"], 3, 1, args.cpu_baseline_budget_s)
+            # the same inputs through a proving lane (an all-zero patch leaves the resident witness as generated): the
+            # headline-size proof must be the oracle's, word for word — outside every timed region
+            gpu_proof = lanes[0].prove("node", np.zeros(PATCH_WORDS, dtype=np.uint32), False)
+            same = bool(np.array_equal(gpu_proof, time_oracle.last_proof))
+            line["parity"] = {"check": "full-size aggregation-node proof: CUDA path == CPU oracle prover, all "
+                                       f"{int(gpu_proof.size)} words", "ok": same}
+            if not same:
+                raise RuntimeError("bench: the GPU proof of the full-size node layer differs from the oracle's proof")
             line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "proofs/s", "cores": cores, "kind": "port",
                                     "sample": f"{n} full-size aggregation-node layer proofs by oracle/liboracle.so (OpenMP, {cores} "
                                               f"threads), {dt:.2f} s each, marshalling outside the loop, no extrapolation; the "

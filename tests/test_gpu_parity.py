@@ -483,10 +483,11 @@ def test_gpu_poseidon2_table_fill_matches_reference_builder(pair):
 
 def test_full_size_layer_is_accepted_by_the_oracle_verifier():
     """BASELINE.json's headline configuration (the KoalaBear steady-state layer `bench.py` times: ALU 2^15 x 80, Poseidon2
-    2^14 x 166, Public 2^16 x 4, production FRI parameters) is too large for the oracle *prover* inside a test, so parity at
-    this size rests on size-independent properties: the oracle VERIFIER accepts the GPU proof; proving is deterministic;
-    matrices, pinned matrices, device-resident traces and operation lists (tables generated on the device) give the same
-    bytes; the specialised and interpreted paths agree; a flipped word anywhere is rejected."""
+    2^14 x 166, Public 2^16 x 4, production FRI parameters): the oracle VERIFIER accepts the GPU proof; the oracle PROVER's
+    proof of the same inputs is word for word the GPU's (through the oracle's CPU-arm routes, which
+    tests/test_oracle_fast_paths.py ties to its plain ones — the plain prover alone needs ~5 s per proof at this size);
+    proving is deterministic; matrices, pinned matrices, device-resident traces and operation lists (tables generated on the
+    device) give the same bytes; the specialised and interpreted paths agree; a flipped word anywhere is rejected."""
     wl = importlib.import_module("plonky3-recursion_b200.workload")
     ctx = lib.Context("koala-bear", lib.DEFAULT_FRI)
     orc = make_oracle("koala-bear", lib.DEFAULT_FRI)
@@ -497,6 +498,8 @@ def test_full_size_layer_is_accepted_by_the_oracle_verifier():
     prover = lib.BatchStarkProver(ctx)
     proof = prover.prove_all_tables(L.traces, pd, L.pubs)
     orc.verify(L.insts, pd.preprocessed_commitment, L.pubs, proof)
+    if orc.set_fast_paths(True):
+        assert np.array_equal(proof, orc.prove(L.insts, L.preps, L.traces, L.pubs))     # headline size, bit for bit
     assert np.array_equal(proof, prover.prove_all_tables(L.traces, pd, L.pubs))
     tb = lib.TraceBatch(ctx, L.traces, L.pubs).upload(pd)
     assert np.array_equal(proof, prover.prove_resident(tb, pd))
