@@ -65,7 +65,7 @@ def test_gpu_uni_stark_bit_identical(field_name, width, log_n):
 @pytest.mark.gpu
 def test_gpu_keccak_shaped_base_layer_is_accepted_by_the_oracle_verifier():
     """The recursive_keccak base-layer shape: 2 600 columns x 4 096 rows (recursive_keccak.rs:22-24,513-517), example FRI
-    parameters. Too large for the oracle PROVER inside a test; its verifier checks the GPU proof."""
+    parameters: the oracle's verifier accepts the GPU proof and the oracle's prover produces the same words."""
     F = field_mod.get_field("koala-bear")
     orc = make_oracle("koala-bear", lib.DEFAULT_FRI)
     ctx = lib.Context("koala-bear", lib.DEFAULT_FRI)
@@ -77,6 +77,7 @@ def test_gpu_keccak_shaped_base_layer_is_accepted_by_the_oracle_verifier():
         prover = lib.BatchStarkProver(ctx)
         proof = prover.prove_all_tables([t], pd, [pubs])
         orc.verify([inst], None, [pubs], proof)
+        assert np.array_equal(proof, orc.prove([inst], [None], [t], [pubs]))
         bad = proof.copy()
         bad[proof.size // 2] = (int(bad[proof.size // 2]) + 1) % F.p
         with pytest.raises(RuntimeError):
