@@ -628,3 +628,24 @@ def test_work_queue_row_hashing_matches_one_cta_per_rows(pair):
         ctx.set_specialization(1)
     assert np.array_equal(got_queue, want) and np.array_equal(got_cta, want)
 
+
+
+@pytest.mark.gpu
+def test_full_size_babybear_layer_matches_the_oracle_prover():
+    """The headline layer over BabyBear (Poseidon2 table 2^14 x 300, S-box degree 7): GPU proof == oracle prover's proof,
+    all words, and the oracle verifier accepts it."""
+    wl = importlib.import_module("plonky3-recursion_b200.workload")
+    ctx = lib.Context("baby-bear", lib.DEFAULT_FRI)
+    orc = make_oracle("baby-bear", lib.DEFAULT_FRI)
+    if not orc.set_fast_paths(True):
+        ctx.close()
+        pytest.skip("the plain oracle prover needs several seconds per proof at this size")
+    L = wl.synthetic_layer(ctx.field, 1, n_const=1500, n_public=43000, n_alu=60000, n_perms=12000, n_recompose=4000,
+                           min_height=256)
+    assert [s[1:3] for s in L.shapes] == [(2048, 4), (65536, 4), (32768, 80), (16384, 300), (4096, 4)]
+    pd = lib.ProverData.from_airs_and_degrees(ctx, L.insts, L.preps)
+    proof = lib.BatchStarkProver(ctx).prove_all_tables(L.traces, pd, L.pubs)
+    orc.verify(L.insts, pd.preprocessed_commitment, L.pubs, proof)
+    assert np.array_equal(proof, orc.prove(L.insts, L.preps, L.traces, L.pubs))
+    pd.close()
+    ctx.close()
