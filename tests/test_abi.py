@@ -74,3 +74,27 @@ def test_host_hasher_matches_the_oracle_and_the_numpy_restatement(field):
     one = hh.permute(st[3])
     assert one.shape == (1, 16) and np.array_equal(one[0], got[3])
     hh.close()
+
+
+def test_null_handles_are_refused_not_dereferenced():
+    """Every context-taking entry point of the boundary answers a NULL context (or NULL out-pointer) with
+    P3R_ERR_INVALID_ARG — checked here without a GPU, the calls never reach CUDA."""
+    import ctypes as C
+    l = lib.load()
+    INVALID = 1
+    zero = C.c_uint32(0)
+    for name, args in [
+        ("p3r_ctx_set_stream_priority", (None, 1)),
+        ("p3r_ctx_set_uni_stark", (None, 1)),
+        ("p3r_ctx_set_conventions", (None, None)),
+        ("p3r_ctx_set_leaf_hasher", (None, None)),
+        ("p3r_poseidon2_permute_w", (None, None, None, 0)),
+        ("p3r_poseidon2_run_chains", (None, None, None, None)),
+        ("p3r_grind", (None, None, None, 0, 4, C.byref(zero))),
+        ("p3r_traces_write_rows", (None, None, None, 0, 0, 0, None)),
+    ]:
+        fn = getattr(l, name)
+        fn.restype = C.c_int
+        assert fn(*args) == INVALID, name
+    out = C.c_void_p()
+    assert l.p3r_ctx_create(0, None, None, None, C.byref(out)) == INVALID and not out.value
