@@ -17,7 +17,12 @@ BASELINE.json's metric has two halves and one command line serves both, so the l
     pinned memory copied to the device per proof, the proof copied back).
   * `ms_per_layer` = latency of ONE prove_next_layer-shaped proof alone on one GPU (BASELINE's first half), L2 flushed between
     steps, with the per-kernel-class breakdown and the roofline of the dominant kernel class.
-A step = `trees_per_step` trees (2 per GPU) = 7 aggregation proofs + 8 leaf proofs each.
+A step = `trees_per_step` trees (2 per GPU) = 7 aggregation proofs + 8 leaf proofs each. Tasks and hand-offs follow
+`aggregation.order_key` (default "block": trees in blocks of eight, higher levels first inside a block, so every rank proves
+runs of same-shaped proofs at any N). At N = 1 the line also carries `cpu_baseline` (the oracle on the host cores, full-size
+node layer) and `parity` (the GPU proof of that layer == the oracle prover's, all words, checked outside the timed regions;
+a mismatch fails the run). `tree.per_rank`, `tree.proof_ms_by_shape_rank0` and `tree.node_proofs_in_flight_hist_rank0`
+are diagnostics of the multi-GPU pipeline.
 Prints ONE JSON line on rank 0 (fd 1 is pointed at stderr for everything else).
 """
 from __future__ import annotations
