@@ -171,14 +171,29 @@ def test_executor_propagates_prover_errors():
         agg.TreeExecutor(0, 1, 4, 3, _x_leaf, bad_node).run(2)
 
 
-def _x_worker(rank, world, port, n_leaves, n_trees, lanes, out_dir, order="wave", skew=6):
+def _x_leaf_jitter(lane, tree, index):
+    import random
+    import time
+    time.sleep(random.Random(tree * 131 + index * 7 + 1).random() * 0.003)     # uneven proof times, different on every rank
+    return _x_leaf(lane, tree, index)
+
+
+def _x_node_jitter(lane, tree, nd, left, right):
+    import random
+    import time
+    time.sleep(random.Random(tree * 977 + nd.level * 31 + nd.index).random() * 0.006)
+    return _x_node(lane, tree, nd, left, right)
+
+
+def _x_worker(rank, world, port, n_leaves, n_trees, lanes, out_dir, order="wave", skew=6, jitter=False):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     tr = agg.TorchTransport(dist, torch, torch.device("cpu"), agg.MSG_HEADER_WORDS + max(PROOF_WORDS.values()), 8)
-    ex = agg.TreeExecutor(rank, world, n_leaves, lanes, _x_leaf, _x_node, tr, PROOF_WORDS, timeout_s=120, order=order, skew=skew)
+    ex = agg.TreeExecutor(rank, world, n_leaves, lanes, _x_leaf_jitter if jitter else _x_leaf, _x_node_jitter if jitter else _x_node,
+                          tr, PROOF_WORDS, timeout_s=120, order=order, skew=skew)
     out = ex.run(n_trees)
     for t, proof in out["roots"].items():
         np.save(os.path.join(out_dir, f"root{t}.npy"), proof)
@@ -207,3 +222,19 @@ def test_executor_over_gloo_ranks(tmp_path, world, n_leaves, n_trees, lanes, ord
     assert stats[:, 0].sum() == stats[:, 1].sum() > 0
     if n_trees >= world:
         assert (stats[:, 0] > 0).all() and (stats[:, 1] > 0).all()
+
+
+@pytest.mark.parametrize("order,skew", [("block", 8), ("wave", 3)])
+def test_executor_with_uneven_proof_times_over_four_ranks(tmp_path, order, skew):
+    """bench.py's configuration in miniature (4 lanes, block order of 8 / wave order) with proof times that differ per task:
+    the in-order posting of sends and receives must not deadlock when ranks drift apart, and every root is the serial one."""
+    import torch.multiprocessing as mp
+    world, n_leaves, n_trees, lanes = 4, 8, 20, 4
+    with socket.socket() as s_:
+        s_.bind(("127.0.0.1", 0))
+        port = s_.getsockname()[1]
+    mp.spawn(_x_worker, args=(world, port, n_leaves, n_trees, lanes, str(tmp_path), order, skew, True), nprocs=world, join=True)
+    for t in range(n_trees):
+        assert np.array_equal(np.load(tmp_path / f"root{t}.npy"), _x_serial_root(t, n_leaves))
+    stats = np.array([np.load(tmp_path / f"stats{r}.npy") for r in range(world)])
+    assert [int(x) for x in stats[:, 2:].sum(axis=0)] == [n_trees * (n_leaves >> l) for l in range(4)]
