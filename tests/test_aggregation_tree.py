@@ -224,12 +224,13 @@ def test_executor_over_gloo_ranks(tmp_path, world, n_leaves, n_trees, lanes, ord
         assert (stats[:, 0] > 0).all() and (stats[:, 1] > 0).all()
 
 
-@pytest.mark.parametrize("order,skew", [("block", 8), ("wave", 3)])
-def test_executor_with_uneven_proof_times_over_four_ranks(tmp_path, order, skew):
-    """bench.py's configuration in miniature (4 lanes, block order of 8 / wave order) with proof times that differ per task:
-    the in-order posting of sends and receives must not deadlock when ranks drift apart, and every root is the serial one."""
+@pytest.mark.parametrize("world,lanes,order,skew", [(4, 4, "block", 8), (4, 4, "wave", 3), (8, 2, "block", 8)])
+def test_executor_with_uneven_proof_times(tmp_path, world, lanes, order, skew):
+    """bench.py's configuration in miniature (block order of 8 / wave order; 8 ranks = one leaf per rank and tree, so leaf
+    proofs travel too) with proof times that differ per task: the in-order posting of sends and receives must not deadlock
+    when ranks drift apart, and every root is the serial one."""
     import torch.multiprocessing as mp
-    world, n_leaves, n_trees, lanes = 4, 8, 20, 4
+    n_leaves, n_trees = 8, 20
     with socket.socket() as s_:
         s_.bind(("127.0.0.1", 0))
         port = s_.getsockname()[1]
