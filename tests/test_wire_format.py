@@ -85,3 +85,32 @@ def test_cap_height_and_no_lookup_shapes():
     assert np.array_equal(back_b, blob_b)
     # ext_degree 1 -> w_binomial None: ... rows(3) alu_variant ext_degree=1 Option tag 0 quintic 0 non_primitives len 0
     assert data_b[pl:pl + 5] == bytes([1, 1, 0, 16, 2]) and data_b[pl + 5: pl + 13] == bytes([2, 1, 39, 0, 1, 0, 0, 0])
+
+
+def test_deserializer_survives_mutated_bytes():
+    """Child proofs arrive from other workers: p3r_proof_deserialize must answer damaged input (flipped bytes, truncation,
+    oversized varints, inserted bytes) with an error or a blob, never with a crash or an out-of-bounds read."""
+    F, L, blob, meta = _layer("koala-bear", SMALL_FRI)
+    rng = np.random.default_rng(0)
+    rejected = 0
+    for flags in range(4):
+        data, _ = lib.serialize_proof(F, SMALL_FRI, L.insts, blob, meta, flags)
+        for it in range(80):
+            b = bytearray(data)
+            mode = it % 4
+            if mode == 0:
+                for _ in range(int(rng.integers(1, 6))):
+                    b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+            elif mode == 1:
+                b = b[: int(rng.integers(0, len(b)))]
+            elif mode == 2:
+                pos = int(rng.integers(0, min(len(b), 200)))
+                b[pos:pos + 5] = b"\xff\xff\xff\xff\x7f"
+            else:
+                pos = int(rng.integers(0, len(b)))
+                b[pos:pos] = bytes(rng.integers(0, 256, size=int(rng.integers(1, 9)), dtype=np.uint8))
+            try:
+                lib.deserialize_proof(F, SMALL_FRI, bytes(b), flags)
+            except lib.P3RError:
+                rejected += 1
+    assert rejected > 200          # truncations and structural damage are refused; a flipped payload byte may still parse
